@@ -1,0 +1,84 @@
+/* C ABI of libnslam_sm100a.so — hand-written sm_100a kernels behind the reference's
+ * `droid_backends` operator surface (reference src/droid.cpp:347-363) and the Python-side hot
+ * loops around it.  Every entry point takes raw DEVICE pointers, sizes and a cudaStream_t
+ * (as void*), launches on that stream, never synchronises the host and returns 0 or a
+ * cudaError_t value.  dtype codes: 0 = fp16, 1 = fp32.
+ *
+ * Each function cites the reference interface it replaces (paths relative to /root/reference).
+ * The BA entry points live in nslam_ba.h, the conv/update-operator ones in nslam_nn.h, the
+ * NeRF ones in nslam_ngp.h.
+ */
+#ifndef NSLAM_H_
+#define NSLAM_H_
+
+#include "nslam_ba.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* droid_backends.corr_index_forward (src/droid.cpp:280-288; kernel src/correlation_kernels.cu:19-70)
+ * volume [n,h1,w1,h2,w2], coords [n,2,h1,w1] fp32, out [n,2r+1,2r+1,h1,w1] (dtype of volume). */
+int nslam_corr_index_forward(const void* volume, int dtype, const float* coords, void* out, int n,
+                             int h1, int w1, int h2, int w2, int radius, void* stream);
+
+/* CorrBlock.__call__ (networks/modules/corr.py:40-50) fused over the pyramid:
+ * volumes: HOST array of num_levels device pointers, h2s/w2s: HOST int arrays;
+ * coords [n,2,h1,w1] in level-0 pixels (level l samples coords/2^l); out [n,L*(2r+1)^2,h1,w1]. */
+int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const int* w2s,
+                              int num_levels, int dtype, const float* coords, void* out, int n,
+                              int h1, int w1, int radius, void* stream);
+
+/* CorrBlock.__init__ + CorrBlock.corr (networks/modules/corr.py:23-38,63-72): all-pairs
+ * correlation (f1/4).(f2/4) and the 3 avg-pooled levels, fp16, in one tcgen05 kernel.
+ * fmaps [NF,H,W,C=128] fp16 channels-last; ii/jj [E] int32 DEVICE frame indices;
+ * out_l [E,H,W,H>>l,W>>l] fp16. */
+int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, const int* ii,
+                            const int* jj, int E, void* out0, void* out1, void* out2, void* out3,
+                            void* stream);
+/* same contract, plain SIMT kernels (test cross-check only) */
+int nslam_corr_volume_build_simt(const void* fmaps, int NF, int H, int W, int C, const int* ii,
+                                 const int* jj, int E, void* out0, void* out1, void* out2,
+                                 void* out3, void* stream);
+
+/* droid_backends.altcorr_forward (src/droid.cpp:303-313; kernel src/altcorr_kernel.cu:27-149)
+ * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,N,H1,W1,2] fp32, corr [B,N,(2r+1)^2,H1,W1]. */
+int nslam_altcorr_forward(const void* fmap1, const void* fmap2, int dtype, const float* coords,
+                          void* corr, int B, int N, int H1, int W1, int H2, int W2, int C,
+                          int radius, void* stream);
+
+/* pops.projective_transform, jacobian=False (networks/geom/projective_ops.py:98-145) as used by
+ * RaftVisualFrontend.reproject (slam/visual_frontends/visual_frontend.py:909-918).
+ * poses [N,7], disps [N,ht,wd], intrinsics [N,4] (intr_stride=4) or [4] (intr_stride=0),
+ * ii/jj [E] int64; coords [E,ht,wd,2], valid [E,ht,wd,1] (may be NULL). */
+int nslam_reproject(const float* poses, const float* disps, const float* intrinsics,
+                    int intr_stride, const long long* ii, const long long* jj, int num_edges,
+                    int ht, int wd, float* coords, float* valid, void* stream);
+
+/* droid_backends.frame_distance (src/droid.cpp:230-246; kernel src/droid_kernels.cu:630-769) */
+int nslam_frame_distance(const float* poses, const float* disps, const float* intrinsics,
+                         const long long* ii, const long long* jj, int num, int ht, int wd,
+                         float beta, float* dist, void* stream);
+
+/* droid_backends.projmap (src/droid.cpp:249-264): coords [n,ht,wd,3], valid [n,ht,wd,1] */
+int nslam_projmap(const float* poses, const float* disps, const float* intrinsics,
+                  const long long* ii, const long long* jj, int num, int ht, int wd,
+                  float* coords, float* valid, void* stream);
+
+/* droid_backends.iproj (src/droid.cpp:267-276): points [N,ht,wd,3] */
+int nslam_iproj(const float* poses, const float* disps, const float* intrinsics, int num, int ht,
+                int wd, float* points, void* stream);
+
+/* droid_backends.depth_filter (src/droid.cpp:330-344): counter [n,ht,wd] */
+int nslam_depth_filter(const float* poses, const float* disps, const float* intrinsics,
+                       const long long* inds, const float* thresh, int num_inds, int num_frames,
+                       int ht, int wd, float* counter, void* stream);
+
+/* cvx_upsample (utils/flow_viz.py:166-183): data [K,ht,wd] fp32, mask [K,576,ht,wd], out [K,8ht,8wd] */
+int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out, int K,
+                       int ht, int wd, float pw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,108 @@
+"""ctypes binding of libnslam_sm100a.so — the only way the Python host code reaches the kernels.
+
+There is deliberately no fallback: if the shared object is missing or a CUDA device is absent
+the operators raise (`NslamUnavailable`), they never route through PyTorch/CPU code.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnslam_sm100a.so")
+
+c_void_p, c_int, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+
+class NslamUnavailable(RuntimeError):
+    pass
+
+
+class BAGraph(ctypes.Structure):
+    """mirror of `nslam_ba_graph` (include/nslam_ba.h)"""
+    _fields_ = [(n, c_int) for n in ("E", "P", "K", "kf0", "NR", "NPAIR", "RMAX", "NHC", "NVC")] + \
+               [(n, c_void_p) for n in ("ii", "jj", "kx", "src_ptr", "src_edges", "row_ptr",
+                                        "row_pose", "row_erow", "pair_off", "hc_ptr", "hc_idx",
+                                        "vc_ptr", "vc_idx")]
+
+
+class BABuffers(ctypes.Structure):
+    """mirror of `nslam_ba_buffers` (include/nslam_ba.h)"""
+    _fields_ = [(n, c_void_p) for n in ("poses", "disps_sens", "intrinsics", "extrinsics",
+                                        "targets", "weights", "eta", "disps", "H", "v", "Q",
+                                        "Emat", "w", "Hs", "vs", "edge_aux", "part", "spart",
+                                        "sblk")] + \
+               [(n, c_int) for n in ("ht", "wd", "T")]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: argtypes (all return int)
+    "nslam_corr_index_forward": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "nslam_corr_lookup_pyramid": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "nslam_corr_volume_build": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "nslam_corr_volume_build_simt": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "nslam_altcorr_forward": [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
+    "nslam_reproject": [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P],
+    "nslam_frame_distance": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P],
+    "nslam_projmap": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P],
+    "nslam_iproj": [_P, _P, _P, c_int, c_int, c_int, _P, _P],
+    "nslam_depth_filter": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "nslam_cvx_upsample": [_P, _P, c_int, _P, c_int, c_int, c_int, c_float, _P],
+    "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],
+    "nslam_ba_solve": [_P, _P, c_int, c_int, _P, c_float, c_float, c_float, _P, _P, _P, _P, _P],
+    "nslam_ba_retract": [_P, _P, _P, _P, c_int, c_int, _P],
+    "nslam_pose_retr": [_P, _P, c_int, c_int, _P],
+    "nslam_pose_prior_error": [_P, _P, _P, _P],
+    "nslam_ba_depth": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, c_float, _P],
+    "nslam_ba_cov": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, _P, _P, _P],
+    "nslam_ba_pose_cov": [_P, c_int, _P, _P],
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load(require_cuda=True):
+    """dlopen the library (once) and attach prototypes. Raises NslamUnavailable, never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NslamUnavailable(
+                f"{LIB_PATH} not built — run `python -m nerf_slam_b200.build` (needs nvcc)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = lib
+    if require_cuda:
+        import torch
+        if not torch.cuda.is_available():
+            raise NslamUnavailable("nerf_slam_b200 operators need a CUDA device (sm_100a); "
+                                   "there is no CPU fallback")
+    return _lib
+
+
+def check(err, what):
+    if err != 0:
+        import torch
+        msg = f"{what} failed with cudaError {err}"
+        try:
+            msg += f" ({torch.cuda.cudart().cudaGetErrorString(err)})"
+        except Exception:
+            pass
+        raise RuntimeError(msg)
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device pointer of a (contiguous) torch tensor, or NULL for None"""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())

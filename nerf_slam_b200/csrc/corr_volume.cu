@@ -1,0 +1,350 @@
+// A2 — all-pairs correlation volume + 4-level pyramid in ONE pass.
+//
+// Replaces CorrBlock.__init__/CorrBlock.corr (reference networks/modules/corr.py:23-38,63-72):
+//   corr = (f1/4)^T (f2/4)  [fp16 out, fp32 accumulate]  followed by 3x F.avg_pool2d(2,2) over the
+//   TARGET dims, each level rounded to fp16 and pooled from the previous fp16 level.
+//
+// The reference runs a cuBLAS HGEMM that writes level 0 (61 MB/edge at 640x480), then three
+// pooling kernels that each re-read the previous level, and `CorrBlock.cat` re-copies the whole
+// pool on every add.  The op is HBM-write bound (AI ~93 FLOP/B, SURVEY.md §8d: 63.6 MB/edge).
+//
+// B200 design: per CTA one (edge, 128-source-pixel) strip.  A (128 px x C=128, fp16) is loaded once
+// by TMA; the CTA then walks the target image in 8x16-pixel tiles: TMA brings the 128x128 B tile
+// (box {64c,16w,8h}, SWIZZLE_128B, OOB rows zero-filled) through a 3-stage mbarrier ring, one
+// thread issues 8 tcgen05.mma (M128 N128 K16, fp32 accumulators in TMEM, double buffered), and
+// four epilogue warps read the accumulators with tcgen05.ld, scale by 1/16, round to fp16 and
+// build pyramid levels 1..3 from the SAME registers (an 8x16 target tile contains complete
+// 2x2/4x4/8x8 pooling cells; the fp16 rounding chain of the reference is reproduced), stage the
+// four tiles in shared memory and write every level once with 16-byte coalesced stores.
+// HBM traffic = algorithmic: features in once (L2 resident), each volume byte written once.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace nslam {
+
+constexpr int CV_STAGES = 3;
+constexpr int CV_THREADS = 192;
+constexpr int CV_TH = 8, CV_TW = 16;       // target tile
+constexpr int CV_L0_STRIDE = 272;          // bytes per staged row, 256 + 16 pad (conflict-free 128-bit)
+constexpr int CV_L1_STRIDE = 80;           // 64 + 16
+constexpr int CV_L2_STRIDE = 16;
+constexpr int CV_L3_STRIDE = 4;
+
+struct CvSmem {
+  // offsets in bytes from the 1024-aligned base
+  static constexpr int A = 0;                          // 2 x 16384
+  static constexpr int B = 32768;                      // STAGES x 2 x 16384
+  static constexpr int L0 = B + CV_STAGES * 32768;     // 128 x 272
+  static constexpr int L1 = L0 + 128 * CV_L0_STRIDE;   // 128 x 80
+  static constexpr int L2 = L1 + 128 * CV_L1_STRIDE;
+  static constexpr int L3 = L2 + 128 * CV_L2_STRIDE;
+  static constexpr int BAR = L3 + 128 * CV_L3_STRIDE;  // mbarriers
+  static constexpr int TOTAL = BAR + 128;
+};
+
+struct CvParams {
+  __half* out[4];
+  const int* ii;   // [E] frame index of fmap1
+  const int* jj;   // [E] frame index of fmap2
+  int HW, H2, W2;
+  int NH, NW;      // target tiles
+};
+
+__device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
+
+// store one pyramid level's staged tile to global memory.
+//   PX: pixels per contiguous segment (16>>l), TH: tile rows (8>>l)
+template <int PX, int TH>
+__device__ __forceinline__ void cv_store_level(const unsigned char* stage, int row_stride,
+                                               __half* __restrict__ out, int e, int HW, int m0,
+                                               int Hl, int Wl, int h0l, int w0l, int tid) {
+  constexpr int SEG_BYTES = PX * 2;
+  const bool vec = (Wl % PX) == 0;
+  if (vec) {
+    // one item = one (row, hh) segment, possibly split in 16-byte pieces
+    constexpr int PIECES = SEG_BYTES >= 16 ? SEG_BYTES / 16 : 1;
+    constexpr int PB = SEG_BYTES >= 16 ? 16 : SEG_BYTES;  // bytes per piece: 16, 8 or 4
+    const int nitems = 128 * TH * PIECES;
+    for (int id = tid; id < nitems; id += 128) {
+      const int row = id / (TH * PIECES);
+      const int rem = id % (TH * PIECES);
+      const int hh = rem / PIECES, j = rem % PIECES;
+      const int m = m0 + row, h = h0l + hh, w = w0l + j * (PB / 2);
+      if (m >= HW || h >= Hl || w >= Wl) continue;
+      const unsigned char* src = stage + row * row_stride + hh * SEG_BYTES + j * PB;
+      __half* dst = out + (((size_t)e * HW + m) * Hl + h) * (size_t)Wl + w;
+      if (PB == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+      else if (PB == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+      else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+    }
+  } else {
+    const int nitems = 128 * TH * PX;
+    for (int id = tid; id < nitems; id += 128) {
+      const int row = id / (TH * PX);
+      const int rem = id % (TH * PX);
+      const int hh = rem / PX, ww = rem % PX;
+      const int m = m0 + row, h = h0l + hh, w = w0l + ww;
+      if (m >= HW || h >= Hl || w >= Wl) continue;
+      const __half* src =
+          reinterpret_cast<const __half*>(stage + row * row_stride + hh * SEG_BYTES) + ww;
+      out[(((size_t)e * HW + m) * Hl + h) * (size_t)Wl + w] = *src;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                      const __grid_constant__ CUtensorMap tmB, CvParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CvSmem::BAR);
+  uint64_t* full_b = bars;                    // [STAGES]
+  uint64_t* empty_b = bars + CV_STAGES;       // [STAGES]
+  uint64_t* a_full = bars + 2 * CV_STAGES;    // [1]
+  uint64_t* tm_full = a_full + 1;             // [2]
+  uint64_t* tm_empty = tm_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.y;
+  const int m0 = blockIdx.x * 128;
+  const int NT = p.NH * p.NW;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < CV_STAGES; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
+    tc::mbar_init(a_full, 1);
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int fi = p.ii[e], fj = p.jj[e];
+      tc::mbar_arrive_expect_tx(a_full, 32768);
+      tc::tma_load_3d(sm + CvSmem::A, &tmA, a_full, 0, m0, fi);
+      tc::tma_load_3d(sm + CvSmem::A + 16384, &tmA, a_full, 64, m0, fi);
+      for (int t = 0; t < NT; t++) {
+        const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
+        tc::mbar_wait(&empty_b[s], ph ^ 1);
+        const int h0 = (t / p.NW) * CV_TH, w0 = (t % p.NW) * CV_TW;
+        unsigned char* dst = sm + CvSmem::B + s * 32768;
+        tc::mbar_arrive_expect_tx(&full_b[s], 32768);
+        tc::tma_load_4d(dst, &tmB, &full_b[s], 0, w0, h0, fj);
+        tc::tma_load_4d(dst + 16384, &tmB, &full_b[s], 64, w0, h0, fj);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_f16(128, 128, 0);
+      const uint32_t a_addr = tc::smem_u32(sm + CvSmem::A);
+      tc::mbar_wait(a_full, 0);
+      for (int t = 0; t < NT; t++) {
+        const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
+        const int as = t & 1, aph = (t >> 1) & 1;
+        tc::mbar_wait(&tm_empty[as], aph ^ 1);
+        tc::mbar_wait(&full_b[s], ph);
+        tc::tc_fence_after();
+        const uint32_t b_addr = tc::smem_u32(sm + CvSmem::B + s * 32768);
+        const uint32_t d_tmem = tmem_base + as * 128;
+#pragma unroll
+        for (int kh = 0; kh < 2; kh++) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint64_t ad = tc::umma_desc_sw128(a_addr + kh * 16384 + k * 32);
+            const uint64_t bd = tc::umma_desc_sw128(b_addr + kh * 16384 + k * 32);
+            tc::umma_f16(d_tmem, ad, bd, idesc, (kh | k) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(&empty_b[s]);
+        tc::umma_commit(&tm_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread <-> accumulator row =====================
+    const int q = warp & 3;               // TMEM lane quarter accessible by this warp
+    const int row = q * 32 + lane;        // row inside the 128-row strip
+    const int etid = (warp - 2) * 32 + lane;
+    unsigned char* st0 = sm + CvSmem::L0 + row * CV_L0_STRIDE;
+    unsigned char* st1 = sm + CvSmem::L1 + row * CV_L1_STRIDE;
+    unsigned char* st2 = sm + CvSmem::L2 + row * CV_L2_STRIDE;
+    unsigned char* st3 = sm + CvSmem::L3 + row * CV_L3_STRIDE;
+    for (int t = 0; t < NT; t++) {
+      const int as = t & 1, aph = (t >> 1) & 1;
+      tc::mbar_wait(&tm_full[as], aph);
+      tc::tc_fence_after();
+      // staging buffers are free again once everybody finished the previous tile's stores
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + as * 128 + ((uint32_t)(q * 32) << 16);
+      __half l1[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c * 32, r);
+        tc::tmem_ld_wait();
+        __half h[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) h[i] = __float2half_rn(__uint_as_float(r[i]) * 0.0625f);
+        // level 0: rows 2c, 2c+1 of the tile (16 px each)
+        uint4* d0 = reinterpret_cast<uint4*>(st0 + c * 64);
+        const uint4* hs = reinterpret_cast<const uint4*>(h);
+        d0[0] = hs[0]; d0[1] = hs[1]; d0[2] = hs[2]; d0[3] = hs[3];
+        // level 1: 2x2 means, summation order (h0,w0),(h0,w1),(h1,w0),(h1,w1) like avg_pool2d
+#pragma unroll
+        for (int wp = 0; wp < 8; wp++) {
+          const float s = ((h2f(h[2 * wp]) + h2f(h[2 * wp + 1])) + h2f(h[16 + 2 * wp])) +
+                          h2f(h[16 + 2 * wp + 1]);
+          l1[c][wp] = __float2half_rn(s * 0.25f);
+        }
+        *reinterpret_cast<uint4*>(st1 + c * 16) = *reinterpret_cast<const uint4*>(l1[c]);
+      }
+      // accumulator stage can be overwritten by the next MMA
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
+      __half l2[2][4];
+#pragma unroll
+      for (int c2 = 0; c2 < 2; c2++) {
+#pragma unroll
+        for (int wq = 0; wq < 4; wq++) {
+          const float s = ((h2f(l1[2 * c2][2 * wq]) + h2f(l1[2 * c2][2 * wq + 1])) +
+                           h2f(l1[2 * c2 + 1][2 * wq])) + h2f(l1[2 * c2 + 1][2 * wq + 1]);
+          l2[c2][wq] = __float2half_rn(s * 0.25f);
+        }
+      }
+      *reinterpret_cast<uint4*>(st2) = *reinterpret_cast<const uint4*>(l2);
+      __half l3[2];
+#pragma unroll
+      for (int wr = 0; wr < 2; wr++) {
+        const float s = ((h2f(l2[0][2 * wr]) + h2f(l2[0][2 * wr + 1])) + h2f(l2[1][2 * wr])) +
+                        h2f(l2[1][2 * wr + 1]);
+        l3[wr] = __float2half_rn(s * 0.25f);
+      }
+      *reinterpret_cast<uint32_t*>(st3) = *reinterpret_cast<const uint32_t*>(l3);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // cooperative, coalesced stores of the four tiles
+      const int h0 = (t / p.NW) * CV_TH, w0 = (t % p.NW) * CV_TW;
+      cv_store_level<16, 8>(sm + CvSmem::L0, CV_L0_STRIDE, p.out[0], e, p.HW, m0, p.H2, p.W2, h0,
+                            w0, etid);
+      cv_store_level<8, 4>(sm + CvSmem::L1, CV_L1_STRIDE, p.out[1], e, p.HW, m0, p.H2 >> 1,
+                           p.W2 >> 1, h0 >> 1, w0 >> 1, etid);
+      cv_store_level<4, 2>(sm + CvSmem::L2, CV_L2_STRIDE, p.out[2], e, p.HW, m0, p.H2 >> 2,
+                           p.W2 >> 2, h0 >> 2, w0 >> 2, etid);
+      cv_store_level<2, 1>(sm + CvSmem::L3, CV_L3_STRIDE, p.out[3], e, p.HW, m0, p.H2 >> 3,
+                           p.W2 >> 3, h0 >> 3, w0 >> 3, etid);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Plain SIMT statement of the same op (test cross-check of the tensor-core path and the path
+// for C % 64 != 0).  level 0: one thread per output element; levels 1..3 pool the previous level.
+__global__ void corr_volume_simt_l0_kernel(const __half* __restrict__ fmaps, const int* ii,
+                                           const int* jj, __half* __restrict__ out, int HW, int C) {
+  const int e = blockIdx.z;
+  const int m = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= HW) return;
+  const __half* a = fmaps + ((size_t)ii[e] * HW + m) * C;
+  const __half* b = fmaps + ((size_t)jj[e] * HW + n) * C;
+  float s = 0.f;
+  for (int c = 0; c < C; c++) s += __half2float(a[c]) * __half2float(b[c]);
+  out[((size_t)e * HW + m) * HW + n] = __float2half_rn(s * 0.0625f);
+}
+__global__ void corr_volume_pool_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                        size_t planes, int Hi, int Wi) {
+  const int Ho = Hi >> 1, Wo = Wi >> 1;
+  const size_t total = planes * Ho * Wo;
+  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < total;
+       id += (size_t)gridDim.x * blockDim.x) {
+    const size_t pl = id / (Ho * Wo);
+    const int r = (int)(id % (Ho * Wo));
+    const int y = r / Wo, x = r % Wo;
+    const __half* s = in + pl * Hi * Wi + (size_t)(2 * y) * Wi + 2 * x;
+    const float v = ((h2f(s[0]) + h2f(s[1])) + h2f(s[Wi])) + h2f(s[Wi + 1]);
+    out[id] = __float2half_rn(v * 0.25f);
+  }
+}
+
+}  // namespace nslam
+
+extern "C" {
+
+// fmaps: [NF, H, W, C] fp16 channels-last; ii/jj: [E] int32 frame indices (device);
+// out[l]: [E, H, W, H>>l, W>>l] fp16, l = 0..3.
+int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, const int* ii,
+                            const int* jj, int E, void* out0, void* out1, void* out2, void* out3,
+                            void* stream) {
+  using namespace nslam;
+  if (E == 0) return 0;
+  if (C != 128) return (int)cudaErrorInvalidValue;  // K = 128 = 2 swizzle atoms (DROID feature dim)
+  const int HW = H * W;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)HW, (uint64_t)NF};
+    uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)HW * C * 2};
+    uint32_t box[3] = {64, 128, 1};
+    int r = tc::make_tmap_f16(&tmA, fmaps, 3, dims, strides, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NF};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)HW * C * 2};
+    uint32_t box[4] = {64, CV_TW, CV_TH, 1};
+    int r = tc::make_tmap_f16(&tmB, fmaps, 4, dims, strides, box);
+    if (r) return r;
+  }
+  CvParams p;
+  p.out[0] = (__half*)out0; p.out[1] = (__half*)out1; p.out[2] = (__half*)out2; p.out[3] = (__half*)out3;
+  p.ii = ii; p.jj = jj; p.HW = HW; p.H2 = H; p.W2 = W;
+  p.NH = (H + CV_TH - 1) / CV_TH; p.NW = (W + CV_TW - 1) / CV_TW;
+  const int smem = CvSmem::TOTAL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t er = cudaFuncSetAttribute(corr_volume_tc_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (er != cudaSuccess) return (int)er;
+    configured = true;
+  }
+  dim3 grid((HW + 127) / 128, E);
+  corr_volume_tc_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+int nslam_corr_volume_build_simt(const void* fmaps, int NF, int H, int W, int C, const int* ii,
+                                 const int* jj, int E, void* out0, void* out1, void* out2,
+                                 void* out3, void* stream) {
+  using namespace nslam;
+  (void)NF;
+  if (E == 0) return 0;
+  const int HW = H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((HW + 127) / 128, HW, E);
+  corr_volume_simt_l0_kernel<<<grid, 128, 0, st>>>((const __half*)fmaps, ii, jj, (__half*)out0, HW, C);
+  NSLAM_CHECK_LAUNCH();
+  void* outs[4] = {out0, out1, out2, out3};
+  int Hi = H, Wi = W;
+  for (int l = 1; l < 4; l++) {
+    const size_t planes = (size_t)E * HW;
+    corr_volume_pool_kernel<<<1184, 256, 0, st>>>((const __half*)outs[l - 1], (__half*)outs[l],
+                                                 planes, Hi, Wi);
+    NSLAM_CHECK_LAUNCH();
+    Hi >>= 1; Wi >>= 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+"""CPU tests of the oracle itself and of the host-side logic (no GPU)."""
+import numpy as np
+import pytest
+
+from oracle import ba, corr, geom, se3
+from tests.util import make_targets, make_window
+
+
+def test_se3_group_laws(rng):
+    p = se3.random_poses(rng, 4, 0.5, 40, np.float64)
+    ti, qi = se3.inv_se3(p[:, :3], p[:, 3:])
+    t, q = se3.mul_se3(p[:, :3], p[:, 3:], ti, qi)
+    assert np.allclose(t, 0, atol=1e-12) and np.allclose(np.abs(q[:, 3]), 1, atol=1e-12)
+    # rel(i,j) = Gj * Gi^-1
+    tr, qr = se3.rel_se3(p[0, :3], p[0, 3:], p[1, :3], p[1, 3:])
+    t2, q2 = se3.mul_se3(p[1, :3], p[1, 3:], ti[0], qi[0])
+    assert np.allclose(tr, t2, atol=1e-12) and np.allclose(qr, q2, atol=1e-12)
+    # exp/retract: small twist composes to first order
+    xi = rng.normal(size=(3, 6)) * 1e-3
+    t, q = se3.exp_se3(xi)
+    assert np.allclose(t, xi[:, :3], atol=1e-5) and np.allclose(2 * q[:, :3], xi[:, 3:], atol=1e-5)
+
+
+def test_adj_is_adjoint_transpose(rng):
+    """Ad(G)^T as applied by adjSE3 satisfies <Ad^T X, xi> = <X, Ad xi> with Ad from exp conjugation"""
+    p = se3.random_poses(rng, 1, 0.5, 40, np.float64)[0]
+    X = rng.normal(size=(6,))
+    xi = rng.normal(size=(6,)) * 1e-6
+    # G exp(xi) G^-1 = exp(Ad xi)
+    te, qe = se3.exp_se3(xi)
+    ti, qi = se3.inv_se3(p[:3], p[3:])
+    t1, q1 = se3.mul_se3(p[:3], p[3:], te, qe)
+    t2, q2 = se3.mul_se3(t1, q1, ti, qi)
+    ad_xi = np.concatenate([t2, 2 * q2[:3]])
+    lhs = se3.adj_se3(p[:3], p[3:], X[None])[0] @ xi
+    rhs = X @ ad_xi
+    assert abs(lhs - rhs) < 1e-10
+
+
+def test_lookup_is_bilinear_interpolation(rng):
+    """A3 property: with fp32 volumes the 7x7 window equals dense bilinear sampling of the volume"""
+    n, h1, w1, h2, w2, r = 2, 3, 4, 9, 11, 3
+    vol = rng.normal(size=(n, h1, w1, h2, w2)).astype(np.float32)
+    coords = np.stack([rng.uniform(-2, w2 + 1, (n, h1, w1)), rng.uniform(-2, h2 + 1, (n, h1, w1))], 1).astype(np.float32)
+    out = corr.corr_index_forward(vol, coords, r)
+
+    def sample(nn, y, x, px, py):
+        x0, y0 = int(np.floor(px)), int(np.floor(py))
+        acc = 0.0
+        for (xx, yy, w) in ((x0, y0, (1 - (px - x0)) * (1 - (py - y0))), (x0 + 1, y0, (px - x0) * (1 - (py - y0))),
+                            (x0, y0 + 1, (1 - (px - x0)) * (py - y0)), (x0 + 1, y0 + 1, (px - x0) * (py - y0))):
+            if 0 <= xx < w2 and 0 <= yy < h2:
+                acc += w * vol[nn, y, x, yy, xx]
+        return acc
+    for nn in range(n):
+        for y in range(h1):
+            for x in range(w1):
+                for i in range(2 * r + 1):
+                    for j in range(2 * r + 1):
+                        ref = sample(nn, y, x, coords[nn, 0, y, x] + i - r, coords[nn, 1, y, x] + j - r)
+                        assert abs(out[nn, i, j, y, x] - ref) < 1e-4
+
+
+def test_altcorr_equals_volume_path(rng):
+    """A4 == A2+A3 in fp32 (same maths, different order)"""
+    E, C, H, W, r = 1, 16, 6, 8, 2
+    f = rng.normal(size=(2, C, H, W)).astype(np.float32)
+    f1, f2 = f[0:1], f[1:2]
+    vol = np.einsum("ecm,ecn->emn", (f1 / 4).reshape(E, C, -1), (f2 / 4).reshape(E, C, -1)).reshape(E, H, W, H, W).astype(np.float32)
+    coords = np.stack([rng.uniform(0, W, (E, H, W)), rng.uniform(0, H, (E, H, W))], 1).astype(np.float32)
+    a = corr.corr_index_forward(vol, coords, r).reshape(E, -1, H, W)
+    b = corr.altcorr_forward((f1 / 4).transpose(0, 2, 3, 1), (f2 / 4).transpose(0, 2, 3, 1),
+                             coords.transpose(0, 2, 3, 1)[:, None], r)[:, 0]
+    assert np.allclose(a, b, atol=1e-4)
+
+
+def test_pyramid_shapes_and_floor():
+    rng = np.random.default_rng(0)
+    f = rng.normal(size=(1, 8, 5, 7)).astype(np.float16)
+    pyr = corr.corr_volume_pyramid(f, f)
+    assert [p.shape for p in pyr] == [(1, 5, 7, 5, 7), (1, 5, 7, 2, 3), (1, 5, 7, 1, 1), (1, 5, 7, 0, 0)]
+
+
+def test_ba_hessian_structure(rng):
+    poses, disps, intr, ii, jj = make_window(rng, 5, 8, 10, extra_edges=2)
+    target, weight = make_targets(rng, poses, disps, intr, ii, jj)
+    ext = np.array([0, 0, 0, 0, 0, 0, 1], np.float32)
+    eta = rng.uniform(1e-3, 1e-1, (5, 8, 10)).astype(np.float32)
+    r = ba.reduced_camera_matrix(poses, disps, intr, ext, np.zeros_like(disps), target, weight, eta, ii, jj, 0, 5)
+    H, A, S = r["H"], r["A"], r["S"]
+    assert np.allclose(A, A.T, atol=1e-9) and np.allclose(S, S.T, atol=1e-9)
+    assert np.linalg.eigvalsh(A).min() > -1e-8
+    assert np.linalg.eigvalsh(H + 1e-6 * np.eye(30)).min() > -1e-6   # Schur complement stays PSD
+    # Schur complement == elimination of the depth block of the full system
+    dx, L = ba.dense_solve(H, r["v"], prior_idx=0, prior_err=np.zeros(6), prior_info=1e8)
+    res = (H + np.pad(1e8 * np.eye(6), ((0, 24), (0, 24)))) @ dx.reshape(-1) - r["v"]
+    assert np.abs(res).max() < 1e-6 * max(1.0, np.abs(r["v"]).max())
+
+
+def test_ba_gauss_newton_reduces_residual(rng):
+    """two BA iterations pull the reprojection towards the (noisy) targets"""
+    poses, disps, intr, ii, jj = make_window(rng, 5, 8, 10, extra_edges=2)
+    target, weight = make_targets(rng, poses, disps, intr, ii, jj, noise=0.05)
+    # perturb the state
+    poses2 = poses.copy()
+    poses2[1:, :3] += rng.normal(0, 0.01, (4, 3)).astype(np.float32)
+    ext = np.array([0, 0, 0, 0, 0, 0, 1], np.float32)
+    eta = np.full((5, 8, 10), 1e-4, np.float32)
+
+    def cost(p, d):
+        c, _ = geom.reproject(p, d, intr, ii, jj)
+        return (weight.transpose(0, 2, 3, 1) * (c - target.transpose(0, 2, 3, 1)) ** 2).sum()
+    wTb = np.stack([np.concatenate(se3.inv_se3(p[:3].astype(np.float64), p[3:].astype(np.float64))) for p in poses2])
+    cam = poses2.astype(np.float64)
+    d = disps.astype(np.float64)
+    c0 = cost(cam, d)
+    for _ in range(3):
+        r = ba.reduced_camera_matrix(cam, d, intr, ext, np.zeros_like(disps), target, weight, eta, ii, jj, 0, 5)
+        err = ba.pose_prior_error(wTb[0], wTb[0])
+        dx, _ = ba.dense_solve(r["H"], r["v"], 0, err, 1e8)
+        wTb, cam = ba.gtsam_retract(wTb, ext, dx, 0)
+        d, _ = ba.solve_depth(dx, d, r["Q"], r["E"], r["w"], ii, jj, 0, 5)
+        d = np.maximum(d, 1e-3)
+    assert cost(cam, d) < 0.5 * c0
+
+
+def test_graph_builder_matches_bruteforce(rng):
+    from nerf_slam_b200.ba_graph import BAGraphHost
+    ii = np.array([3, 4, 5, 6, 4, 5, 2, 6, 3], np.int64)
+    jj = np.array([4, 3, 4, 5, 6, 3, 3, 2, 5], np.int64)
+    kf0, kf1 = 3, 7
+    g = BAGraphHost(ii, jj, kf0, kf1)
+    t = g.tables
+    assert list(t["kx"]) == [2, 3, 4, 5, 6] and g.K == 5 and g.P == 4
+    # every edge appears once under its source
+    for k in range(g.K):
+        es = t["src_edges"][t["src_ptr"][k]:t["src_ptr"][k + 1]]
+        assert all(ii[e] == t["kx"][k] for e in es)
+    assert sorted(t["src_edges"]) == list(range(len(ii)))
+    # rows: self rows for frames in the window + edges with target in window
+    nrows = sum(1 for f in t["kx"] if kf0 <= f < kf1) + sum(1 for j in jj if kf0 <= j < kf1)
+    assert g.NR == nrows
+    # dense assembly tables reproduce the brute-force block pattern
+    pat = np.zeros((g.P, g.P), int)
+    for a, b in zip(ii - kf0, jj - kf0):
+        for (x, y) in ((a, a), (a, b), (b, a), (b, b)):
+            if 0 <= x < g.P and 0 <= y < g.P:
+                pat[x, y] += 1
+    cnt = np.diff(t["hc_ptr"]).reshape(g.P, g.P)
+    hs_cnt = np.zeros_like(pat)
+    for blk in range(g.P * g.P):
+        ids = t["hc_idx"][t["hc_ptr"][blk]:t["hc_ptr"][blk + 1]]
+        hs_cnt[blk // g.P, blk % g.P] = (ids >= 0).sum()
+    assert (hs_cnt == pat).all() and (cnt >= pat).all()
+
+
+def test_cvx_upsample_partition_of_unity(rng):
+    K, ht, wd = 2, 5, 6
+    mask = rng.normal(size=(K, 576, ht, wd)).astype(np.float32)
+    ones = geom.cvx_upsample(np.ones((K, ht, wd)), mask)
+    assert np.allclose(ones, 1.0, atol=1e-12)   # convex combination of valid neighbours only
+
+
+def test_frame_distance_f32_tree_close_to_f64(rng):
+    poses, disps, intr, ii, jj = make_window(rng, 4, 16, 20, extra_edges=0)
+    a = geom.frame_distance(poses, disps, intr, ii, jj, 0.3, np.float32)
+    b = geom.frame_distance(poses, disps, intr, ii, jj, 0.3, np.float64)
+    assert np.allclose(a, b, rtol=1e-4)
