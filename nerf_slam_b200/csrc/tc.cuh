@@ -42,8 +42,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol bug must trap (launch error) instead of hanging the GPU.
+#ifndef NSLAM_MBAR_SPIN_LIMIT
+#define NSLAM_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > NSLAM_MBAR_SPIN_LIMIT) __trap();
   }
 }
 

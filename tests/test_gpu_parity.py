@@ -1,0 +1,315 @@
+"""GPU parity tests: hand-written sm_100a kernels (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Tolerances are stated per test (SURVEY.md §8c / north_star: bit-exact for the
+fp16 lookup and integer work, fp32 tolerances elsewhere)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ba as oba
+from oracle import corr as ocorr
+from oracle import geom as ogeom
+from oracle import se3
+from tests.util import make_targets, make_window
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope="module")
+def db():
+    from nerf_slam_b200 import droid_backends
+    return droid_backends
+
+
+# ------------------------------------------------------------------------------------------ A3
+@pytest.mark.parametrize("shape", [(2, 6, 8, 6, 8), (3, 30, 40, 30, 40), (1, 5, 7, 3, 2)])
+def test_corr_lookup_fp16_bit_exact(db, shape):
+    rng = np.random.default_rng(11)
+    n, h1, w1, h2, w2 = shape
+    vol = rng.normal(0, 1, shape).astype(np.float16)
+    base = np.stack(np.meshgrid(np.arange(w1), np.arange(h1)), 0)[None].astype(np.float32) * (w2 / w1)
+    coords = (base + rng.uniform(-8, 8, (n, 2, h1, w1))).astype(np.float32)
+    ref = ocorr.corr_index_forward(vol, coords, 3)
+    out, = db.corr_index_forward(T(vol), T(coords), 3)
+    got = out.cpu().numpy()
+    assert got.dtype == np.float16 and got.shape == ref.shape
+    # bit-exact up to the sign of zero
+    assert np.array_equal(got.astype(np.float32), ref.astype(np.float32))
+
+
+def test_corr_lookup_fp32(db):
+    rng = np.random.default_rng(12)
+    vol = rng.normal(0, 1, (2, 6, 8, 6, 8)).astype(np.float32)
+    coords = rng.uniform(-3, 10, (2, 2, 6, 8)).astype(np.float32)
+    ref = ocorr.corr_index_forward(vol, coords, 3)
+    out, = db.corr_index_forward(T(vol), T(coords), 3)
+    assert np.allclose(out.cpu().numpy(), ref, atol=1e-6)
+
+
+def test_corr_lookup_pyramid_fused_equals_per_level(db):
+    rng = np.random.default_rng(13)
+    E, C, H, W = 2, 16, 16, 24
+    f = rng.normal(0, 1, (2 * E, C, H, W)).astype(np.float16)
+    pyr = ocorr.corr_volume_pyramid(f[:E], f[E:])
+    coords = (np.stack(np.meshgrid(np.arange(W), np.arange(H)), 0)[None] + rng.uniform(-6, 6, (E, 2, H, W))).astype(np.float32)
+    ref = ocorr.corr_lookup_pyramid(pyr, coords, 3)
+    got = db.corr_lookup_pyramid([T(p) for p in pyr], T(coords), 3).cpu().numpy()
+    assert np.array_equal(got.astype(np.float32), ref.astype(np.float32))
+
+
+def test_corr_lookup_empty(db):
+    out, = db.corr_index_forward(torch.zeros(0, 4, 4, 4, 4, dtype=torch.float16, device=DEV),
+                                 torch.zeros(0, 2, 4, 4, device=DEV), 3)
+    assert out.shape == (0, 7, 7, 4, 4)
+
+
+# ------------------------------------------------------------------------------------------ A2
+@pytest.mark.parametrize("hw", [(16, 32), (30, 40), (60, 80), (43, 77)])
+@pytest.mark.parametrize("simt", [True, False])
+def test_corr_volume_pyramid(db, hw, simt):
+    """fp16 volume: tensor-core accumulation order differs from the oracle's -> allow 1 fp16 ulp
+    on level 0 (|x| <~ 8 => 2^-8 abs... use 2e-2 abs) and on the pooled levels."""
+    rng = np.random.default_rng(21)
+    H, W = hw
+    C, NF = 128, 3
+    fm = rng.normal(0, 1, (NF, C, H, W)).astype(np.float16)
+    ii = np.array([0, 1, 2, 0], np.int32); jj = np.array([1, 0, 2, 2], np.int32)
+    ref = ocorr.corr_volume_pyramid(fm[ii], fm[jj])
+    nhwc = T(np.ascontiguousarray(fm.transpose(0, 2, 3, 1)))
+    outs = db.corr_volume_build(nhwc, T(ii), T(jj), simt=simt)
+    torch.cuda.synchronize()
+    for l in range(4):
+        got = outs[l].cpu().numpy().astype(np.float32)
+        r = ref[l].astype(np.float32)
+        assert got.shape == r.shape
+        if r.size:
+            err = np.abs(got - r).max()
+            assert err <= 2e-2, f"level {l}: max err {err}"
+            assert (got == r).mean() > 0.98, f"level {l}: only {(got == r).mean():.4f} bit-equal"
+
+
+# ------------------------------------------------------------------------------------------ A4
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_altcorr(db, dtype):
+    rng = np.random.default_rng(31)
+    B, H, W, C = 2, 12, 16, 128
+    f1 = (rng.normal(0, 1, (B, H, W, C)) / 4).astype(dtype)
+    f2 = (rng.normal(0, 1, (B, H // 2, W // 2, C)) / 4).astype(dtype)
+    coords = (np.stack(np.meshgrid(np.arange(W), np.arange(H)), -1)[None, None] / 2 + rng.uniform(-4, 4, (B, 1, H, W, 2))).astype(np.float32)
+    ref = ocorr.altcorr_forward(f1, f2, coords, 3).astype(np.float32)
+    out, = db.altcorr_forward(T(f1), T(f2), T(coords), 3)
+    got = out.float().cpu().numpy()
+    tol = 1e-4 if dtype == np.float32 else 2e-2
+    assert np.allclose(got, ref, atol=tol), np.abs(got - ref).max()
+
+
+# ------------------------------------------------------------------------------------------ A6 / A16 / misc geometry
+def test_reproject(db):
+    rng = np.random.default_rng(41)
+    poses, disps, intr, ii, jj = make_window(rng, 6, 30, 40)
+    ii = np.concatenate([ii, [2]]); jj = np.concatenate([jj, [2]])   # a stereo edge
+    K = np.tile(intr, (6, 1)) * rng.uniform(0.95, 1.05, (6, 1)).astype(np.float32)
+    ref_c, ref_v = ogeom.reproject(poses, disps, K, ii, jj)
+    c, v = db.reproject(T(poses), T(disps), T(K.astype(np.float32)), T(ii), T(jj))
+    assert np.allclose(c.cpu().numpy(), ref_c, atol=2e-3)
+    assert (v.cpu().numpy() == ref_v).mean() > 0.999
+
+
+def test_frame_distance(db):
+    rng = np.random.default_rng(42)
+    poses, disps, intr, _, _ = make_window(rng, 8, 60, 80)
+    ii, jj = np.meshgrid(np.arange(8), np.arange(8), indexing="ij")
+    ii, jj = ii.reshape(-1), jj.reshape(-1)
+    ref = ogeom.frame_distance(poses, disps, intr, ii, jj, 0.3, np.float32)
+    got = db.frame_distance(T(poses), T(disps), T(intr), T(ii), T(jj), 0.3).cpu().numpy()
+    assert np.allclose(got, ref, rtol=2e-5, atol=1e-6)
+    # ordering contract: argsort agrees wherever the oracle gap exceeds fp32 noise
+    o = np.argsort(ref, kind="stable")
+    gaps = np.diff(ref[o])
+    safe = gaps > 1e-4 * np.maximum(1, ref[o][1:])
+    assert np.all(np.diff(got[o])[safe] > 0)
+
+
+def test_frame_distance_invalid_returns_1000(db):
+    poses = np.array([[0, 0, 0, 0, 0, 0, 1], [0, 0, -10, 0, 0, 0, 1]], np.float32)  # target far behind
+    disps = np.ones((2, 8, 8), np.float32)
+    intr = np.array([8, 8, 3.5, 3.5], np.float32)
+    got = db.frame_distance(T(poses), T(disps), T(intr), T(np.array([0])), T(np.array([1])), 0.3).cpu().numpy()
+    assert got[0] == 1000.0
+
+
+def test_projmap_iproj_depth_filter(db):
+    rng = np.random.default_rng(43)
+    poses, disps, intr, ii, jj = make_window(rng, 7, 20, 24)
+    c, v = db.projmap(T(poses), T(disps), T(intr), T(ii), T(jj))
+    rc, rv = ogeom.projmap(poses, disps, intr, ii, jj)
+    assert np.allclose(c.cpu().numpy(), rc, atol=2e-3) and (v.cpu().numpy() == rv).mean() > 0.999
+    p = db.iproj(T(poses), T(disps), T(intr)).cpu().numpy()
+    assert np.allclose(p, ogeom.iproj(poses, disps, intr), rtol=1e-4, atol=1e-4)
+    inds = np.array([0, 3, 6]); th = np.array([0.05, 0.1, 0.2], np.float32)
+    cnt = db.depth_filter(T(poses), T(disps), T(intr), T(inds), T(th)).cpu().numpy()
+    rc = ogeom.depth_filter(poses, disps, intr, inds, th)
+    assert (cnt == rc).mean() > 0.995
+
+
+# ------------------------------------------------------------------------------------------ A17
+@pytest.mark.parametrize("mdt", [np.float32, np.float16])
+def test_cvx_upsample(db, mdt):
+    rng = np.random.default_rng(51)
+    K, ht, wd = 3, 30, 40
+    data = rng.uniform(0.1, 2, (K, ht, wd)).astype(np.float32)
+    mask = rng.normal(0, 2, (K, 576, ht, wd)).astype(mdt)
+    ref = ogeom.cvx_upsample(data, mask, 1.0, half_weights=(mdt == np.float16))
+    m = T(mask)
+    got = db.cvx_upsample(T(data).unsqueeze(-1), m, 1.0).squeeze(-1).cpu().numpy()
+    assert np.allclose(got, ref, atol=2e-3 if mdt == np.float16 else 1e-5)
+    assert torch.isfinite(m.float()).all()   # caller's mask is not mutated (the reference writes -inf)
+    got2 = db.cvx_upsample(T(data).unsqueeze(-1), m, 0.5).squeeze(-1).cpu().numpy()
+    ref2 = ogeom.cvx_upsample(data, mask, 0.5, half_weights=(mdt == np.float16))
+    assert np.allclose(got2, ref2, atol=5e-3 if mdt == np.float16 else 1e-4)
+
+
+# ------------------------------------------------------------------------------------------ A7-A14
+def _ba_problem(seed, nframes=6, ht=30, wd=40, kf0=0, with_sensor=False, ext=None):
+    rng = np.random.default_rng(seed)
+    poses, disps, intr, ii, jj = make_window(rng, nframes, ht, wd)
+    target, weight = make_targets(rng, poses, disps, intr, ii, jj)
+    if ext is None:
+        ext = np.array([0, 0, 0, 0, 0, 0, 1], np.float32)
+    kf1 = int(max(ii.max(), jj.max())) + 1
+    kx = np.unique(np.concatenate([np.arange(kf0, kf1), ii]))
+    eta = rng.uniform(1e-3, 1e-1, (len(kx), ht, wd)).astype(np.float32)
+    sens = np.zeros_like(disps)
+    if with_sensor:
+        sens[::2] = disps[::2] * rng.uniform(0.9, 1.1, disps[::2].shape).astype(np.float32)
+        sens[:, :3] = 0
+    return dict(poses=poses, disps=disps, intr=intr, ii=ii, jj=jj, target=target, weight=weight,
+                ext=ext, kf0=kf0, kf1=kf1, eta=eta, sens=sens)
+
+
+@pytest.mark.parametrize("cfg", [dict(seed=61), dict(seed=62, kf0=2), dict(seed=63, with_sensor=True),
+                                 dict(seed=64, ext=np.array([0.06, -0.02, -0.01, 0.0077, -0.0105, -0.7018, 0.7123], np.float32)),
+                                 dict(seed=65, nframes=10, ht=60, wd=80)])
+def test_reduced_camera_matrix(db, cfg):
+    """H, v, Q, E, w against the fp64 oracle. fp32 kernels: rel 2e-4 of the block scale."""
+    p = _ba_problem(**cfg)
+    ref = oba.reduced_camera_matrix(p["poses"], p["disps"], p["intr"], p["ext"], p["sens"], p["target"],
+                                    p["weight"], p["eta"], p["ii"], p["jj"], p["kf0"], p["kf1"])
+    H, v, Q, E, w = db.reduced_camera_matrix(
+        T(p["poses"]), T(p["poses"]), T(p["disps"]), T(p["intr"]), T(p["ext"]), T(p["sens"]),
+        T(p["target"]), T(p["weight"]), T(p["eta"]), T(p["ii"]), T(p["jj"]), p["kf0"], p["kf1"])
+    prob = db.reduced_camera_matrix.last_problem
+
+    def close(a, b, rel, name):
+        a = a.cpu().numpy().reshape(b.shape)
+        scale = np.abs(b).max() + 1e-12
+        err = np.abs(a - b).max() / scale
+        assert err < rel, f"{name}: rel err {err:.3e}"
+    close(prob.Hs, ref["Hs"], 2e-4, "Hs")
+    close(prob.vs, ref["vs"], 2e-4, "vs")
+    close(Q, ref["Q"], 1e-4, "Q")
+    close(w, ref["w"], 2e-4, "w")
+    close(E, ref["E"], 2e-4, "E")
+    close(H, ref["H"], 5e-4, "H")
+    close(v, ref["v"].reshape(-1, 1), 5e-4, "v")
+
+
+def test_ba_full_iteration(db):
+    """linearise -> solve (+prior) -> retract -> depth update, vs oracle; then covariances."""
+    p = _ba_problem(66, nframes=7)
+    dev_poses = T(p["poses"])
+    wTb0 = np.stack([np.concatenate(se3.inv_se3(q[:3].astype(np.float64), q[3:].astype(np.float64))) for q in p["poses"]]).astype(np.float32)
+    disps = T(p["disps"])
+    prob = db.BAProblem(dev_poses, disps, T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]),
+                        T(p["weight"]), T(p["eta"]), p["ii"], p["jj"], p["kf0"], p["kf1"])
+    prob.linearize()
+    ref = oba.reduced_camera_matrix(p["poses"], p["disps"], p["intr"], p["ext"], p["sens"], p["target"],
+                                    p["weight"], p["eta"], p["ii"], p["jj"], p["kf0"], p["kf1"])
+    err6 = torch.zeros(6, device=DEV)
+    dx, linv, status = prob.solve(prior_idx=0, prior_err=err6, prior_info=1e8, want_linv=True)
+    assert int(status.item()) == 0
+    # the solve is checked against the system the GPU itself assembled (fp32 H -> fp64 Cholesky)
+    Hg = prob.H.double().cpu().numpy(); vg = prob.v.double().cpu().numpy().reshape(-1)
+    rdx, L = oba.dense_solve(Hg, vg, 0, np.zeros(6), 1e8)
+    assert np.allclose(dx.cpu().numpy(), rdx, rtol=1e-4, atol=1e-7)
+    Hp = Hg.copy(); Hp[:6, :6] += 1e8 * np.eye(6)
+    res = Hp @ dx.double().cpu().numpy().reshape(-1) - vg
+    assert np.abs(res).max() <= 1e-5 * max(1.0, np.abs(vg).max())
+    # and against the oracle's own linearisation (looser: fp32 assembly)
+    odx, _ = oba.dense_solve(ref["H"], ref["v"], 0, np.zeros(6), 1e8)
+    assert np.allclose(dx.cpu().numpy(), odx, rtol=5e-2, atol=5e-5)
+    # L^-1
+    Li = np.linalg.inv(L)
+    assert np.allclose(linv.cpu().numpy(), Li, rtol=1e-3, atol=1e-6 * np.abs(Li).max())
+    # retract
+    from nerf_slam_b200 import _lib
+    lib = _lib.load()
+    wTb = T(wTb0.copy()); cTw = T(p["poses"].copy())
+    _lib.check(lib.nslam_ba_retract(_lib.ptr(wTb), _lib.ptr(cTw), _lib.ptr(T(p["ext"])), _lib.ptr(dx),
+                                    p["kf0"], prob.gh.P, _lib.stream_ptr()), "retract")
+    rw, rc = oba.gtsam_retract(wTb0, p["ext"], dx.cpu().numpy(), p["kf0"])
+
+    def pose_close(a, b, tol):
+        a = a.astype(np.float64); sgn = np.sign((a[:, 3:] * b[:, 3:]).sum(-1, keepdims=True))
+        return np.allclose(a[:, :3], b[:, :3], atol=tol) and np.allclose(a[:, 3:] * sgn, b[:, 3:], atol=tol)
+    assert pose_close(wTb.cpu().numpy(), rw, 1e-6) and pose_close(cTw.cpu().numpy(), rc, 1e-5)
+    # depth update (uses the GPU's own Q,E,w; oracle formula)
+    rd, _ = oba.solve_depth(dx.cpu().numpy(), p["disps"], prob.Q.cpu().numpy(), prob.E.cpu().numpy(),
+                            prob.w.cpu().numpy(), p["ii"], p["jj"], p["kf0"], p["kf1"])
+    prob.depth_update(dx, clamp_min=1e-3)
+    assert np.allclose(disps.cpu().numpy(), np.maximum(rd, 1e-3), rtol=1e-4, atol=1e-5)
+    # covariances
+    sg, zc, dc = prob.covariances(linv)
+    rsg, rzc, rdc = oba.covariances(L, prob.E.double().cpu().numpy(), prob.Q.double().cpu().numpy(),
+                                    p["ii"], p["jj"], p["kf0"], p["kf1"], disps.cpu().numpy())
+    assert np.allclose(sg.cpu().numpy(), rsg, rtol=2e-3, atol=1e-9)
+    assert np.allclose(zc.cpu().numpy().reshape(rzc.shape), rzc, rtol=2e-3, atol=1e-9)
+    assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9)
+
+
+def test_solve_depth_and_poses_api(db):
+    p = _ba_problem(67)
+    H, v, Q, E, w = db.reduced_camera_matrix(
+        T(p["poses"]), T(p["poses"]), T(p["disps"]), T(p["intr"]), T(p["ext"]), T(p["sens"]),
+        T(p["target"]), T(p["weight"]), T(p["eta"]), T(p["ii"]), T(p["jj"]), p["kf0"], p["kf1"])
+    rng = np.random.default_rng(0)
+    dx = (rng.normal(0, 1e-2, (p["kf1"] - p["kf0"], 6))).astype(np.float32)
+    disps = T(p["disps"].copy())
+    db.solve_depth(T(dx), disps, Q, E, w, T(p["ii"]), T(p["jj"]), p["kf0"], p["kf1"])
+    rd, _ = oba.solve_depth(dx, p["disps"], Q.cpu().numpy(), E.cpu().numpy(), w.cpu().numpy(),
+                            p["ii"], p["jj"], p["kf0"], p["kf1"])
+    assert np.allclose(disps.cpu().numpy(), rd, rtol=1e-4, atol=1e-5)
+    poses = T(p["poses"].copy())
+    db.solve_poses(poses, T(dx), p["kf0"], p["kf1"])
+    t, q = se3.retr_se3(dx.astype(np.float64), p["poses"][:, :3].astype(np.float64), p["poses"][:, 3:].astype(np.float64))
+    assert np.allclose(poses.cpu().numpy(), np.concatenate([t, q], -1), atol=1e-5)
+
+
+def test_solver_failure_zeroes_update(db):
+    """Cholesky failure => zero step, never crash (src/droid_kernels.cu:1333-1337)"""
+    from nerf_slam_b200 import _lib
+    lib = _lib.load()
+    H = -torch.eye(12, device=DEV); v = torch.ones(12, 1, device=DEV)
+    work = torch.empty(2 * 144 + 24, dtype=torch.float64, device=DEV)
+    dx = torch.ones(2, 6, device=DEV); st = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(lib.nslam_ba_solve(_lib.ptr(H), _lib.ptr(v), 2, -1, None, 0.0, 0.0, 0.0, _lib.ptr(work),
+                                  _lib.ptr(dx), None, _lib.ptr(st), _lib.stream_ptr()), "solve")
+    assert int(st.item()) == 1 and float(dx.abs().max()) == 0.0
+
+
+def test_pose_prior_error(db):
+    from nerf_slam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    p = se3.random_poses(rng, 2, 0.3, 20, np.float32)
+    err = torch.zeros(6, device=DEV)
+    _lib.check(lib.nslam_pose_prior_error(_lib.ptr(T(p[0])), _lib.ptr(T(p[1])), _lib.ptr(err), _lib.stream_ptr()), "prior")
+    assert np.allclose(err.cpu().numpy(), oba.pose_prior_error(p[0], p[1]), atol=1e-5)
+    # retract(prior, err) == x
+    t, q = se3.pose3_retract(p[1, :3].astype(np.float64), p[1, 3:].astype(np.float64), err.double().cpu().numpy())
+    assert np.allclose(t, p[0, :3], atol=1e-5)
