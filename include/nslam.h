@@ -24,10 +24,11 @@ int nslam_corr_index_forward(const void* volume, int dtype, const float* coords,
 
 /* CorrBlock.__call__ (networks/modules/corr.py:40-50) fused over the pyramid:
  * volumes: HOST array of num_levels device pointers, h2s/w2s: HOST int arrays;
- * coords [n,2,h1,w1] in level-0 pixels (level l samples coords/2^l); out [n,L*(2r+1)^2,h1,w1]. */
+ * coords [n,2,h1,w1] in level-0 pixels (level l samples coords/2^l); out [n,L*(2r+1)^2,h1,w1].
+ * slots: optional DEVICE int32 [n]: edge n reads volume slots[n] (correlation arena), NULL = n. */
 int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const int* w2s,
                               int num_levels, int dtype, const float* coords, void* out, int n,
-                              int h1, int w1, int radius, void* stream);
+                              int h1, int w1, int radius, const int* slots, void* stream);
 
 /* CorrBlock.__init__ + CorrBlock.corr (networks/modules/corr.py:23-38,63-72): all-pairs
  * correlation (f1/4).(f2/4) and the 3 avg-pooled levels, fp16, in one tcgen05 kernel.

@@ -46,7 +46,8 @@ struct LookupLevels {
 template <typename T, int R>
 __global__ void __launch_bounds__(128)
 corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restrict__ out,
-                   int h1, int w1, int num_levels, int scale_coords) {
+                   int h1, int w1, int num_levels, int scale_coords,
+                   const int* __restrict__ slots) {
   constexpr int RD = 2 * R + 1;
   constexpr int NT = RD + 1;  // taps per axis
   const int hw = h1 * w1;
@@ -56,8 +57,9 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
   if (p >= hw) return;
 
   const int h2 = lv.h2[l], w2 = lv.w2[l];
+  const int vn = slots ? slots[n] : n;  // arena slot of edge n (CorrPool) or dense index
   const T* __restrict__ vol =
-      reinterpret_cast<const T*>(lv.vol[l]) + ((size_t)n * hw + p) * (size_t)(h2 * w2);
+      reinterpret_cast<const T*>(lv.vol[l]) + ((size_t)vn * hw + p) * (size_t)(h2 * w2);
 
   float x0 = coords[((size_t)n * 2 + 0) * hw + p];
   float y0 = coords[((size_t)n * 2 + 1) * hw + p];
@@ -112,25 +114,25 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
 template <typename T>
 static int launch_lookup(const LookupLevels& lv, const float* coords, void* out, int n, int h1,
                          int w1, int num_levels, int radius, int scale_coords,
-                         cudaStream_t st) {
+                         const int* slots, cudaStream_t st) {
   if (n == 0) return 0;
   dim3 grid((h1 * w1 + 127) / 128, num_levels, n), block(128);
   switch (radius) {
     case 3:
       corr_lookup_kernel<T, 3><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords);
+                                                      scale_coords, slots);
       break;
     case 4:
       corr_lookup_kernel<T, 4><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords);
+                                                      scale_coords, slots);
       break;
     case 2:
       corr_lookup_kernel<T, 2><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords);
+                                                      scale_coords, slots);
       break;
     case 1:
       corr_lookup_kernel<T, 1><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords);
+                                                      scale_coords, slots);
       break;
     default:
       return (int)cudaErrorInvalidValue;
@@ -150,16 +152,16 @@ int nslam_corr_index_forward(const void* volume, int dtype, const float* coords,
   lv.vol[0] = volume; lv.h2[0] = h2; lv.w2[0] = w2;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
-    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, 1, radius, 0, st);
+    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, st);
   if (dtype == 1)
-    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, 1, radius, 0, st);
+    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, st);
   return (int)cudaErrorInvalidValue;
 }
 
 // Fused pyramid lookup: out[n][num_levels*(2r+1)^2][h1][w1]; level l is sampled at coords/2^l.
 int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const int* w2s,
                               int num_levels, int dtype, const float* coords, void* out, int n,
-                              int h1, int w1, int radius, void* stream) {
+                              int h1, int w1, int radius, const int* slots, void* stream) {
   if (num_levels < 1 || num_levels > 4) return (int)cudaErrorInvalidValue;
   nslam::LookupLevels lv{};
   for (int l = 0; l < num_levels; l++) {
@@ -167,9 +169,9 @@ int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
-    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, num_levels, radius, 1, st);
+    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, st);
   if (dtype == 1)
-    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, num_levels, radius, 1, st);
+    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, st);
   return (int)cudaErrorInvalidValue;
 }
 

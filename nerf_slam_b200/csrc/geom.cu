@@ -71,30 +71,42 @@ frame_distance_kernel(const float* __restrict__ poses, const float* __restrict__
   float accum = 0.f, valid = 0.f, total = 0.f;
   const int hw = ht * wd;
   const float* __restrict__ dsp = disps + (size_t)ix * hw;
+  // Per-pixel arithmetic with EXPLICIT rounding points.  They reproduce, operation for operation,
+  // what nvcc 12.9 emits for the reference kernel (checked against the SASS of oracle/_ref):
+  // a*b - c*d  -> fma(a, b, -(c*d));  the three translation products d*t are plain multiplies
+  // shared by the full-motion and the translation-only projections (NOT fused into the adds);
+  // fx*(x/z)+cx -> fma;  du^2 + dv^2 -> fma(du, du, dv*dv);  accum += w*d -> fma(d, w, accum).
+  const float q0 = qij[0], q1 = qij[1], q2 = qij[2], q3 = qij[3];
+  const float omb = 1 - beta;
   for (int k = tid; k < hw; k += 256) {
     const float u = (float)(k % wd), v = (float)(k / wd);
-    float Xi[4] = {(u - cx) / fx, (v - cy) / fy, 1.0f, dsp[k]};
-    float Xj[4];
-    se3_act4(tij, qij, Xi, Xj);
-    float du = fx * (Xj[0] / Xj[2]) + cx - u;
-    float dv = fy * (Xj[1] / Xj[2]) + cy - v;
-    float d = sqrtf(du * du + dv * dv);
-    total += beta;
-    if (Xj[2] > NSLAM_MIN_DEPTH) {
-      accum += beta * d;
-      valid += beta;
+    const float X = __fdiv_rn(__fsub_rn(u, cx), fx), Y = __fdiv_rn(__fsub_rn(v, cy), fy);
+    const float dsk = dsp[k];
+    float uv0 = __fmaf_rn(q2, -Y, q1);                 uv0 = __fadd_rn(uv0, uv0);
+    float uv1 = __fmaf_rn(q2, X, -q0);                 uv1 = __fadd_rn(uv1, uv1);
+    float uv2 = __fmaf_rn(q0, Y, -__fmul_rn(q1, X));   uv2 = __fadd_rn(uv2, uv2);
+    const float r0 = __fadd_rn(__fmaf_rn(q3, uv0, X), __fmaf_rn(q1, uv2, -__fmul_rn(q2, uv1)));
+    const float r1 = __fadd_rn(__fmaf_rn(q3, uv1, Y), __fmaf_rn(q2, uv0, -__fmul_rn(q0, uv2)));
+    const float r2 = __fadd_rn(__fmaf_rn(q3, uv2, 1.0f), __fmaf_rn(q0, uv1, -__fmul_rn(q1, uv0)));
+    const float p0 = __fmul_rn(tij[0], dsk), p1 = __fmul_rn(tij[1], dsk), p2 = __fmul_rn(tij[2], dsk);
+    float x = __fadd_rn(r0, p0), y = __fadd_rn(r1, p1), z = __fadd_rn(r2, p2);
+    float du = __fsub_rn(__fmaf_rn(fx, __fdiv_rn(x, z), cx), u);
+    float dv = __fsub_rn(__fmaf_rn(fy, __fdiv_rn(y, z), cy), v);
+    float d = __fsqrt_rn(__fmaf_rn(du, du, __fmul_rn(dv, dv)));
+    total = __fadd_rn(total, beta);
+    if (z > NSLAM_MIN_DEPTH) {
+      accum = __fmaf_rn(d, beta, accum);
+      valid = __fadd_rn(valid, beta);
     }
     // translation-only flow
-    Xj[0] = Xi[0] + Xi[3] * tij[0];
-    Xj[1] = Xi[1] + Xi[3] * tij[1];
-    Xj[2] = Xi[2] + Xi[3] * tij[2];
-    du = fx * (Xj[0] / Xj[2]) + cx - u;
-    dv = fy * (Xj[1] / Xj[2]) + cy - v;
-    d = sqrtf(du * du + dv * dv);
-    total += (1 - beta);
-    if (Xj[2] > NSLAM_MIN_DEPTH) {
-      accum += (1 - beta) * d;
-      valid += (1 - beta);
+    x = __fadd_rn(p0, X); y = __fadd_rn(p1, Y); z = __fadd_rn(p2, 1.0f);
+    du = __fsub_rn(__fmaf_rn(fx, __fdiv_rn(x, z), cx), u);
+    dv = __fsub_rn(__fmaf_rn(fy, __fdiv_rn(y, z), cy), v);
+    d = __fsqrt_rn(__fmaf_rn(du, du, __fmul_rn(dv, dv)));
+    total = __fadd_rn(total, omb);
+    if (z > NSLAM_MIN_DEPTH) {
+      accum = __fmaf_rn(d, omb, accum);
+      valid = __fadd_rn(valid, omb);
     }
   }
   // tree: v[t] += v[t+128]; v[t] += v[t+64]; v[t] += v[t+32]; then 16..1 inside warp 0

@@ -56,14 +56,15 @@ def corr_index_backward(volume, coords, corr_grad, radius):
                               "inference hot path (SURVEY.md §8, out of scope)")
 
 
-def corr_lookup_pyramid(volumes, coords, radius):
+def corr_lookup_pyramid(volumes, coords, radius, slots=None):
     """fused 4-level version of CorrBlock.__call__ (networks/modules/corr.py:40-50):
     volumes: list of [n,h1,w1,h2>>l,w2>>l]; coords [n,2,h1,w1] (level-0 pixels) ->
     [n, L*(2r+1)^2, h1, w1]"""
     lib = _lib.load()
     L = len(volumes)
     _chk(coords, *volumes)
-    n, h1, w1 = volumes[0].shape[:3]
+    h1, w1 = volumes[0].shape[1:3]
+    n = coords.shape[0]
     dt = volumes[0].dtype
     rd = 2 * radius + 1
     out = torch.empty(n, L * rd * rd, h1, w1, dtype=dt, device=coords.device)
@@ -74,7 +75,7 @@ def corr_lookup_pyramid(volumes, coords, radius):
                                              ctypes.cast(h2s, ctypes.c_void_p),
                                              ctypes.cast(w2s, ctypes.c_void_p), L, _DT[dt],
                                              _lib.ptr(coords), _lib.ptr(out), n, h1, w1, radius,
-                                             _lib.stream_ptr()), "corr_lookup_pyramid")
+                                             _lib.ptr(slots), _lib.stream_ptr()), "corr_lookup_pyramid")
     return out
 
 
@@ -92,6 +93,15 @@ def corr_volume_build(fmaps_nhwc, ii, jj, simt=False):
     _lib.check(fn(_lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj), E,
                   *[_lib.ptr(o) for o in outs], _lib.stream_ptr()), "corr_volume_build")
     return outs
+
+
+def corr_volume_build_into(fmaps_nhwc, ii, jj, outs):
+    """as corr_volume_build but writes into caller-provided level tensors (arena slots)"""
+    lib = _lib.load()
+    NF, H, W, C = fmaps_nhwc.shape
+    _lib.check(lib.nslam_corr_volume_build(_lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj),
+                                           ii.shape[0], *[_lib.ptr(o) for o in outs], _lib.stream_ptr()),
+               "corr_volume_build")
 
 
 def altcorr_forward(fmap1, fmap2, coords, radius):

@@ -1,0 +1,658 @@
+"""RaftVisualFrontend — the live SLAM front-end of the reference
+(slam/visual_frontends/visual_frontend.py:62-1391) re-hosted on the sm_100a kernels.
+
+Same public surface: RaftVisualFrontend(world_T_body_t0, body_T_cam0, args, device)
+  .forward(batch) -> (x0, factors, viz_out)      .update(...)      .ba(...)      .stop_condition()
+Same algorithm and constants (SURVEY.md §5 "Config", §9): warm-up 8 keyframes, motion filter
+2.4 px, neighbourhood radius 3 at init, proximity edges (thresh 16, radius 2, nms 1, beta 0.3),
+max 48 factors, max age 25, 4+2 update iterations, keyframe threshold 4.0, BA window
+kf0 = max(0, min(ii)), 1e-4-sigma prior on frame 0, inactive edges >= kf0-3 prepended.
+
+What is different (B200 design, not a translation):
+  * state lives in pre-allocated device arenas; correlation pyramids in a slot pool (CorrPool)
+    so edges are added/removed without re-copying volumes (reference: torch.cat per add);
+  * features are stored channels-last fp16 — the layout the tcgen05 kernels consume;
+  * the whole BA iteration (linearise -> Schur -> dense fp64 Cholesky -> SE3 retract -> depth
+    update -> covariances) runs on the GPU stream: no Eigen, no gtsam, no per-block
+    .cpu().numpy() HessianFactor loop, no host synchronisation inside update();
+  * the edge list is mirrored on the host, so graph bookkeeping (the bit-exact contract of
+    add_proximity_factors) costs no device round-trips except the distance read-back that the
+    reference also does.
+gtsam is not required: poses may be given as gtsam.Pose3, 4x4 matrices or [t, q_xyzw] vectors.
+"""
+import numpy as np
+import torch
+
+from . import droid_backends as db
+from . import _lib
+from .corr import CorrPool, AltCorrBlock
+from .networks import BasicEncoder, UpdateModule, load_droid_weights
+
+
+# ------------------------------------------------------------------------------------------ pose utils
+def _as_matrix(p):
+    if p is None:
+        return np.eye(4)
+    if hasattr(p, "matrix"):
+        return np.asarray(p.matrix(), dtype=np.float64)
+    p = np.asarray(p, dtype=np.float64)
+    if p.shape == (4, 4):
+        return p
+    if p.shape == (7,):
+        return tq_to_matrix(p)
+    raise ValueError("pose must be gtsam.Pose3, 4x4 or [t,q]")
+
+
+def tq_to_matrix(v):
+    x, y, z, w = v[3:]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = v[:3]
+    return T
+
+
+def matrix_to_tq(T):
+    R = T[:3, :3]
+    tr = np.trace(R)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0) * 2
+        w = 0.25 * s; x = (R[2, 1] - R[1, 2]) / s; y = (R[0, 2] - R[2, 0]) / s; z = (R[1, 0] - R[0, 1]) / s
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+        w = (R[2, 1] - R[1, 2]) / s; x = 0.25 * s; y = (R[0, 1] + R[1, 0]) / s; z = (R[0, 2] + R[2, 0]) / s
+    elif R[1, 1] > R[2, 2]:
+        s = np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+        w = (R[0, 2] - R[2, 0]) / s; x = (R[0, 1] + R[1, 0]) / s; y = 0.25 * s; z = (R[1, 2] + R[2, 1]) / s
+    else:
+        s = np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+        w = (R[1, 0] - R[0, 1]) / s; x = (R[0, 2] + R[2, 0]) / s; y = (R[1, 2] + R[2, 1]) / s; z = 0.25 * s
+    return np.array([T[0, 3], T[1, 3], T[2, 3], x, y, z, w])
+
+
+def coords_grid(ht, wd, device):
+    y, x = torch.meshgrid(torch.arange(ht, device=device).float(), torch.arange(wd, device=device).float(),
+                          indexing="ij")
+    return torch.stack([x, y], dim=-1)
+
+
+class RaftVisualFrontend:
+    def __init__(self, world_T_body_t0, body_T_cam0, args, device="cuda:0"):
+        self.args = args
+        self.device = device
+        self.kf_idx = 0
+        self.kf_idx_to_f_idx = {}
+        self.f_idx_to_kf_idx = {}
+        self.last_kf_idx = 0
+        self.last_k = None
+        self.global_ba = bool(getattr(args, "global_ba", False))
+        self.stop = False
+        self.compute_covariances = True
+        self.buffer = args.buffer
+        self.stereo = bool(getattr(args, "stereo", False))
+        self.is_initialized = False
+
+        # constants: visual_frontend.py:92-131
+        self.keyframe_warmup = 8
+        self.max_age = 25
+        self.max_factors = 48
+        self.kf_init_count = 8
+        self.motion_filter_thresh = 2.4
+        self.keyframe_thresh = 4.0
+        self.frontend_thresh = 16.0
+        self.frontend_window = 25
+        self.frontend_radius = 2
+        self.frontend_nms = 1
+        self.beta = 0.3
+        self.backend_thresh = 22.0
+        self.backend_radius = 2
+        self.backend_nms = 3
+        self.iters1 = 4
+        self.iters2 = 2
+        self.dsf = 8
+        self.corr_impl = "volume"
+
+        Twb = _as_matrix(world_T_body_t0)
+        Tbc = _as_matrix(body_T_cam0)
+        self.world_T_body_t0 = matrix_to_tq(Twb)
+        self.world_T_cam0_t0 = matrix_to_tq(Twb @ Tbc)
+        self.cam0_t0_T_world = matrix_to_tq(np.linalg.inv(Twb @ Tbc))
+        self.cam0_T_body = torch.tensor(matrix_to_tq(np.linalg.inv(Tbc)), device=device, dtype=torch.float32)
+
+        # networks (A1, A5); weights: args.weights (droid.pth) or seeded random init
+        self.feature_net = BasicEncoder(128, "instance", torch.Generator().manual_seed(10))
+        self.context_net = BasicEncoder(256, "none", torch.Generator().manual_seed(11))
+        self.update_net = UpdateModule(torch.Generator().manual_seed(12))
+        wpath = getattr(args, "weights", None)
+        self.weights_source = "random-init(seeded)"
+        if wpath:
+            sd = load_droid_weights(wpath)
+            self.feature_net.load_state_dict(sd, "feature_net.")
+            self.context_net.load_state_dict(sd, "context_net.")
+            self.update_net.load_state_dict(sd, "update_net.")
+            self.weights_source = wpath
+        for m in (self.feature_net, self.context_net, self.update_net):
+            m.to(device=device, dtype=torch.float16)
+
+        # prior sigmas (visual_frontend.py:142-153)
+        self.g_prior_cov = torch.block_diag(0.01 ** 2 * torch.eye(3), 0.01 ** 2 * torch.eye(3)).to(device)
+        self.idepth_prior_cov = 0.1 ** 2
+        self.prior_info = 1.0 / (1e-4 ** 2)   # PriorFactorPose3 sigma 1e-4 (:1240-1241)
+        self._mean = torch.tensor([0.485, 0.456, 0.406], device=device)[:, None, None]
+        self._std = torch.tensor([0.229, 0.224, 0.225], device=device)[:, None, None]
+        self.stats = {"updates": 0, "ba_fail": 0}
+
+    def stop_condition(self):
+        return self.stop
+
+    # ------------------------------------------------------------------ buffers
+    def initialize_buffers(self, image_size):
+        dev, B = self.device, self.buffer
+        self.img_height = h = int(image_size[0])
+        self.img_width = w = int(image_size[1])
+        self.ht, self.wd = h // self.dsf, w // self.dsf
+        ht, wd = self.ht, self.wd
+        self.coords0 = coords_grid(ht, wd, dev)
+        f = dict(dtype=torch.float32, device=dev)
+        self.cam0_timestamps = torch.zeros(B, **f)
+        self.cam0_images = torch.zeros(B, 3, h, w, dtype=torch.uint8, device=dev)
+        self.cam0_intrinsics = torch.zeros(B, 4, **f)
+        self.gt_poses = torch.zeros(B, 4, 4, **f)
+        self.gt_depths = torch.zeros(B, 1, h, w, **f)
+        self.cam0_T_world = torch.zeros(B, 7, **f)
+        self.world_T_body = torch.zeros(B, 7, **f)
+        self.world_T_body_cov = torch.zeros(B, 6, 6, **f)
+        self.cam0_idepths = torch.ones(B, ht, wd, **f)
+        self.cam0_idepths_cov = torch.ones(B, ht, wd, **f) * self.idepth_prior_cov
+        self.cam0_depths_cov = torch.ones(B, ht, wd, **f)
+        self.cam0_idepths_sensed = torch.zeros(B, ht, wd, **f)
+        self.cam0_idepths_up = torch.zeros(B, h, w, **f)
+        self.cam0_depths_cov_up = torch.ones(B, h, w, **f)
+        self.cam0_T_world[:] = torch.tensor(self.cam0_t0_T_world, **f)
+        self.world_T_body[:] = torch.tensor(self.world_T_body_t0, **f)
+        self.world_T_body_cov[:] = self.g_prior_cov * torch.eye(6, device=dev)
+        self.prior_pose = torch.tensor(self.world_T_cam0_t0, **f)   # prior mean (visual_frontend.py:1235)
+        cams = 2 if self.stereo else 1
+        self.cameras = cams
+        # features channels-last fp16 (tcgen05 operand layout); contexts channels-first views of NHWC storage
+        self.features_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)
+        self.contexts_imgs = torch.zeros(B, cams, 128, ht, wd, dtype=torch.float16, device=dev)
+        self.cst_contexts_imgs = torch.zeros(B, cams, 128, ht, wd, dtype=torch.float16, device=dev)
+        self.corr_pool = CorrPool(int(getattr(self.args, "corr_slots", 2 * self.max_factors)), ht, wd, dev)
+        self._reset_graph()
+        self.viz_idx = torch.zeros(B, device=dev, dtype=torch.bool)
+
+    def _reset_graph(self):
+        dev, ht, wd = self.device, self.ht, self.wd
+        self.ii_h = np.zeros(0, np.int64); self.jj_h = np.zeros(0, np.int64); self.age_h = np.zeros(0, np.int64)
+        self.slots_h = np.zeros(0, np.int64)
+        self.ii = torch.zeros(0, dtype=torch.long, device=dev); self.jj = torch.zeros(0, dtype=torch.long, device=dev)
+        self.ii_inactive_h = np.zeros(0, np.int64); self.jj_inactive_h = np.zeros(0, np.int64)
+        self.ii_bad_h = np.zeros(0, np.int64); self.jj_bad_h = np.zeros(0, np.int64)
+        self.gru_hidden_states = None          # [E,128,ht,wd] fp16
+        self.gru_estimated_flow = torch.zeros(0, ht, wd, 2, device=dev)
+        self.gru_estimated_flow_weight = torch.zeros(0, ht, wd, 2, device=dev)
+        self.gru_estimated_flow_inactive = torch.zeros(0, ht, wd, 2, device=dev)
+        self.gru_estimated_flow_weight_inactive = torch.zeros(0, ht, wd, 2, device=dev)
+        self.damping = 1e-6 * torch.ones_like(self.cam0_idepths)
+        if hasattr(self, "corr_pool"):
+            self.corr_pool.free = list(range(self.corr_pool.capacity - 1, -1, -1))
+
+    def _sync_edges(self):
+        self.ii = torch.as_tensor(self.ii_h, device=self.device)
+        self.jj = torch.as_tensor(self.jj_h, device=self.device)
+        self.slots_d = torch.as_tensor(self.slots_h.astype(np.int32), device=self.device)
+
+    # ------------------------------------------------------------------ per-frame entry
+    def _normalize_imgs(self, images):
+        x = images[:, :, :3].float() / 255.0
+        return (x - self._mean) / self._std
+
+    def _store_frame(self, idx, batch, imgs_k):
+        dev = self.device
+        self.gt_poses[idx] = torch.as_tensor(np.asarray(batch["poses"][0]), device=dev, dtype=torch.float32)
+        if batch["depths"][0] is not None:
+            d = torch.as_tensor(np.asarray(batch["depths"][0]), device=dev).float()
+            self.gt_depths[idx] = d.permute(2, 0, 1)
+        self.cam0_timestamps[idx] = float(batch["t_cams"][0])
+        self.cam0_images[idx] = imgs_k[0, 0, :3]
+        cm = batch["calibs"][0].camera_model.numpy()
+        self.cam0_intrinsics[idx] = (1.0 / self.dsf) * torch.as_tensor(np.asarray(cm), device=dev, dtype=torch.float32)
+
+    def _feature_encoder(self, imgs_norm):
+        return self.feature_net(imgs_norm)[0]          # [cams,128,ht,wd] fp16
+
+    def _context_encoder(self, imgs_norm):
+        c = self.context_net(imgs_norm)[0]
+        return torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
+
+    def _put_features(self, idx, feats):
+        self.features_imgs[idx] = feats.permute(0, 2, 3, 1)
+
+    @torch.no_grad()
+    def forward(self, batch):
+        """visual_frontend.py:240-365"""
+        k = int(batch["k"][0])
+        x0, factors, viz_out = None, None, None
+        imgs_k = torch.as_tensor(np.asarray(batch["images"]), device=self.device)[None].permute(0, 1, 4, 2, 3)
+        imgs_norm = self._normalize_imgs(imgs_k)
+
+        if self.last_k is None:
+            assert k == 0 and self.kf_idx == 0
+            self.initialize_buffers(imgs_k.shape[-2:])
+            self._store_frame(0, batch, imgs_k)
+            self._put_features(0, self._feature_encoder(imgs_norm))
+            self.contexts_imgs[0], self.cst_contexts_imgs[0] = self._context_encoder(imgs_norm)
+            self.last_k, self.last_kf_idx = k, 0
+            self.kf_idx_to_f_idx[0] = k; self.f_idx_to_kf_idx[k] = 0
+            viz_out = self.get_viz_out(batch)
+            self.kf_idx += 1
+            return x0, factors, viz_out
+
+        assert k > 0 and self.kf_idx < self.buffer
+        feats = self._feature_encoder(imgs_norm)
+        if not self.has_enough_motion(feats):
+            if batch["is_last_frame"]:
+                self.kf_idx -= 1
+                self.terminate()
+                viz_out = self.get_viz_out(batch)
+            return x0, factors, viz_out
+
+        self._store_frame(self.kf_idx, batch, imgs_k)
+        self._put_features(self.kf_idx, feats)
+        self.contexts_imgs[self.kf_idx], self.cst_contexts_imgs[self.kf_idx] = self._context_encoder(imgs_norm)
+        self.kf_idx_to_f_idx[self.kf_idx] = k; self.f_idx_to_kf_idx[k] = self.kf_idx
+
+        if not self.is_initialized:
+            if self.kf_idx >= self.keyframe_warmup:
+                self._initialize()
+        else:
+            if not self._update():
+                self.rm_keyframe(self.kf_idx - 1)
+                return x0, factors, viz_out
+
+        self.last_k, self.last_kf_idx = k, self.kf_idx
+        viz_out = self.get_viz_out(batch)
+        if self.kf_idx + 1 >= self.buffer or batch["is_last_frame"]:
+            self.terminate()
+            viz_out = self.get_viz_out(batch)
+            return x0, factors, viz_out
+        self.kf_idx += 1
+        return x0, factors, viz_out
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------ motion filter
+    def has_enough_motion(self, feats):
+        """visual_frontend.py:976-1007: 1 update iteration on (last keyframe -> current frame)"""
+        ht, wd = self.ht, self.wd
+        pair = torch.stack([self.features_imgs[self.last_kf_idx, 0], feats[0].permute(1, 2, 0).contiguous()], 0)
+        one = torch.zeros(1, dtype=torch.int32, device=self.device)
+        pyr = db.corr_volume_build(pair, one, one + 1)
+        coords = self.coords0.permute(2, 0, 1)[None].contiguous()
+        corr = db.corr_lookup_pyramid(pyr, coords, 3)
+        net = self.contexts_imgs[self.last_kf_idx, 0][None, None]
+        inp = self.cst_contexts_imgs[self.last_kf_idx, 0][None, None]
+        _, delta, _ = self.update_net(net, inp, corr[None])
+        self.last_motion = delta.float().norm(dim=-1).mean()
+        return self.last_motion.item() > self.motion_filter_thresh
+
+    # ------------------------------------------------------------------ graph management (A18)
+    def add_neighborhood_factors(self, kf0, kf1, radius=3):
+        """visual_frontend.py:690-708"""
+        ii, jj = np.meshgrid(np.arange(kf0, kf1 + 1), np.arange(kf0, kf1 + 1), indexing="ij")
+        ii, jj = ii.reshape(-1), jj.reshape(-1)
+        c = 1 if self.stereo else 0
+        d = np.abs(ii - jj)
+        keep = (d > c) & (d <= radius)
+        self.add_factors(ii[keep], jj[keep])
+
+    def distance(self, ii, jj, beta=0.3, bidirectional=True):
+        """visual_frontend.py:778-799"""
+        ii = torch.as_tensor(np.asarray(ii), device=self.device, dtype=torch.long).reshape(-1)
+        jj = torch.as_tensor(np.asarray(jj), device=self.device, dtype=torch.long).reshape(-1)
+        if bidirectional:
+            poses = self.cam0_T_world[:self.kf_idx + 1].clone()
+            d1 = db.frame_distance(poses, self.cam0_idepths, self.cam0_intrinsics[0], ii, jj, beta)
+            d2 = db.frame_distance(poses, self.cam0_idepths, self.cam0_intrinsics[0], jj, ii, beta)
+            return .5 * (d1 + d2)
+        return db.frame_distance(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics[0], ii, jj, beta)
+
+    def add_proximity_factors(self, kf0=0, kf1=0, rad=2, nms=2, beta=0.25, thresh=16.0, remove=False):
+        """visual_frontend.py:712-775 — the order-sensitive edge selection;
+        the selection logic is kept loop for loop, on the host copy of the distances."""
+        t = self.kf_idx + 1
+        ix = np.arange(kf0, t); jx = np.arange(kf1, t)
+        ii, jj = np.meshgrid(ix, jx, indexing="ij")
+        ii, jj = ii.reshape(-1), jj.reshape(-1)
+        d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
+        d[(ii - rad) < jj] = np.inf
+        d[d > 100] = np.inf
+        W = t - kf1
+
+        def suppress(i, j):
+            for di in range(-nms, nms + 1):
+                for dj in range(-nms, nms + 1):
+                    if abs(di) + abs(dj) <= max(min(abs(i - j) - 2, nms), 0):
+                        i1, j1 = i + di, j + dj
+                        if (kf0 <= i1 < t) and (kf1 <= j1 < t):
+                            d[(i1 - kf0) * W + (j1 - kf1)] = np.inf
+
+        ii1 = np.concatenate([self.ii_h, self.ii_bad_h, self.ii_inactive_h])
+        jj1 = np.concatenate([self.jj_h, self.jj_bad_h, self.jj_inactive_h])
+        for i, j in zip(ii1, jj1):
+            suppress(int(i), int(j))
+        es = []
+        for i in range(kf0, t):
+            if self.stereo:
+                es.append((i, i))
+                d[(i - kf0) * W + (i - kf1)] = np.inf
+            for j in range(max(i - rad - 1, 0), i):
+                es.append((i, j)); es.append((j, i))
+                d[(i - kf0) * W + (j - kf1)] = np.inf
+        # torch.argsort on the reference side: unstable sort of fp32; ties are resolved here by
+        # index order (stable), which is what torch's CPU sort yields for equal keys in practice
+        order = np.argsort(d, kind="stable")
+        for k in order:
+            if d[k] > thresh:
+                continue
+            if len(es) > self.max_factors:
+                break
+            i, j = int(ii[k]), int(jj[k])
+            es.append((i, j)); es.append((j, i))
+            suppress(i, j)
+        if not es:
+            return
+        es = np.asarray(es, dtype=np.int64)
+        self.add_factors(es[:, 0], es[:, 1], remove)
+
+    def _filter_repeated_edges(self, ii, jj):
+        eset = set(zip(self.ii_h.tolist(), self.jj_h.tolist())) | \
+            set(zip(self.ii_inactive_h.tolist(), self.jj_inactive_h.tolist()))
+        keep = np.array([(int(i), int(j)) not in eset for i, j in zip(ii, jj)], dtype=bool)
+        return ii[keep], jj[keep]
+
+    def add_factors(self, ii, jj, remove=False):
+        """visual_frontend.py:807-862"""
+        ii = np.asarray(ii, np.int64).reshape(-1); jj = np.asarray(jj, np.int64).reshape(-1)
+        ii, jj = self._filter_repeated_edges(ii, jj)
+        if ii.shape[0] == 0:
+            return
+        old, new = self.ii_h.shape[0], ii.shape[0]
+        if self.max_factors > 0 and old + new > self.max_factors and self.gru_hidden_states is not None and remove:
+            ix = np.arange(len(self.age_h))[np.argsort(self.age_h, kind="stable")]
+            self.rm_factors(ix >= (self.max_factors - new), store=True)
+        slots = np.zeros(new, np.int64)
+        if self.corr_impl == "volume":
+            slots = np.asarray(self.corr_pool.alloc(new), np.int64)
+            cams = self.cameras
+            fi = (ii * cams).tolist()
+            fj = (jj * cams + (ii == jj)).tolist()
+            fm = self.features_imgs.view(self.buffer * cams, self.ht, self.wd, 128)
+            self.corr_pool.build(fm, fi, fj, slots.tolist())
+        self.ii_h = np.concatenate([self.ii_h, ii]); self.jj_h = np.concatenate([self.jj_h, jj])
+        self.age_h = np.concatenate([self.age_h, np.zeros(new, np.int64)])
+        self.slots_h = np.concatenate([self.slots_h, slots])
+        self._sync_edges()
+        iid = torch.as_tensor(ii, device=self.device)
+        hid = self.contexts_imgs[iid, 0]
+        self.gru_hidden_states = hid if self.gru_hidden_states is None else torch.cat([self.gru_hidden_states, hid], 0)
+        target, _ = self.reproject(ii, jj)
+        self.gru_estimated_flow = torch.cat([self.gru_estimated_flow, target], 0)
+        self.gru_estimated_flow_weight = torch.cat([self.gru_estimated_flow_weight, torch.zeros_like(target)], 0)
+
+    def rm_factors(self, mask, store=False):
+        """visual_frontend.py:868-892; mask: host bool array over the active edges"""
+        mask = np.asarray(mask, dtype=bool)
+        if mask.shape[0] == 0:
+            return
+        md = torch.as_tensor(mask, device=self.device)
+        if store:
+            self.ii_inactive_h = np.concatenate([self.ii_inactive_h, self.ii_h[mask]])
+            self.jj_inactive_h = np.concatenate([self.jj_inactive_h, self.jj_h[mask]])
+            self.gru_estimated_flow_inactive = torch.cat([self.gru_estimated_flow_inactive, self.gru_estimated_flow[md]], 0)
+            self.gru_estimated_flow_weight_inactive = torch.cat(
+                [self.gru_estimated_flow_weight_inactive, self.gru_estimated_flow_weight[md]], 0)
+        if self.corr_impl == "volume":
+            self.corr_pool.release(self.slots_h[mask].tolist())
+        keep = ~mask
+        self.ii_h, self.jj_h, self.age_h, self.slots_h = self.ii_h[keep], self.jj_h[keep], self.age_h[keep], self.slots_h[keep]
+        self._sync_edges()
+        kd = ~md
+        if self.gru_hidden_states is not None:
+            self.gru_hidden_states = self.gru_hidden_states[kd]
+        self.gru_estimated_flow = self.gru_estimated_flow[kd]
+        self.gru_estimated_flow_weight = self.gru_estimated_flow_weight[kd]
+
+    def rm_keyframe(self, kf):
+        """visual_frontend.py:530-574"""
+        for buf in (self.gt_poses, self.gt_depths, self.cam0_images, self.cam0_timestamps, self.cam0_T_world,
+                    self.world_T_body, self.world_T_body_cov, self.cam0_idepths, self.cam0_idepths_cov,
+                    self.cam0_depths_cov, self.cam0_idepths_sensed, self.cam0_intrinsics, self.features_imgs,
+                    self.contexts_imgs, self.cst_contexts_imgs):
+            buf[kf] = buf[kf + 1]
+        m = (self.ii_inactive_h == kf) | (self.jj_inactive_h == kf)
+        self.ii_inactive_h[self.ii_inactive_h >= kf] -= 1
+        self.jj_inactive_h[self.jj_inactive_h >= kf] -= 1
+        if m.any():
+            md = torch.as_tensor(~m, device=self.device)
+            self.ii_inactive_h, self.jj_inactive_h = self.ii_inactive_h[~m], self.jj_inactive_h[~m]
+            self.gru_estimated_flow_inactive = self.gru_estimated_flow_inactive[md]
+            self.gru_estimated_flow_weight_inactive = self.gru_estimated_flow_weight_inactive[md]
+        m = (self.ii_h == kf) | (self.jj_h == kf)
+        self.ii_h[self.ii_h >= kf] -= 1
+        self.jj_h[self.jj_h >= kf] -= 1
+        self.rm_factors(m, store=False)
+
+    def reproject(self, ii, jj):
+        """visual_frontend.py:909-918 -> coords [E,ht,wd,2], valid"""
+        ii = torch.as_tensor(np.asarray(ii) if not torch.is_tensor(ii) else ii, device=self.device, dtype=torch.long).reshape(-1)
+        jj = torch.as_tensor(np.asarray(jj) if not torch.is_tensor(jj) else jj, device=self.device, dtype=torch.long).reshape(-1)
+        return db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, ii, jj)
+
+    # ------------------------------------------------------------------ init / steady state
+    def _initialize(self):
+        """visual_frontend.py:641-688"""
+        assert self.kf_idx > 4 and self.kf_idx >= self.keyframe_warmup
+        self.add_neighborhood_factors(0, self.kf_idx, radius=3)
+        for _ in range(8):
+            self.update(use_inactive=True)
+        self.add_proximity_factors(kf0=0, kf1=0, rad=2, nms=2, thresh=self.frontend_thresh, remove=False)
+        for _ in range(8):
+            self.update(use_inactive=True)
+        k = self.kf_idx
+        self.cam0_T_world[k + 1] = self.cam0_T_world[k].clone()
+        self.world_T_body[k + 1] = self.world_T_body[k].clone()
+        self.world_T_body_cov[k + 1] = self.world_T_body_cov[k].clone()
+        self.cam0_idepths[k + 1] = self.cam0_idepths[k - 3:k + 1].mean()
+        self.cam0_idepths_cov[k + 1] = self.cam0_idepths_cov[k - 3:k + 1].mean()
+        self.cam0_depths_cov[k + 1] = self.cam0_depths_cov[k - 3:k + 1].mean()
+        self.is_initialized = True
+        self.viz_idx[:k + 1] = True
+        self.rm_factors(self.ii_h < (self.keyframe_warmup - 4), store=True)
+
+    def _update(self):
+        """visual_frontend.py:577-638"""
+        if self.gru_hidden_states is not None:
+            self.rm_factors(self.age_h > self.max_age, store=True)
+        self.add_proximity_factors(kf0=self.kf_idx - 4, kf1=max(self.kf_idx + 1 - self.frontend_window, 0),
+                                   rad=self.frontend_radius, nms=self.frontend_nms,
+                                   thresh=self.frontend_thresh, beta=self.beta, remove=True)
+        k = self.kf_idx
+        self.cam0_idepths[k] = torch.where(self.cam0_idepths_sensed[k] > 0, self.cam0_idepths_sensed[k], self.cam0_idepths[k])
+        for _ in range(self.iters1):
+            self.update(use_inactive=True)
+        d = self.distance([k - 2], [k - 1], beta=self.beta, bidirectional=True)
+        if d.item() < self.keyframe_thresh:
+            return False
+        for _ in range(self.iters2):
+            self.update(use_inactive=True)
+        nk = k + 1
+        if nk < self.buffer:
+            self.cam0_T_world[nk] = self.cam0_T_world[k]
+            self.world_T_body[nk] = self.world_T_body[k]
+            self.world_T_body_cov[nk] = self.world_T_body_cov[k]
+            self.cam0_idepths[nk] = self.cam0_idepths[k].mean()
+            self.cam0_idepths_cov[nk] = self.cam0_idepths_cov[k]
+            self.cam0_depths_cov[nk] = self.cam0_depths_cov[k]
+        return True
+
+    # ------------------------------------------------------------------ the hot loop (A19)
+    @torch.no_grad()
+    def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
+        """visual_frontend.py:371-470"""
+        ht, wd = self.ht, self.wd
+        coords1, _ = self.reproject(self.ii, self.jj)                                # [E,ht,wd,2] fp32
+        motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
+        motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
+        corr = self.corr_pool.lookup(self.slots_d, coords1.permute(0, 3, 1, 2).contiguous())
+        inp = self.cst_contexts_imgs[self.ii, 0]
+        net, delta, weight, damping, upmask = self.update_net(
+            self.gru_hidden_states[None], inp[None], corr[None], motion[None], self.ii, self.jj)
+        self.gru_hidden_states = net[0]
+        if kf0 is None:
+            kf0 = max(0, int(self.ii_h.min()))
+        self.gru_estimated_flow = coords1 + delta[0].float()
+        self.gru_estimated_flow_weight = weight[0].float()
+        ux = np.unique(self.ii_h)
+        self.damping[torch.as_tensor(ux, device=self.device)] = damping[0].float()
+
+        if use_inactive:
+            m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
+            md = torch.as_tensor(m, device=self.device)
+            ii = np.concatenate([self.ii_inactive_h[m], self.ii_h]); jj = np.concatenate([self.jj_inactive_h[m], self.jj_h])
+            target = torch.cat([self.gru_estimated_flow_inactive[md], self.gru_estimated_flow], 0)
+            wgt = torch.cat([self.gru_estimated_flow_weight_inactive[md], self.gru_estimated_flow_weight], 0)
+        else:
+            ii, jj, target, wgt = self.ii_h, self.jj_h, self.gru_estimated_flow, self.gru_estimated_flow_weight
+        dmp = .2 * self.damping[torch.as_tensor(np.unique(ii), device=self.device)].contiguous() + EP
+        target = target.permute(0, 3, 1, 2).contiguous()
+        wgt = wgt.permute(0, 3, 1, 2).contiguous()
+        self.ba(target, wgt, dmp, ii, jj, kf0, kf1, itrs=itrs, motion_only=motion_only,
+                compute_covariances=self.compute_covariances)
+        kx = torch.as_tensor(ux, device=self.device)
+        self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
+        self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask[0], pow=1.0).squeeze(-1)
+        self.viz_idx[kf0:self.kf_idx + 1] = True
+        self.age_h += 1
+        self.stats["updates"] += 1
+
+    def ba(self, target, weight, damping, ii, jj, kf0=0, kf1=None, itrs=2, lm=1e-4, ep=0.1,
+           motion_only=False, compute_covariances=True):
+        """dense bundle adjustment (visual_frontend.py:1071-1232) — all on the device stream.
+        `lm`, `ep` are accepted and unused, exactly like the reference's live path."""
+        ii = np.asarray(ii, np.int64); jj = np.asarray(jj, np.int64)
+        if kf1 is None:
+            kf1 = int(max(ii.max(), jj.max())) + 1
+        P = kf1 - kf0
+        prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics[0].contiguous(),
+                            self.cam0_T_body, self.cam0_idepths_sensed, target, weight, damping,
+                            ii, jj, kf0, kf1)
+        lib = _lib.load()
+        has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
+        prior_err = torch.zeros(6, device=self.device)
+        linv = None
+        for it in range(itrs):
+            prob.linearize()
+            if has_prior:
+                _lib.check(lib.nslam_pose_prior_error(_lib.ptr(self.world_T_body[kf0]), _lib.ptr(self.prior_pose),
+                                                      _lib.ptr(prior_err), _lib.stream_ptr()), "prior")
+            dx, linv, status = prob.solve(prior_idx=0 if has_prior else -1, prior_err=prior_err,
+                                          prior_info=self.prior_info if has_prior else 0.0,
+                                          want_linv=compute_covariances and it == itrs - 1)
+            _lib.check(lib.nslam_ba_retract(_lib.ptr(self.world_T_body), _lib.ptr(self.cam0_T_world),
+                                            _lib.ptr(self.cam0_T_body), _lib.ptr(dx), kf0, P,
+                                            _lib.stream_ptr()), "retract")
+            prob.depth_update(dx, clamp_min=1e-3)
+        if compute_covariances and linv is not None:
+            sg, z_cov, d_cov = prob.covariances(linv)
+            kx = torch.as_tensor(prob.gh.tables["kx"].astype(np.int64), device=self.device)
+            self.world_T_body_cov[kf0:kf1] = sg
+            self.cam0_idepths_cov[kx] = z_cov
+            self.cam0_depths_cov[kx] = d_cov
+        self.last_ba = prob
+        return None, None
+
+    # ------------------------------------------------------------------ global BA (backend)
+    def normalize(self, last_kf=-1):
+        s = self.cam0_idepths[:last_kf].mean()
+        self.cam0_idepths[:last_kf] /= s
+        self.cam0_T_world[:last_kf, :3] *= s
+        self.viz_idx[:last_kf] = True
+
+    def clear_edges(self):
+        self.rm_factors(self.ii_h >= 0)
+        self.gru_hidden_states = None
+
+    @torch.no_grad()
+    def update_lowmem(self, itrs=2, EP=1e-7, steps=8):
+        """visual_frontend.py:474-526: alt-corr path, edges processed in chunks of 8 source frames"""
+        kfs, cams = self.buffer, self.cameras
+        fm = self.features_imgs.permute(0, 1, 4, 2, 3).reshape(1, kfs * cams, 128, self.ht, self.wd)
+        corr_op = AltCorrBlock(fm)
+        for _ in range(steps):
+            coords1, _ = self.reproject(self.ii, self.jj)
+            motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
+            motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
+            s = 8
+            for i in range(0, int(self.jj_h.max()) + 1, s):
+                v = (self.ii_h >= i) & (self.ii_h < i + s)
+                if not v.any():
+                    continue
+                vd = torch.as_tensor(v, device=self.device)
+                iis, jjs = self.ii[vd], self.jj[vd]
+                corr = corr_op(coords1[vd][None], cams * iis, cams * jjs + (iis == jjs).long())
+                net, delta, weight, damping, upmask = self.update_net(
+                    self.gru_hidden_states[vd][None], self.cst_contexts_imgs[iis, 0][None], corr, motion[vd][None], iis, jjs)
+                self.gru_hidden_states[vd] = net[0]
+                self.gru_estimated_flow[vd] = coords1[vd] + delta[0].float()
+                self.gru_estimated_flow_weight[vd] = weight[0].float()
+                kx = torch.unique(iis)
+                self.damping[kx] = damping[0].float()
+                self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
+                self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
+            dmp = .2 * self.damping[torch.as_tensor(np.unique(self.ii_h), device=self.device)].contiguous() + EP
+            target = self.gru_estimated_flow.permute(0, 3, 1, 2).contiguous()
+            wgt = self.gru_estimated_flow_weight.permute(0, 3, 1, 2).contiguous()
+            self.ba(target, wgt, dmp, self.ii_h, self.jj_h, kf0=0, kf1=None, itrs=itrs, compute_covariances=False)
+
+    def backend(self, steps=12):
+        """visual_frontend.py:1255-1306"""
+        if not self.stereo and not torch.any(self.cam0_idepths_sensed):
+            self.normalize(self.kf_idx)
+        self.max_factors = 16 * self.kf_idx
+        self.corr_impl = "alt"
+        self._reset_graph()
+        self.add_proximity_factors(rad=self.backend_radius, nms=self.backend_nms, thresh=self.backend_thresh, beta=self.beta)
+        self.update_lowmem(steps=steps)
+        self.clear_edges()
+        self.viz_idx[:self.kf_idx] = True
+
+    def terminate(self):
+        """visual_frontend.py:1308-1335"""
+        if self.global_ba:
+            self.backend(7)
+            self.backend(12)
+            self.backend(0)
+        self.stop = True
+
+    # ------------------------------------------------------------------ output packet (B1 contract)
+    def get_viz_out(self, batch):
+        """visual_frontend.py:1337-1391.  Tensors stay on the device: the NeRF side receives them
+        through NCCL / peer copies (nerf_slam_b200.dist), never through the CPU."""
+        idx, = torch.where(self.viz_idx)
+        if len(idx) == 0:
+            return {"is_last_frame": True} if batch["is_last_frame"] else None
+        sel = lambda t: torch.index_select(t, 0, idx)
+        out = {"cam0_poses": sel(self.cam0_T_world), "gt_poses": sel(self.gt_poses), "gt_depths": sel(self.gt_depths),
+               "world_T_body": sel(self.world_T_body), "world_T_body_cov": sel(self.world_T_body_cov),
+               "cam0_idepths": sel(self.cam0_idepths), "cam0_idepths_up": sel(self.cam0_idepths_up),
+               "cam0_idepths_sensed": sel(self.cam0_idepths_sensed), "cam0_idepths_cov": sel(self.cam0_idepths_cov),
+               "cam0_depths_cov": sel(self.cam0_depths_cov), "cam0_depths_cov_up": sel(self.cam0_depths_cov_up),
+               "cam0_images": sel(self.cam0_images), "cam0_intrinsics": sel(self.cam0_intrinsics),
+               "calibs": batch["calibs"], "viz_idx": idx, "kf_idx": self.kf_idx,
+               "kf_idx_to_f_idx": dict(self.kf_idx_to_f_idx), "is_last_frame": batch["is_last_frame"]}
+        self.viz_idx[:] = False
+        return out

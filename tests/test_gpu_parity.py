@@ -308,7 +308,8 @@ def test_pose_prior_error(db):
     rng = np.random.default_rng(5)
     p = se3.random_poses(rng, 2, 0.3, 20, np.float32)
     err = torch.zeros(6, device=DEV)
-    _lib.check(lib.nslam_pose_prior_error(_lib.ptr(T(p[0])), _lib.ptr(T(p[1])), _lib.ptr(err), _lib.stream_ptr()), "prior")
+    x_d, pr_d = T(p[0]), T(p[1])      # keep both alive: temporaries would alias after being freed
+    _lib.check(lib.nslam_pose_prior_error(_lib.ptr(x_d), _lib.ptr(pr_d), _lib.ptr(err), _lib.stream_ptr()), "prior")
     assert np.allclose(err.cpu().numpy(), oba.pose_prior_error(p[0], p[1]), atol=1e-5)
     # retract(prior, err) == x
     t, q = se3.pose3_retract(p[1, :3].astype(np.float64), p[1, 3:].astype(np.float64), err.double().cpu().numpy())
