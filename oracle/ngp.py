@@ -1,0 +1,146 @@
+"""ORACLE (test infrastructure only — never imported by the product path).
+
+Path B: PARITY UNPINNED.  The reference's NeRF back-end is the `pyngp` module of the fork
+ToniRV/instant-ngp@54aba7cfbeaf6a60f29469a9938485bebeba24c3 (branch feature/nerf_slam, with
+tiny-cuda-nn as its submodule); that submodule is EMPTY under /root/reference/thirdparty, so no
+source, config (configs/nerf/base.json) or golden output exists here.  What follows restates the
+PUBLISHED instant-ngp algorithm (Mueller et al. 2022; tiny-cuda-nn GridEncoding / SphericalHarmonics
+/ FullyFusedMLP; instant-ngp testbed_nerf.cu) in plain PyTorch fp32 with autograd; the CUDA product
+path (csrc/ngp*.cu) is checked against THIS, plus convergence tests on synthetic scenes and the
+call-site contract of fusion/nerf_fusion.py:57-101,285-289,296-300,388-424.
+
+Conventions (upstream defaults for configs/nerf/base.json):
+  hash grid: 16 levels x 2 features, T = 2^19 entries/level, base resolution 16,
+             per-level scale = exp(ln(2048*aabb_scale/16)/15); dense indexing while res^3 <= T;
+             hash(x,y,z) = x ^ y*2654435761 ^ z*805459861 (uint32) mod T; trilinear interpolation
+             at pos*scale + 0.5, scale = 16*b^l - 1
+  density MLP 32 -> 64 (ReLU) -> 16, sigma = exp(out[0]);  SH degree 4 on the direction;
+  rgb MLP 32 (=16+16) -> 64 -> 64 (ReLU) -> 3 (sigmoid);
+  compositing: alpha = 1 - exp(-sigma dt), T *= 1 - alpha, stop when T < 1e-4;
+  loss: Huber(delta=0.1)/5 on RGB (+ background blend) + lambda_d * (d - d*)^2 / cov  (fork's
+  depth supervision, fusion/nerf_fusion.py:99-101,285-289), averaged over rays.
+"""
+import math
+
+import numpy as np
+import torch
+
+N_LEVELS, N_FEAT, LOG2_T, BASE_RES = 16, 2, 19, 16
+PRIMES = (1, 2654435761, 805459861)
+
+
+def per_level_scale(aabb_scale):
+    return math.exp(math.log(2048.0 * aabb_scale / BASE_RES) / (N_LEVELS - 1))
+
+
+def level_params(aabb_scale):
+    """-> list of (scale, resolution, n_params, offset) ; n_params multiple of 8 capped at T"""
+    b = per_level_scale(aabb_scale)
+    T = 1 << LOG2_T
+    out, off = [], 0
+    for l in range(N_LEVELS):
+        scale = BASE_RES * (b ** l) - 1.0
+        res = int(math.ceil(scale)) + 1
+        n = min(((res ** 3 + 7) // 8) * 8, T) if res ** 3 < (1 << 62) else T
+        out.append((float(np.float32(scale)), res, n, off))
+        off += n
+    return out, off
+
+
+def grid_index(ix, iy, iz, res, n_params):
+    """ix,iy,iz int64 tensors. dense if res^3 <= n_params else hashed"""
+    if res ** 3 <= n_params:
+        return (ix + iy * res + iz * res * res) % n_params
+    h = (ix * PRIMES[0]) ^ ((iy * PRIMES[1]) & 0xFFFFFFFF) ^ ((iz * PRIMES[2]) & 0xFFFFFFFF)
+    return (h & 0xFFFFFFFF) % n_params
+
+
+def hash_encode(x, grid, aabb_scale):
+    """x [S,3] in [0,1]^3 (fp32), grid [total,2] fp32 -> [S,32]"""
+    lv, _ = level_params(aabb_scale)
+    feats = []
+    for (scale, res, n, off) in lv:
+        pos = x * scale + 0.5
+        p0 = torch.floor(pos)
+        w = pos - p0
+        p0 = p0.long()
+        acc = 0
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    idx = grid_index(p0[:, 0] + dx, p0[:, 1] + dy, p0[:, 2] + dz, res, n)
+                    wgt = (w[:, 0] if dx else 1 - w[:, 0]) * (w[:, 1] if dy else 1 - w[:, 1]) * \
+                          (w[:, 2] if dz else 1 - w[:, 2])
+                    acc = acc + wgt[:, None] * grid[off + idx]
+        feats.append(acc)
+    return torch.cat(feats, -1)
+
+
+def sh4(d):
+    """spherical harmonics degree 4 (16 coefficients), tiny-cuda-nn convention, d unit [S,3]"""
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    xy, xz, yz, x2, y2, z2 = x * y, x * z, y * z, x * x, y * y, z * z
+    return torch.stack([
+        0.28209479177387814 * torch.ones_like(x),
+        -0.48860251190291987 * y, 0.48860251190291987 * z, -0.48860251190291987 * x,
+        1.0925484305920792 * xy, -1.0925484305920792 * yz, 0.94617469575755997 * z2 - 0.31539156525251999,
+        -1.0925484305920792 * xz, 0.54627421529603959 * x2 - 0.54627421529603959 * y2,
+        0.59004358992664352 * y * (-3.0 * x2 + y2), 2.8906114426405538 * xy * z,
+        0.45704579946446572 * y * (1.0 - 5.0 * z2), 0.3731763325901154 * z * (5.0 * z2 - 3.0),
+        0.45704579946446572 * x * (1.0 - 5.0 * z2), 1.4453057213202769 * z * (x2 - y2),
+        0.59004358992664352 * x * (-x2 + 3.0 * y2)], -1)
+
+
+def network(x01, d, P, aabb_scale):
+    """P: dict(grid [total,2], W1 [32,64], W2 [64,16], W3 [32,64], W4 [64,64], W5 [64,16]) -> rgb [S,3], sigma [S]"""
+    enc = hash_encode(x01, P["grid"], aabb_scale)
+    h = torch.relu(enc @ P["W1"])
+    o = h @ P["W2"]
+    sigma = torch.exp(o[:, 0])
+    inp = torch.cat([o, sh4(d)], -1)
+    h = torch.relu(inp @ P["W3"])
+    h = torch.relu(h @ P["W4"])
+    rgb = torch.sigmoid((h @ P["W5"])[:, :3])
+    return rgb, sigma
+
+
+def composite_loss(rgb, sigma, dt, tdist, ray_ptr, target_rgb, target_depth, depth_cov, bg, lambda_d,
+                   min_T=1e-4):
+    """per-ray volume rendering + loss. ray_ptr [R+1] CSR over samples (host list).
+    returns (loss, rgb_ray [R,3], depth_ray [R])"""
+    R = len(ray_ptr) - 1
+    tot = 0
+    rgbs, deps = [], []
+    for r in range(R):
+        a, b = ray_ptr[r], ray_ptr[r + 1]
+        T = torch.ones((), dtype=rgb.dtype)
+        c = torch.zeros(3, dtype=rgb.dtype)
+        dep = torch.zeros((), dtype=rgb.dtype)
+        for s in range(a, b):
+            if float(T) < min_T:
+                break
+            alpha = 1 - torch.exp(-sigma[s] * dt[s])
+            w = alpha * T
+            c = c + w * rgb[s]
+            dep = dep + w * tdist[s]
+            T = T * (1 - alpha)
+        c = c + T * bg[r]
+        diff = c - target_rgb[r]
+        ad = diff.abs()
+        hub = torch.where(ad < 0.1, 0.5 * diff * diff / 0.1, ad - 0.05) / 5.0
+        l = hub.mean()
+        if target_depth[r] > 0:
+            l = l + lambda_d * (dep - target_depth[r]) ** 2 / depth_cov[r]
+        tot = tot + l
+        rgbs.append(c); deps.append(dep)
+    return tot / R, torch.stack(rgbs), torch.stack(deps)
+
+
+def init_params(aabb_scale, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    _, total = level_params(aabb_scale)
+    P = {"grid": (torch.rand(total, 2, generator=g, dtype=dtype) * 2 - 1) * 1e-4}
+    for name, (i, o) in dict(W1=(32, 64), W2=(64, 16), W3=(32, 64), W4=(64, 64), W5=(64, 16)).items():
+        s = math.sqrt(6.0 / (i + o))       # xavier uniform (tcnn default for FullyFusedMLP)
+        P[name] = (torch.rand(i, o, generator=g, dtype=dtype) * 2 - 1) * s
+    return P

@@ -1,0 +1,22 @@
+"""run the front-end on the procedural stream and print timing / state statistics (GPU)"""
+import os, sys, time, types, json
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from nerf_slam_b200.frontend import RaftVisualFrontend
+from nerf_slam_b200.synthetic import SyntheticRoom
+W, H, N = int(os.environ.get("W", 640)), int(os.environ.get("H", 480)), int(os.environ.get("N", 120))
+wp = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
+args = types.SimpleNamespace(buffer=int(os.environ.get("BUF", 100)), stereo=False, multi_gpu=False, weights=wp if os.path.exists(wp) else None)
+room = SyntheticRoom(W, H, N, seed=0, step=float(os.environ.get("STEP", 0.012)))
+pk = [room.packet(k) for k in range(N)]
+fe = RaftVisualFrontend(np.linalg.inv(pk[0]["poses"][0]), np.eye(4), args, "cuda:0")
+ts = []
+for k in range(N):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    fe.forward(pk[k])
+    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    print(f"frame {k:4d} kf_idx {fe.kf_idx:3d} edges {len(getattr(fe,'ii_h',[])):3d} motion {float(getattr(fe,'last_motion',0)):.2f} {ts[-1]*1e3:8.2f} ms", flush=True)
+    if fe.stop_condition(): break
+ts = np.array(ts)
+print(json.dumps(dict(frames=len(ts), kf=fe.kf_idx, total_s=float(ts.sum()), fps=float(len(ts)/ts.sum()),
+                      steady_fps=float(len(ts[40:])/ts[40:].sum()) if len(ts) > 50 else None, weights=fe.weights_source, updates=fe.stats["updates"])))
