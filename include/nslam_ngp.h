@@ -1,0 +1,74 @@
+/* C ABI of Path B — hash-grid NeRF training / rendering.
+ *
+ * Replaces the `pyngp` module of the reference's instant-ngp fork as driven by
+ * fusion/nerf_fusion.py: Testbed.frame() (:299) = nslam_ngp_train_step + nslam_ngp_adam
+ * (+ nslam_ngp_update_density_grid every 16 steps), Testbed.render() (:416,424) =
+ * nslam_ngp_render_tile, nerf.training.update_training_images() (:285-289) = nslam_ngp_ingest_image
+ * into pre-allocated device slots.  The fork's sources are absent from /root/reference
+ * (empty submodule) — semantics follow the published instant-ngp algorithm; see oracle/ngp.py.
+ *
+ * All pointers are DEVICE pointers (the structs themselves live on the host); every call
+ * launches on `stream` and never synchronises.  Returns 0 or a cudaError_t value.
+ */
+#ifndef NSLAM_NGP_H_
+#define NSLAM_NGP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nslam_ngp_model {
+  void* grid_half;        /* __half2 [n_grid]   fp16 compute copy of the hash table            */
+  float* grid_master;     /* [n_grid*2]         fp32 master                                    */
+  float* grid_grad;       /* [n_grid*2]                                                        */
+  float* grid_m; float* grid_v;   /* Adam moments                                              */
+  float* mlp;             /* [10240] fp32: W1[32][64] W2[64][16] W3[32][64] W4[64][64] W5[64][16] */
+  float* mlp_grad; float* mlp_m; float* mlp_v;
+  float* density;         /* [cascades*128^3] optical thickness, -1 = never visible            */
+  unsigned char* bits;    /* [cascades*128^3/8] occupancy bitfield                             */
+  float* stats;           /* [2] scratch                                                       */
+  float aabb_scale; int cascades; float cone; float near_distance;
+  float scale[16]; int res[16]; unsigned size[16]; unsigned offset[16]; int dense[16];
+  unsigned n_grid;
+} nslam_ngp_model;
+
+typedef struct nslam_ngp_images {
+  const void* rgba;       /* __half [N,H,W,4] linear premultiplied                             */
+  const float* depth;     /* [N,H,W] metric z-depth, <= 0 = none                               */
+  const float* depth_cov; /* [N,H,W]                                                           */
+  const void* cams;       /* [N] {float c2w[12]; float fx,fy,cx,cy; int w,h;}                  */
+  const int* active;      /* [n_active] slots used for training                                */
+  int n_active, H, W;
+} nslam_ngp_images;
+
+typedef struct nslam_ngp_batch {
+  float* rays;       /* [max_rays,16]   */
+  float* coords;     /* [max_samples,7] */
+  float* tdist;      /* [max_samples]   */
+  float* rgbsigma;   /* [max_samples,4] */
+  float* dout;       /* [max_samples,4] */
+  int* counters;     /* [4]: samples, rays kept */
+  float* loss;       /* [1] */
+  int max_rays, max_samples;
+} nslam_ngp_batch;
+
+int nslam_ngp_train_step(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
+                         int n_rays, unsigned seed, float lambda_depth, float bg_r, float bg_g,
+                         float bg_b, int num_sms, void* stream);
+int nslam_ngp_adam(const nslam_ngp_model* m, int step, float lr, float beta1, float beta2, float eps,
+                   float l2_mlp, void* stream);
+int nslam_ngp_forward(const nslam_ngp_model* m, const float* coords, int n, float* rgbsigma, void* stream);
+int nslam_ngp_loss_backward(const nslam_ngp_model* m, const nslam_ngp_batch* b, int n_rays, int n_samples,
+                            float lambda_depth, float bg_r, float bg_g, float bg_b, int num_sms, void* stream);
+int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_images* im, int n_per_cascade,
+                                  unsigned seed, float decay, float min_thickness, void* stream);
+int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, const float* cam18_host,
+                          int x0, int y0, int tw, int th, int max_per_ray, float bg_r, float bg_g,
+                          float bg_b, float* out_rgbd, void* stream);
+int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
+                           int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

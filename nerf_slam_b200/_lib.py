@@ -55,6 +55,14 @@ _SIGNATURES = {
     "nslam_ba_depth": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, c_float, _P],
     "nslam_ba_cov": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, _P, _P, _P],
     "nslam_ba_pose_cov": [_P, c_int, _P, _P],
+    # Path B (include/nslam_ngp.h); struct pointers are passed with ctypes.byref
+    "nslam_ngp_train_step": [_P, _P, _P, c_int, ctypes.c_uint, c_float, c_float, c_float, c_float, c_int, _P],
+    "nslam_ngp_adam": [_P, c_int, c_float, c_float, c_float, c_float, c_float, _P],
+    "nslam_ngp_forward": [_P, _P, c_int, _P, _P],
+    "nslam_ngp_loss_backward": [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_int, _P],
+    "nslam_ngp_update_density_grid": [_P, _P, c_int, ctypes.c_uint, c_float, c_float, _P],
+    "nslam_ngp_render_tile": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P],
+    "nslam_ngp_ingest_image": [_P, _P, _P, c_int, c_int, _P, _P, _P, _P],
 }
 
 _lib = None

@@ -23,6 +23,7 @@
 //   ngp_adam           fused Adam (+L2 on the MLP, zero-gradient skip on hash entries) writing
 //                      the fp32 master and the fp16 compute copy
 #include "ngp_common.cuh"
+#include "../../include/nslam_ngp.h"
 
 #define NGP_CHECK_LAUNCH()                        \
   do {                                            \
@@ -83,7 +84,7 @@ __device__ __forceinline__ void dense_bwd_in(const float (&d)[N], const float* _
 }
 // dW[k][n] += sum_rows A[k][row] D[n][row], thread owns NB 4x4 blocks (block b = tid + j*TILE)
 template <int K, int N, int NB>
-__device__ __forceinline__ void outer_acc(const float* __restrict__ A, const float* __restrict__ D,
+__device__ __forceinline__ void outer_acc(const __half* __restrict__ A, const float* __restrict__ D,
                                           float (&acc)[NB][16], int tid, int rows) {
   constexpr int NBLK = (K / 4) * (N / 4);
 #pragma unroll
@@ -94,7 +95,7 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ A, const flo
       for (int r = 0; r < rows; r++) {
         float a[4], d[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { a[i] = A[(k0 + i) * LD + r]; d[i] = D[(n0 + i) * LD + r]; }
+        for (int i = 0; i < 4; i++) { a[i] = __half2float(A[(k0 + i) * LD + r]); d[i] = D[(n0 + i) * LD + r]; }
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -242,43 +243,43 @@ struct NetState {
 
 // runs the network for the calling thread's sample; leaves h3 (last hidden) in S.
 // If KEEP != nullptr the layer inputs are additionally stored for the backward pass:
-//   KEEP rows: [0,32) enc, [32,96) h1, [96,128) in2, [128,192) h2, [192,256) h3  (feature-major, LD)
+//   KEEP (fp16) rows: [0,32) enc, [32,96) h1, [96,128) in2, [128,192) h2, [192,256) h3  (feature-major, LD)
 __device__ __forceinline__ void net_forward(const float* c7, const __half2* __restrict__ grid,
                                             const LevelInfo& lv, const float* __restrict__ sW,
-                                            float* __restrict__ S, float* __restrict__ KEEP, int tid,
+                                            float* __restrict__ S, __half* __restrict__ KEEP, int tid,
                                             NetState& ns) {
   {
     float enc[ENC_DIM];
     hash_encode(c7, grid, lv, enc);
 #pragma unroll
-    for (int k = 0; k < ENC_DIM; k++) { S[k * LD + tid] = enc[k]; if (KEEP) KEEP[k * LD + tid] = enc[k]; }
+    for (int k = 0; k < ENC_DIM; k++) { S[k * LD + tid] = enc[k]; if (KEEP) KEEP[k * LD + tid] = __float2half_rn(enc[k]); }
   }
   {
     float h[HID];
     dense_fwd<ENC_DIM, HID, HID>(S, sW + W1_OFF, h, tid);
 #pragma unroll
-    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(32 + k) * LD + tid] = v; }
+    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(32 + k) * LD + tid] = __float2half_rn(v); }
   }
   dense_fwd<HID, DOUT, DOUT>(S, sW + W2_OFF, ns.o, tid);
   {
     float sh[SH_DIM];
     sh4(c7 + 4, sh);
 #pragma unroll
-    for (int k = 0; k < DOUT; k++) { S[k * LD + tid] = ns.o[k]; if (KEEP) KEEP[(96 + k) * LD + tid] = ns.o[k]; }
+    for (int k = 0; k < DOUT; k++) { S[k * LD + tid] = ns.o[k]; if (KEEP) KEEP[(96 + k) * LD + tid] = __float2half_rn(ns.o[k]); }
 #pragma unroll
-    for (int k = 0; k < SH_DIM; k++) { S[(DOUT + k) * LD + tid] = sh[k]; if (KEEP) KEEP[(96 + DOUT + k) * LD + tid] = sh[k]; }
+    for (int k = 0; k < SH_DIM; k++) { S[(DOUT + k) * LD + tid] = sh[k]; if (KEEP) KEEP[(96 + DOUT + k) * LD + tid] = __float2half_rn(sh[k]); }
   }
   {
     float h[HID];
     dense_fwd<32, HID, HID>(S, sW + W3_OFF, h, tid);
 #pragma unroll
-    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(128 + k) * LD + tid] = v; }
+    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(128 + k) * LD + tid] = __float2half_rn(v); }
   }
   {
     float h[HID];
     dense_fwd<HID, HID, HID>(S, sW + W4_OFF, h, tid);
 #pragma unroll
-    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(192 + k) * LD + tid] = v; }
+    for (int k = 0; k < HID; k++) { const float v = fmaxf(h[k], 0.f); S[k * LD + tid] = v; if (KEEP) KEEP[(192 + k) * LD + tid] = __float2half_rn(v); }
   }
   dense_fwd<HID, 4, 16>(S, sW + W5_OFF, ns.rgbraw, tid);
 }
@@ -400,7 +401,7 @@ backward_kernel(const float* __restrict__ coords, const int* __restrict__ counte
   float* sW = sm;
   float* S = sW + W_TOTAL;         // [64][LD]
   float* D = S + 64 * LD;          // [64][LD]
-  float* KEEP = D + 64 * LD;       // [256][LD]
+  __half* KEEP = reinterpret_cast<__half*>(D + 64 * LD);   // [256][LD] fp16
   const int tid = threadIdx.x;
   const int n = counters[0];
   for (int i = tid; i < W_TOTAL; i += TILE) sW[i] = mlp[i];
@@ -432,7 +433,7 @@ backward_kernel(const float* __restrict__ coords, const int* __restrict__ counte
       __syncthreads();
       dense_bwd_in<HID, 4, 16>(d4, sW + W5_OFF, D, tid);    // D[k] = dL/dh3[k] (pre-mask)
 #pragma unroll 4
-      for (int k = 0; k < HID; k++) { const float v = (KEEP[(192 + k) * LD + tid] > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
+      for (int k = 0; k < HID; k++) { const float v = (__half2float(KEEP[(192 + k) * LD + tid]) > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
     }
     __syncthreads();
     // ---- layer 4 (64 -> 64)
@@ -442,7 +443,7 @@ backward_kernel(const float* __restrict__ coords, const int* __restrict__ counte
     __syncthreads();
     dense_bwd_in<HID, HID, HID>(d64, sW + W4_OFF, D, tid);
 #pragma unroll 4
-    for (int k = 0; k < HID; k++) { const float v = (KEEP[(128 + k) * LD + tid] > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
+    for (int k = 0; k < HID; k++) { const float v = (__half2float(KEEP[(128 + k) * LD + tid]) > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
     __syncthreads();
     // ---- layer 3 (32 -> 64)
     outer_acc<32, HID, 1>(KEEP + 96 * LD, D, g3, tid, rows);
@@ -463,7 +464,7 @@ backward_kernel(const float* __restrict__ coords, const int* __restrict__ counte
     __syncthreads();
     dense_bwd_in<HID, DOUT, DOUT>(d16, sW + W2_OFF, D, tid);
 #pragma unroll 4
-    for (int k = 0; k < HID; k++) { const float v = (KEEP[(32 + k) * LD + tid] > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
+    for (int k = 0; k < HID; k++) { const float v = (__half2float(KEEP[(32 + k) * LD + tid]) > 0.f) ? D[k * LD + tid] : 0.f; D[k * LD + tid] = v; }
     __syncthreads();
     // ---- layer 1 (32 -> 64)
     outer_acc<ENC_DIM, HID, 1>(KEEP, D, g1, tid, rows);
@@ -640,45 +641,6 @@ __global__ void ingest_image_kernel(const uint8_t* __restrict__ rgb_chw, const f
 }  // namespace ngp
 
 // ============================================================================================
-extern "C" {
-
-typedef struct nslam_ngp_model {
-  // parameters
-  void* grid_half;        // __half2 [n_grid]
-  float* grid_master;     // [n_grid*2]
-  float* grid_grad;       // [n_grid*2]
-  float* grid_m; float* grid_v;
-  float* mlp;             // [10240]
-  float* mlp_grad; float* mlp_m; float* mlp_v;
-  // occupancy
-  float* density;         // [cascades*128^3]
-  unsigned char* bits;    // [cascades*128^3/8]
-  float* stats;           // [2]
-  // scene
-  float aabb_scale; int cascades; float cone; float near_distance;
-  // level table (host-filled)
-  float scale[16]; int res[16]; unsigned size[16]; unsigned offset[16]; int dense[16];
-  unsigned n_grid;        // total entries
-} nslam_ngp_model;
-
-typedef struct nslam_ngp_images {
-  const void* rgba; const float* depth; const float* depth_cov; const void* cams; const int* active;
-  int n_active, H, W;
-} nslam_ngp_images;
-
-typedef struct nslam_ngp_batch {
-  float* rays;       // [max_rays,16]
-  float* coords;     // [max_samples,7]
-  float* tdist;      // [max_samples]
-  float* rgbsigma;   // [max_samples,4]
-  float* dout;       // [max_samples,4]
-  int* counters;     // [4]
-  float* loss;       // [1]
-  int max_rays, max_samples;
-} nslam_ngp_batch;
-
-}  // extern "C"
-
 namespace ngp {
 static LevelInfo make_lv(const nslam_ngp_model* m) {
   LevelInfo lv;
@@ -701,7 +663,7 @@ static ImageStore make_store(const nslam_ngp_images* im) {
   return st;
 }
 constexpr size_t FWD_SMEM = (W_TOTAL + 64 * LD) * sizeof(float);
-constexpr size_t BWD_SMEM = (W_TOTAL + (64 + 64 + 256) * LD) * sizeof(float);
+constexpr size_t BWD_SMEM = (W_TOTAL + (64 + 64) * LD) * sizeof(float) + 256 * LD * sizeof(__half);
 static int ensure_attrs() {
   static bool done = false;
   if (done) return 0;

@@ -236,7 +236,10 @@ class RaftVisualFrontend:
         """visual_frontend.py:240-365"""
         k = int(batch["k"][0])
         x0, factors, viz_out = None, None, None
-        imgs_k = torch.as_tensor(np.asarray(batch["images"]), device=self.device)[None].permute(0, 1, 4, 2, 3)
+        img = batch["images"]
+        if not torch.is_tensor(img):
+            img = torch.as_tensor(np.asarray(img))
+        imgs_k = img.to(self.device, non_blocking=True)[None].permute(0, 1, 4, 2, 3)   # H2D when host-resident
         imgs_norm = self._normalize_imgs(imgs_k)
 
         if self.last_k is None:

@@ -1,0 +1,334 @@
+"""`pyngp`-shaped façade over the sm_100a NeRF kernels (Path B).
+
+Exposes exactly the surface that the reference's fusion/nerf_fusion.py uses of the instant-ngp
+fork's python module (SURVEY.md §8b "pyngp surface used"):
+
+  TestbedMode.Nerf, Testbed(mode, 0), BoundingBox(min, max), LossType.L2, Shade / Depth,
+  .create_empty_nerf_dataset(n_images, nerf_scale, offset, aabb_scale, render_aabb)
+  .reload_network_from_file(path)      (no-op: the base.json architecture is built in)
+  .shall_train .dynamic_res .dynamic_res_target_fps .camera_smoothing .display_gui ...
+  .nerf.training.{n_images_for_training, optimize_extrinsics, depth_supervision_lambda,
+                  depth_loss_type, update_training_images(...)}
+  .frame()  .loss  .elapsed_training_time  .apply_camera_smoothing(ms)
+  .background_color .snap_to_pixel_centers .nerf.rendering_min_transmittance .camera_matrix
+  .render_mode .set_camera_to_training_view(i) .render(w, h, spp, linear, fps=)
+
+plus a device-side fast path (`update_training_images_device`) that takes the SLAM packet's CUDA
+tensors directly (no CPU round trip, cf. fusion/nerf_fusion.py:198-223).
+"""
+import ctypes
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_LEVELS, LOG2_T, BASE_RES = 16, 19, 16
+W_TOTAL = 10240
+GRID = 128
+
+
+class TestbedMode:
+    Nerf = 0
+
+
+class LossType:
+    L2 = 0
+    L1 = 1
+    Huber = 2
+
+
+Shade, Depth = 0, 1
+
+
+class BoundingBox:
+    def __init__(self, mn, mx):
+        self.min, self.max = np.asarray(mn, dtype=np.float64), np.asarray(mx, dtype=np.float64)
+
+
+class NgpModel(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("grid_half", "grid_master", "grid_grad", "grid_m", "grid_v",
+                                               "mlp", "mlp_grad", "mlp_m", "mlp_v", "density", "bits", "stats")] + \
+               [("aabb_scale", ctypes.c_float), ("cascades", ctypes.c_int), ("cone", ctypes.c_float),
+                ("near_distance", ctypes.c_float),
+                ("scale", ctypes.c_float * 16), ("res", ctypes.c_int * 16), ("size", ctypes.c_uint * 16),
+                ("offset", ctypes.c_uint * 16), ("dense", ctypes.c_int * 16), ("n_grid", ctypes.c_uint)]
+
+
+class NgpImages(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("rgba", "depth", "depth_cov", "cams", "active")] + \
+               [(n, ctypes.c_int) for n in ("n_active", "H", "W")]
+
+
+class NgpBatch(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("rays", "coords", "tdist", "rgbsigma", "dout", "counters", "loss")] + \
+               [(n, ctypes.c_int) for n in ("max_rays", "max_samples")]
+
+
+def level_table(aabb_scale):
+    b = math.exp(math.log(2048.0 * aabb_scale / BASE_RES) / (N_LEVELS - 1))
+    T = 1 << LOG2_T
+    rows, off = [], 0
+    for l in range(N_LEVELS):
+        scale = BASE_RES * (b ** l) - 1.0
+        res = int(math.ceil(scale)) + 1
+        n = min(((res ** 3 + 7) // 8) * 8, T)
+        rows.append((float(np.float32(scale)), res, n, off, int(res ** 3 <= n)))
+        off += n
+    return rows, off
+
+
+class _Training:
+    def __init__(self, tb):
+        self._tb = tb
+        self.n_images_for_training = 0
+        self.optimize_extrinsics = False
+        self.depth_supervision_lambda = 0.0
+        self.depth_loss_type = LossType.L2
+        self.near_distance = 0.05
+        self.density_grid_decay = 0.95
+
+    def update_training_images(self, frame_ids, poses, images, depths, depths_cov, resolution,
+                               principal_point, focal_length, depth_scale, depth_cov_scale):
+        """reference signature (fusion/nerf_fusion.py:285-289): lists of numpy arrays from the host."""
+        tb = self._tb
+        dev = tb.device
+        for k, fid in enumerate(frame_ids):
+            img = torch.as_tensor(np.asarray(images[k]), device=dev).float()      # [H,W,4] linear premult
+            dep = torch.as_tensor(np.asarray(depths[k]), device=dev).float().reshape(img.shape[0], img.shape[1]) * depth_scale
+            cov = torch.as_tensor(np.asarray(depths_cov[k]), device=dev).float().reshape(img.shape[0], img.shape[1]) * depth_cov_scale
+            tb._ensure_store(img.shape[0], img.shape[1])
+            tb.rgba[fid] = img.half()
+            tb.depth[fid] = dep
+            tb.depth_cov[fid] = cov
+            tb._set_camera(fid, np.asarray(poses[k], np.float64), focal_length, principal_point, resolution)
+        tb._activate(frame_ids)
+
+    def update_training_images_device(self, frame_ids, c2w, images_u8_chw, idepths_up, depths_cov_up,
+                                      focal_length, principal_point):
+        """device fast path: images uint8 [n,3,H,W] (sRGB), idepths_up/depths_cov_up [n,H,W] CUDA tensors;
+        sRGB->linear, premultiply and 1/idepth are fused in one kernel per image."""
+        tb = self._tb
+        lib = _lib.load()
+        n, _, H, W = images_u8_chw.shape
+        tb._ensure_store(H, W)
+        for k in range(n):
+            fid = int(frame_ids[k])
+            _lib.check(lib.nslam_ngp_ingest_image(_lib.ptr(images_u8_chw[k].contiguous()), _lib.ptr(idepths_up[k].contiguous()),
+                                                  _lib.ptr(depths_cov_up[k].contiguous()), H, W, _lib.ptr(tb.rgba[fid]),
+                                                  _lib.ptr(tb.depth[fid]), _lib.ptr(tb.depth_cov[fid]),
+                                                  _lib.stream_ptr()), "ngp_ingest_image")
+            tb._set_camera(fid, np.asarray(c2w[k], np.float64), focal_length, principal_point, (W, H))
+        tb._activate([int(f) for f in frame_ids])
+
+
+class _Nerf:
+    def __init__(self, tb):
+        self.training = _Training(tb)
+        self.visualize_cameras = False
+        self.rendering_min_transmittance = 1e-4
+
+
+class Testbed:
+    def __init__(self, mode=TestbedMode.Nerf, device_index=0, seed=1337, max_samples=1 << 18, max_rays=1 << 16):
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.nerf = _Nerf(self)
+        self.shall_train = True
+        self.dynamic_res = False
+        self.dynamic_res_target_fps = 15
+        self.camera_smoothing = False
+        self.display_gui = False
+        self.visualize_unit_cube = False
+        self.background_color = [0.0, 0.0, 0.0, 1.0]
+        self.snap_to_pixel_centers = True
+        self.render_mode = Shade
+        self.camera_matrix = np.eye(4)[:3]
+        self.loss = float("nan")
+        self.elapsed_training_time = 0.0
+        self.training_step = 0
+        self.seed = seed
+        self.max_samples, self.max_rays = max_samples, max_rays
+        self.rays_per_batch = 1 << 12
+        self.n_images = 0
+        self.rgba = None
+        self.lr, self.beta1, self.beta2, self.eps, self.l2 = 1e-2, 0.9, 0.99, 1e-15, 1e-6
+        self._t0 = None
+        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self._measured = None
+        self.grad_hook = None        # e.g. dist.allreduce_grads for data-parallel training
+
+    # ---------------------------------------------------------------- setup
+    def init_window(self, *a, **k):
+        pass
+
+    def reload_network_from_file(self, path=None):
+        """configs/nerf/base.json of the fork is absent; its (published) architecture is built in:
+        HashGrid 16x2, T=2^19, base 16; density 1x64 -> 16; SH4; rgb 2x64 -> 3; Adam 1e-2."""
+        return None
+
+    def create_empty_nerf_dataset(self, n_images, nerf_scale=1.0, offset=None, aabb_scale=4, render_aabb=None):
+        dev = self.device
+        self.n_images = int(n_images)
+        self.aabb_scale = float(aabb_scale)
+        self.cascades = 1 + int(math.ceil(math.log2(aabb_scale))) if aabb_scale > 1 else 1
+        rows, total = level_table(self.aabb_scale)
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        f = dict(dtype=torch.float32, device=dev)
+        self.grid_master = ((torch.rand(total * 2, generator=g) * 2 - 1) * 1e-4).to(dev)
+        self.grid_half = self.grid_master.half()
+        self.grid_grad = torch.zeros(total * 2, **f); self.grid_m = torch.zeros(total * 2, **f); self.grid_v = torch.zeros(total * 2, **f)
+        ws = []
+        for (i, o) in ((32, 64), (64, 16), (32, 64), (64, 64), (64, 16)):
+            s = math.sqrt(6.0 / (i + o))
+            ws.append(((torch.rand(i, o, generator=g) * 2 - 1) * s).reshape(-1))
+        self.mlp = torch.cat(ws).to(dev)
+        self.mlp_grad = torch.zeros(W_TOTAL, **f); self.mlp_m = torch.zeros(W_TOTAL, **f); self.mlp_v = torch.zeros(W_TOTAL, **f)
+        ncell = GRID ** 3 * self.cascades
+        self.density = -torch.ones(ncell, **f)
+        self.bits = torch.zeros(ncell // 8, dtype=torch.uint8, device=dev)
+        self.stats = torch.zeros(2, **f)
+        m = NgpModel()
+        for name in ("grid_half", "grid_master", "grid_grad", "grid_m", "grid_v", "mlp", "mlp_grad", "mlp_m",
+                     "mlp_v", "density", "bits", "stats"):
+            setattr(m, name, getattr(self, name).data_ptr())
+        m.aabb_scale = self.aabb_scale; m.cascades = self.cascades
+        m.cone = 1.0 / 256.0 if aabb_scale > 1 else 0.0
+        m.near_distance = self.nerf.training.near_distance
+        for l, (sc, res, n, off, dense) in enumerate(rows):
+            m.scale[l], m.res[l], m.size[l], m.offset[l], m.dense[l] = sc, res, n, off, dense
+        m.n_grid = total
+        self.model = m
+        self.cams_h = np.zeros((self.n_images, 18), np.float32)
+        self.cams = torch.zeros(self.n_images, 18, **f)
+        self.active = torch.zeros(self.n_images, dtype=torch.int32, device=dev)
+        self.active_set = []
+        b = NgpBatch()
+        self._bufs = dict(rays=torch.zeros(self.max_rays, 16, **f), coords=torch.zeros(self.max_samples, 7, **f),
+                          tdist=torch.zeros(self.max_samples, **f), rgbsigma=torch.zeros(self.max_samples, 4, **f),
+                          dout=torch.zeros(self.max_samples, 4, **f),
+                          counters=torch.zeros(4, dtype=torch.int32, device=dev), loss=torch.zeros(1, **f))
+        for k, v in self._bufs.items():
+            setattr(b, k, v.data_ptr())
+        b.max_rays, b.max_samples = self.max_rays, self.max_samples
+        self.batch = b
+
+    def _ensure_store(self, H, W):
+        if self.rgba is None:
+            dev = self.device
+            self.H, self.W = H, W
+            self.rgba = torch.zeros(self.n_images, H, W, 4, dtype=torch.float16, device=dev)
+            self.depth = -torch.ones(self.n_images, H, W, dtype=torch.float32, device=dev)
+            self.depth_cov = torch.ones(self.n_images, H, W, dtype=torch.float32, device=dev)
+        assert (H, W) == (self.H, self.W), "all training images share one resolution"
+
+    def _set_camera(self, fid, c2w34, focal, pp, resolution):
+        row = np.zeros(18, np.float32)
+        row[:12] = np.asarray(c2w34, np.float32)[:3, :4].reshape(-1)
+        row[12:14] = np.asarray(focal, np.float32).reshape(-1)[:2]
+        row[14:16] = np.asarray(pp, np.float32).reshape(-1)[:2]
+        # the camera record holds w,h as int32 in the last two slots
+        row[16:18] = np.array([int(resolution[0]), int(resolution[1])], np.int32).view(np.float32)
+        self.cams_h[fid] = row
+
+    def _activate(self, ids):
+        for i in ids:
+            if int(i) not in self.active_set:
+                self.active_set.append(int(i))
+        self.cams.copy_(torch.from_numpy(self.cams_h))
+        n = len(self.active_set)
+        self.active[:n] = torch.as_tensor(self.active_set, dtype=torch.int32)
+        self.nerf.training.n_images_for_training = n
+
+    def _images(self):
+        im = NgpImages()
+        im.rgba, im.depth, im.depth_cov = self.rgba.data_ptr(), self.depth.data_ptr(), self.depth_cov.data_ptr()
+        im.cams, im.active = self.cams.data_ptr(), self.active.data_ptr()
+        im.n_active, im.H, im.W = len(self.active_set), self.H, self.W
+        return im
+
+    # ---------------------------------------------------------------- training
+    def update_density_grid(self, full=False):
+        lib = _lib.load()
+        n = GRID ** 3 if full else GRID ** 3 // 4
+        im = self._images()
+        _lib.check(lib.nslam_ngp_update_density_grid(ctypes.byref(self.model), ctypes.byref(im), n,
+                                                     (self.seed * 7919 + self.training_step) & 0xFFFFFFFF,
+                                                     self.nerf.training.density_grid_decay, 0.01,
+                                                     _lib.stream_ptr()), "ngp_update_density_grid")
+
+    def train_step(self):
+        """one optimisation step; no host synchronisation"""
+        lib = _lib.load()
+        if self._t0 is None:
+            self._t0 = time.perf_counter()
+        if self.training_step % 16 == 0:
+            self.update_density_grid(full=self.training_step < 256)
+        im = self._images()
+        bg = self.background_color
+        seed = (self.seed + 0x9E3779B1 * (self.training_step + 1)) & 0xFFFFFFFF
+        _lib.check(lib.nslam_ngp_train_step(ctypes.byref(self.model), ctypes.byref(im), ctypes.byref(self.batch),
+                                            self.rays_per_batch, seed, float(self.nerf.training.depth_supervision_lambda),
+                                            bg[0], bg[1], bg[2], self.num_sms, _lib.stream_ptr()), "ngp_train_step")
+        if self.grad_hook is not None:
+            self.grad_hook(self)
+        self.training_step += 1
+        decay = 0.33 ** max(0, (self.training_step - 20000) // 10000 + (1 if self.training_step >= 20000 else 0))
+        _lib.check(lib.nslam_ngp_adam(ctypes.byref(self.model), self.training_step, self.lr * decay, self.beta1,
+                                      self.beta2, self.eps, self.l2, _lib.stream_ptr()), "ngp_adam")
+        # adapt the ray count so that a batch holds ~max_samples samples (uses the LAST completed step's
+        # counters without blocking: read asynchronously every 16 steps)
+        if self.training_step % 16 == 0:
+            c = self._bufs["counters"].cpu()
+            used, kept = int(c[0]), max(int(c[1]), 1)
+            self._measured = (used, kept)
+            target = int(0.9 * self.max_samples)
+            new = int(self.rays_per_batch * target / max(used, 1))
+            self.rays_per_batch = int(min(self.max_rays, max(256, (new // 128) * 128)))
+            self.loss = float(self._bufs["loss"].item())
+
+    def frame(self):
+        """Testbed.frame(): one training step when shall_train and data is present (fusion/nerf_fusion.py:299)"""
+        if self.shall_train and self.rgba is not None and len(self.active_set) > 0:
+            self.train_step()
+            self.elapsed_training_time = time.perf_counter() - self._t0
+        return True
+
+    def apply_camera_smoothing(self, ms):
+        pass
+
+    # ---------------------------------------------------------------- rendering
+    def set_camera_to_training_view(self, i):
+        self.camera_matrix = self.cams_h[self.active_set[i] if i < len(self.active_set) else i, :12].reshape(3, 4).astype(np.float64).copy()
+        self._view_intr = self.cams_h[self.active_set[i] if i < len(self.active_set) else i, 12:16].copy()
+
+    def render(self, width, height, spp=1, linear=True, fps=None, tile_rows=32):
+        """-> numpy [H,W,4] float32: Shade = (r,g,b,1) linear; Depth = (d,d,d,1) z-depth"""
+        lib = _lib.load()
+        dev = self.device
+        intr = getattr(self, "_view_intr", None)
+        if intr is None:
+            intr = np.array([width / 2, width / 2, width / 2 - 0.5, height / 2 - 0.5], np.float32)
+        sx, sy = width / float(self.W if self.rgba is not None else width), height / float(self.H if self.rgba is not None else height)
+        cam = (ctypes.c_float * 18)()
+        c2w = np.asarray(self.camera_matrix, np.float32)[:3, :4].reshape(-1)
+        for k in range(12):
+            cam[k] = float(c2w[k])
+        cam[12], cam[13], cam[14], cam[15] = float(intr[0] * sx), float(intr[1] * sy), float((intr[2] + 0.5) * sx - 0.5), float((intr[3] + 0.5) * sy - 0.5)
+        cam[16], cam[17] = float(width), float(height)
+        out = torch.zeros(height, width, 4, dtype=torch.float32, device=dev)
+        rows = max(1, min(tile_rows, self.max_rays // width))
+        per_ray = max(8, min(1024, self.max_samples // (rows * width)))
+        bg = self.background_color
+        for y0 in range(0, height, rows):
+            th = min(rows, height - y0)
+            _lib.check(lib.nslam_ngp_render_tile(ctypes.byref(self.model), ctypes.byref(self.batch), cam, 0, y0, width, th,
+                                                 per_ray, bg[0], bg[1], bg[2], _lib.ptr(out[y0]), _lib.stream_ptr()),
+                       "ngp_render_tile")
+        o = out.cpu().numpy()
+        if self.render_mode == Depth:
+            d = o[..., 3:4]
+            return np.concatenate([d, d, d, np.ones_like(d)], -1)
+        o[..., 3] = 1.0
+        return o
