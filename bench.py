@@ -242,6 +242,9 @@ def run_ours(a):
         up0 = job.fe.stats["updates"] if job.is_slam else 0
         it0 = job.nf.total_iters if job.is_nerf else 0
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        prof = os.environ.get("NSLAM_CUDA_PROFILER") == "1" and not e2e
+        if prof:
+            torch.cuda.profiler.start()          # ncu --profile-from-start off captures only the timed region
         t0 = time.perf_counter()
         e0.record()
         for p in frames[a.warmup:]:
@@ -250,6 +253,8 @@ def run_ours(a):
             torch.cuda.current_stream().wait_stream(job.nerf_stream)
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=job.dev)

@@ -25,10 +25,13 @@ int nslam_corr_index_forward(const void* volume, int dtype, const float* coords,
 /* CorrBlock.__call__ (networks/modules/corr.py:40-50) fused over the pyramid:
  * volumes: HOST array of num_levels device pointers, h2s/w2s: HOST int arrays;
  * coords [n,2,h1,w1] in level-0 pixels (level l samples coords/2^l); out [n,L*(2r+1)^2,h1,w1].
- * slots: optional DEVICE int32 [n]: edge n reads volume slots[n] (correlation arena), NULL = n. */
+ * slots: optional DEVICE int32 [n]: edge n reads volume slots[n] (correlation arena), NULL = n.
+ * nhwc_stride > 0: out is channels-last [n,h1,w1,nhwc_stride] (tail channels zero-filled);
+ * coords_nhwc != 0: coords are [n,h1,w1,2]. */
 int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const int* w2s,
                               int num_levels, int dtype, const float* coords, void* out, int n,
-                              int h1, int w1, int radius, const int* slots, void* stream);
+                              int h1, int w1, int radius, const int* slots, int nhwc_stride,
+                              int coords_nhwc, void* stream);
 
 /* CorrBlock.__init__ + CorrBlock.corr (networks/modules/corr.py:23-38,63-72): all-pairs
  * correlation (f1/4).(f2/4) and the 3 avg-pooled levels, fp16, in one tcgen05 kernel.
@@ -75,9 +78,10 @@ int nslam_depth_filter(const float* poses, const float* disps, const float* intr
                        const long long* inds, const float* thresh, int num_inds, int num_frames,
                        int ht, int wd, float* counter, void* stream);
 
-/* cvx_upsample (utils/flow_viz.py:166-183): data [K,ht,wd] fp32, mask [K,576,ht,wd], out [K,8ht,8wd] */
+/* cvx_upsample (utils/flow_viz.py:166-183): data [K,ht,wd] fp32, mask [K,576,ht,wd]
+ * (or [K,ht,wd,576] when mask_nhwc != 0), out [K,8ht,8wd] */
 int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out, int K,
-                       int ht, int wd, float pw, void* stream);
+                       int ht, int wd, float pw, int mask_nhwc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,14 @@ int nslam_ba_cov(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float
 /* block-diagonal 6x6 blocks of (L L^T)^-1 = Linv^T Linv: sigma_g [P,6,6] */
 int nslam_ba_pose_cov(const float* Linv, int P, float* sigma_g, void* stream);
 
+/* `iters` full Gauss-Newton iterations (A7-A13) in one host call; see csrc/ba.cu.
+ * prior_pose [7] DEVICE (t,q) or NULL when prior_pose_idx < 0; prior_err [6] DEVICE scratch. */
+int nslam_ba_gn_iterations(const nslam_ba_graph* g, const nslam_ba_buffers* b, int iters,
+                           float* world_T_body, float* cam_T_world, const float* cam_T_body,
+                           int prior_pose_idx, const float* prior_pose, float prior_info,
+                           double* work, float* dx, float* Linv, float* prior_err, int* status,
+                           float clamp_min, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,7 +37,7 @@ _P = c_void_p
 _SIGNATURES = {
     # name: argtypes (all return int)
     "nslam_corr_index_forward": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
-    "nslam_corr_lookup_pyramid": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "nslam_corr_lookup_pyramid": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "nslam_corr_volume_build": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_corr_volume_build_simt": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_altcorr_forward": [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
@@ -46,7 +46,7 @@ _SIGNATURES = {
     "nslam_projmap": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P],
     "nslam_iproj": [_P, _P, _P, c_int, c_int, c_int, _P, _P],
     "nslam_depth_filter": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
-    "nslam_cvx_upsample": [_P, _P, c_int, _P, c_int, c_int, c_int, c_float, _P],
+    "nslam_cvx_upsample": [_P, _P, c_int, _P, c_int, c_int, c_int, c_float, c_int, _P],
     "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],
     "nslam_ba_solve": [_P, _P, c_int, c_int, _P, c_float, c_float, c_float, _P, _P, _P, _P, _P],
     "nslam_ba_retract": [_P, _P, _P, _P, c_int, c_int, _P],
@@ -55,6 +55,8 @@ _SIGNATURES = {
     "nslam_ba_depth": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, c_float, _P],
     "nslam_ba_cov": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, _P, _P, _P],
     "nslam_ba_pose_cov": [_P, c_int, _P, _P],
+    "nslam_ba_gn_iterations": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), c_int, _P, _P, _P, c_int, _P,
+                               c_float, _P, _P, _P, _P, _P, c_float, _P],
     # Path B (include/nslam_ngp.h); struct pointers are passed with ctypes.byref
     "nslam_ngp_train_step": [_P, _P, _P, c_int, ctypes.c_uint, c_float, c_float, c_float, c_float, c_int, _P],
     "nslam_ngp_adam": [_P, c_int, c_float, c_float, c_float, c_float, c_float, _P],
@@ -63,6 +65,9 @@ _SIGNATURES = {
     "nslam_ngp_update_density_grid": [_P, _P, c_int, ctypes.c_uint, c_float, c_float, _P],
     "nslam_ngp_render_tile": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P],
     "nslam_ngp_ingest_image": [_P, _P, _P, c_int, c_int, _P, _P, _P, _P],
+    # tensor-core convolution (include/nslam_nn.h)
+    "nslam_conv_igemm": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
+                         _P, _P, _P, _P, _P, c_int, _P, c_int, _P],
 }
 
 _lib = None

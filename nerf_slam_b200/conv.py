@@ -1,0 +1,168 @@
+"""Tensor-core (tcgen05) execution of the update operator — host side.
+
+`UpdateOperatorTC` evaluates the reference's UpdateModule.forward (networks/droid_net.py:118-150;
+ConvGRU networks/modules/gru.py:19-32; GraphAgg networks/droid_net.py:59-75) with every 3x3 / 1x1
+convolution on the hand-written implicit-GEMM kernel (csrc/conv_igemm.cu, C ABI
+include/nslam_nn.h).  Activations are NHWC fp16 end to end; `torch.cat` inputs are never
+materialised (multi-source K loop); sigmoid/tanh/GRU gating/global-context reduction are epilogues.
+
+Fusions (what replaces what):
+  z, r gates      : ONE conv with N=256 over [net|inp|corr|flow] -> z and r*net    (2 convs + cat + 3 elementwise)
+  q + state update: ONE conv, epilogue (1-z)*net + z*tanh(.)                      (conv + cat + 3 elementwise)
+  glo             : 1x1 conv with epilogue sigmoid(.)*net and per-image column sums (conv + mul + mean)
+  delta.0|weight.0: ONE conv with N=256 from the shared input
+  delta.2|weight.2: ONE block-diagonal conv with N=16
+The 7x7 conv on the 4-channel motion input (1 % of the FLOPs, K=196 not a multiple of 64) stays on
+the library path for now.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def pack_weights(w, src_channels, n_pad=None):
+    """w [N, sum(src_channels), KH, KW] (torch conv layout) -> packed fp16 image for conv_igemm:
+    [KH*KW * sum(ceil(C_s/64))] blocks of [N_pad][64], each row 128-B swizzled (16-B chunk j of row n
+    stored at chunk j ^ (n & 7)).  Channels beyond a source's real count are zero."""
+    N, Cin, KH, KW = w.shape
+    assert Cin == sum(src_channels)
+    Np = n_pad or N
+    dev = w.device
+    blocks = []
+    wf = w.float()
+    rows = torch.arange(Np, device=dev)
+    perm = (torch.arange(8, device=dev)[None, :] ^ (rows % 8)[:, None])        # [Np,8]: dest chunk of src chunk j
+    for ky in range(KH):
+        for kx in range(KW):
+            off = 0
+            for C in src_channels:
+                for cb in range((C + 63) // 64):
+                    blk = torch.zeros(Np, 64, device=dev)
+                    cs, ce = cb * 64, min(C, cb * 64 + 64)
+                    blk[:N, :ce - cs] = wf[:, off + cs:off + ce, ky, kx]
+                    src = blk.view(Np, 8, 8)
+                    dst = torch.empty_like(src)
+                    dst.scatter_(1, perm[:, :, None].expand(Np, 8, 8), src)
+                    blocks.append(dst.reshape(-1))
+                off += C
+    return torch.cat(blocks).half().contiguous()
+
+
+def conv_tc(srcs, wpacked, bias, B, H, W, KH, pad, N, mode=0, act=0, gctx=None, net=None, zbuf=None,
+            gsum=None, out0=None, out0_channels=None, out1=None, num_sms=148):
+    lib = _lib.load()
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    chans = (ctypes.c_int * n)(*[s.shape[-1] for s in srcs])
+    _lib.check(lib.nslam_conv_igemm(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(chans, ctypes.c_void_p), n,
+                                    B, H, W, KH, KH, pad, N, _lib.ptr(wpacked), _lib.ptr(bias), mode, act,
+                                    _lib.ptr(gctx), _lib.ptr(net), _lib.ptr(zbuf), _lib.ptr(gsum), _lib.ptr(out0),
+                                    int(out0_channels or 0), _lib.ptr(out1), num_sms, _lib.stream_ptr()), "conv_igemm")
+
+
+CORR_PAD = 200      # 196 correlation channels padded to a multiple of 8 (TMA stride rule), zero tail
+
+
+class UpdateOperatorTC:
+    """drop-in for networks.UpdateModule.__call__ with NHWC tensors.
+
+    __call__(net [E,ht,wd,128] f16, inp [E,ht,wd,128] f16, corr [E,ht,wd,CORR_PAD] f16,
+             motion [E,4,ht,wd] f32|f16 or None, ii (device long) or None)
+      -> net' [E,ht,wd,128], delta [E,ht,wd,2] f32, weight [E,ht,wd,2] f32 (, eta [K,ht,wd] f32, upmask [K,ht,wd,576] f16)
+    """
+
+    def __init__(self, params, device):
+        """params: networks.UpdateModule (its state_dict tensors)"""
+        sd = {k: v.to(device).float() for k, v in params.state_dict().items()}
+        self.dev = device
+        self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        f32 = lambda t: t.float().contiguous()
+        P = {}
+        P["ce0"] = (pack_weights(sd["corr_encoder.0.weight"], [196]), f32(sd["corr_encoder.0.bias"]))
+        # the packed block layout depends on the channel count of the SOURCE TENSOR (CORR_PAD), whose
+        # 64-blocks coincide with those of 196 real channels (4 blocks either way)
+        P["ce2"] = (pack_weights(sd["corr_encoder.2.weight"], [128]), f32(sd["corr_encoder.2.bias"]))
+        P["fe2"] = (pack_weights(sd["flow_encoder.2.weight"], [128]), f32(sd["flow_encoder.2.bias"]))
+        self.fe0_w = sd["flow_encoder.0.weight"].half().contiguous(memory_format=torch.channels_last)
+        self.fe0_b = sd["flow_encoder.0.bias"].half()
+        P["glo"] = (pack_weights(sd["gru.w.weight"], [128]), f32(sd["gru.w.bias"]))
+        src4 = [128, 128, 128, 64]
+        P["zr"] = (pack_weights(torch.cat([sd["gru.convz.weight"], sd["gru.convr.weight"]], 0), src4),
+                   f32(torch.cat([sd["gru.convz.bias"], sd["gru.convr.bias"]])))
+        P["q"] = (pack_weights(sd["gru.convq.weight"], src4), f32(sd["gru.convq.bias"]))
+        self.glo_w = torch.cat([sd["gru.convz_glo.weight"], sd["gru.convr_glo.weight"], sd["gru.convq_glo.weight"]], 0)[:, :, 0, 0].contiguous()
+        self.glo_b = torch.cat([sd["gru.convz_glo.bias"], sd["gru.convr_glo.bias"], sd["gru.convq_glo.bias"]]).contiguous()
+        P["h0"] = (pack_weights(torch.cat([sd["delta.0.weight"], sd["weight.0.weight"]], 0), [128]),
+                   f32(torch.cat([sd["delta.0.bias"], sd["weight.0.bias"]])))
+        w2 = torch.zeros(16, 256, 3, 3, device=device)
+        w2[0:2, 0:128] = sd["delta.2.weight"]; w2[2:4, 128:256] = sd["weight.2.weight"]
+        b2 = torch.zeros(16, device=device); b2[0:2] = sd["delta.2.bias"]; b2[2:4] = sd["weight.2.bias"]
+        P["h2"] = (pack_weights(w2, [256]), b2)
+        P["a1"] = (pack_weights(sd["agg.conv1.weight"], [128]), f32(sd["agg.conv1.bias"]))
+        P["a2"] = (pack_weights(sd["agg.conv2.weight"], [128]), f32(sd["agg.conv2.bias"]))
+        we = torch.zeros(16, 128, 3, 3, device=device); we[0:1] = sd["agg.eta.0.weight"]
+        be = torch.zeros(16, device=device); be[0:1] = sd["agg.eta.0.bias"]
+        P["eta"] = (pack_weights(we, [128]), be)
+        um_w, um_b = sd["agg.upmask.0.weight"], sd["agg.upmask.0.bias"]
+        P["um"] = [(pack_weights(um_w[c0:c0 + n], [128]), f32(um_b[c0:c0 + n]), c0, n) for c0, n in ((0, 256), (256, 256), (512, 64))]
+        self.P = P
+
+    def _conv(self, key, srcs, B, H, W, k, N, out, **kw):
+        wp, b = self.P[key][:2]
+        conv_tc(srcs, wp, b, B, H, W, k, k // 2, N, out0=out, out0_channels=out.shape[-1] if out is not None else 0,
+                num_sms=self.num_sms, **kw)
+
+    def __call__(self, net, inp, corr, motion=None, ii=None):
+        E, H, W, _ = net.shape
+        dev = net.device
+        h16 = dict(dtype=torch.float16, device=dev)
+        new = lambda c: torch.empty(E, H, W, c, **h16)
+        # correlation / motion encoders
+        c1 = new(128); self._conv("ce0", [corr], E, H, W, 1, 128, c1, act=1)
+        c2 = new(128); self._conv("ce2", [c1], E, H, W, 3, 128, c2, act=1)
+        if motion is None:
+            motion = torch.zeros(E, 4, H, W, **h16)
+        f1 = F.relu(F.conv2d(motion.half().contiguous(memory_format=torch.channels_last), self.fe0_w, self.fe0_b, padding=3), inplace=True)
+        f1 = f1.permute(0, 2, 3, 1)                                 # NHWC view of channels_last storage
+        if not f1.is_contiguous():
+            f1 = f1.contiguous()
+        f2 = new(64); self._conv("fe2", [f1], E, H, W, 3, 64, f2, act=1)
+        # global context: glo = mean_hw(sigmoid(w(net)) * net) ; then the three 1x1 "glo" convs as one GEMV batch
+        gsum = torch.zeros(E, 128, dtype=torch.float32, device=dev)
+        self._conv("glo", [net], E, H, W, 1, 128, None, mode=3, net=net, gsum=gsum)
+        glo = (gsum * (1.0 / (H * W))).half().float()               # the reference's glo is an fp16 tensor
+        g3 = torch.addmm(self.glo_b, glo, self.glo_w.t())           # [E,384] = z|r|q context terms
+        gzr = g3[:, :256].contiguous(); gq = g3[:, 256:].contiguous()
+        # GRU
+        z = new(128); rnet = new(128)
+        srcs = [net, inp, c2, f2]
+        wp, b = self.P["zr"]
+        conv_tc(srcs, wp, b, E, H, W, 3, 1, 256, mode=1, gctx=gzr, net=net, out0=z, out0_channels=128, out1=rnet, num_sms=self.num_sms)
+        net2 = new(128)
+        wp, b = self.P["q"]
+        conv_tc([rnet, inp, c2, f2], wp, b, E, H, W, 3, 1, 128, mode=2, gctx=gq, net=net, zbuf=z, out0=net2, out0_channels=128,
+                num_sms=self.num_sms)
+        # heads
+        h0 = new(256); self._conv("h0", [net2], E, H, W, 3, 256, h0, act=1)
+        h2 = new(16); self._conv("h2", [h0], E, H, W, 3, 16, h2, act=0)
+        delta = h2[..., 0:2].float()
+        weight = torch.sigmoid(h2[..., 2:4].float())
+        if ii is None:
+            return net2, delta, weight
+        # GraphAgg
+        a1 = new(128); self._conv("a1", [net2], E, H, W, 3, 128, a1, act=1)
+        _, ix = torch.unique(ii, return_inverse=True)
+        K = int(ix.max().item()) + 1
+        s = torch.zeros(K, H, W, 128, dtype=torch.float32, device=dev).index_add_(0, ix, a1.float())
+        cnt = torch.zeros(K, dtype=torch.float32, device=dev).index_add_(0, ix, torch.ones_like(ix, dtype=torch.float32))
+        am = (s / cnt.view(-1, 1, 1, 1)).half()
+        a2 = torch.empty(K, H, W, 128, **h16); self._conv("a2", [am], K, H, W, 3, 128, a2, act=1)
+        e16 = torch.empty(K, H, W, 16, **h16); self._conv("eta", [a2], K, H, W, 3, 16, e16, act=0)
+        eta = 0.01 * F.softplus(e16[..., 0].float())
+        upmask = torch.empty(K, H, W, 576, **h16)
+        for wp, b, c0, n in self.P["um"]:
+            conv_tc([a2], wp, b, K, H, W, 1, 0, n, out0=upmask[..., c0:], out0_channels=576, num_sms=self.num_sms)
+        return net2, delta, weight, eta, upmask

@@ -763,4 +763,30 @@ int nslam_ba_pose_cov(const float* Linv, int P, float* sigma_g, void* stream) {
   return 0;
 }
 
+/* Front-end fast path: `iters` complete Gauss-Newton iterations in ONE host call
+ * (linearise -> Schur -> assemble -> [prior] -> fp64 Cholesky -> gtsam-style retract -> depth update).
+ * b->poses must alias cam_T_world (it is refreshed by the retraction between iterations). */
+int nslam_ba_gn_iterations(const nslam_ba_graph* g, const nslam_ba_buffers* b, int iters,
+                           float* world_T_body, float* cam_T_world, const float* cam_T_body,
+                           int prior_pose_idx, const float* prior_pose, float prior_info,
+                           double* work, float* dx, float* Linv, float* prior_err, int* status,
+                           float clamp_min, void* stream) {
+  for (int it = 0; it < iters; it++) {
+    int r = nslam_ba_reduced_camera_matrix(g, b, stream);
+    if (r) return r;
+    if (prior_pose_idx >= 0) {
+      r = nslam_pose_prior_error(world_T_body + (size_t)(g->kf0 + prior_pose_idx) * 7, prior_pose, prior_err, stream);
+      if (r) return r;
+    }
+    r = nslam_ba_solve(b->H, b->v, g->P, prior_pose_idx, prior_err, prior_pose_idx >= 0 ? prior_info : 0.f, 0.f, 0.f,
+                       work, dx, (it == iters - 1) ? Linv : nullptr, status, stream);
+    if (r) return r;
+    r = nslam_ba_retract(world_T_body, cam_T_world, cam_T_body, dx, g->kf0, g->P, stream);
+    if (r) return r;
+    r = nslam_ba_depth(g, b, dx, clamp_min, stream);
+    if (r) return r;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,390 @@
+// A5/A1 — convolutions of the update operator as implicit GEMM on tcgen05 (sm_100a).
+//
+// Replaces the cuDNN convolutions behind UpdateModule / ConvGRU / GraphAgg
+// (reference networks/droid_net.py:78-150, networks/modules/gru.py:5-32) and the
+// torch.cat / sigmoid / tanh / gating elementwise kernels around them.
+//
+//   out[n,h,w,:] = epilogue( sum_{taps, sources} A_src[n, h+dy, w+dx, :] . W[tap, src] + bias )
+//
+// * activations are NHWC fp16; the concatenated conv input (hidden | context | corr | flow, 448
+//   channels for the GRU) is never materialised: every 64-channel K-block is fetched by TMA from
+//   the SOURCE tensor it belongs to (up to 4 tensor maps);
+// * one CTA tile = 8x16 output pixels (M = 128) x N output channels (N = 16..256); for tap
+//   (dy,dx) the A tile is the TMA box {64c, 16w, 8h} shifted by (dx-pad, dy-pad): out-of-image
+//   rows/cols are zero-filled by TMA, which IS the convolution's zero padding;
+// * weights are pre-packed on the host into the exact 128B-swizzled K-major smem image, one
+//   contiguous N*128-byte block per (tap, channel-block): a 1-D bulk copy lands it UMMA-ready;
+// * 4-stage mbarrier ring, one thread issues tcgen05.mma (M128, N, K16), fp32 accumulators in
+//   TMEM, double buffered so the epilogue of tile t overlaps the MMAs of tile t+1;
+// * persistent CTAs (grid = #SMs) walk the (image, tile) list;
+// * epilogue (4 warps, thread = pixel): tcgen05.ld -> +bias (+ per-image global-context vector)
+//   -> activation / GRU gating -> fp16 -> swizzled smem -> TMA store (clips partial tiles).
+//
+// Epilogue modes:
+//   0 ACT   y = act(acc + bias [+ gctx[n]])                          act: 0 none 1 relu 2 sigmoid 3 tanh
+//   1 ZR    N = 256: z = sigmoid(acc[0:128]+..), r = sigmoid(acc[128:256]+..);
+//           out0 = z, out1 = r * net          (ConvGRU z,r gates, gru.py:27-29)
+//   2 Q     q = tanh(acc + ..); out0 = (1 - z) * net + z * q         (gru.py:29-31)
+//   3 GLO   y = sigmoid(acc + bias) * net; column sums over the image atomically added to
+//           gsum[n][c] (fp32)  -> glo = mean (gru.py:23-25); nothing is stored
+// Roofline: tensor pipe; FLOPs = 2 * pixels * taps * Cin * Cout.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace nslam {
+
+constexpr int CG_THREADS = 192;
+template <int N> struct CgStages { static constexpr int value = (N >= 256) ? 3 : 4; };
+constexpr int CG_TH = 8, CG_TW = 16;
+
+struct ConvParams {
+  int B, H, W;
+  int tiles_h, tiles_w;
+  int n_src;
+  int src_cb[4];       // 64-channel blocks per source
+  int cb_total;
+  int KH, KW, pad;
+  int N;               // output channels of this launch (multiple of 16, <= 256)
+  int mode, act;
+  const __half* wpacked;   // [taps*cb_total][N][64] swizzled image
+  const float* bias;       // [N]
+  const float* gctx;       // [B][N] or null
+  const __half* net;       // [B,H,W,128] (modes 1,2,3)
+  const __half* zbuf;      // [B,H,W,128] (mode 2)
+  float* gsum;             // [B][128] (mode 3)
+};
+
+struct ConvMaps {
+  CUtensorMap src[4];
+  CUtensorMap out[2];
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 1.f / (1.f + __expf(-x));
+  if (act == 3) return tanhf(x);
+  return x;
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          tc::smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(tc::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// smem: A stages [S][16384] | B stages [S][N*128] | out staging [NOUT64][16384] | bias/gctx | barriers
+template <int N>
+struct CgSmem {
+  static constexpr int STAGES = CgStages<N>::value;
+  static constexpr int A = 0;
+  static constexpr int B = STAGES * 16384;
+  static constexpr int OUT = B + STAGES * N * 128;
+  static constexpr int NOUT64 = (N >= 64) ? N / 64 : 1;    // 64-channel staging tiles
+  static constexpr int BIAS = OUT + NOUT64 * 16384;
+  static constexpr int BAR = BIAS + 2 * N * 4;
+  static constexpr int TOTAL = BAR + 256;
+};
+
+template <int N>
+__global__ void __launch_bounds__(CG_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
+  using SM = CgSmem<N>;
+  constexpr int CG_STAGES = SM::STAGES;
+  constexpr int TCOLS = (N <= 32) ? 64 : (N <= 64 ? 128 : (N <= 128 ? 256 : 512));   // 2 accumulator stages
+  constexpr int ACC_STRIDE = TCOLS / 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::BAR);
+  uint64_t* full_b = bars;
+  uint64_t* empty_b = bars + CG_STAGES;
+  uint64_t* tm_full = bars + 2 * CG_STAGES;
+  uint64_t* tm_empty = tm_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+  float* sbias = reinterpret_cast<float*>(sm + SM::BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int ntiles = p.B * tiles_per_img;
+  const int taps = p.KH * p.KW;
+  const int nkb = taps * p.cb_total;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_src; s++) tc::tma_prefetch_desc(&maps.src[s]);
+    for (int s = 0; s < CG_STAGES; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<TCOLS>(tmem_slot);
+  for (int i = threadIdx.x; i < N; i += CG_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+        for (int tap = 0; tap < taps; tap++) {
+          const int dy = tap / p.KW - p.pad, dx = tap % p.KW - p.pad;
+          int cbg = 0;
+          for (int s = 0; s < p.n_src; s++) {
+            for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
+              const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
+              tc::mbar_wait(&empty_b[st], ph ^ 1);
+              tc::mbar_arrive_expect_tx(&full_b[st], 16384 + N * 128);
+              tc::tma_load_4d(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n);
+              bulk_copy_g2s(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
+                            N * 128, &full_b[st]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+        const int as = tcount & 1, aph = (tcount >> 1) & 1;
+        tc::mbar_wait(&tm_empty[as], aph ^ 1);
+        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
+          tc::mbar_wait(&full_b[st], ph);
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(sm + SM::A + st * 16384);
+          const uint32_t b_addr = tc::smem_u32(sm + SM::B + st * (N * 128));
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
+                         (kb | k) ? 1u : 0u);
+          tc::umma_commit(&empty_b[st]);
+        }
+        tc::umma_commit(&tm_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hh = row / CG_TW, ww = row % CG_TW;
+    const int etid = (warp - 2) * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+      const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+      const int h = h0 + hh, w = w0 + ww;
+      const bool valid = (h < p.H) && (w < p.W);
+      const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+      const int as = tcount & 1, aph = (tcount >> 1) & 1;
+      tc::mbar_wait(&tm_full[as], aph);
+      tc::tc_fence_after();
+      // staging buffers free again once the previous tile's TMA stores have read them
+      if (etid == 0) tma_store_wait_read();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      const float* g = p.gctx ? p.gctx + (size_t)n * N : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        if (N >= 32) {
+          tc::tmem_ld_32x32(taddr + c0, r);
+        } else {
+          // N == 16: only 16 columns are valid; load 32 (allocated) and ignore the rest
+          tc::tmem_ld_32x32(taddr + c0, r);
+        }
+        tc::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const int c = c0 + i;
+          float x = __uint_as_float(r[i]) + ((c < N) ? sbias[c] : 0.f);
+          if (g && c < N) x += g[c];
+          v[i] = x;
+        }
+        if (p.mode == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = act_apply(v[i], p.act);
+        } else if (p.mode == 1) {
+          // cols [0,128) -> z ; [128,256) -> r * net
+          if (c0 < 128) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+          } else {
+            const __half* np = p.net + pix * 128 + (c0 - 128);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 raw = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
+              const __half* hv = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[i + j] = __half2float(hv[j]) / (1.f + __expf(-v[i + j]));
+            }
+          }
+        } else if (p.mode == 2) {
+          const __half* np = p.net + pix * 128 + c0;
+          const __half* zp = p.zbuf + pix * 128 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 rn = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
+            uint4 rz = valid ? *reinterpret_cast<const uint4*>(zp + i) : make_uint4(0, 0, 0, 0);
+            const __half* hn = reinterpret_cast<const __half*>(&rn);
+            const __half* hz = reinterpret_cast<const __half*>(&rz);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float z = __half2float(hz[j]), nt = __half2float(hn[j]);
+              v[i + j] = (1.f - z) * nt + z * tanhf(v[i + j]);
+            }
+          }
+        } else {  // mode 3: sigmoid(acc) * net, column sums
+          const __half* np = p.net + pix * 128 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 rn = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
+            const __half* hn = reinterpret_cast<const __half*>(&rn);
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[i + j] = valid ? __half2float(hn[j]) / (1.f + __expf(-v[i + j])) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float s = warp_sum(v[i]);
+            if (lane == 0) atomicAdd(p.gsum + (size_t)n * 128 + c0 + i, s);
+          }
+        }
+        if (p.mode != 3) {
+          // fp16, into the 128B-swizzled staging tile of this 64-channel group
+          const int t64 = c0 / 64;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (c0 + i >= N) break;
+            __half2 h2[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+            if (N >= 64) {
+              // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
+              unsigned char* st = sm + SM::OUT + t64 * 16384 + row * 128;
+              const int chunk = ((c0 % 64) + i) / 8;
+              *reinterpret_cast<uint4*>(st + ((chunk ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
+            } else {
+              // narrow outputs: dense rows of N halfs, un-swizzled tensor map
+              unsigned char* st = sm + SM::OUT + row * (N * 2);
+              *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
+      if (p.mode != 3) {
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (etid == 0) {
+          if (p.mode == 1) {
+            tma_store_4d(&maps.out[0], sm + SM::OUT + 0 * 16384, 0, w0, h0, n);
+            tma_store_4d(&maps.out[0], sm + SM::OUT + 1 * 16384, 64, w0, h0, n);
+            tma_store_4d(&maps.out[1], sm + SM::OUT + 2 * 16384, 0, w0, h0, n);
+            tma_store_4d(&maps.out[1], sm + SM::OUT + 3 * 16384, 64, w0, h0, n);
+          } else {
+            for (int t = 0; t < SM::NOUT64; t++)
+              tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, t * 64, w0, h0, n);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<TCOLS>(tmem_base);
+}
+
+template <int N>
+static int launch_conv(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
+  const int smem = CgSmem<N>::TOTAL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int ntiles = p.B * p.tiles_h * p.tiles_w;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  conv_igemm_kernel<N><<<grid, CG_THREADS, smem, st>>>(maps, p);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace nslam
+
+extern "C" {
+
+/* NHWC fp16 convolution (stride 1) on tensor cores.
+ *   srcs[i]: [B,H,W,src_channels[i]] fp16 (channels need not be multiples of 64: the tail of the
+ *            last 64-block is zero-filled by TMA; the packed weights must be zero there too)
+ *   wpacked: produced by nslam_conv_pack_weights; bias [N] fp32 or NULL
+ *   out0 (and out1 for mode 1): [B,H,W,out_channels] fp16; N = 16,32,64,128,256 columns per launch
+ *   mode/act/gctx/net/zbuf/gsum: see the epilogue modes above. */
+int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src, int B, int H, int W,
+                     int KH, int KW, int pad, int N, const void* wpacked, const float* bias, int mode,
+                     int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
+                     void* out0, int out0_channels, void* out1, int num_sms, void* stream) {
+  using namespace nslam;
+  if (n_src < 1 || n_src > 4 || B <= 0) return (int)cudaErrorInvalidValue;
+  ConvMaps maps;
+  ConvParams p{};
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_h = (H + CG_TH - 1) / CG_TH; p.tiles_w = (W + CG_TW - 1) / CG_TW;
+  p.n_src = n_src; p.KH = KH; p.KW = KW; p.pad = pad; p.N = N; p.mode = mode; p.act = act;
+  p.wpacked = (const __half*)wpacked; p.bias = bias; p.gctx = gctx; p.net = (const __half*)net;
+  p.zbuf = (const __half*)zbuf; p.gsum = gsum;
+  int cbt = 0;
+  for (int s = 0; s < n_src; s++) {
+    const int C = src_channels[s];
+    if (C % 8 != 0) return (int)cudaErrorInvalidValue;   // TMA strides must be multiples of 16 bytes
+    p.src_cb[s] = (C + 63) / 64;
+    cbt += p.src_cb[s];
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, CG_TW, CG_TH, 1};
+    int r = tc::make_tmap_f16(&maps.src[s], srcs[s], 4, dims, strides, box);
+    if (r) return r;
+  }
+  p.cb_total = cbt;
+  if (mode != 3) {
+    void* outs[2] = {out0, out1};
+    const int nout = (mode == 1) ? 2 : 1;
+    for (int o = 0; o < nout; o++) {
+      const int C = (mode == 1) ? 128 : out0_channels;
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+      uint32_t box[4] = {(uint32_t)(C < 64 ? C : 64), CG_TW, CG_TH, 1};
+      int r = tc::make_tmap_f16(&maps.out[o], outs[o], 4, dims, strides, box, false, nullptr, /*swizzle128=*/N >= 64);
+      if (r) return r;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (N) {
+    case 16: return launch_conv<16>(maps, p, num_sms, st);
+    case 64: return launch_conv<64>(maps, p, num_sms, st);
+    case 128: return launch_conv<128>(maps, p, num_sms, st);
+    case 256: return launch_conv<256>(maps, p, num_sms, st);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+}  // extern "C"

@@ -47,7 +47,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(128)
 corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restrict__ out,
                    int h1, int w1, int num_levels, int scale_coords,
-                   const int* __restrict__ slots) {
+                   const int* __restrict__ slots, int nhwc_stride, int coords_nhwc) {
   constexpr int RD = 2 * R + 1;
   constexpr int NT = RD + 1;  // taps per axis
   const int hw = h1 * w1;
@@ -61,8 +61,15 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
   const T* __restrict__ vol =
       reinterpret_cast<const T*>(lv.vol[l]) + ((size_t)vn * hw + p) * (size_t)(h2 * w2);
 
-  float x0 = coords[((size_t)n * 2 + 0) * hw + p];
-  float y0 = coords[((size_t)n * 2 + 1) * hw + p];
+  // coords either [n,2,h1,w1] (reference layout) or [n,h1,w1,2] (what reproject produces)
+  float x0, y0;
+  if (coords_nhwc) {
+    const float2 c = reinterpret_cast<const float2*>(coords)[(size_t)n * hw + p];
+    x0 = c.x; y0 = c.y;
+  } else {
+    x0 = coords[((size_t)n * 2 + 0) * hw + p];
+    y0 = coords[((size_t)n * 2 + 1) * hw + p];
+  }
   if (scale_coords) {
     // coords / 2**l of the python caller: exact power-of-two scaling
     const float s = 1.0f / (float)(1 << l);
@@ -93,7 +100,15 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
   const T w01 = Arith<T>::cvt((1.0f - dx) * dy);
   const T w00 = Arith<T>::cvt((1.0f - dx) * (1.0f - dy));
 
-  T* __restrict__ o = out + ((size_t)n * num_levels + l) * (size_t)(RD * RD) * hw + p;
+  // output: reference layout [n][L*RD*RD][h1][w1], or channels-last [n][h1][w1][nhwc_stride]
+  // (operand layout of the tcgen05 convolution; channels >= L*RD*RD are zero-filled by level 0)
+  const size_t ostride = nhwc_stride ? 1 : (size_t)hw;
+  T* __restrict__ o = nhwc_stride
+                          ? out + ((size_t)n * hw + p) * nhwc_stride + (size_t)l * (RD * RD)
+                          : out + ((size_t)n * num_levels + l) * (size_t)(RD * RD) * hw + p;
+  if (nhwc_stride && l == 0)
+    for (int c = num_levels * RD * RD; c < nhwc_stride; c++)
+      out[((size_t)n * hw + p) * nhwc_stride + c] = Arith<T>::zero();
 #pragma unroll
   for (int i = 0; i < RD; i++) {
 #pragma unroll
@@ -106,7 +121,7 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
       acc = Arith<T>::mac(acc, tap[i][j + 1], w01);
       acc = Arith<T>::mac(acc, tap[i + 1][j], w10);
       acc = Arith<T>::mac(acc, tap[i + 1][j + 1], w11);
-      o[(size_t)(i * RD + j) * hw] = acc;
+      o[(size_t)(i * RD + j) * ostride] = acc;
     }
   }
 }
@@ -114,25 +129,25 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
 template <typename T>
 static int launch_lookup(const LookupLevels& lv, const float* coords, void* out, int n, int h1,
                          int w1, int num_levels, int radius, int scale_coords,
-                         const int* slots, cudaStream_t st) {
+                         const int* slots, int nhwc_stride, int coords_nhwc, cudaStream_t st) {
   if (n == 0) return 0;
   dim3 grid((h1 * w1 + 127) / 128, num_levels, n), block(128);
   switch (radius) {
     case 3:
       corr_lookup_kernel<T, 3><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords, slots);
+                                                      scale_coords, slots, nhwc_stride, coords_nhwc);
       break;
     case 4:
       corr_lookup_kernel<T, 4><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords, slots);
+                                                      scale_coords, slots, nhwc_stride, coords_nhwc);
       break;
     case 2:
       corr_lookup_kernel<T, 2><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords, slots);
+                                                      scale_coords, slots, nhwc_stride, coords_nhwc);
       break;
     case 1:
       corr_lookup_kernel<T, 1><<<grid, block, 0, st>>>(lv, coords, (T*)out, h1, w1, num_levels,
-                                                      scale_coords, slots);
+                                                      scale_coords, slots, nhwc_stride, coords_nhwc);
       break;
     default:
       return (int)cudaErrorInvalidValue;
@@ -152,16 +167,17 @@ int nslam_corr_index_forward(const void* volume, int dtype, const float* coords,
   lv.vol[0] = volume; lv.h2[0] = h2; lv.w2[0] = w2;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
-    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, st);
+    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, 0, 0, st);
   if (dtype == 1)
-    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, st);
+    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, 1, radius, 0, nullptr, 0, 0, st);
   return (int)cudaErrorInvalidValue;
 }
 
 // Fused pyramid lookup: out[n][num_levels*(2r+1)^2][h1][w1]; level l is sampled at coords/2^l.
 int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const int* w2s,
                               int num_levels, int dtype, const float* coords, void* out, int n,
-                              int h1, int w1, int radius, const int* slots, void* stream) {
+                              int h1, int w1, int radius, const int* slots, int nhwc_stride,
+                              int coords_nhwc, void* stream) {
   if (num_levels < 1 || num_levels > 4) return (int)cudaErrorInvalidValue;
   nslam::LookupLevels lv{};
   for (int l = 0; l < num_levels; l++) {
@@ -169,9 +185,9 @@ int nslam_corr_lookup_pyramid(const void* const* volumes, const int* h2s, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
-    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, st);
+    return nslam::launch_lookup<__half>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, nhwc_stride, coords_nhwc, st);
   if (dtype == 1)
-    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, st);
+    return nslam::launch_lookup<float>(lv, coords, out, n, h1, w1, num_levels, radius, 1, slots, nhwc_stride, coords_nhwc, st);
   return (int)cudaErrorInvalidValue;
 }
 

@@ -189,7 +189,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // fp16/bf16 tensor, innermost dim first. box innermost = 64 elements (128 B) with SWIZZLE_128B.
 inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                         bool bf16 = false, const uint32_t* elem_strides = nullptr) {
+                         bool bf16 = false, const uint32_t* elem_strides = nullptr, bool swizzle128 = true) {
   auto fn = get_encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   uint32_t es[5] = {1, 1, 1, 1, 1};
@@ -197,7 +197,7 @@ inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uin
   CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
                   (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, (const cuuint32_t*)es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }

@@ -26,16 +26,25 @@ constexpr int UX = 32;  // coarse pixels per CTA
 template <typename T>
 __global__ void __launch_bounds__(256)
 cvx_upsample_kernel(const float* __restrict__ data, const T* __restrict__ mask,
-                    float* __restrict__ out, int ht, int wd, float pw) {
+                    float* __restrict__ out, int ht, int wd, float pw, int mask_nhwc) {
   extern __shared__ unsigned char smraw[];
   T* ms = reinterpret_cast<T*>(smraw);  // [576][UX]
   __shared__ float nb[3][UX + 2];
   const int k = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * UX;
   const int hw = ht * wd;
-  const T* mk = mask + (size_t)k * 576 * hw + (size_t)y * wd + x0;
-  for (int id = threadIdx.x; id < 576 * UX; id += 256) {
-    const int c = id / UX, xx = id % UX;
-    ms[id] = (x0 + xx < wd) ? mk[(size_t)c * hw + xx] : T(0);
+  if (mask_nhwc) {
+    // channels-last mask [K,ht,wd,576] (what the tensor-core update operator produces)
+    const T* mk = mask + ((size_t)k * hw + (size_t)y * wd + x0) * 576;
+    for (int id = threadIdx.x; id < 576 * UX; id += 256) {
+      const int xx = id / 576, c = id % 576;
+      ms[c * UX + xx] = (x0 + xx < wd) ? mk[(size_t)xx * 576 + c] : T(0);
+    }
+  } else {
+    const T* mk = mask + (size_t)k * 576 * hw + (size_t)y * wd + x0;
+    for (int id = threadIdx.x; id < 576 * UX; id += 256) {
+      const int c = id / UX, xx = id % UX;
+      ms[id] = (x0 + xx < wd) ? mk[(size_t)c * hw + xx] : T(0);
+    }
   }
   for (int id = threadIdx.x; id < 3 * (UX + 2); id += 256) {
     const int r = id / (UX + 2), xx = id % (UX + 2);
@@ -76,14 +85,14 @@ cvx_upsample_kernel(const float* __restrict__ data, const T* __restrict__ mask,
 }  // namespace nslam
 
 extern "C" int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out,
-                                  int K, int ht, int wd, float pw, void* stream) {
+                                  int K, int ht, int wd, float pw, int mask_nhwc, void* stream) {
   using namespace nslam;
   if (K == 0) return 0;
   dim3 grid((wd + UX - 1) / UX, ht, K);
   cudaStream_t st = (cudaStream_t)stream;
   if (mask_dtype == 0) {
     const size_t smem = 576 * UX * sizeof(__half);
-    cvx_upsample_kernel<__half><<<grid, 256, smem, st>>>(data, (const __half*)mask, out, ht, wd, pw);
+    cvx_upsample_kernel<__half><<<grid, 256, smem, st>>>(data, (const __half*)mask, out, ht, wd, pw, mask_nhwc);
   } else if (mask_dtype == 1) {
     const size_t smem = 576 * UX * sizeof(float);
     static bool configured = false;
@@ -93,7 +102,7 @@ extern "C" int nslam_cvx_upsample(const float* data, const void* mask, int mask_
       if (e != cudaSuccess) return (int)e;
       configured = true;
     }
-    cvx_upsample_kernel<float><<<grid, 256, smem, st>>>(data, (const float*)mask, out, ht, wd, pw);
+    cvx_upsample_kernel<float><<<grid, 256, smem, st>>>(data, (const float*)mask, out, ht, wd, pw, mask_nhwc);
   } else {
     return (int)cudaErrorInvalidValue;
   }

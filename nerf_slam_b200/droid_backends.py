@@ -56,7 +56,7 @@ def corr_index_backward(volume, coords, corr_grad, radius):
                               "inference hot path (SURVEY.md §8, out of scope)")
 
 
-def corr_lookup_pyramid(volumes, coords, radius, slots=None):
+def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coords_nhwc=False):
     """fused 4-level version of CorrBlock.__call__ (networks/modules/corr.py:40-50):
     volumes: list of [n,h1,w1,h2>>l,w2>>l]; coords [n,2,h1,w1] (level-0 pixels) ->
     [n, L*(2r+1)^2, h1, w1]"""
@@ -67,7 +67,10 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None):
     n = coords.shape[0]
     dt = volumes[0].dtype
     rd = 2 * radius + 1
-    out = torch.empty(n, L * rd * rd, h1, w1, dtype=dt, device=coords.device)
+    if nhwc_stride:
+        out = torch.empty(n, h1, w1, nhwc_stride, dtype=dt, device=coords.device)
+    else:
+        out = torch.empty(n, L * rd * rd, h1, w1, dtype=dt, device=coords.device)
     vptr = (ctypes.c_void_p * L)(*[v.data_ptr() for v in volumes])
     h2s = (ctypes.c_int * L)(*[v.shape[3] for v in volumes])
     w2s = (ctypes.c_int * L)(*[v.shape[4] for v in volumes])
@@ -75,7 +78,8 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None):
                                              ctypes.cast(h2s, ctypes.c_void_p),
                                              ctypes.cast(w2s, ctypes.c_void_p), L, _DT[dt],
                                              _lib.ptr(coords), _lib.ptr(out), n, h1, w1, radius,
-                                             _lib.ptr(slots), _lib.stream_ptr()), "corr_lookup_pyramid")
+                                             _lib.ptr(slots), int(nhwc_stride), int(bool(coords_nhwc)),
+                                             _lib.stream_ptr()), "corr_lookup_pyramid")
     return out
 
 
@@ -199,20 +203,21 @@ def reproject(poses, disps, intrinsics, ii, jj, want_valid=True):
     return coords, valid
 
 
-def cvx_upsample(data, mask, pow=1.0):
-    """A17 (utils/flow_viz.py:166-183): data [K,ht,wd,1] fp32, mask [K,576,ht,wd] -> [K,8ht,8wd,1].
+def cvx_upsample(data, mask, pow=1.0, mask_nhwc=False):
+    """A17 (utils/flow_viz.py:166-183): data [K,ht,wd,1] fp32, mask [K,576,ht,wd] (or channels-last
+    [K,ht,wd,576] with mask_nhwc) -> [K,8ht,8wd,1].
     Does NOT write -inf into `mask` (the reference mutates its argument)."""
     lib = _lib.load()
     K, ht, wd = data.shape[:3]
     data = data.reshape(K, ht, wd).float().contiguous()
-    mask = mask.reshape(K, 576, ht, wd)
+    mask = mask.reshape(K, ht, wd, 576) if mask_nhwc else mask.reshape(K, 576, ht, wd)
     if mask.dtype not in _DT:
         mask = mask.float()
     mask = mask.contiguous()
     out = torch.empty(K, 8 * ht, 8 * wd, dtype=torch.float32, device=data.device)
     _lib.check(lib.nslam_cvx_upsample(_lib.ptr(data), _lib.ptr(mask), _DT[mask.dtype],
-                                      _lib.ptr(out), K, ht, wd, float(pow), _lib.stream_ptr()),
-               "cvx_upsample")
+                                      _lib.ptr(out), K, ht, wd, float(pow), int(bool(mask_nhwc)),
+                                      _lib.stream_ptr()), "cvx_upsample")
     return out.unsqueeze(-1)
 
 
@@ -278,6 +283,27 @@ class BAProblem:
                                       _lib.ptr(work), _lib.ptr(dx), _lib.ptr(linv), _lib.ptr(status),
                                       _lib.stream_ptr()), "ba_solve")
         self._work = work
+        return dx, linv, status
+
+    def gauss_newton(self, iters, world_T_body, cam_T_world, cam_T_body, prior_idx=-1, prior_pose=None,
+                     prior_info=0.0, want_linv=False, clamp_min=1e-3):
+        """`iters` full BA iterations (linearise .. depth update) with ONE host call, no syncs.
+        cam_T_world must be the `poses` tensor this problem was built on. Returns (dx, linv, status)."""
+        lib = _lib.load()
+        P = self.gh.P
+        n = 6 * P
+        dev = self.H.device
+        work = torch.empty(2 * n * n + 2 * n, dtype=torch.float64, device=dev)
+        dx = torch.empty(P, 6, dtype=torch.float32, device=dev)
+        linv = torch.empty(n, n, dtype=torch.float32, device=dev) if want_linv else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        perr = torch.zeros(6, dtype=torch.float32, device=dev)
+        _lib.check(lib.nslam_ba_gn_iterations(ctypes.byref(self.g), ctypes.byref(self.b), int(iters),
+                                              _lib.ptr(world_T_body), _lib.ptr(cam_T_world), _lib.ptr(cam_T_body),
+                                              int(prior_idx), _lib.ptr(prior_pose), float(prior_info), _lib.ptr(work),
+                                              _lib.ptr(dx), _lib.ptr(linv), _lib.ptr(perr), _lib.ptr(status),
+                                              float(clamp_min), _lib.stream_ptr()), "ba_gn_iterations")
+        self._work = (work, perr)
         return dx, linv, status
 
     def depth_update(self, dx, clamp_min=0.0):

@@ -135,6 +135,13 @@ class RaftVisualFrontend:
             self.weights_source = wpath
         for m in (self.feature_net, self.context_net, self.update_net):
             m.to(device=device, dtype=torch.float16)
+        # update operator: hand-written tcgen05 implicit-GEMM convolutions (default) or the cuDNN
+        # library path (args.conv_backend == "cudnn"; kept as the A/B reference for the parity tests)
+        self.conv_backend = getattr(args, "conv_backend", "tcgen05")
+        self.update_tc = None
+        if self.conv_backend == "tcgen05":
+            from .conv import UpdateOperatorTC
+            self.update_tc = UpdateOperatorTC(self.update_net, device)
 
         # prior sigmas (visual_frontend.py:142-153)
         self.g_prior_cov = torch.block_diag(0.01 ** 2 * torch.eye(3), 0.01 ** 2 * torch.eye(3)).to(device)
@@ -178,8 +185,8 @@ class RaftVisualFrontend:
         self.cameras = cams
         # features channels-last fp16 (tcgen05 operand layout); contexts channels-first views of NHWC storage
         self.features_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)
-        self.contexts_imgs = torch.zeros(B, cams, 128, ht, wd, dtype=torch.float16, device=dev)
-        self.cst_contexts_imgs = torch.zeros(B, cams, 128, ht, wd, dtype=torch.float16, device=dev)
+        self.contexts_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)       # NHWC
+        self.cst_contexts_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)   # NHWC
         self.corr_pool = CorrPool(int(getattr(self.args, "corr_slots", 2 * self.max_factors)), ht, wd, dev)
         self._reset_graph()
         self.viz_idx = torch.zeros(B, device=dev, dtype=torch.bool)
@@ -191,7 +198,7 @@ class RaftVisualFrontend:
         self.ii = torch.zeros(0, dtype=torch.long, device=dev); self.jj = torch.zeros(0, dtype=torch.long, device=dev)
         self.ii_inactive_h = np.zeros(0, np.int64); self.jj_inactive_h = np.zeros(0, np.int64)
         self.ii_bad_h = np.zeros(0, np.int64); self.jj_bad_h = np.zeros(0, np.int64)
-        self.gru_hidden_states = None          # [E,128,ht,wd] fp16
+        self.gru_hidden_states = None          # [E,ht,wd,128] fp16 (NHWC)
         self.gru_estimated_flow = torch.zeros(0, ht, wd, 2, device=dev)
         self.gru_estimated_flow_weight = torch.zeros(0, ht, wd, 2, device=dev)
         self.gru_estimated_flow_inactive = torch.zeros(0, ht, wd, 2, device=dev)
@@ -225,8 +232,22 @@ class RaftVisualFrontend:
         return self.feature_net(imgs_norm)[0]          # [cams,128,ht,wd] fp16
 
     def _context_encoder(self, imgs_norm):
-        c = self.context_net(imgs_norm)[0]
-        return torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
+        """-> (tanh(context), relu(gru input)), both channels-last [cams,ht,wd,128]"""
+        c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
+        return torch.tanh(c[..., :128]), torch.relu(c[..., 128:])
+
+    def _run_update_net(self, net, inp, corr_nhwc, motion, ii=None):
+        """update operator on NHWC tensors: net/inp [E,ht,wd,128], corr [E,ht,wd,CORR_PAD], motion [E,4,ht,wd]
+        -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32 (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576])"""
+        if self.update_tc is not None:
+            return self.update_tc(net, inp, corr_nhwc, motion, ii)
+        nchw = lambda t: t.permute(0, 3, 1, 2)
+        out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None],
+                              None if motion is None else motion[None], ii, ii)
+        net2 = out[0][0].permute(0, 2, 3, 1).contiguous()
+        if ii is None:
+            return net2, out[1][0].float(), out[2][0].float()
+        return net2, out[1][0].float(), out[2][0].float(), out[3][0].float(), out[4][0].permute(0, 2, 3, 1).contiguous()
 
     def _put_features(self, idx, feats):
         self.features_imgs[idx] = feats.permute(0, 2, 3, 1)
@@ -294,11 +315,11 @@ class RaftVisualFrontend:
         pair = torch.stack([self.features_imgs[self.last_kf_idx, 0], feats[0].permute(1, 2, 0).contiguous()], 0)
         one = torch.zeros(1, dtype=torch.int32, device=self.device)
         pyr = db.corr_volume_build(pair, one, one + 1)
-        coords = self.coords0.permute(2, 0, 1)[None].contiguous()
-        corr = db.corr_lookup_pyramid(pyr, coords, 3)
-        net = self.contexts_imgs[self.last_kf_idx, 0][None, None]
-        inp = self.cst_contexts_imgs[self.last_kf_idx, 0][None, None]
-        _, delta, _ = self.update_net(net, inp, corr[None])
+        from .conv import CORR_PAD
+        corr = db.corr_lookup_pyramid(pyr, self.coords0[None].contiguous(), 3, nhwc_stride=CORR_PAD, coords_nhwc=True)
+        net = self.contexts_imgs[self.last_kf_idx, 0][None]
+        inp = self.cst_contexts_imgs[self.last_kf_idx, 0][None]
+        _, delta, _ = self._run_update_net(net, inp, corr, None)
         self.last_motion = delta.float().norm(dim=-1).mean()
         return self.last_motion.item() > self.motion_filter_thresh
 
@@ -510,17 +531,16 @@ class RaftVisualFrontend:
         coords1, _ = self.reproject(self.ii, self.jj)                                # [E,ht,wd,2] fp32
         motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
         motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
-        corr = self.corr_pool.lookup(self.slots_d, coords1.permute(0, 3, 1, 2).contiguous())
+        corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
         inp = self.cst_contexts_imgs[self.ii, 0]
-        net, delta, weight, damping, upmask = self.update_net(
-            self.gru_hidden_states[None], inp[None], corr[None], motion[None], self.ii, self.jj)
-        self.gru_hidden_states = net[0]
+        net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, inp, corr, motion, self.ii)
+        self.gru_hidden_states = net
         if kf0 is None:
             kf0 = max(0, int(self.ii_h.min()))
-        self.gru_estimated_flow = coords1 + delta[0].float()
-        self.gru_estimated_flow_weight = weight[0].float()
+        self.gru_estimated_flow = coords1 + delta
+        self.gru_estimated_flow_weight = weight
         ux = np.unique(self.ii_h)
-        self.damping[torch.as_tensor(ux, device=self.device)] = damping[0].float()
+        self.damping[torch.as_tensor(ux, device=self.device)] = damping
 
         if use_inactive:
             m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
@@ -536,8 +556,8 @@ class RaftVisualFrontend:
         self.ba(target, wgt, dmp, ii, jj, kf0, kf1, itrs=itrs, motion_only=motion_only,
                 compute_covariances=self.compute_covariances)
         kx = torch.as_tensor(ux, device=self.device)
-        self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
-        self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask[0], pow=1.0).squeeze(-1)
+        self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
+        self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask, pow=1.0, mask_nhwc=True).squeeze(-1)
         self.viz_idx[kf0:self.kf_idx + 1] = True
         self.age_h += 1
         self.stats["updates"] += 1
@@ -553,22 +573,12 @@ class RaftVisualFrontend:
         prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics[0].contiguous(),
                             self.cam0_T_body, self.cam0_idepths_sensed, target, weight, damping,
                             ii, jj, kf0, kf1)
-        lib = _lib.load()
         has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
-        prior_err = torch.zeros(6, device=self.device)
-        linv = None
-        for it in range(itrs):
-            prob.linearize()
-            if has_prior:
-                _lib.check(lib.nslam_pose_prior_error(_lib.ptr(self.world_T_body[kf0]), _lib.ptr(self.prior_pose),
-                                                      _lib.ptr(prior_err), _lib.stream_ptr()), "prior")
-            dx, linv, status = prob.solve(prior_idx=0 if has_prior else -1, prior_err=prior_err,
-                                          prior_info=self.prior_info if has_prior else 0.0,
-                                          want_linv=compute_covariances and it == itrs - 1)
-            _lib.check(lib.nslam_ba_retract(_lib.ptr(self.world_T_body), _lib.ptr(self.cam0_T_world),
-                                            _lib.ptr(self.cam0_T_body), _lib.ptr(dx), kf0, P,
-                                            _lib.stream_ptr()), "retract")
-            prob.depth_update(dx, clamp_min=1e-3)
+        dx, linv, status = prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
+                                             prior_idx=0 if has_prior else -1,
+                                             prior_pose=self.prior_pose if has_prior else None,
+                                             prior_info=self.prior_info if has_prior else 0.0,
+                                             want_linv=compute_covariances, clamp_min=1e-3)
         if compute_covariances and linv is not None:
             sg, z_cov, d_cov = prob.covariances(linv)
             kx = torch.as_tensor(prob.gh.tables["kx"].astype(np.int64), device=self.device)
@@ -606,16 +616,18 @@ class RaftVisualFrontend:
                     continue
                 vd = torch.as_tensor(v, device=self.device)
                 iis, jjs = self.ii[vd], self.jj[vd]
-                corr = corr_op(coords1[vd][None], cams * iis, cams * jjs + (iis == jjs).long())
-                net, delta, weight, damping, upmask = self.update_net(
-                    self.gru_hidden_states[vd][None], self.cst_contexts_imgs[iis, 0][None], corr, motion[vd][None], iis, jjs)
-                self.gru_hidden_states[vd] = net[0]
-                self.gru_estimated_flow[vd] = coords1[vd] + delta[0].float()
-                self.gru_estimated_flow_weight[vd] = weight[0].float()
+                from .conv import CORR_PAD
+                corr = corr_op(coords1[vd][None], cams * iis, cams * jjs + (iis == jjs).long())[0]      # [e,196,ht,wd] fp32
+                corr = torch.nn.functional.pad(corr.permute(0, 2, 3, 1), (0, CORR_PAD - 196)).half().contiguous()
+                net, delta, weight, damping, upmask = self._run_update_net(
+                    self.gru_hidden_states[vd], self.cst_contexts_imgs[iis, 0], corr, motion[vd], iis)
+                self.gru_hidden_states[vd] = net
+                self.gru_estimated_flow[vd] = coords1[vd] + delta
+                self.gru_estimated_flow_weight[vd] = weight
                 kx = torch.unique(iis)
-                self.damping[kx] = damping[0].float()
-                self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
-                self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask[0]).squeeze(-1)
+                self.damping[kx] = damping
+                self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
+                self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
             dmp = .2 * self.damping[torch.as_tensor(np.unique(self.ii_h), device=self.device)].contiguous() + EP
             target = self.gru_estimated_flow.permute(0, 3, 1, 2).contiguous()
             wgt = self.gru_estimated_flow_weight.permute(0, 3, 1, 2).contiguous()

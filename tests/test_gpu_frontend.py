@@ -12,10 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WEIGHTS = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
 
 
-def _run(n_frames, W=320, H=240, buffer=24, step=0.03):
+def _run(n_frames, W=320, H=240, buffer=24, step=0.03, conv_backend="tcgen05"):
     from nerf_slam_b200.frontend import RaftVisualFrontend
     from nerf_slam_b200.synthetic import SyntheticRoom
-    args = types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False,
+    args = types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False, conv_backend=conv_backend,
                                  weights=WEIGHTS if os.path.exists(WEIGHTS) else None)
     room = SyntheticRoom(W, H, n_frames, seed=0, step=step)
     fe = RaftVisualFrontend(np.linalg.inv(room.packet(0)["poses"][0]), np.eye(4), args, "cuda:0")
@@ -28,8 +28,9 @@ def _run(n_frames, W=320, H=240, buffer=24, step=0.03):
     return fe, room, outs
 
 
-def test_frontend_runs_and_tracks():
-    fe, room, outs = _run(60)
+@pytest.mark.parametrize("conv_backend", ["tcgen05", "cudnn"])
+def test_frontend_runs_and_tracks(conv_backend):
+    fe, room, outs = _run(60, conv_backend=conv_backend)
     torch.cuda.synchronize()
     assert fe.is_initialized, f"not initialised after 60 frames (kf_idx={fe.kf_idx})"
     n = fe.kf_idx
