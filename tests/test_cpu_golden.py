@@ -1,0 +1,69 @@
+"""Pin the CPU oracle and the host-side network mirrors against golden vectors produced by the
+reference's OWN Python modules (tests/golden/make_golden_py.py).  No GPU."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import corr as ocorr, geom as ogeom
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WEIGHTS = [p for p in (os.path.join(ROOT, "oracle", "_ref", "droid.pth"), "/root/reference/droid.pth") if os.path.exists(p)]
+
+
+def test_oracle_corr_pyramid_vs_reference_python():
+    d = np.load(os.path.join(G, "ref_py_corr.npz"))
+    f1, f2 = d["f1"][0], d["f2"][0]                        # [E,128,16,16] fp32
+    E, C, H, W = f1.shape
+    # fp32 restatement of the same maths (the fp16 rounding chain is exercised on the GPU goldens)
+    vol = np.einsum("ecm,ecn->emn", (f1 / 4).reshape(E, C, -1), (f2 / 4).reshape(E, C, -1)).reshape(E, H, W, H, W)
+    assert np.allclose(vol, d["l0"], atol=2e-4)
+    cur = vol.reshape(E * H * W, H, W)
+    for l in range(1, 4):
+        cur = 0.25 * (cur[:, 0::2, 0::2] + cur[:, 0::2, 1::2] + cur[:, 1::2, 0::2] + cur[:, 1::2, 1::2])
+        assert np.allclose(cur.reshape(d[f"l{l}"].shape), d[f"l{l}"], atol=2e-4)
+    # and the fp16 oracle agrees with it to fp16 resolution
+    pyr = ocorr.corr_volume_pyramid(f1.astype(np.float16), f2.astype(np.float16))
+    for l in range(4):
+        assert np.abs(pyr[l].astype(np.float32) - d[f"l{l}"]).max() < 6e-2
+
+
+def test_oracle_cvx_upsample_vs_reference_python():
+    d = np.load(os.path.join(G, "ref_py_upsample.npz"))
+    up = ogeom.cvx_upsample(d["data"][..., 0], d["mask"], 1.0)
+    assert np.allclose(up, d["up"][..., 0], atol=1e-5)
+    up2 = ogeom.cvx_upsample(d["data"][..., 0], d["mask"], 0.5)
+    assert np.allclose(up2, d["up_pow"][..., 0], atol=1e-5)
+
+
+def _weights():
+    import pytest
+    if not WEIGHTS:
+        pytest.skip("droid.pth not available")
+    from nerf_slam_b200.networks import load_droid_weights
+    return load_droid_weights(WEIGHTS[0])
+
+
+def test_network_mirror_encoders_vs_reference_python():
+    from nerf_slam_b200.networks import BasicEncoder
+    sd = _weights()
+    d = np.load(os.path.join(G, "ref_py_encoders.npz"))
+    f = BasicEncoder(128, "instance"); f.load_state_dict(sd, "feature_net.")
+    c = BasicEncoder(256, "none"); c.load_state_dict(sd, "context_net.")
+    with torch.no_grad():
+        x = torch.from_numpy(d["img"])
+        assert np.allclose(f(x).numpy(), d["fnet"], atol=2e-4)
+        assert np.allclose(c(x).numpy(), d["cnet"], atol=2e-4)
+
+
+def test_network_mirror_update_module_vs_reference_python():
+    from nerf_slam_b200.networks import UpdateModule
+    sd = _weights()
+    d = np.load(os.path.join(G, "ref_py_update.npz"))
+    um = UpdateModule(); um.load_state_dict(sd, "update_net.")
+    T = torch.from_numpy
+    with torch.no_grad():
+        o = um(T(d["net"]), T(d["inp"]), T(d["corr"]), T(d["flow"]), T(d["ii"]), T(d["jj"]))
+    for got, key, tol in zip(o, ("out_net", "delta", "weight", "eta", "upmask"), (2e-4, 5e-4, 2e-4, 1e-5, 5e-4)):
+        assert np.allclose(got.numpy(), d[key], atol=tol), (key, np.abs(got.numpy() - d[key]).max())
