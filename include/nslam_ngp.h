@@ -68,6 +68,13 @@ int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, co
 int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream);
 
+/* tensor-core (tcgen05) variant of the network forward, fused with the hash encoding
+ * (csrc/ngp_tc.cu).  `packed` = 28 672-byte fp16 weight images produced by nslam_ngp_pack_mlp from
+ * the fp32 MLP blob (re-run after every optimiser step).  n < 0: sample count read from counters[0]. */
+int nslam_ngp_pack_mlp(const float* mlp, void* packed, void* stream);
+int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
+                         int n, int max_samples, float* rgbsigma, int num_sms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,7 +115,7 @@ class UpdateOperatorTC:
         conv_tc(srcs, wp, b, B, H, W, k, k // 2, N, out0=out, out0_channels=out.shape[-1] if out is not None else 0,
                 num_sms=self.num_sms, **kw)
 
-    def __call__(self, net, inp, corr, motion=None, ii=None):
+    def __call__(self, net, inp, corr, motion=None, ii=None, agg=None):
         E, H, W, _ = net.shape
         dev = net.device
         h16 = dict(dtype=torch.float16, device=dev)
@@ -154,8 +154,11 @@ class UpdateOperatorTC:
             return net2, delta, weight
         # GraphAgg
         a1 = new(128); self._conv("a1", [net2], E, H, W, 3, 128, a1, act=1)
-        _, ix = torch.unique(ii, return_inverse=True)
-        K = int(ix.max().item()) + 1
+        if agg is not None:
+            ix, K = agg                                  # precomputed on the host: no device sync
+        else:
+            _, ix = torch.unique(ii, return_inverse=True)
+            K = int(ix.max().item()) + 1
         s = torch.zeros(K, H, W, 128, dtype=torch.float32, device=dev).index_add_(0, ix, a1.float())
         cnt = torch.zeros(K, dtype=torch.float32, device=dev).index_add_(0, ix, torch.ones_like(ix, dtype=torch.float32))
         am = (s / cnt.view(-1, 1, 1, 1)).half()

@@ -126,11 +126,95 @@ corr_lookup_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restr
   }
 }
 
+// Channels-last variant (operand layout of the tensor-core update operator): one CTA = 32 pixels x
+// 4 levels (thread = (level, pixel)); the 32 x nhwc_stride output rows are assembled in shared
+// memory and written as ONE contiguous, 16-byte-vectorised chunk (32 pixels x 400 B at stride 200).
+// grid: (ceil(h1*w1/32), 1, n)   block: 32 * num_levels   dynamic smem: 32 * nhwc_stride * sizeof(T)
+template <typename T, int R>
+__global__ void __launch_bounds__(128)
+corr_lookup_nhwc_kernel(LookupLevels lv, const float* __restrict__ coords, T* __restrict__ out,
+                        int h1, int w1, int num_levels, const int* __restrict__ slots,
+                        int nhwc_stride, int coords_nhwc) {
+  constexpr int RD = 2 * R + 1;
+  constexpr int NT = RD + 1;
+  extern __shared__ unsigned char lk_smem[];
+  T* tile = reinterpret_cast<T*>(lk_smem);           // [32][nhwc_stride]
+  const int hw = h1 * w1;
+  const int pp = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32;
+  const int p = p0 + pp;
+  const int n = blockIdx.z;
+  // zero the padding channels
+  const int used = num_levels * RD * RD;
+  for (int id = threadIdx.x; id < 32 * (nhwc_stride - used); id += blockDim.x)
+    tile[(id / (nhwc_stride - used)) * nhwc_stride + used + id % (nhwc_stride - used)] = Arith<T>::zero();
+  if (p < hw) {
+    const int h2 = lv.h2[l], w2 = lv.w2[l];
+    const int vn = slots ? slots[n] : n;
+    const T* __restrict__ vol = reinterpret_cast<const T*>(lv.vol[l]) + ((size_t)vn * hw + p) * (size_t)(h2 * w2);
+    float x0, y0;
+    if (coords_nhwc) {
+      const float2 c = reinterpret_cast<const float2*>(coords)[(size_t)n * hw + p];
+      x0 = c.x; y0 = c.y;
+    } else {
+      x0 = coords[((size_t)n * 2 + 0) * hw + p];
+      y0 = coords[((size_t)n * 2 + 1) * hw + p];
+    }
+    const float sc = 1.0f / (float)(1 << l);
+    x0 *= sc; y0 *= sc;
+    const float fx0 = floorf(x0), fy0 = floorf(y0);
+    const float dx = x0 - fx0, dy = y0 - fy0;
+    const int xb = (int)fx0 - R, yb = (int)fy0 - R;
+    T tap[NT][NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int y1 = yb + j;
+      const bool yin = (y1 >= 0) && (y1 < h2);
+      const T* row = vol + (size_t)(yin ? y1 : 0) * w2;
+#pragma unroll
+      for (int i = 0; i < NT; i++) {
+        const int x1 = xb + i;
+        tap[i][j] = (yin && x1 >= 0 && x1 < w2) ? __ldg(row + x1) : Arith<T>::zero();
+      }
+    }
+    const T w11 = Arith<T>::cvt(dx * dy), w10 = Arith<T>::cvt(dx * (1.0f - dy));
+    const T w01 = Arith<T>::cvt((1.0f - dx) * dy), w00 = Arith<T>::cvt((1.0f - dx) * (1.0f - dy));
+    T* o = tile + pp * nhwc_stride + l * (RD * RD);
+#pragma unroll
+    for (int i = 0; i < RD; i++) {
+#pragma unroll
+      for (int j = 0; j < RD; j++) {
+        T acc = Arith<T>::zero();
+        acc = Arith<T>::mac(acc, tap[i][j], w00);
+        acc = Arith<T>::mac(acc, tap[i][j + 1], w01);
+        acc = Arith<T>::mac(acc, tap[i + 1][j], w10);
+        acc = Arith<T>::mac(acc, tap[i + 1][j + 1], w11);
+        o[i * RD + j] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // contiguous chunk: pixels p0 .. p0+31 (clipped) x nhwc_stride channels
+  const int npx = min(32, hw - p0);
+  const size_t bytes = (size_t)npx * nhwc_stride * sizeof(T);
+  unsigned char* dst = reinterpret_cast<unsigned char*>(out + ((size_t)n * hw + p0) * nhwc_stride);
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(tile);
+  for (size_t b = (size_t)threadIdx.x * 16; b < bytes; b += (size_t)blockDim.x * 16)
+    *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(src + b);
+}
+
 template <typename T>
 static int launch_lookup(const LookupLevels& lv, const float* coords, void* out, int n, int h1,
                          int w1, int num_levels, int radius, int scale_coords,
                          const int* slots, int nhwc_stride, int coords_nhwc, cudaStream_t st) {
   if (n == 0) return 0;
+  if (nhwc_stride > 0 && radius == 3 && scale_coords && (nhwc_stride * sizeof(T)) % 16 == 0 && num_levels <= 4) {
+    dim3 g2((h1 * w1 + 31) / 32, 1, n);
+    corr_lookup_nhwc_kernel<T, 3><<<g2, 32 * num_levels, 32 * nhwc_stride * sizeof(T), st>>>(
+        lv, coords, (T*)out, h1, w1, num_levels, slots, nhwc_stride, coords_nhwc);
+    NSLAM_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((h1 * w1 + 127) / 128, num_levels, n), block(128);
   switch (radius) {
     case 3:

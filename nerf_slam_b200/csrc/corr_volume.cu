@@ -23,22 +23,24 @@
 namespace nslam {
 
 constexpr int CV_STAGES = 3;
-constexpr int CV_THREADS = 192;
+constexpr int CV_THREADS = 320;            // TMA warp, MMA warp, 2 epilogue groups of 4 warps
 constexpr int CV_TH = 8, CV_TW = 16;       // target tile
 constexpr int CV_L0_STRIDE = 272;          // bytes per staged row, 256 + 16 pad (conflict-free 128-bit)
 constexpr int CV_L1_STRIDE = 80;           // 64 + 16
 constexpr int CV_L2_STRIDE = 16;
 constexpr int CV_L3_STRIDE = 4;
+constexpr int CV_STAGE_BYTES = 128 * (CV_L0_STRIDE + CV_L1_STRIDE + CV_L2_STRIDE + CV_L3_STRIDE);
 
 struct CvSmem {
   // offsets in bytes from the 1024-aligned base
   static constexpr int A = 0;                          // 2 x 16384
   static constexpr int B = 32768;                      // STAGES x 2 x 16384
-  static constexpr int L0 = B + CV_STAGES * 32768;     // 128 x 272
-  static constexpr int L1 = L0 + 128 * CV_L0_STRIDE;   // 128 x 80
+  static constexpr int ST = B + CV_STAGES * 32768;     // 2 epilogue groups x staging (L0|L1|L2|L3)
+  static constexpr int L0 = 0;
+  static constexpr int L1 = L0 + 128 * CV_L0_STRIDE;
   static constexpr int L2 = L1 + 128 * CV_L1_STRIDE;
   static constexpr int L3 = L2 + 128 * CV_L2_STRIDE;
-  static constexpr int BAR = L3 + 128 * CV_L3_STRIDE;  // mbarriers
+  static constexpr int BAR = ST + 2 * CV_STAGE_BYTES;  // mbarriers
   static constexpr int TOTAL = BAR + 128;
 };
 
@@ -48,6 +50,8 @@ struct CvParams {
   const int* jj;   // [E] frame index of fmap2
   int HW, H2, W2;
   int NH, NW;      // target tiles
+  int MT;          // 128-pixel source strips per edge
+  int nwork;       // E * MT work items, walked persistently
 };
 
 __device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
@@ -92,6 +96,9 @@ __device__ __forceinline__ void cv_store_level(const unsigned char* stage, int r
   }
 }
 
+// Persistent kernel: grid = min(#SMs, nwork).  Work item = (edge, 128-source-pixel strip); the
+// B-tile ring, the TMEM accumulator stages and the two epilogue groups run across work items
+// without draining (global tile counter t: ring slot = t % STAGES, epilogue group = t & 1).
 __global__ void __launch_bounds__(CV_THREADS, 1)
 corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                       const __grid_constant__ CUtensorMap tmB, CvParams p) {
@@ -102,13 +109,12 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* full_b = bars;                    // [STAGES]
   uint64_t* empty_b = bars + CV_STAGES;       // [STAGES]
   uint64_t* a_full = bars + 2 * CV_STAGES;    // [1]
-  uint64_t* tm_full = a_full + 1;             // [2]
+  uint64_t* a_empty = a_full + 1;             // [1]
+  uint64_t* tm_full = a_empty + 1;            // [2]
   uint64_t* tm_empty = tm_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.y;
-  const int m0 = blockIdx.x * 128;
   const int NT = p.NH * p.NW;
 
   if (warp == 0 && lane == 0) {
@@ -116,6 +122,7 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     tc::tma_prefetch_desc(&tmB);
     for (int s = 0; s < CV_STAGES; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
     tc::mbar_init(a_full, 1);
+    tc::mbar_init(a_empty, 1);
     for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], 4); }
     tc::fence_barrier_init();
   }
@@ -128,18 +135,23 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int fi = p.ii[e], fj = p.jj[e];
-      tc::mbar_arrive_expect_tx(a_full, 32768);
-      tc::tma_load_3d(sm + CvSmem::A, &tmA, a_full, 0, m0, fi);
-      tc::tma_load_3d(sm + CvSmem::A + 16384, &tmA, a_full, 64, m0, fi);
-      for (int t = 0; t < NT; t++) {
-        const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
-        tc::mbar_wait(&empty_b[s], ph ^ 1);
-        const int h0 = (t / p.NW) * CV_TH, w0 = (t % p.NW) * CV_TW;
-        unsigned char* dst = sm + CvSmem::B + s * 32768;
-        tc::mbar_arrive_expect_tx(&full_b[s], 32768);
-        tc::tma_load_4d(dst, &tmB, &full_b[s], 0, w0, h0, fj);
-        tc::tma_load_4d(dst + 16384, &tmB, &full_b[s], 64, w0, h0, fj);
+      uint32_t t = 0, wi = 0;
+      for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, wi++) {
+        const int e = w / p.MT, m0 = (w % p.MT) * 128;
+        const int fi = p.ii[e], fj = p.jj[e];
+        tc::mbar_wait(a_empty, (wi & 1) ^ 1);          // MMAs of the previous strip are done with A
+        tc::mbar_arrive_expect_tx(a_full, 32768);
+        tc::tma_load_3d(sm + CvSmem::A, &tmA, a_full, 0, m0, fi);
+        tc::tma_load_3d(sm + CvSmem::A + 16384, &tmA, a_full, 64, m0, fi);
+        for (int n = 0; n < NT; n++, t++) {
+          const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
+          tc::mbar_wait(&empty_b[s], ph ^ 1);
+          const int h0 = (n / p.NW) * CV_TH, w0 = (n % p.NW) * CV_TW;
+          unsigned char* dst = sm + CvSmem::B + s * 32768;
+          tc::mbar_arrive_expect_tx(&full_b[s], 32768);
+          tc::tma_load_4d(dst, &tmB, &full_b[s], 0, w0, h0, fj);
+          tc::tma_load_4d(dst + 16384, &tmB, &full_b[s], 64, w0, h0, fj);
+        }
       }
     }
   } else if (warp == 1) {
@@ -147,100 +159,113 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_f16(128, 128, 0);
       const uint32_t a_addr = tc::smem_u32(sm + CvSmem::A);
-      tc::mbar_wait(a_full, 0);
-      for (int t = 0; t < NT; t++) {
-        const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
-        const int as = t & 1, aph = (t >> 1) & 1;
-        tc::mbar_wait(&tm_empty[as], aph ^ 1);
-        tc::mbar_wait(&full_b[s], ph);
-        tc::tc_fence_after();
-        const uint32_t b_addr = tc::smem_u32(sm + CvSmem::B + s * 32768);
-        const uint32_t d_tmem = tmem_base + as * 128;
+      uint32_t t = 0, wi = 0;
+      for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, wi++) {
+        tc::mbar_wait(a_full, wi & 1);
+        for (int n = 0; n < NT; n++, t++) {
+          const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
+          const int as = t & 1, aph = (t >> 1) & 1;
+          tc::mbar_wait(&tm_empty[as], aph ^ 1);
+          tc::mbar_wait(&full_b[s], ph);
+          tc::tc_fence_after();
+          const uint32_t b_addr = tc::smem_u32(sm + CvSmem::B + s * 32768);
+          const uint32_t d_tmem = tmem_base + as * 128;
 #pragma unroll
-        for (int kh = 0; kh < 2; kh++) {
+          for (int kh = 0; kh < 2; kh++) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint64_t ad = tc::umma_desc_sw128(a_addr + kh * 16384 + k * 32);
-            const uint64_t bd = tc::umma_desc_sw128(b_addr + kh * 16384 + k * 32);
-            tc::umma_f16(d_tmem, ad, bd, idesc, (kh | k) ? 1u : 0u);
+            for (int k = 0; k < 4; k++) {
+              const uint64_t ad = tc::umma_desc_sw128(a_addr + kh * 16384 + k * 32);
+              const uint64_t bd = tc::umma_desc_sw128(b_addr + kh * 16384 + k * 32);
+              tc::umma_f16(d_tmem, ad, bd, idesc, (kh | k) ? 1u : 0u);
+            }
           }
+          tc::umma_commit(&empty_b[s]);
+          tc::umma_commit(&tm_full[as]);
         }
-        tc::umma_commit(&empty_b[s]);
-        tc::umma_commit(&tm_full[as]);
+        tc::umma_commit(a_empty);
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread <-> accumulator row =====================
+    // ===================== epilogue: 2 groups x 4 warps, thread <-> accumulator row =====================
+    const int grp = (warp - 2) >> 2;      // group g serves tiles with (t & 1) == g == TMEM stage g
     const int q = warp & 3;               // TMEM lane quarter accessible by this warp
     const int row = q * 32 + lane;        // row inside the 128-row strip
-    const int etid = (warp - 2) * 32 + lane;
-    unsigned char* st0 = sm + CvSmem::L0 + row * CV_L0_STRIDE;
-    unsigned char* st1 = sm + CvSmem::L1 + row * CV_L1_STRIDE;
-    unsigned char* st2 = sm + CvSmem::L2 + row * CV_L2_STRIDE;
-    unsigned char* st3 = sm + CvSmem::L3 + row * CV_L3_STRIDE;
-    for (int t = 0; t < NT; t++) {
-      const int as = t & 1, aph = (t >> 1) & 1;
-      tc::mbar_wait(&tm_full[as], aph);
-      tc::tc_fence_after();
-      // staging buffers are free again once everybody finished the previous tile's stores
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t taddr = tmem_base + as * 128 + ((uint32_t)(q * 32) << 16);
-      __half l1[4][8];
+    const int etid = ((warp - 2) & 3) * 32 + lane;
+    unsigned char* stg = sm + CvSmem::ST + grp * CV_STAGE_BYTES;
+    unsigned char* st0 = stg + CvSmem::L0 + row * CV_L0_STRIDE;
+    unsigned char* st1 = stg + CvSmem::L1 + row * CV_L1_STRIDE;
+    unsigned char* st2 = stg + CvSmem::L2 + row * CV_L2_STRIDE;
+    unsigned char* st3 = stg + CvSmem::L3 + row * CV_L3_STRIDE;
+    const uint32_t taddr = tmem_base + grp * 128 + ((uint32_t)(q * 32) << 16);
+    uint32_t t = 0, use = 0;
+    for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+      const int e = w / p.MT, m0 = (w % p.MT) * 128;
+      for (int n = 0; n < NT; n++, t++) {
+        if ((int)(t & 1) != grp) continue;
+        tc::mbar_wait(&tm_full[grp], use & 1);
+        use++;
+        tc::tc_fence_after();
+        // this group's staging buffers are free once its previous tile's stores were issued
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
+        __half l1[4][8];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(taddr + c * 32, r);
-        tc::tmem_ld_wait();
-        __half h[32];
+        for (int c = 0; c < 4; c++) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(taddr + c * 32, r);
+          tc::tmem_ld_wait();
+          __half h[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) h[i] = __float2half_rn(__uint_as_float(r[i]) * 0.0625f);
-        // level 0: rows 2c, 2c+1 of the tile (16 px each)
-        uint4* d0 = reinterpret_cast<uint4*>(st0 + c * 64);
-        const uint4* hs = reinterpret_cast<const uint4*>(h);
-        d0[0] = hs[0]; d0[1] = hs[1]; d0[2] = hs[2]; d0[3] = hs[3];
-        // level 1: 2x2 means, summation order (h0,w0),(h0,w1),(h1,w0),(h1,w1) like avg_pool2d
+          for (int i = 0; i < 32; i++) h[i] = __float2half_rn(__uint_as_float(r[i]) * 0.0625f);
+          // level 0: rows 2c, 2c+1 of the tile (16 px each)
+          uint4* d0 = reinterpret_cast<uint4*>(st0 + c * 64);
+          const uint4* hs = reinterpret_cast<const uint4*>(h);
+          d0[0] = hs[0]; d0[1] = hs[1]; d0[2] = hs[2]; d0[3] = hs[3];
+          // level 1: 2x2 means, summation order (h0,w0),(h0,w1),(h1,w0),(h1,w1) like avg_pool2d
 #pragma unroll
-        for (int wp = 0; wp < 8; wp++) {
-          const float s = ((h2f(h[2 * wp]) + h2f(h[2 * wp + 1])) + h2f(h[16 + 2 * wp])) +
-                          h2f(h[16 + 2 * wp + 1]);
-          l1[c][wp] = __float2half_rn(s * 0.25f);
+          for (int wp = 0; wp < 8; wp++) {
+            const float s = ((h2f(h[2 * wp]) + h2f(h[2 * wp + 1])) + h2f(h[16 + 2 * wp])) +
+                            h2f(h[16 + 2 * wp + 1]);
+            l1[c][wp] = __float2half_rn(s * 0.25f);
+          }
+          *reinterpret_cast<uint4*>(st1 + c * 16) = *reinterpret_cast<const uint4*>(l1[c]);
         }
-        *reinterpret_cast<uint4*>(st1 + c * 16) = *reinterpret_cast<const uint4*>(l1[c]);
-      }
-      // accumulator stage can be overwritten by the next MMA
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
-      __half l2[2][4];
+        // accumulator stage can be overwritten by the next MMA
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[grp]);
+        __half l2[2][4];
 #pragma unroll
-      for (int c2 = 0; c2 < 2; c2++) {
+        for (int c2 = 0; c2 < 2; c2++) {
 #pragma unroll
-        for (int wq = 0; wq < 4; wq++) {
-          const float s = ((h2f(l1[2 * c2][2 * wq]) + h2f(l1[2 * c2][2 * wq + 1])) +
-                           h2f(l1[2 * c2 + 1][2 * wq])) + h2f(l1[2 * c2 + 1][2 * wq + 1]);
-          l2[c2][wq] = __float2half_rn(s * 0.25f);
+          for (int wq = 0; wq < 4; wq++) {
+            const float s = ((h2f(l1[2 * c2][2 * wq]) + h2f(l1[2 * c2][2 * wq + 1])) +
+                             h2f(l1[2 * c2 + 1][2 * wq])) + h2f(l1[2 * c2 + 1][2 * wq + 1]);
+            l2[c2][wq] = __float2half_rn(s * 0.25f);
+          }
         }
-      }
-      *reinterpret_cast<uint4*>(st2) = *reinterpret_cast<const uint4*>(l2);
-      __half l3[2];
+        *reinterpret_cast<uint4*>(st2) = *reinterpret_cast<const uint4*>(l2);
+        __half l3[2];
 #pragma unroll
-      for (int wr = 0; wr < 2; wr++) {
-        const float s = ((h2f(l2[0][2 * wr]) + h2f(l2[0][2 * wr + 1])) + h2f(l2[1][2 * wr])) +
-                        h2f(l2[1][2 * wr + 1]);
-        l3[wr] = __float2half_rn(s * 0.25f);
+        for (int wr = 0; wr < 2; wr++) {
+          const float s = ((h2f(l2[0][2 * wr]) + h2f(l2[0][2 * wr + 1])) + h2f(l2[1][2 * wr])) +
+                          h2f(l2[1][2 * wr + 1]);
+          l3[wr] = __float2half_rn(s * 0.25f);
+        }
+        *reinterpret_cast<uint32_t*>(st3) = *reinterpret_cast<const uint32_t*>(l3);
+        if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 4, 128;" ::: "memory");
+        // cooperative, coalesced stores of the four tiles
+        const int h0 = (n / p.NW) * CV_TH, w0 = (n % p.NW) * CV_TW;
+        cv_store_level<16, 8>(stg + CvSmem::L0, CV_L0_STRIDE, p.out[0], e, p.HW, m0, p.H2, p.W2, h0,
+                              w0, etid);
+        cv_store_level<8, 4>(stg + CvSmem::L1, CV_L1_STRIDE, p.out[1], e, p.HW, m0, p.H2 >> 1,
+                             p.W2 >> 1, h0 >> 1, w0 >> 1, etid);
+        cv_store_level<4, 2>(stg + CvSmem::L2, CV_L2_STRIDE, p.out[2], e, p.HW, m0, p.H2 >> 2,
+                             p.W2 >> 2, h0 >> 2, w0 >> 2, etid);
+        cv_store_level<2, 1>(stg + CvSmem::L3, CV_L3_STRIDE, p.out[3], e, p.HW, m0, p.H2 >> 3,
+                             p.W2 >> 3, h0 >> 3, w0 >> 3, etid);
       }
-      *reinterpret_cast<uint32_t*>(st3) = *reinterpret_cast<const uint32_t*>(l3);
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      // cooperative, coalesced stores of the four tiles
-      const int h0 = (t / p.NW) * CV_TH, w0 = (t % p.NW) * CV_TW;
-      cv_store_level<16, 8>(sm + CvSmem::L0, CV_L0_STRIDE, p.out[0], e, p.HW, m0, p.H2, p.W2, h0,
-                            w0, etid);
-      cv_store_level<8, 4>(sm + CvSmem::L1, CV_L1_STRIDE, p.out[1], e, p.HW, m0, p.H2 >> 1,
-                           p.W2 >> 1, h0 >> 1, w0 >> 1, etid);
-      cv_store_level<4, 2>(sm + CvSmem::L2, CV_L2_STRIDE, p.out[2], e, p.HW, m0, p.H2 >> 2,
-                           p.W2 >> 2, h0 >> 2, w0 >> 2, etid);
-      cv_store_level<2, 1>(sm + CvSmem::L3, CV_L3_STRIDE, p.out[3], e, p.HW, m0, p.H2 >> 3,
-                           p.W2 >> 3, h0 >> 3, w0 >> 3, etid);
     }
   }
   tc::tc_fence_before();
@@ -310,6 +335,7 @@ int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, cons
   p.out[0] = (__half*)out0; p.out[1] = (__half*)out1; p.out[2] = (__half*)out2; p.out[3] = (__half*)out3;
   p.ii = ii; p.jj = jj; p.HW = HW; p.H2 = H; p.W2 = W;
   p.NH = (H + CV_TH - 1) / CV_TH; p.NW = (W + CV_TW - 1) / CV_TW;
+  p.MT = (HW + 127) / 128; p.nwork = E * p.MT;
   const int smem = CvSmem::TOTAL + 1024;
   static bool configured = false;
   if (!configured) {
@@ -318,7 +344,10 @@ int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, cons
     if (er != cudaSuccess) return (int)er;
     configured = true;
   }
-  dim3 grid((HW + 127) / 128, E);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.nwork < sms ? p.nwork : sms;
   corr_volume_tc_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   NSLAM_CHECK_LAUNCH();
   return 0;

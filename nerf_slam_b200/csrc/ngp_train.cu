@@ -504,24 +504,33 @@ backward_kernel(const float* __restrict__ coords, const int* __restrict__ counte
 
 // ------------------------------------------------------------------------------------------
 // Adam.  is_grid: skip entries with zero gradient (untouched hash slots), no L2.
-__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, __half* __restrict__ p_half, size_t n, float lr,
-                            float b1, float b2, float eps, float l2, int is_grid, int step) {
+// float4-vectorised; bias corrections (1/(1-b^t)) are computed once on the host.  Writes g = 0.
+__global__ void adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                            float4* __restrict__ v, __half2* __restrict__ p_half, size_t n4, float lr,
+                            float b1, float b2, float eps, float l2, int is_grid, float bc1, float bc2) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float grad = g[i];
-  g[i] = 0.f;
-  if (is_grid && grad == 0.f) return;
-  const float w = p[i];
-  grad += l2 * w;
-  const float mi = b1 * m[i] + (1.f - b1) * grad;
-  const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
-  m[i] = mi; v[i] = vi;
-  const float mh = mi / (1.f - powf(b1, (float)step));
-  const float vh = vi / (1.f - powf(b2, (float)step));
-  const float nw = w - lr * mh / (sqrtf(vh) + eps);
-  p[i] = nw;
-  if (p_half) p_half[i] = __float2half_rn(nw);
+  if (i >= n4) return;
+  const float4 g4 = g[i];
+  if (g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) {
+    if (is_grid) return;           // untouched hash slots keep their moments (tiny-cuda-nn semantics)
+  } else {
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 w4 = p[i], m4 = m[i], v4 = v[i];
+  float* w = reinterpret_cast<float*>(&w4);
+  float* mm = reinterpret_cast<float*>(&m4);
+  float* vv = reinterpret_cast<float*>(&v4);
+  const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (is_grid && gg[k] == 0.f) continue;
+    const float grad = gg[k] + l2 * w[k];
+    mm[k] = b1 * mm[k] + (1.f - b1) * grad;
+    vv[k] = b2 * vv[k] + (1.f - b2) * grad * grad;
+    w[k] -= lr * (mm[k] * bc1) / (sqrtf(vv[k] * bc2) + eps);
+  }
+  p[i] = w4; m[i] = m4; v[i] = v4;
+  if (p_half) { p_half[2 * i] = __floats2half2_rn(w[0], w[1]); p_half[2 * i + 1] = __floats2half2_rn(w[2], w[3]); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -714,12 +723,15 @@ int nslam_ngp_adam(const nslam_ngp_model* m, int step, float lr, float beta1, fl
                    float l2_mlp, void* stream) {
   using namespace ngp;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t ng = (size_t)m->n_grid * 2;
-  adam_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(m->grid_master, m->grid_grad, m->grid_m, m->grid_v,
-                                                           (__half*)m->grid_half, ng, lr, beta1, beta2, eps, 0.f, 1, step);
+  const size_t ng4 = (size_t)m->n_grid * 2 / 4;   // level sizes are multiples of 8 entries
+  const float bc1 = 1.f / (1.f - powf(beta1, (float)step)), bc2 = 1.f / (1.f - powf(beta2, (float)step));
+  adam_kernel<<<(unsigned)((ng4 + 255) / 256), 256, 0, st>>>((float4*)m->grid_master, (float4*)m->grid_grad, (float4*)m->grid_m,
+                                                            (float4*)m->grid_v, (__half2*)m->grid_half, ng4, lr, beta1, beta2,
+                                                            eps, 0.f, 1, bc1, bc2);
   NGP_CHECK_LAUNCH();
-  adam_kernel<<<(W_TOTAL + 255) / 256, 256, 0, st>>>(m->mlp, m->mlp_grad, m->mlp_m, m->mlp_v, nullptr, W_TOTAL,
-                                                     lr, beta1, beta2, eps, l2_mlp, 0, step);
+  adam_kernel<<<(W_TOTAL / 4 + 255) / 256, 256, 0, st>>>((float4*)m->mlp, (float4*)m->mlp_grad, (float4*)m->mlp_m,
+                                                         (float4*)m->mlp_v, nullptr, W_TOTAL / 4, lr, beta1, beta2, eps,
+                                                         l2_mlp, 0, bc1, bc2);
   NGP_CHECK_LAUNCH();
   return 0;
 }

@@ -150,6 +150,13 @@ class RaftVisualFrontend:
         self._mean = torch.tensor([0.485, 0.456, 0.406], device=device)[:, None, None]
         self._std = torch.tensor([0.229, 0.224, 0.225], device=device)[:, None, None]
         self.stats = {"updates": 0, "ba_fail": 0}
+        self.use_cuda_graphs = bool(getattr(args, "cuda_graphs", True))
+        if self.conv_backend != "tcgen05":
+            self.use_cuda_graphs = False       # the library path syncs inside GraphAgg (torch.unique)
+        self._static = None
+        self._img_static = None
+        self._graph_pool = torch.cuda.graph_pool_handle() if self.use_cuda_graphs else None
+        self._capture_stream = torch.cuda.Stream() if self.use_cuda_graphs else None
 
     def stop_condition(self):
         return self.stop
@@ -187,6 +194,7 @@ class RaftVisualFrontend:
         self.features_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)
         self.contexts_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)       # NHWC
         self.cst_contexts_imgs = torch.zeros(B, cams, ht, wd, 128, dtype=torch.float16, device=dev)   # NHWC
+        self.intr0 = self.cam0_intrinsics[0]      # the kernels only ever see the first keyframe's intrinsics
         self.corr_pool = CorrPool(int(getattr(self.args, "corr_slots", 2 * self.max_factors)), ht, wd, dev)
         self._reset_graph()
         self.viz_idx = torch.zeros(B, device=dev, dtype=torch.bool)
@@ -208,6 +216,7 @@ class RaftVisualFrontend:
             self.corr_pool.free = list(range(self.corr_pool.capacity - 1, -1, -1))
 
     def _sync_edges(self):
+        self._static = None            # edge set changed: static part / CUDA graph of update() is stale
         self.ii = torch.as_tensor(self.ii_h, device=self.device)
         self.jj = torch.as_tensor(self.jj_h, device=self.device)
         self.slots_d = torch.as_tensor(self.slots_h.astype(np.int32), device=self.device)
@@ -236,11 +245,12 @@ class RaftVisualFrontend:
         c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
         return torch.tanh(c[..., :128]), torch.relu(c[..., 128:])
 
-    def _run_update_net(self, net, inp, corr_nhwc, motion, ii=None):
+    def _run_update_net(self, net, inp, corr_nhwc, motion, ii=None, agg=None):
         """update operator on NHWC tensors: net/inp [E,ht,wd,128], corr [E,ht,wd,CORR_PAD], motion [E,4,ht,wd]
-        -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32 (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576])"""
+        -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32 (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576]).
+        agg = (ix, K): host-precomputed inverse index of unique(ii) (keeps the call free of device syncs)."""
         if self.update_tc is not None:
-            return self.update_tc(net, inp, corr_nhwc, motion, ii)
+            return self.update_tc(net, inp, corr_nhwc, motion, ii, agg=agg)
         nchw = lambda t: t.permute(0, 3, 1, 2)
         out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None],
                               None if motion is None else motion[None], ii, ii)
@@ -261,10 +271,10 @@ class RaftVisualFrontend:
         if not torch.is_tensor(img):
             img = torch.as_tensor(np.asarray(img))
         imgs_k = img.to(self.device, non_blocking=True)[None].permute(0, 1, 4, 2, 3)   # H2D when host-resident
-        imgs_norm = self._normalize_imgs(imgs_k)
 
         if self.last_k is None:
             assert k == 0 and self.kf_idx == 0
+            imgs_norm = self._normalize_imgs(imgs_k)
             self.initialize_buffers(imgs_k.shape[-2:])
             self._store_frame(0, batch, imgs_k)
             self._put_features(0, self._feature_encoder(imgs_norm))
@@ -276,8 +286,8 @@ class RaftVisualFrontend:
             return x0, factors, viz_out
 
         assert k > 0 and self.kf_idx < self.buffer
-        feats = self._feature_encoder(imgs_norm)
-        if not self.has_enough_motion(feats):
+        feats = self._frame_front(imgs_k)              # feature encoder + motion filter (CUDA graph)
+        if not (self.last_motion.item() > self.motion_filter_thresh):
             if batch["is_last_frame"]:
                 self.kf_idx -= 1
                 self.terminate()
@@ -286,7 +296,7 @@ class RaftVisualFrontend:
 
         self._store_frame(self.kf_idx, batch, imgs_k)
         self._put_features(self.kf_idx, feats)
-        self.contexts_imgs[self.kf_idx], self.cst_contexts_imgs[self.kf_idx] = self._context_encoder(imgs_norm)
+        self.contexts_imgs[self.kf_idx], self.cst_contexts_imgs[self.kf_idx] = self._context_encoder(self._normalize_imgs(imgs_k))
         self.kf_idx_to_f_idx[self.kf_idx] = k; self.f_idx_to_kf_idx[k] = self.kf_idx
 
         if not self.is_initialized:
@@ -308,19 +318,56 @@ class RaftVisualFrontend:
 
     __call__ = forward
 
-    # ------------------------------------------------------------------ motion filter
-    def has_enough_motion(self, feats):
-        """visual_frontend.py:976-1007: 1 update iteration on (last keyframe -> current frame)"""
-        ht, wd = self.ht, self.wd
-        pair = torch.stack([self.features_imgs[self.last_kf_idx, 0], feats[0].permute(1, 2, 0).contiguous()], 0)
-        one = torch.zeros(1, dtype=torch.int32, device=self.device)
-        pyr = db.corr_volume_build(pair, one, one + 1)
+    # ------------------------------------------------------------------ per-frame front (A1 + motion filter)
+    def _frame_front_body(self):
+        """device-only: static image buffer -> fnet -> motion filter (1 update iteration on
+        (last keyframe -> current frame), visual_frontend.py:976-1007) -> self.last_motion"""
         from .conv import CORR_PAD
-        corr = db.corr_lookup_pyramid(pyr, self.coords0[None].contiguous(), 3, nhwc_stride=CORR_PAD, coords_nhwc=True)
-        net = self.contexts_imgs[self.last_kf_idx, 0][None]
-        inp = self.cst_contexts_imgs[self.last_kf_idx, 0][None]
+        imgs_norm = self._normalize_imgs(self._img_static)
+        feats = self._feature_encoder(imgs_norm)                       # [cams,128,ht,wd]
+        self._feats_cur.copy_(feats)
+        idx = self._last_kf_d
+        self._pair[0].copy_(self.features_imgs[:, 0].index_select(0, idx)[0])
+        self._pair[1].copy_(feats[0].permute(1, 2, 0))
+        pyr = db.corr_volume_build(self._pair, self._i32_0, self._i32_1)
+        corr = db.corr_lookup_pyramid(pyr, self._coords0_b, 3, nhwc_stride=CORR_PAD, coords_nhwc=True)
+        net = self.contexts_imgs[:, 0].index_select(0, idx)
+        inp = self.cst_contexts_imgs[:, 0].index_select(0, idx)
         _, delta, _ = self._run_update_net(net, inp, corr, None)
-        self.last_motion = delta.float().norm(dim=-1).mean()
+        self.last_motion.copy_(delta.float().norm(dim=-1).mean())
+
+    def _frame_front(self, imgs_k):
+        """imgs_k [1,cams,C,H,W] uint8 on the device -> features [cams,128,ht,wd]; sets self.last_motion"""
+        if self._img_static is None:
+            dev = self.device
+            self._img_static = torch.zeros_like(imgs_k)
+            self._feats_cur = torch.zeros(self.cameras, 128, self.ht, self.wd, dtype=torch.float16, device=dev)
+            self._pair = torch.zeros(2, self.ht, self.wd, 128, dtype=torch.float16, device=dev)
+            self._last_kf_d = torch.zeros(1, dtype=torch.long, device=dev)
+            self._i32_0 = torch.zeros(1, dtype=torch.int32, device=dev); self._i32_1 = torch.ones(1, dtype=torch.int32, device=dev)
+            self._coords0_b = self.coords0[None].contiguous()
+            self.last_motion = torch.zeros((), device=dev)
+            self._front_graph, self._front_calls = None, 0
+        self._img_static.copy_(imgs_k)
+        self._last_kf_d.fill_(self.last_kf_idx)
+        if self.use_cuda_graphs and self._front_calls >= 2:
+            if self._front_graph is None:
+                g = torch.cuda.CUDAGraph()
+                cs = self._capture_stream
+                cs.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cs):
+                    g.capture_begin(pool=self._graph_pool)
+                    self._frame_front_body()
+                    g.capture_end()
+                torch.cuda.current_stream().wait_stream(cs)
+                self._front_graph = g
+            self._front_graph.replay()
+        else:
+            self._frame_front_body()
+        self._front_calls += 1
+        return self._feats_cur
+
+    def has_enough_motion(self, feats=None):
         return self.last_motion.item() > self.motion_filter_thresh
 
     # ------------------------------------------------------------------ graph management (A18)
@@ -524,43 +571,103 @@ class RaftVisualFrontend:
         return True
 
     # ------------------------------------------------------------------ the hot loop (A19)
-    @torch.no_grad()
-    def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
-        """visual_frontend.py:371-470"""
-        ht, wd = self.ht, self.wd
-        coords1, _ = self.reproject(self.ii, self.jj)                                # [E,ht,wd,2] fp32
+    def _prepare_static(self, use_inactive, EP):
+        """Everything of update() that depends only on the EDGE SET (not on the evolving state) is
+        computed once here: device index tensors, gathered GRU inputs, the BA window (graph tables,
+        buffers) with the stored flows of the inactive edges already in place.  The per-call body
+        (_update_body) then consists of device work on fixed addresses only -> it can be captured in
+        a CUDA graph and replayed for the 4+2 (or 8+8) updates that share the edge set."""
+        import types
+        dev, ht, wd = self.device, self.ht, self.wd
+        st = types.SimpleNamespace(graph=None, calls=0)
+        ii_h, jj_h = self.ii_h, self.jj_h
+        kf0 = max(0, int(ii_h.min()))
+        st.kf0, st.EP = kf0, EP
+        ux, inv = np.unique(ii_h, return_inverse=True)
+        st.ux = torch.as_tensor(ux, device=dev); st.ix = torch.as_tensor(inv, device=dev); st.K = len(ux)
+        st.inp = self.cst_contexts_imgs[self.ii, 0].contiguous()
+        if use_inactive:
+            m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
+            md = torch.as_tensor(m, device=dev)
+            ii = np.concatenate([self.ii_inactive_h[m], ii_h]); jj = np.concatenate([self.jj_inactive_h[m], jj_h])
+            tin = self.gru_estimated_flow_inactive[md]; win = self.gru_estimated_flow_weight_inactive[md]
+        else:
+            ii, jj = ii_h, jj_h
+            tin = win = torch.zeros(0, ht, wd, 2, device=dev)
+        st.n_in = int(tin.shape[0])
+        Eba = len(ii)
+        st.target = torch.empty(Eba, 2, ht, wd, device=dev); st.weight = torch.empty(Eba, 2, ht, wd, device=dev)
+        st.target[:st.n_in] = tin.permute(0, 3, 1, 2); st.weight[:st.n_in] = win.permute(0, 3, 1, 2)
+        kxb = np.unique(ii)
+        st.kx_ba = torch.as_tensor(kxb, device=dev)
+        st.damp = torch.empty(len(kxb), ht, wd, device=dev)
+        kf1 = int(max(ii.max(), jj.max())) + 1
+        st.kf1 = kf1
+        st.prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
+                               self.cam0_idepths_sensed, st.target, st.weight, st.damp, ii, jj, kf0, kf1)
+        st.kx_prob = torch.as_tensor(st.prob.gh.tables["kx"].astype(np.int64), device=dev)
+        st.has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
+        return st
+
+    def _update_body(self, st, itrs, compute_covariances):
+        """device-only part of update() (visual_frontend.py:371-470); no host<->device traffic, no syncs"""
+        coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
         motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
         motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
         corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
-        inp = self.cst_contexts_imgs[self.ii, 0]
-        net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, inp, corr, motion, self.ii)
-        self.gru_hidden_states = net
-        if kf0 is None:
-            kf0 = max(0, int(self.ii_h.min()))
-        self.gru_estimated_flow = coords1 + delta
-        self.gru_estimated_flow_weight = weight
-        ux = np.unique(self.ii_h)
-        self.damping[torch.as_tensor(ux, device=self.device)] = damping
+        net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, st.inp, corr, motion,
+                                                                   self.ii, agg=(st.ix, st.K))
+        self.gru_hidden_states.copy_(net)
+        torch.add(coords1, delta, out=self.gru_estimated_flow)
+        self.gru_estimated_flow_weight.copy_(weight)
+        self.damping[st.ux] = damping
+        st.target[st.n_in:].copy_(self.gru_estimated_flow.permute(0, 3, 1, 2))
+        st.weight[st.n_in:].copy_(self.gru_estimated_flow_weight.permute(0, 3, 1, 2))
+        torch.mul(self.damping[st.kx_ba], 0.2, out=st.damp)
+        st.damp.add_(st.EP)
+        dx, linv, status = st.prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
+                                                prior_idx=0 if st.has_prior else -1,
+                                                prior_pose=self.prior_pose if st.has_prior else None,
+                                                prior_info=self.prior_info if st.has_prior else 0.0,
+                                                want_linv=compute_covariances, clamp_min=1e-3)
+        if compute_covariances:
+            sg, z_cov, d_cov = st.prob.covariances(linv)
+            self.world_T_body_cov[st.kf0:st.kf1] = sg
+            self.cam0_idepths_cov[st.kx_prob] = z_cov
+            self.cam0_depths_cov[st.kx_prob] = d_cov
+        self.cam0_idepths_up[st.ux] = db.cvx_upsample(self.cam0_idepths[st.ux].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
+        self.cam0_depths_cov_up[st.ux] = db.cvx_upsample(self.cam0_depths_cov[st.ux].unsqueeze(-1), upmask, pow=1.0,
+                                                         mask_nhwc=True).squeeze(-1)
 
-        if use_inactive:
-            m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
-            md = torch.as_tensor(m, device=self.device)
-            ii = np.concatenate([self.ii_inactive_h[m], self.ii_h]); jj = np.concatenate([self.jj_inactive_h[m], self.jj_h])
-            target = torch.cat([self.gru_estimated_flow_inactive[md], self.gru_estimated_flow], 0)
-            wgt = torch.cat([self.gru_estimated_flow_weight_inactive[md], self.gru_estimated_flow_weight], 0)
+    @torch.no_grad()
+    def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
+        """visual_frontend.py:371-470.  The first call after an edge-set change prepares the static
+        part; from the second call on the device work is replayed from a CUDA graph."""
+        st = self._static
+        if st is None or st.use_inactive != use_inactive:
+            st = self._prepare_static(use_inactive, EP)
+            st.use_inactive = use_inactive
+            self._static = st
+        cc = self.compute_covariances
+        if self.use_cuda_graphs and st.calls >= 1:
+            if st.graph is None:
+                g = torch.cuda.CUDAGraph()
+                cs = self._capture_stream
+                cs.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cs):
+                    g.capture_begin(pool=self._graph_pool)
+                    self._update_body(st, itrs, cc)
+                    g.capture_end()
+                torch.cuda.current_stream().wait_stream(cs)
+                st.graph = g
+            st.graph.replay()
         else:
-            ii, jj, target, wgt = self.ii_h, self.jj_h, self.gru_estimated_flow, self.gru_estimated_flow_weight
-        dmp = .2 * self.damping[torch.as_tensor(np.unique(ii), device=self.device)].contiguous() + EP
-        target = target.permute(0, 3, 1, 2).contiguous()
-        wgt = wgt.permute(0, 3, 1, 2).contiguous()
-        self.ba(target, wgt, dmp, ii, jj, kf0, kf1, itrs=itrs, motion_only=motion_only,
-                compute_covariances=self.compute_covariances)
-        kx = torch.as_tensor(ux, device=self.device)
-        self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
-        self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask, pow=1.0, mask_nhwc=True).squeeze(-1)
-        self.viz_idx[kf0:self.kf_idx + 1] = True
+            self._update_body(st, itrs, cc)
+        st.calls += 1
+        self.viz_idx[st.kf0:self.kf_idx + 1] = True
         self.age_h += 1
         self.stats["updates"] += 1
+        self.last_ba = st.prob
 
     def ba(self, target, weight, damping, ii, jj, kf0=0, kf1=None, itrs=2, lm=1e-4, ep=0.1,
            motion_only=False, compute_covariances=True):
@@ -569,10 +676,8 @@ class RaftVisualFrontend:
         ii = np.asarray(ii, np.int64); jj = np.asarray(jj, np.int64)
         if kf1 is None:
             kf1 = int(max(ii.max(), jj.max())) + 1
-        P = kf1 - kf0
-        prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics[0].contiguous(),
-                            self.cam0_T_body, self.cam0_idepths_sensed, target, weight, damping,
-                            ii, jj, kf0, kf1)
+        prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
+                            self.cam0_idepths_sensed, target, weight, damping, ii, jj, kf0, kf1)
         has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
         dx, linv, status = prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
                                              prior_idx=0 if has_prior else -1,

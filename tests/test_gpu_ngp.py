@@ -151,3 +151,31 @@ def test_nerf_fits_synthetic_room():
     r = nf.eval_gt_traj(stride=4)
     assert np.isfinite(nf.ngp.loss)
     assert r["psnr"] > psnr0 + 5.0 and r["psnr"] > 18.0, (psnr0, r)
+
+
+def test_forward_tc_matches_oracle():
+    """tcgen05 MLP forward (fp16 weights + fp16 inter-layer activations, fp32 accumulate) vs the fp32
+    oracle: rgb in (0,1) abs 1e-2, sigma rel 3e-2."""
+    from nerf_slam_b200 import _lib
+    tb = _testbed(seed=8)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    n = 1000                                    # not a multiple of 128: exercises the partial tile
+    x = torch.rand(n, 3, generator=g)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    coords = torch.cat([x, torch.full((n, 1), 0.01), d], -1).contiguous().to(DEV)
+    packed = torch.zeros(28672, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.nslam_ngp_pack_mlp(_lib.ptr(tb.mlp), _lib.ptr(packed), _lib.stream_ptr()), "pack")
+    out = torch.zeros(n, 4, device=DEV)
+    _lib.check(lib.nslam_ngp_forward_tc(ctypes.byref(tb.model), _lib.ptr(packed), _lib.ptr(coords), None, n, n,
+                                        _lib.ptr(out), tb.num_sms, _lib.stream_ptr()), "fwd_tc")
+    torch.cuda.synchronize()
+    rgb, sigma = ongp.network(x, d, _oracle_params(tb), 4.0)
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    assert float((got[:, :3] - rgb).abs().max()) < 1e-2
+    assert float(((got[:, 3] - sigma).abs() / sigma).max()) < 3e-2
+    # and against the SIMT forward kernel on the same inputs
+    out2 = torch.zeros(n, 4, device=DEV)
+    _lib.check(lib.nslam_ngp_forward(ctypes.byref(tb.model), _lib.ptr(coords), n, _lib.ptr(out2), _lib.stream_ptr()), "fwd")
+    assert float((out[:, :3] - out2[:, :3]).abs().max()) < 1e-2

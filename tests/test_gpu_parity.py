@@ -314,3 +314,19 @@ def test_pose_prior_error(db):
     # retract(prior, err) == x
     t, q = se3.pose3_retract(p[1, :3].astype(np.float64), p[1, 3:].astype(np.float64), err.double().cpu().numpy())
     assert np.allclose(t, p[0, :3], atol=1e-5)
+
+
+def test_corr_lookup_nhwc_equals_reference_layout(db):
+    """channels-last / slot-indirected variant == reference-layout kernel (bit for bit)"""
+    rng = np.random.default_rng(14)
+    E, C, H, W = 3, 16, 30, 41          # odd width: partial 32-pixel groups
+    f = rng.normal(0, 1, (2 * E, C, H, W)).astype(np.float16)
+    pyr = [T(p) for p in ocorr.corr_volume_pyramid(f[:E], f[E:])]
+    coords = (np.stack(np.meshgrid(np.arange(W), np.arange(H)), 0)[None] + rng.uniform(-6, 6, (E, 2, H, W))).astype(np.float32)
+    ref = db.corr_lookup_pyramid(pyr, T(coords), 3)                                     # [E,196,H,W]
+    slots = T(np.array([2, 0, 1], np.int32))
+    perm = [pyr_l[[1, 2, 0]] for pyr_l in pyr]                                         # slot s holds edge perm^-1
+    got = db.corr_lookup_pyramid([p.contiguous() for p in perm], T(np.ascontiguousarray(coords.transpose(0, 2, 3, 1))), 3,
+                                 slots=slots, nhwc_stride=200, coords_nhwc=True)        # [E,H,W,200]
+    assert torch.equal(got[..., :196].permute(0, 3, 1, 2).float(), ref.float())
+    assert float(got[..., 196:].abs().max()) == 0.0

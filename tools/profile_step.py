@@ -44,7 +44,7 @@ img = job.make_frames(1, True)[0]
 imgs = fe._normalize_imgs(img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3))
 T(lambda: fe._feature_encoder(imgs), name="feature_encoder")
 T(lambda: fe._context_encoder(imgs), name="context_encoder")
-T(lambda: fe.has_enough_motion(fe._feature_encoder(imgs)), name="motion filter incl. fnet (has .item sync)")
+T(lambda: (fe._frame_front(img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3)), fe.last_motion.item()), name="frame front: fnet + motion filter (graph) + .item sync")
 # NeRF
 job2 = bench.SlamNerfJob(0, 1, 1)
 while not (job2.fe.is_initialized and job2.fe.kf_idx >= 12):
