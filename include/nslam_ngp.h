@@ -68,12 +68,28 @@ int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, co
 int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream);
 
-/* tensor-core (tcgen05) variant of the network forward, fused with the hash encoding
- * (csrc/ngp_tc.cu).  `packed` = 28 672-byte fp16 weight images produced by nslam_ngp_pack_mlp from
- * the fp32 MLP blob (re-run after every optimiser step).  n < 0: sample count read from counters[0]. */
+/* tensor-core (tcgen05) variants of the network forward / backward, fused with the hash encoding
+ * (csrc/ngp_tc.cu).  `packed` = 61 440-byte buffer of fp16 UMMA-ready weight images (forward images
+ * B[n][k] at 0, backward images B[k][n] at 28 672) produced by nslam_ngp_pack_mlp from the fp32 MLP blob
+ * (re-run after every optimiser step).  n < 0: sample count read from counters[0].  The backward
+ * carries its deltas in fp16 multiplied by `loss_scale` (instant-ngp's mixed-precision recipe) and
+ * accumulates weight gradients in TMEM across all tiles of a CTA. */
 int nslam_ngp_pack_mlp(const float* mlp, void* packed, void* stream);
 int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
                          int n, int max_samples, float* rgbsigma, int num_sms, void* stream);
+int nslam_ngp_backward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
+                          const float* dout, float loss_scale, int num_sms, void* stream);
+int nslam_ngp_train_step_tc(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
+                            const void* packed, int n_rays, unsigned seed, float lambda_depth, float bg_r,
+                            float bg_g, float bg_b, float loss_scale, int num_sms, void* stream);
+int nslam_ngp_loss_backward_tc(const nslam_ngp_model* m, const nslam_ngp_batch* b, const void* packed, int n_rays,
+                               int n_samples, float lambda_depth, float bg_r, float bg_g, float bg_b,
+                               float loss_scale, int num_sms, void* stream);
+/* the non-network phases of a step (shared by both variants) */
+int nslam_ngp_sample_phase(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
+                           int n_rays, unsigned seed, void* stream);
+int nslam_ngp_loss_phase(const nslam_ngp_batch* b, int n_rays, float lambda_depth, float bg_r, float bg_g,
+                         float bg_b, void* stream);
 
 #ifdef __cplusplus
 }

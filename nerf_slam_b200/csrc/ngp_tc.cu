@@ -207,6 +207,362 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
   if (warp == 0) tc::tmem_dealloc<64>(tmem);
 }
 
+
+// ============================================================================================
+// Backward on tensor cores.  Per 128-sample tile (thread = sample):
+//   forward recompute (layers 1-4) keeping every layer's INPUT tile in shared memory,
+//   then for l = 5..1 two MMA groups per layer, issued together:
+//     dW_l   += A_l^T (features x samples) . delta_l (samples x N_l)     [accumulates in TMEM across tiles]
+//     dIn_l   = delta_l (samples x N_l)    . W_l^T                       [-> ACC, masked by ReLU']
+//   Operands are fp16 (deltas carry a loss scale), accumulation fp32.  The transposed operand
+//   tiles (K = the 128 samples) are written by the owning threads with 2-byte swizzled stores.
+//   At the end of the persistent loop each CTA flushes its dW accumulators with fp32 atomics.
+// TMEM (512 columns): ACC [0,64) | dW1 [64,128) | dW2 [128,144) | dW3 [160,224) | dW4 [224,288) | dW5 [288,304)
+constexpr int TM_ACC = 0, TM_DW1 = 64, TM_DW2 = 128, TM_DW3 = 160, TM_DW4 = 224, TM_DW5 = 288;
+// backward weight images B[k][n] = W[k][n], n padded to 64: WB5 [64][128B], WB4 [64][128B], WB3 [32][128B], WB2 [64][128B], WB1 [32][128B]
+constexpr int PB5 = 0, PB4 = 8192, PB3 = 16384, PB2 = 20480, PB1 = 28672, PB_TOTAL = 32768;
+
+__global__ void pack_mlp_bwd_kernel(const float* __restrict__ mlp, unsigned char* __restrict__ packed) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int offs[5] = {PB5, PB4, PB3, PB2, PB1};
+  const int Ks[5] = {64, 64, 32, 64, 32};      // rows
+  const int Ns[5] = {16, 64, 64, 16, 64};      // real columns
+  const int woff[5] = {W5_OFF, W4_OFF, W3_OFF, W2_OFF, W1_OFF};
+  int base = 0;
+  for (int l = 0; l < 5; l++) {
+    const int cnt = Ks[l] * 64;
+    if (id < base + cnt) {
+      const int e = id - base, k = e / 64, n = e % 64;
+      const float v = (n < Ns[l]) ? mlp[woff[l] + k * Ns[l] + n] : 0.f;
+      __half* dst = reinterpret_cast<__half*>(packed + offs[l] + k * 128 + (((n >> 3) ^ (k & 7)) << 4)) + (n & 7);
+      *dst = __float2half_rn(v);
+      return;
+    }
+    base += cnt;
+  }
+}
+
+struct BwdSmem {
+  static constexpr int W = 0;                      // forward images   28672
+  static constexpr int WB = 28672;                 // backward images  32768
+  static constexpr int ACT = WB + PB_TOTAL;        // 5 x 16384 : inputs of layers 1..5 (row-major, swizzled)
+  static constexpr int AT = ACT + 5 * 16384;       // transposed activations: 2 halves x [128][128B]
+  static constexpr int D = AT + 32768;             // delta, row-major [128][128B]
+  static constexpr int DT = D + 16384;             // delta transposed: 2 halves x [64][128B]
+  static constexpr int BAR = DT + 16384;
+  static constexpr int TOTAL = BAR + 64;
+};
+
+// element (row f, sample s) of a K-major [rows][128 samples] operand split in two 64-sample halves
+__device__ __forceinline__ void store_T(unsigned char* base, int half_bytes, int f, int s, float v) {
+  __half* p = reinterpret_cast<__half*>(base + (s >> 6) * half_bytes + f * 128 + ((((s & 63) >> 3) ^ (f & 7)) << 4)) + (s & 7);
+  *p = __float2half_rn(v);
+}
+// transpose this thread's row of a row-major swizzled tile (first nf features) into AT
+__device__ __forceinline__ void transpose_row(const unsigned char* tile, unsigned char* at, int row, int nf) {
+  const unsigned char* arow = tile + row * 128;
+  for (int c = 0; c < nf / 8; c++) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int f = c * 8 + j;
+      __half* p = reinterpret_cast<__half*>(at + (row >> 6) * 16384 + f * 128 + ((((row & 63) >> 3) ^ (f & 7)) << 4)) + (row & 7);
+      *p = h[j];
+    }
+  }
+}
+// write a delta vector (n values, fp32) as this thread's row of D (zero-padded to 64) and column of DT
+template <int NV>
+__device__ __forceinline__ void store_delta(unsigned char* dtile, unsigned char* dt, int row, const float* d) {
+  unsigned char* drow = dtile + row * 128;
+  const float z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 8; c++) store_row_chunk(drow, row, c, (c * 8 < NV) ? d + c * 8 : z8);
+#pragma unroll
+  for (int n = 0; n < NV; n++) store_T(dt, 8192, n, row, d[n]);
+}
+
+// dW (TMEM cols at `tm_dw`, N columns) += AT^T-operand x DT-operand over the 128 samples; then
+// ACC = D x WB (N_out columns, `ks` K-steps).  Issued by one thread; one commit covers both.
+template <int N, int NOUT>
+__device__ __forceinline__ void issue_bwd_layer(uint32_t at_addr, uint32_t dt_addr, uint32_t d_addr, uint32_t wb_addr,
+                                                uint32_t tmem, int tm_dw, int ks, bool first_tile, uint64_t* bar) {
+  constexpr uint32_t idw = tc::umma_idesc_f16(128, N, 0);
+  constexpr uint32_t idp = tc::umma_idesc_f16(128, NOUT, 0);
+  tc::tc_fence_after();
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      tc::umma_f16(tmem + tm_dw, tc::umma_desc_sw128(at_addr + h * 16384 + k * 32),
+                   tc::umma_desc_sw128(dt_addr + h * 8192 + k * 32), idw, (first_tile && h == 0 && k == 0) ? 0u : 1u);
+  for (int k = 0; k < ks; k++)
+    tc::umma_f16(tmem + TM_ACC, tc::umma_desc_sw128(d_addr + k * 32), tc::umma_desc_sw128(wb_addr + k * 32), idp, k ? 1u : 0u);
+  tc::umma_commit(bar);
+}
+
+__device__ __forceinline__ void ld_relu_store(uint32_t taddr, unsigned char* arow, int row, uint32_t* mask) {
+  uint32_t r[32];
+  float v[8];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    tc::tmem_ld_32x32(taddr + h * 32, r);
+    tc::tmem_ld_wait();
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float x = __uint_as_float(r[c * 8 + j]);
+        m |= (x > 0.f ? 1u : 0u) << (c * 8 + j);
+        v[j] = fmaxf(x, 0.f);
+      }
+      store_row_chunk(arow, row, h * 4 + c, v);
+    }
+    mask[h] = m;
+  }
+}
+
+#define NGP_TC_SYNC()            \
+  do {                           \
+    tc::fence_proxy_async();     \
+    tc::tc_fence_before();       \
+    __syncthreads();             \
+  } while (0)
+
+__global__ void __launch_bounds__(128, 1)
+backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ counters,
+                   const __half2* __restrict__ grid, LevelInfo lv, const unsigned char* __restrict__ packed_fwd,
+                   const unsigned char* __restrict__ packed_bwd, const float* __restrict__ dout,
+                   float* __restrict__ mlp_grad, float* __restrict__ grid_grad, float loss_scale) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BwdSmem::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n = counters[0];
+  const int ntiles = (n + 127) / 128;
+  for (int i = tid; i < PW_TOTAL / 16; i += 128) reinterpret_cast<uint4*>(sm + BwdSmem::W)[i] = reinterpret_cast<const uint4*>(packed_fwd)[i];
+  for (int i = tid; i < PB_TOTAL / 16; i += 128) reinterpret_cast<uint4*>(sm + BwdSmem::WB)[i] = reinterpret_cast<const uint4*>(packed_bwd)[i];
+  for (int i = tid; i < (32768 + 16384 + 16384) / 16; i += 128) reinterpret_cast<uint4*>(sm + BwdSmem::AT)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+  NGP_TC_SYNC();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t w_addr = tc::smem_u32(sm + BwdSmem::W), wb_addr = tc::smem_u32(sm + BwdSmem::WB);
+  const uint32_t act_addr = tc::smem_u32(sm + BwdSmem::ACT);
+  const uint32_t at_addr = tc::smem_u32(sm + BwdSmem::AT), d_addr = tc::smem_u32(sm + BwdSmem::D), dt_addr = tc::smem_u32(sm + BwdSmem::DT);
+  unsigned char* act = sm + BwdSmem::ACT;
+  unsigned char* AT = sm + BwdSmem::AT;
+  unsigned char* Dt = sm + BwdSmem::D;
+  unsigned char* DT = sm + BwdSmem::DT;
+  uint32_t phase = 0;
+  bool first = true;
+  const float inv_scale = 1.f / loss_scale;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s = tile * 128 + tid;
+    const bool actv = s < n;
+    float c7[7] = {0.5f, 0.5f, 0.5f, 0.f, 0.f, 0.f, 1.f};
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (actv) {
+#pragma unroll
+      for (int k = 0; k < 7; k++) c7[k] = coords[(size_t)s * 7 + k];
+      dg = reinterpret_cast<const float4*>(dout)[s];
+      dg.x *= loss_scale; dg.y *= loss_scale; dg.z *= loss_scale; dg.w *= loss_scale;
+    }
+    uint32_t m1[2], m3[2], m4[2];
+    // ---------------- forward recompute, keeping the layer inputs
+    {
+      float enc[ENC_DIM];
+      hash_encode(c7, grid, lv, enc);
+      const float z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unsigned char* a0 = act + 0 * 16384 + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 4; c++) store_row_chunk(a0, tid, c, enc + 8 * c);
+#pragma unroll
+      for (int c = 4; c < 8; c++) store_row_chunk(a0, tid, c, z8);
+    }
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<64>(act_addr + 0 * 16384, w_addr + PW1, tmem + TM_ACC, 2, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    ld_relu_store(taddr + TM_ACC, act + 1 * 16384 + tid * 128, tid, m1);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<16>(act_addr + 1 * 16384, w_addr + PW2, tmem + TM_ACC, 4, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(taddr + TM_ACC, r);
+      tc::tmem_ld_wait();
+      float o[16], sh[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) o[j] = __uint_as_float(r[j]);
+      sh4(c7 + 4, sh);
+      const float z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unsigned char* a2 = act + 2 * 16384 + tid * 128;
+      store_row_chunk(a2, tid, 0, o); store_row_chunk(a2, tid, 1, o + 8);
+      store_row_chunk(a2, tid, 2, sh); store_row_chunk(a2, tid, 3, sh + 8);
+#pragma unroll
+      for (int c = 4; c < 8; c++) store_row_chunk(a2, tid, c, z8);
+    }
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<64>(act_addr + 2 * 16384, w_addr + PW3, tmem + TM_ACC, 2, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    ld_relu_store(taddr + TM_ACC, act + 3 * 16384 + tid * 128, tid, m3);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<64>(act_addr + 3 * 16384, w_addr + PW4, tmem + TM_ACC, 4, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    ld_relu_store(taddr + TM_ACC, act + 4 * 16384 + tid * 128, tid, m4);
+    // ---------------- layer 5 backward: delta5 = d(raw rgb)
+    float d64[64];
+    {
+      float d16[16] = {dg.x, dg.y, dg.z, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      store_delta<16>(Dt, DT, tid, d16);
+    }
+    __syncthreads();                                   // ACT4 rows complete before anyone transposes... (own row only) 
+    transpose_row(act + 4 * 16384, AT, tid, 64);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB5, tmem, TM_DW5, 1, first, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        tc::tmem_ld_32x32(taddr + TM_ACC + h * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) d64[h * 32 + j] = ((m4[h] >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 4
+    store_delta<64>(Dt, DT, tid, d64);
+    transpose_row(act + 3 * 16384, AT, tid, 64);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_bwd_layer<64, 64>(at_addr, dt_addr, d_addr, wb_addr + PB4, tmem, TM_DW4, 4, first, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        tc::tmem_ld_32x32(taddr + TM_ACC + h * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) d64[h * 32 + j] = ((m3[h] >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 3 (input = [o(16) | sh(16)])
+    store_delta<64>(Dt, DT, tid, d64);
+    transpose_row(act + 2 * 16384, AT, tid, 32);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB3, tmem, TM_DW3, 4, first, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    float d16[16];
+    {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(taddr + TM_ACC, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j++) d16[j] = __uint_as_float(r[j]);
+      d16[0] += dg.w;                                   // sigma path: d/d o0
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 2
+    store_delta<16>(Dt, DT, tid, d16);
+    transpose_row(act + 1 * 16384, AT, tid, 64);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB2, tmem, TM_DW2, 1, first, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        tc::tmem_ld_32x32(taddr + TM_ACC + h * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) d64[h * 32 + j] = ((m1[h] >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 1
+    store_delta<64>(Dt, DT, tid, d64);
+    transpose_row(act + 0 * 16384, AT, tid, 32);
+    NGP_TC_SYNC();
+    if (tid == 0) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB1, tmem, TM_DW1, 4, first, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(taddr + TM_ACC, r);             // d/d enc [32], still loss-scaled
+      tc::tmem_ld_wait();
+      if (actv) {
+#pragma unroll 2
+        for (int l = 0; l < N_LEVELS; l++) {
+          const float ga = __uint_as_float(r[2 * l]) * inv_scale, gb = __uint_as_float(r[2 * l + 1]) * inv_scale;
+          if (ga == 0.f && gb == 0.f) continue;
+          const float sc = lv.scale[l];
+          const float px = fmaf(c7[0], sc, 0.5f), py = fmaf(c7[1], sc, 0.5f), pz = fmaf(c7[2], sc, 0.5f);
+          const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+          const float wx = px - fx, wy = py - fy, wz = pz - fz;
+          const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+          float2* gg = reinterpret_cast<float2*>(grid_grad) + lv.offset[l];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+            const float w = (dx ? wx : 1.f - wx) * (dy ? wy : 1.f - wy) * (dz ? wz : 1.f - wz);
+            atomicAdd(gg + grid_index(ix + dx, iy + dy, iz + dz, lv.res[l], lv.size[l], lv.dense[l]), make_float2(w * ga, w * gb));
+          }
+        }
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    first = false;
+  }
+  // ---------------- flush the weight-gradient accumulators (row = input feature k = TMEM lane)
+  if (!first) {
+    tc::tc_fence_after();
+    const int k = tid;
+    uint32_t r[32];
+    // dW1 [32][64]
+    for (int h = 0; h < 2; h++) {
+      tc::tmem_ld_32x32(taddr + TM_DW1 + h * 32, r); tc::tmem_ld_wait();
+      if (k < 32) for (int j = 0; j < 32; j++) atomicAdd(mlp_grad + W1_OFF + k * 64 + h * 32 + j, __uint_as_float(r[j]) * inv_scale);
+    }
+    tc::tmem_ld_32x32(taddr + TM_DW2, r); tc::tmem_ld_wait();
+    if (k < 64) for (int j = 0; j < 16; j++) atomicAdd(mlp_grad + W2_OFF + k * 16 + j, __uint_as_float(r[j]) * inv_scale);
+    for (int h = 0; h < 2; h++) {
+      tc::tmem_ld_32x32(taddr + TM_DW3 + h * 32, r); tc::tmem_ld_wait();
+      if (k < 32) for (int j = 0; j < 32; j++) atomicAdd(mlp_grad + W3_OFF + k * 64 + h * 32 + j, __uint_as_float(r[j]) * inv_scale);
+    }
+    for (int h = 0; h < 2; h++) {
+      tc::tmem_ld_32x32(taddr + TM_DW4 + h * 32, r); tc::tmem_ld_wait();
+      if (k < 64) for (int j = 0; j < 32; j++) atomicAdd(mlp_grad + W4_OFF + k * 64 + h * 32 + j, __uint_as_float(r[j]) * inv_scale);
+    }
+    tc::tmem_ld_32x32(taddr + TM_DW5, r); tc::tmem_ld_wait();
+    if (k < 64) for (int j = 0; j < 16; j++) atomicAdd(mlp_grad + W5_OFF + k * 16 + j, __uint_as_float(r[j]) * inv_scale);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
 }  // namespace ngp
 
 extern "C" {
@@ -214,8 +570,9 @@ extern "C" {
 int nslam_ngp_pack_mlp(const float* mlp, void* packed, void* stream) {
   const int total = (64 + 16 + 64 + 64 + 16) * 64;
   ngp::pack_mlp_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, (unsigned char*)packed);
-  cudaError_t e = cudaGetLastError();
-  return (int)e;
+  const int totalb = (64 + 64 + 32 + 64 + 32) * 64;
+  ngp::pack_mlp_bwd_kernel<<<(totalb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mlp, (unsigned char*)packed + ngp::PW_TOTAL);
+  return (int)cudaGetLastError();
 }
 
 /* tensor-core variant of nslam_ngp_forward: coords [n,7] (n < 0: read counters[0]) -> rgbsigma [n,4] */
@@ -242,6 +599,59 @@ int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const flo
                                                               (const unsigned char*)packed, rgbsigma);
   cudaError_t e = cudaGetLastError();
   return (int)e;
+}
+
+/* tensor-core backward: recompute + all gradients; reads the sample count from counters[0].
+ * mlp_grad / grid_grad accumulate (fp32 atomics); `dout` as produced by the loss kernel. */
+int nslam_ngp_backward_tc(const nslam_ngp_model* m, const void* packed,
+                          const float* coords, const int* counters, const float* dout, float loss_scale,
+                          int num_sms, void* stream) {
+  using namespace ngp;
+  LevelInfo lv;
+  for (int l = 0; l < N_LEVELS; l++) {
+    lv.scale[l] = m->scale[l]; lv.res[l] = m->res[l]; lv.size[l] = m->size[l];
+    lv.offset[l] = m->offset[l]; lv.dense[l] = m->dense[l];
+  }
+  const int smem = BwdSmem::TOTAL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  backward_tc_kernel<<<num_sms, 128, smem, (cudaStream_t)stream>>>(coords, counters, (const __half2*)m->grid_half, lv,
+                                                                 (const unsigned char*)packed, (const unsigned char*)packed + PW_TOTAL,
+                                                                 dout, m->mlp_grad, m->grid_grad, loss_scale);
+  return (int)cudaGetLastError();
+}
+
+/* one training step with the network on tensor cores: sample -> forward_tc -> loss -> backward_tc
+ * (same contract as nslam_ngp_train_step; `packed` from nslam_ngp_pack_mlp of the CURRENT weights) */
+int nslam_ngp_train_step_tc(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
+                            const void* packed, int n_rays, unsigned seed, float lambda_depth, float bg_r,
+                            float bg_g, float bg_b, float loss_scale, int num_sms, void* stream) {
+  int r = nslam_ngp_sample_phase(m, im, b, n_rays, seed, stream);
+  if (r) return r;
+  r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, num_sms, stream);
+  if (r) return r;
+  r = nslam_ngp_loss_phase(b, n_rays, lambda_depth, bg_r, bg_g, bg_b, stream);
+  if (r) return r;
+  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, num_sms, stream);
+}
+
+/* tests: loss + gradients on caller-provided rays/samples through the tensor-core kernels */
+int nslam_ngp_loss_backward_tc(const nslam_ngp_model* m, const nslam_ngp_batch* b, const void* packed, int n_rays,
+                               int n_samples, float lambda_depth, float bg_r, float bg_g, float bg_b,
+                               float loss_scale, int num_sms, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int h[4] = {n_samples, n_rays, n_rays, 0};
+  cudaMemcpyAsync(b->counters, h, sizeof(h), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(b->loss, 0, sizeof(float), st);
+  int r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, num_sms, stream);
+  if (r) return r;
+  r = nslam_ngp_loss_phase(b, n_rays, lambda_depth, bg_r, bg_g, bg_b, stream);
+  if (r) return r;
+  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, num_sms, stream);
 }
 
 }  // extern "C"

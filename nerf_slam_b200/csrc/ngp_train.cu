@@ -719,6 +719,31 @@ int nslam_ngp_train_step(const nslam_ngp_model* m, const nslam_ngp_images* im, c
   return 0;
 }
 
+/* the two non-network phases of a training step, exported so that the tensor-core step
+ * (csrc/ngp_tc.cu: nslam_ngp_train_step_tc) can reuse them: ray/sample generation and the loss */
+int nslam_ngp_sample_phase(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
+                           int n_rays, unsigned seed, void* stream) {
+  using namespace ngp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rays > b->max_rays) return (int)cudaErrorInvalidValue;
+  cudaMemsetAsync(b->counters, 0, 4 * sizeof(int), st);
+  cudaMemsetAsync(b->loss, 0, sizeof(float), st);
+  sample_rays_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(make_store(im), make_scene(m), m->bits, n_rays, seed,
+                                                         b->max_samples, b->rays, b->coords, b->tdist, b->counters);
+  NGP_CHECK_LAUNCH();
+  return 0;
+}
+
+int nslam_ngp_loss_phase(const nslam_ngp_batch* b, int n_rays, float lambda_depth, float bg_r, float bg_g,
+                         float bg_b, void* stream) {
+  using namespace ngp;
+  loss_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma,
+                                                                       b->counters, lambda_depth,
+                                                                       make_float3(bg_r, bg_g, bg_b), 0, b->dout, b->loss, nullptr);
+  NGP_CHECK_LAUNCH();
+  return 0;
+}
+
 int nslam_ngp_adam(const nslam_ngp_model* m, int step, float lr, float beta1, float beta2, float eps,
                    float l2_mlp, void* stream) {
   using namespace ngp;

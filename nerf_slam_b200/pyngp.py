@@ -158,6 +158,9 @@ class Testbed:
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self._measured = None
         self.grad_hook = None        # e.g. dist.allreduce_grads for data-parallel training
+        # "tcgen05": MLP forward/backward on tensor cores (csrc/ngp_tc.cu); "simt": fp32 CUDA-core kernels
+        self.mlp_backend = "tcgen05"
+        self.loss_scale = 1024.0
 
     # ---------------------------------------------------------------- setup
     def init_window(self, *a, **k):
@@ -213,6 +216,12 @@ class Testbed:
             setattr(b, k, v.data_ptr())
         b.max_rays, b.max_samples = self.max_rays, self.max_samples
         self.batch = b
+        self.packed = torch.zeros(61440, dtype=torch.uint8, device=dev)
+        self.pack_weights()
+
+    def pack_weights(self):
+        """fp16 UMMA-ready images of the current fp32 MLP weights (after init / every optimiser step)"""
+        _lib.check(_lib.load().nslam_ngp_pack_mlp(_lib.ptr(self.mlp), _lib.ptr(self.packed), _lib.stream_ptr()), "ngp_pack_mlp")
 
     def _ensure_store(self, H, W):
         if self.rgba is None:
@@ -268,15 +277,22 @@ class Testbed:
         im = self._images()
         bg = self.background_color
         seed = (self.seed + 0x9E3779B1 * (self.training_step + 1)) & 0xFFFFFFFF
-        _lib.check(lib.nslam_ngp_train_step(ctypes.byref(self.model), ctypes.byref(im), ctypes.byref(self.batch),
-                                            self.rays_per_batch, seed, float(self.nerf.training.depth_supervision_lambda),
-                                            bg[0], bg[1], bg[2], self.num_sms, _lib.stream_ptr()), "ngp_train_step")
+        lam = float(self.nerf.training.depth_supervision_lambda)
+        if self.mlp_backend == "tcgen05":
+            _lib.check(lib.nslam_ngp_train_step_tc(ctypes.byref(self.model), ctypes.byref(im), ctypes.byref(self.batch),
+                                                   _lib.ptr(self.packed), self.rays_per_batch, seed, lam, bg[0], bg[1], bg[2],
+                                                   float(self.loss_scale), self.num_sms, _lib.stream_ptr()), "ngp_train_step_tc")
+        else:
+            _lib.check(lib.nslam_ngp_train_step(ctypes.byref(self.model), ctypes.byref(im), ctypes.byref(self.batch),
+                                                self.rays_per_batch, seed, lam, bg[0], bg[1], bg[2], self.num_sms,
+                                                _lib.stream_ptr()), "ngp_train_step")
         if self.grad_hook is not None:
             self.grad_hook(self)
         self.training_step += 1
         decay = 0.33 ** max(0, (self.training_step - 20000) // 10000 + (1 if self.training_step >= 20000 else 0))
         _lib.check(lib.nslam_ngp_adam(ctypes.byref(self.model), self.training_step, self.lr * decay, self.beta1,
                                       self.beta2, self.eps, self.l2, _lib.stream_ptr()), "ngp_adam")
+        self.pack_weights()
         # adapt the ray count so that a batch holds ~max_samples samples (uses the LAST completed step's
         # counters without blocking: read asynchronously every 16 steps)
         if self.training_step % 16 == 0:

@@ -60,12 +60,14 @@ def test_forward_matches_oracle():
     assert torch.allclose(got[:, 3], sigma, rtol=5e-4, atol=1e-5), (got[:, 3] - sigma).abs().max()
 
 
-def test_loss_and_gradients_match_autograd():
+@pytest.mark.parametrize("backend,R,per,tol", [("simt", 24, 11, 3e-3), ("tcgen05", 24, 11, 2e-2), ("tcgen05", 300, 13, 2e-2)])
+def test_loss_and_gradients_match_autograd(backend, R, per, tol):
+    """simt: fp32 CUDA-core kernels, tight tolerance.  tcgen05: fp16 operands (weights, activations,
+    loss-scaled deltas), fp32 accumulation in TMEM -> gradients within 2 % of the largest entry."""
     from nerf_slam_b200 import _lib
     tb = _testbed(seed=5)
     lib = _lib.load()
     g = torch.Generator().manual_seed(1)
-    R, per = 24, 11
     n = R * per
     x = torch.rand(n, 3, generator=g) * 0.6 + 0.2
     d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).repeat_interleave(per, 0)
@@ -86,8 +88,13 @@ def test_loss_and_gradients_match_autograd():
     tb._bufs["rays"][:R].copy_(rays.to(DEV)); tb._bufs["coords"][:n].copy_(coords.to(DEV)); tb._bufs["tdist"][:n].copy_(tdist.to(DEV))
     tb.mlp_grad.zero_(); tb.grid_grad.zero_()
     bg = (0.2, 0.4, 0.6)
-    _lib.check(lib.nslam_ngp_loss_backward(ctypes.byref(tb.model), ctypes.byref(tb.batch), R, n, 1.0, *bg,
-                                           tb.num_sms, _lib.stream_ptr()), "loss_bwd")
+    if backend == "simt":
+        _lib.check(lib.nslam_ngp_loss_backward(ctypes.byref(tb.model), ctypes.byref(tb.batch), R, n, 1.0, *bg,
+                                               tb.num_sms, _lib.stream_ptr()), "loss_bwd")
+    else:
+        tb.pack_weights()
+        _lib.check(lib.nslam_ngp_loss_backward_tc(ctypes.byref(tb.model), ctypes.byref(tb.batch), _lib.ptr(tb.packed), R, n,
+                                                  1.0, *bg, 1024.0, tb.num_sms, _lib.stream_ptr()), "loss_bwd_tc")
     torch.cuda.synchronize()
     # oracle with autograd
     P = _oracle_params(tb)
@@ -97,7 +104,7 @@ def test_loss_and_gradients_match_autograd():
     loss, _, _ = ongp.composite_loss(rgb, sigma, dt, tdist * 0.9, [i * per for i in range(R + 1)], tgt_rgb, tgt_dep, cov,
                                      torch.tensor(bg).repeat(R, 1), 1.0)
     loss.backward()
-    assert abs(float(tb._bufs["loss"].item()) - float(loss)) < 1e-4 * max(1.0, abs(float(loss)))
+    assert abs(float(tb._bufs["loss"].item()) - float(loss)) < (1e-4 if backend == "simt" else 5e-3) * max(1.0, abs(float(loss)))
     gw = tb.mlp_grad.cpu()
     off = 0
     for name, (i, o) in dict(W1=(32, 64), W2=(64, 16), W3=(32, 64), W4=(64, 64), W5=(64, 16)).items():
@@ -106,11 +113,11 @@ def test_loss_and_gradients_match_autograd():
         if name == "W5":
             ref, got = ref[:, :3], got[:, :3]
         err = (got - ref).abs().max() / (ref.abs().max() + 1e-12)
-        assert err < 3e-3, f"{name}: rel err {err:.2e}"
+        assert err < tol, f"{name}: rel err {err:.2e}"
     gg = tb.grid_grad.cpu().view(-1, 2)
     ref = P["grid"].grad
     err = (gg - ref).abs().max() / (ref.abs().max() + 1e-12)
-    assert err < 3e-3, f"grid: rel err {err:.2e}"
+    assert err < tol, f"grid: rel err {err:.2e}"
 
 
 def test_adam_step_matches_torch():
@@ -130,7 +137,8 @@ def test_adam_step_matches_torch():
     assert float(tb.mlp_grad.abs().max()) == 0.0
 
 
-def test_nerf_fits_synthetic_room():
+@pytest.mark.parametrize("backend", ["tcgen05", "simt"])
+def test_nerf_fits_synthetic_room(backend):
     """convergence: train on GT-posed views of the procedural room; PSNR must rise clearly"""
     from nerf_slam_b200.synthetic import SyntheticRoom
     import types
@@ -139,6 +147,7 @@ def test_nerf_fits_synthetic_room():
     args = types.SimpleNamespace(buffer=12, eval=False, mask_type="ours")
     nf = NerfFusion("nerf", args, DEV)
     nf.ngp.nerf.training.depth_supervision_lambda = 1.0
+    nf.ngp.mlp_backend = backend
     pk = [room.packet(k) for k in range(12)]
     packet = {"k": np.arange(12), "poses": np.stack([p["poses"][0] for p in pk]), "images": np.stack([p["images"][0] for p in pk]),
               "depths": np.stack([p["depths"][0] for p in pk]), "calibs": pk[0]["calibs"]}
@@ -164,7 +173,7 @@ def test_forward_tc_matches_oracle():
     x = torch.rand(n, 3, generator=g)
     d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
     coords = torch.cat([x, torch.full((n, 1), 0.01), d], -1).contiguous().to(DEV)
-    packed = torch.zeros(28672, dtype=torch.uint8, device=DEV)
+    packed = torch.zeros(61440, dtype=torch.uint8, device=DEV)
     _lib.check(lib.nslam_ngp_pack_mlp(_lib.ptr(tb.mlp), _lib.ptr(packed), _lib.stream_ptr()), "pack")
     out = torch.zeros(n, 4, device=DEV)
     _lib.check(lib.nslam_ngp_forward_tc(ctypes.byref(tb.model), _lib.ptr(packed), _lib.ptr(coords), None, n, n,
