@@ -9,7 +9,7 @@
 //
 // Kernel structure (all launches are sized for the buffer capacity and read the live sample
 // count from a device counter, so a step never synchronises the host):
-//   ngp_sample_rays    thread per ray: two-pass march through the cascaded occupancy bitfield,
+//   ngp_sample_rays    warp per ray: 32 lattice points per iteration through the cascaded occupancy bitfield,
 //                      contiguous sample ranges claimed with one atomic per ray
 //   ngp_forward        thread per sample: 128 independent hash-table gathers (table is fp16 and
 //                      L2-resident: 16 levels x 2^19 x 4 B = 33 MB << 126 MB), then the two tiny
@@ -145,47 +145,100 @@ __device__ __forceinline__ void make_ray(const Camera& c, float px, float py, fl
   }
 }
 
-// returns number of samples; when `out` != nullptr writes them (7 floats each: pos01(3), dt, dir(3))
-// and their ray distances to tdist.
-__device__ int march(const float* o, const float* d, const Scene& sc, const uint8_t* __restrict__ bits,
-                     float jitter, int max_n, float* __restrict__ out, float* __restrict__ tdist) {
-  float id[3] = {1.f / d[0], 1.f / d[1], 1.f / d[2]};
+// Warp-cooperative march (one warp = one ray; all lanes hold identical o, d, jitter).
+// The step lattice t_{k+1} = t_k + calc_dt(t_k) does not depend on occupancy, so the warp tests 32
+// consecutive lattice points per iteration (one dependent bitfield load per 32 steps instead of one
+// per step): lane l rebuilds t_{base+l} with the same serial recurrence a single thread would run
+// (bit-identical t), the ballot of occupied points is kept in registers (lane c%32 holds chunk c),
+// the ray reserves its contiguous sample range with ONE atomicAdd, and the write pass replays the
+// kept masks without touching the bitfield again.  A sample is emitted for every lattice point that
+// lies in an occupied cell of its cascade, up to max_n samples / 4096 lattice points per ray.
+constexpr int MW_SLOTS = 4;                 // 4 x 32 chunks x 32 points
+
+__device__ __forceinline__ float lattice_t(float tbase, int lane, float cone) {
+  float t = tbase;
+  for (int i = 0; i < lane; i++) t += calc_dt(t, cone);
+  return t;
+}
+
+// returns the number of samples (uniform over the warp); writes them at coords/tdist[base...]
+__device__ int march_warp(const float* o, const float* d, const Scene& sc, const uint8_t* __restrict__ bits,
+                          float jitter, int max_n, int max_samples, int* __restrict__ counters,
+                          float* __restrict__ coords, float* __restrict__ tdist, int& base_out) {
+  const int lane = threadIdx.x & 31;
+  const float id[3] = {1.f / d[0], 1.f / d[1], 1.f / d[2]};
   float tmin, tmax;
   ray_aabb(o, id, sc.aabb_lo, sc.aabb_hi, tmin, tmax);
   if (tmax <= fmaxf(tmin, 0.f)) return 0;
-  float t = fmaxf(tmin, sc.near) + 1e-6f;
-  t += calc_dt(t, sc.cone) * jitter;
-  int n = 0;
-  while (t < tmax && n < max_n) {
-    float p[3] = {fmaf(d[0], t, o[0]), fmaf(d[1], t, o[1]), fmaf(d[2], t, o[2])};
-    const float dt = calc_dt(t, sc.cone);
-    const int mip = mip_from_dt(dt, p, sc.cascades);
-    if (occupied(p, mip, bits)) {
-      if (out) {
-        float* s = out + (size_t)n * 7;
-        s[0] = (p[0] - sc.aabb_lo) * sc.inv_extent; s[1] = (p[1] - sc.aabb_lo) * sc.inv_extent;
-        s[2] = (p[2] - sc.aabb_lo) * sc.inv_extent; s[3] = dt;
-        s[4] = d[0]; s[5] = d[1]; s[6] = d[2];
-        tdist[n] = t;
+  float tbase = fmaxf(tmin, sc.near) + 1e-6f;
+  tbase += calc_dt(tbase, sc.cone) * jitter;
+  uint32_t mk[MW_SLOTS];
+  float tb[MW_SLOTS];
+  int n = 0, nchunks = 0;
+  bool done = false;
+#pragma unroll
+  for (int slot = 0; slot < MW_SLOTS; slot++) {
+    mk[slot] = 0u; tb[slot] = 0.f;
+    for (int j = 0; j < 32 && !done; j++) {
+      if (tbase >= tmax || n >= max_n) { done = true; break; }
+      const float t = lattice_t(tbase, lane, sc.cone);
+      const float dt = calc_dt(t, sc.cone);
+      bool occ = false;
+      if (t < tmax) {
+        const float p[3] = {fmaf(d[0], t, o[0]), fmaf(d[1], t, o[1]), fmaf(d[2], t, o[2])};
+        occ = occupied(p, mip_from_dt(dt, p, sc.cascades), bits);
       }
-      n++;
-      t += dt;
-    } else {
-      t = advance_to_next_voxel(t, sc.cone, p, d, id, mip);
+      uint32_t m = __ballot_sync(0xffffffffu, occ);
+      const int c = __popc(m);
+      if (n + c > max_n) m &= (1u << __fns(m, 0, max_n - n + 1)) - 1u;   // keep the first max_n - n points
+      n += __popc(m);
+      if (lane == j) { mk[slot] = m; tb[slot] = tbase; }
+      nchunks++;
+      tbase = __shfl_sync(0xffffffffu, t + dt, 31);
+    }
+  }
+  if (n == 0) return 0;
+  int base = 0;
+  if (lane == 0) {
+    base = atomicAdd(&counters[0], n);
+    if (base + n > max_samples) { atomicSub(&counters[0], n); base = -1; }
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base < 0) return 0;
+  base_out = base;
+  int off = 0, ci = 0;
+#pragma unroll
+  for (int slot = 0; slot < MW_SLOTS; slot++) {
+    for (int j = 0; j < 32 && ci < nchunks; j++, ci++) {
+      const uint32_t m = __shfl_sync(0xffffffffu, mk[slot], j);
+      const float tbs = __shfl_sync(0xffffffffu, tb[slot], j);
+      if (m == 0u) continue;
+      if ((m >> lane) & 1u) {
+        const float t = lattice_t(tbs, lane, sc.cone);
+        const float dt = calc_dt(t, sc.cone);
+        const int k = base + off + __popc(m & ((1u << lane) - 1u));
+        float* s = coords + (size_t)k * 7;
+        s[0] = (fmaf(d[0], t, o[0]) - sc.aabb_lo) * sc.inv_extent;
+        s[1] = (fmaf(d[1], t, o[1]) - sc.aabb_lo) * sc.inv_extent;
+        s[2] = (fmaf(d[2], t, o[2]) - sc.aabb_lo) * sc.inv_extent;
+        s[3] = dt; s[4] = d[0]; s[5] = d[1]; s[6] = d[2];
+        tdist[k] = t;
+      }
+      off += __popc(m);
     }
   }
   return n;
 }
 
-// counters: [0] samples used, [1] rays kept, [2] rays tried
+// counters: [0] samples used, [1] rays kept, [2] rays tried.  One WARP per ray.
 __global__ void sample_rays_kernel(ImageStore st, Scene sc, const uint8_t* __restrict__ bits,
                                    int n_rays, uint32_t seed, int max_samples,
                                    float* __restrict__ rays, float* __restrict__ coords,
                                    float* __restrict__ tdist, int* __restrict__ counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_rays) return;
   float* R = rays + (size_t)i * 16;
-  reinterpret_cast<int*>(R)[13] = 0;
+  if (lane == 0) reinterpret_cast<int*>(R)[13] = 0;
   if (st.n_active <= 0) return;
   const int img = st.active[min((int)(rnd01(seed, i, 1) * st.n_active), st.n_active - 1)];
   const int px = min((int)(rnd01(seed, i, 2) * st.W), st.W - 1);
@@ -193,11 +246,9 @@ __global__ void sample_rays_kernel(ImageStore st, Scene sc, const uint8_t* __res
   float o[3], d[3], inv_len;
   make_ray(st.cams[img], px + 0.5f, py + 0.5f, o, d, inv_len);
   const float jit = rnd01(seed, i, 4);
-  const int n = march(o, d, sc, bits, jit, MAX_STEPS, nullptr, nullptr);
-  if (n == 0) return;
-  const int base = atomicAdd(&counters[0], n);
-  if (base + n > max_samples) { atomicSub(&counters[0], n); return; }
-  march(o, d, sc, bits, jit, n, coords + (size_t)base * 7, tdist + base);
+  int base = 0;
+  const int n = march_warp(o, d, sc, bits, jit, MAX_STEPS, max_samples, counters, coords, tdist, base);
+  if (n == 0 || lane != 0) return;
   const size_t pix = ((size_t)img * st.H + py) * st.W + px;
   R[0] = o[0]; R[1] = o[1]; R[2] = o[2]; R[3] = d[0]; R[4] = d[1]; R[5] = d[2]; R[6] = inv_len;
   R[7] = st.depth ? st.depth[pix] : -1.f;
@@ -211,25 +262,23 @@ __global__ void sample_rays_kernel(ImageStore st, Scene sc, const uint8_t* __res
   atomicAdd(&counters[1], 1);
 }
 
-// rays of one image tile (render): ray r <-> pixel (x0 + r % tw, y0 + r / tw)
+// rays of one image tile (render): ray r <-> pixel (x0 + r % tw, y0 + r / tw).  One WARP per ray.
 __global__ void render_rays_kernel(Camera cam, Scene sc, const uint8_t* __restrict__ bits, int x0,
                                    int y0, int tw, int th, int max_samples, int max_per_ray,
                                    float* __restrict__ rays, float* __restrict__ coords,
                                    float* __restrict__ tdist, int* __restrict__ counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= tw * th) return;
   float* R = rays + (size_t)i * 16;
-  reinterpret_cast<int*>(R)[13] = 0;
+  if (lane == 0) reinterpret_cast<int*>(R)[13] = 0;
   const int px = x0 + i % tw, py = y0 + i / tw;
   if (px >= cam.w || py >= cam.h) return;
   float o[3], d[3], inv_len;
   make_ray(cam, px + 0.5f, py + 0.5f, o, d, inv_len);
-  const int n = march(o, d, sc, bits, 0.f, max_per_ray, nullptr, nullptr);
-  R[6] = inv_len;
-  if (n == 0) return;
-  const int base = atomicAdd(&counters[0], n);
-  if (base + n > max_samples) { atomicSub(&counters[0], n); return; }
-  march(o, d, sc, bits, 0.f, n, coords + (size_t)base * 7, tdist + base);
+  if (lane == 0) R[6] = inv_len;
+  int base = 0;
+  const int n = march_warp(o, d, sc, bits, 0.f, max_per_ray, max_samples, counters, coords, tdist, base);
+  if (n == 0 || lane != 0) return;
   reinterpret_cast<int*>(R)[12] = base;
   reinterpret_cast<int*>(R)[13] = n;
 }
@@ -312,35 +361,71 @@ forward_kernel(const float* __restrict__ coords, const int* __restrict__ counter
 }
 
 // ------------------------------------------------------------------------------------------
-// compositing + loss + closed-form backward of the volume rendering, one thread per ray.
+// compositing + loss + closed-form backward of the volume rendering, one WARP per ray: the samples
+// of a ray are processed 32 at a time, transmittance by a multiplicative warp scan, the suffix terms
+// of d/d(sigma) as (ray total - inclusive prefix) from additive warp scans.  Loads and the dout
+// stores are coalesced (consecutive lanes = consecutive samples).
 //   mode 0: training (writes dL/d(rgb,sigma) per sample, accumulates loss)
-//   mode 1: render   (writes out_rgbd[r] = (r,g,b,z-depth), optional accumulated alpha)
+//   mode 1: render   (writes out_rgbd[r] = (r,g,b,z-depth))
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v *= u; }
+  return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+  return v;
+}
+
 __global__ void loss_kernel(const float* __restrict__ rays, int n_rays, const float* __restrict__ coords,
                             const float* __restrict__ tdist, const float* __restrict__ rgbsigma,
                             const int* __restrict__ counters, float lambda_d, float3 bg, int mode,
                             float* __restrict__ dout, float* __restrict__ loss_acc,
                             float* __restrict__ out_rgbd) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n_rays) return;
   const float* R = rays + (size_t)r * 16;
   const int base = reinterpret_cast<const int*>(R)[12], n = reinterpret_cast<const int*>(R)[13];
   const float inv_len = R[6];
+  // ---- forward sweep: a sample is used while the transmittance in front of it is >= MIN_T
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f;
   int used = 0;
-  for (int k = 0; k < n; k++) {
-    if (T < MIN_T) break;
-    const float4 v = reinterpret_cast<const float4*>(rgbsigma)[base + k];
-    const float dt = coords[(size_t)(base + k) * 7 + 3];
-    const float alpha = 1.f - __expf(-v.w * dt);
-    const float w = alpha * T;
-    cr += w * v.x; cg += w * v.y; cb += w * v.z;
-    dep += w * tdist[base + k] * inv_len;
-    T *= (1.f - alpha);
-    used++;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int k = c0 + lane;
+    const bool valid = k < n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dt = 0.f, tz = 0.f;
+    if (valid) {
+      v = reinterpret_cast<const float4*>(rgbsigma)[base + k];
+      dt = coords[(size_t)(base + k) * 7 + 3];
+      tz = tdist[base + k] * inv_len;
+    }
+    const float e = valid ? __expf(-v.w * dt) : 1.f;
+    const float pin = warp_scan_mul(e, lane);
+    float pex = __shfl_up_sync(0xffffffffu, pin, 1);
+    if (lane == 0) pex = 1.f;
+    const float Tb = T * pex;                                    // transmittance in front of sample k
+    const bool use = valid && Tb >= MIN_T;
+    const float w = use ? (1.f - e) * Tb : 0.f;
+    cr += w * v.x; cg += w * v.y; cb += w * v.z; dep += w * tz;
+    const uint32_t um = __ballot_sync(0xffffffffu, use);
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    used += __popc(um);
+    if (um != vm) {                                               // cut inside this chunk
+      T = __shfl_sync(0xffffffffu, Tb, __popc(um));               // T in front of the first unused sample
+      break;
+    }
+    T *= __shfl_sync(0xffffffffu, pin, 31);
   }
+  cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dep = warp_sum(dep);
   if (mode == 1) {
-    float4 o = make_float4(cr + T * bg.x, cg + T * bg.y, cb + T * bg.z, dep);
-    reinterpret_cast<float4*>(out_rgbd)[r] = o;
+    if (lane == 0) reinterpret_cast<float4*>(out_rgbd)[r] = make_float4(cr + T * bg.x, cg + T * bg.y, cb + T * bg.z, dep);
     return;
   }
   if (n == 0) return;
@@ -364,29 +449,43 @@ __global__ void loss_kernel(const float* __restrict__ rays, int n_rays, const fl
     loss += lambda_d * e * e / cov;
     ld = 2.f * lambda_d * e / cov * invR;
   }
-  atomicAdd(loss_acc, loss * invR);
-  // backward sweep
-  float T2 = 1.f, r2 = 0.f, g2 = 0.f, b2 = 0.f, d2 = 0.f;
-  for (int k = 0; k < n; k++) {
+  if (lane == 0) atomicAdd(loss_acc, loss * invR);
+  // ---- backward sweep
+  float T2 = 1.f, r2 = 0.f, g2 = 0.f, b2 = 0.f, d2 = 0.f;       // carries: values after the previous chunk
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int k = c0 + lane;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < used) {
-      const float4 v = reinterpret_cast<const float4*>(rgbsigma)[base + k];
-      const float dt = coords[(size_t)(base + k) * 7 + 3];
-      const float tz = tdist[base + k] * inv_len;
-      const float alpha = 1.f - __expf(-v.w * dt);
-      const float w = alpha * T2;
-      r2 += w * v.x; g2 += w * v.y; b2 += w * v.z; d2 += w * tz;
-      T2 *= (1.f - alpha);
-      // d(colour)/d(rgb_s) = w ;  d(C)/d(sigma_s) = dt (T_after c_s - suffix)
-      g.x = lg[0] * w * v.x * (1.f - v.x);   // through the sigmoid
-      g.y = lg[1] * w * v.y * (1.f - v.y);
-      g.z = lg[2] * w * v.z * (1.f - v.z);
-      const float sr = col[0] - r2, sg = col[1] - g2, sb = col[2] - b2;
-      float ds = lg[0] * (T2 * v.x - sr) + lg[1] * (T2 * v.y - sg) + lg[2] * (T2 * v.z - sb);
-      ds += ld * (T2 * tz - (dep - d2));
-      g.w = ds * dt * v.w;                    // through sigma = exp(o0)
+    if (c0 < used) {                                              // warp-uniform
+      const bool use = k < used;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float dt = 0.f, tz = 0.f;
+      if (use) {
+        v = reinterpret_cast<const float4*>(rgbsigma)[base + k];
+        dt = coords[(size_t)(base + k) * 7 + 3];
+        tz = tdist[base + k] * inv_len;
+      }
+      const float e = use ? __expf(-v.w * dt) : 1.f;
+      const float pin = warp_scan_mul(e, lane);
+      float pex = __shfl_up_sync(0xffffffffu, pin, 1);
+      if (lane == 0) pex = 1.f;
+      const float w = use ? (1.f - e) * (T2 * pex) : 0.f;
+      const float Ta = T2 * pin;                                  // transmittance behind sample k
+      const float sr = r2 + warp_scan_add(w * v.x, lane), sg = g2 + warp_scan_add(w * v.y, lane);
+      const float sb = b2 + warp_scan_add(w * v.z, lane), sd = d2 + warp_scan_add(w * tz, lane);
+      if (use) {
+        // d(colour)/d(rgb_s) = w ;  d(C)/d(sigma_s) = dt (T_after c_s - suffix)
+        g.x = lg[0] * w * v.x * (1.f - v.x);                      // through the sigmoid
+        g.y = lg[1] * w * v.y * (1.f - v.y);
+        g.z = lg[2] * w * v.z * (1.f - v.z);
+        float ds = lg[0] * (Ta * v.x - (col[0] - sr)) + lg[1] * (Ta * v.y - (col[1] - sg)) + lg[2] * (Ta * v.z - (col[2] - sb));
+        ds += ld * (Ta * tz - (dep - sd));
+        g.w = ds * dt * v.w;                                      // through sigma = exp(o0)
+      }
+      T2 = __shfl_sync(0xffffffffu, Ta, 31);
+      r2 = __shfl_sync(0xffffffffu, sr, 31); g2 = __shfl_sync(0xffffffffu, sg, 31);
+      b2 = __shfl_sync(0xffffffffu, sb, 31); d2 = __shfl_sync(0xffffffffu, sd, 31);
     }
-    reinterpret_cast<float4*>(dout)[base + k] = g;   // d/d(raw rgb outputs), d/d(o0)
+    if (k < n) reinterpret_cast<float4*>(dout)[base + k] = g;     // d/d(raw rgb outputs), d/d(o0)
   }
 }
 
@@ -703,13 +802,13 @@ int nslam_ngp_train_step(const nslam_ngp_model* m, const nslam_ngp_images* im, c
   cudaMemsetAsync(b->loss, 0, sizeof(float), st);
   const LevelInfo lv = make_lv(m);
   const Scene sc = make_scene(m);
-  sample_rays_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(make_store(im), sc, m->bits, n_rays, seed,
+  sample_rays_kernel<<<(n_rays + 3) / 4, 128, 0, st>>>(make_store(im), sc, m->bits, n_rays, seed,
                                                          b->max_samples, b->rays, b->coords, b->tdist, b->counters);
   NGP_CHECK_LAUNCH();
   forward_kernel<<<(b->max_samples + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>(
       b->coords, b->counters, -1, (const __half2*)m->grid_half, lv, m->mlp, b->rgbsigma);
   NGP_CHECK_LAUNCH();
-  loss_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma,
+  loss_kernel<<<(n_rays + 3) / 4, 128, 0, st>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma,
                                                      b->counters, lambda_depth, make_float3(bg_r, bg_g, bg_b),
                                                      0, b->dout, b->loss, nullptr);
   NGP_CHECK_LAUNCH();
@@ -728,7 +827,7 @@ int nslam_ngp_sample_phase(const nslam_ngp_model* m, const nslam_ngp_images* im,
   if (n_rays > b->max_rays) return (int)cudaErrorInvalidValue;
   cudaMemsetAsync(b->counters, 0, 4 * sizeof(int), st);
   cudaMemsetAsync(b->loss, 0, sizeof(float), st);
-  sample_rays_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(make_store(im), make_scene(m), m->bits, n_rays, seed,
+  sample_rays_kernel<<<(n_rays + 3) / 4, 128, 0, st>>>(make_store(im), make_scene(m), m->bits, n_rays, seed,
                                                          b->max_samples, b->rays, b->coords, b->tdist, b->counters);
   NGP_CHECK_LAUNCH();
   return 0;
@@ -737,7 +836,7 @@ int nslam_ngp_sample_phase(const nslam_ngp_model* m, const nslam_ngp_images* im,
 int nslam_ngp_loss_phase(const nslam_ngp_batch* b, int n_rays, float lambda_depth, float bg_r, float bg_g,
                          float bg_b, void* stream) {
   using namespace ngp;
-  loss_kernel<<<(n_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma,
+  loss_kernel<<<(n_rays + 3) / 4, 128, 0, (cudaStream_t)stream>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma,
                                                                        b->counters, lambda_depth,
                                                                        make_float3(bg_r, bg_g, bg_b), 0, b->dout, b->loss, nullptr);
   NGP_CHECK_LAUNCH();
@@ -787,7 +886,7 @@ int nslam_ngp_loss_backward(const nslam_ngp_model* m, const nslam_ngp_batch* b, 
   forward_kernel<<<(n_samples + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>(b->coords, b->counters, -1,
                                                                        (const __half2*)m->grid_half, lv, m->mlp, b->rgbsigma);
   NGP_CHECK_LAUNCH();
-  loss_kernel<<<(n_rays + 127) / 128, 128, 0, st>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma, b->counters,
+  loss_kernel<<<(n_rays + 3) / 4, 128, 0, st>>>(b->rays, n_rays, b->coords, b->tdist, b->rgbsigma, b->counters,
                                                      lambda_depth, make_float3(bg_r, bg_g, bg_b), 0, b->dout, b->loss, nullptr);
   NGP_CHECK_LAUNCH();
   backward_kernel<<<2 * num_sms, TILE, BWD_SMEM, st>>>(b->coords, b->counters, (const __half2*)m->grid_half, lv,
@@ -836,13 +935,13 @@ int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, co
   cam.w = (int)cam16[16]; cam.h = (int)cam16[17];
   cudaMemsetAsync(b->counters, 0, 4 * sizeof(int), st);
   const LevelInfo lv = make_lv(m);
-  render_rays_kernel<<<(tw * th + 127) / 128, 128, 0, st>>>(cam, make_scene(m), m->bits, x0, y0, tw, th,
+  render_rays_kernel<<<(tw * th + 3) / 4, 128, 0, st>>>(cam, make_scene(m), m->bits, x0, y0, tw, th,
                                                            b->max_samples, max_per_ray, b->rays, b->coords, b->tdist, b->counters);
   NGP_CHECK_LAUNCH();
   forward_kernel<<<(b->max_samples + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>(b->coords, b->counters, -1,
                                                                             (const __half2*)m->grid_half, lv, m->mlp, b->rgbsigma);
   NGP_CHECK_LAUNCH();
-  loss_kernel<<<(tw * th + 127) / 128, 128, 0, st>>>(b->rays, tw * th, b->coords, b->tdist, b->rgbsigma, b->counters,
+  loss_kernel<<<(tw * th + 3) / 4, 128, 0, st>>>(b->rays, tw * th, b->coords, b->tdist, b->rgbsigma, b->counters,
                                                       0.f, make_float3(bg_r, bg_g, bg_b), 1, nullptr, nullptr, out_rgbd);
   NGP_CHECK_LAUNCH();
   return 0;

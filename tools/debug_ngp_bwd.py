@@ -36,6 +36,7 @@ for (R, per) in ((1, 8), (8, 16), (24, 11), (300, 13)):
         a = res["simt"][0][off:off + i * o].view(i, o); b = res["tc"][0][off:off + i * o].view(i, o); off += i * o
         err = float((a - b).abs().max() / (a.abs().max() + 1e-20))
         rowerr = ((a - b).abs().max(1).values / (a.abs().max() + 1e-20))
-        print(f"  {name}: rel err {err:.3e}  |ref|max {float(a.abs().max()):.3e}  finite {bool(torch.isfinite(b).all())}  worst rows {rowerr.topk(3).indices.tolist()} cols {((a-b).abs().max(0).values).topk(3).indices.tolist()}")
+        fro = float((a - b).norm() / (a.norm() + 1e-20))
+        print(f"  {name}: fro {fro:.3e} rel err {err:.3e}  |ref|max {float(a.abs().max()):.3e}  finite {bool(torch.isfinite(b).all())}  worst rows {rowerr.topk(3).indices.tolist()} cols {((a-b).abs().max(0).values).topk(3).indices.tolist()}")
     a, b = res["simt"][1], res["tc"][1]
-    print(f"  grid: rel err {float((a - b).abs().max() / (a.abs().max() + 1e-20)):.3e}")
+    print(f"  grid: fro {float((a - b).norm() / (a.norm() + 1e-20)):.3e} rel err {float((a - b).abs().max() / (a.abs().max() + 1e-20)):.3e}")
