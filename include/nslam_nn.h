@@ -19,6 +19,35 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
                      int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
                      void* out0, int out0_channels, void* out1, int num_sms, void* stream);
 
+/* ---- fused glue around the update operator (csrc/update_glue.cu); all DEVICE pointers -------------
+ * motion_im2col: motion = clamp([coords1-coords0 | target-coords1], +-64) (visual_frontend.py:392-394)
+ *   laid out as the 7x7 im2col [E,ht,wd,200] fp16 (tap-major, 4 channels per tap, cols 196..199 zero) so
+ *   that flow_encoder.0 (droid_net.py:95) runs as a 1x1 GEMM; target may be NULL (motion filter: zeros).
+ * flow_heads_post: h2 [E,ht,wd,16] fp16 (delta | weight logits, droid_net.py:138-139) ->
+ *   flow = coords1 + delta, conf = sigmoid(.) as [E,ht,wd,2] fp32 and (optional) planar [E,2,ht,wd] copies
+ *   straight into the BA input buffers (visual_frontend.py:404-405,431-436).
+ * segment_mean: GraphAgg scatter_mean over edges with the same source keyframe (droid_net.py:67);
+ *   seg_ptr [K+1], seg_edges [E] (CSR, host-built), a [E,hw,128] fp16 -> out [K,hw,128] fp16.
+ * eta_damping: e16 [K,hw,16] fp16 -> damping[ux[k]] = 0.01 softplus(col 0) (droid_net.py:73);
+ *   ba_damp[j] = 0.2 damping[kx_ba[j]] + ep (visual_frontend.py:423). */
+int nslam_motion_im2col(const float* coords1, const float* coords0, const float* target, void* out,
+                        int E, int ht, int wd, void* stream);
+int nslam_flow_heads_post(const void* h2, const float* coords1, float* flow, float* conf, float* ba_target,
+                          float* ba_weight, int E, int hw, void* stream);
+int nslam_segment_mean(const void* a, const int* seg_ptr, const int* seg_edges, void* out, int K, int hw,
+                       void* stream);
+int nslam_eta_damping(const void* e16, const long long* ux, float* damping, int K, const long long* kx_ba,
+                      float* ba_damp, int Kba, int hw, float ep, void* stream);
+
+/* ---- instance norm of the feature encoder (csrc/inorm.cu), NHWC fp16 ----------------------------------
+ * Replaces F.instance_norm + ReLU (+ residual add + ReLU) of BasicEncoder/ResidualBlock with
+ * norm_fn='instance' (networks/modules/extractor.py:6-60,118-198): biased variance, eps 1e-5, fp32
+ * statistics, fp16 rounding after the normalisation and after the residual add like the library path.
+ * stats [B,C,2] = per-(image, channel) sum and sum of squares. */
+int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, void* stream);
+int nslam_inorm_apply(const void* x, const float* stats, const void* res, const float* res_stats, void* out,
+                      int B, int HW, int C, float eps, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,13 @@ _SIGNATURES = {
     "nslam_iproj": [_P, _P, _P, c_int, c_int, c_int, _P, _P],
     "nslam_depth_filter": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "nslam_cvx_upsample": [_P, _P, c_int, _P, c_int, c_int, c_int, c_float, c_int, _P],
+    "nslam_cvx_upsample2": [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P],
+    "nslam_motion_im2col": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
+    "nslam_flow_heads_post": [_P, _P, _P, _P, _P, _P, c_int, c_int, _P],
+    "nslam_segment_mean": [_P, _P, _P, _P, c_int, c_int, _P],
+    "nslam_eta_damping": [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P],
+    "nslam_inorm_stats": [_P, _P, c_int, c_int, c_int, _P],
+    "nslam_inorm_apply": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P],
     "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],
     "nslam_ba_solve": [_P, _P, c_int, c_int, _P, c_float, c_float, c_float, _P, _P, _P, _P, _P],
     "nslam_ba_retract": [_P, _P, _P, _P, c_int, c_int, _P],

@@ -12,13 +12,13 @@ Fusions (what replaces what):
   glo             : 1x1 conv with epilogue sigmoid(.)*net and per-image column sums (conv + mul + mean)
   delta.0|weight.0: ONE conv with N=256 from the shared input
   delta.2|weight.2: ONE block-diagonal conv with N=16
-The 7x7 conv on the 4-channel motion input (1 % of the FLOPs, K=196 not a multiple of 64) stays on
-the library path for now.
+The 7x7 conv on the 4-channel motion input runs as a 1x1 GEMM on an im2col tile written by
+nslam_motion_im2col together with the motion features themselves; the head outputs, GraphAgg's
+scatter-mean and the damping update are small fused kernels (csrc/update_glue.cu).
 """
 import ctypes
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 
@@ -64,14 +64,13 @@ def conv_tc(srcs, wpacked, bias, B, H, W, KH, pad, N, mode=0, act=0, gctx=None, 
 
 
 CORR_PAD = 200      # 196 correlation channels padded to a multiple of 8 (TMA stride rule), zero tail
+MOTION_COLS = 200   # 7x7x4 im2col of the motion input (196) padded the same way
 
 
 class UpdateOperatorTC:
     """drop-in for networks.UpdateModule.__call__ with NHWC tensors.
 
-    __call__(net [E,ht,wd,128] f16, inp [E,ht,wd,128] f16, corr [E,ht,wd,CORR_PAD] f16,
-             motion [E,4,ht,wd] f32|f16 or None, ii (device long) or None)
-      -> net' [E,ht,wd,128], delta [E,ht,wd,2] f32, weight [E,ht,wd,2] f32 (, eta [K,ht,wd] f32, upmask [K,ht,wd,576] f16)
+    see __call__.
     """
 
     def __init__(self, params, device):
@@ -86,8 +85,10 @@ class UpdateOperatorTC:
         # 64-blocks coincide with those of 196 real channels (4 blocks either way)
         P["ce2"] = (pack_weights(sd["corr_encoder.2.weight"], [128]), f32(sd["corr_encoder.2.bias"]))
         P["fe2"] = (pack_weights(sd["flow_encoder.2.weight"], [128]), f32(sd["flow_encoder.2.bias"]))
-        self.fe0_w = sd["flow_encoder.0.weight"].half().contiguous(memory_format=torch.channels_last)
-        self.fe0_b = sd["flow_encoder.0.bias"].half()
+        # 7x7 conv on the 4-channel motion input = 1x1 GEMM on its im2col (csrc/update_glue.cu): K index = tap*4 + c
+        w0 = torch.zeros(128, MOTION_COLS, 1, 1, device=device)
+        w0[:, :196, 0, 0] = sd["flow_encoder.0.weight"].permute(0, 2, 3, 1).reshape(128, 196)
+        P["fe0"] = (pack_weights(w0, [MOTION_COLS]), f32(sd["flow_encoder.0.bias"]))
         P["glo"] = (pack_weights(sd["gru.w.weight"], [128]), f32(sd["gru.w.bias"]))
         src4 = [128, 128, 128, 64]
         P["zr"] = (pack_weights(torch.cat([sd["gru.convz.weight"], sd["gru.convr.weight"]], 0), src4),
@@ -115,20 +116,27 @@ class UpdateOperatorTC:
         conv_tc(srcs, wp, b, B, H, W, k, k // 2, N, out0=out, out0_channels=out.shape[-1] if out is not None else 0,
                 num_sms=self.num_sms, **kw)
 
-    def __call__(self, net, inp, corr, motion=None, ii=None, agg=None):
+    def __call__(self, net, inp, corr, coords1, coords0, target=None, agg=None, post=None):
+        """net, inp [E,ht,wd,128] f16; corr [E,ht,wd,CORR_PAD] f16; coords1 [E,ht,wd,2] f32 (reprojected
+        grid), coords0 [ht,wd,2] f32, target [E,ht,wd,2] f32 or None (-> zero flow residual).
+        agg = (seg_ptr int32 [K+1], seg_edges int32 [E], K): CSR of the edges per source keyframe, or None.
+        post = (flow, conf, ba_target, ba_weight) output tensors ([E,ht,wd,2] x2, planar [E,2,ht,wd] x2
+        or None x2), or None to allocate flow/conf.
+        -> net' [E,ht,wd,128] f16, flow = coords1 + delta, conf = sigmoid(weight logits)
+           (, e16 [K,ht,wd,16] f16 with the eta logit in column 0, upmask [K,ht,wd,576] f16)"""
+        lib = _lib.load()
         E, H, W, _ = net.shape
         dev = net.device
         h16 = dict(dtype=torch.float16, device=dev)
         new = lambda c: torch.empty(E, H, W, c, **h16)
+        sp = _lib.stream_ptr()
         # correlation / motion encoders
         c1 = new(128); self._conv("ce0", [corr], E, H, W, 1, 128, c1, act=1)
         c2 = new(128); self._conv("ce2", [c1], E, H, W, 3, 128, c2, act=1)
-        if motion is None:
-            motion = torch.zeros(E, 4, H, W, **h16)
-        f1 = F.relu(F.conv2d(motion.half().contiguous(memory_format=torch.channels_last), self.fe0_w, self.fe0_b, padding=3), inplace=True)
-        f1 = f1.permute(0, 2, 3, 1)                                 # NHWC view of channels_last storage
-        if not f1.is_contiguous():
-            f1 = f1.contiguous()
+        mcol = new(MOTION_COLS)
+        _lib.check(lib.nslam_motion_im2col(_lib.ptr(coords1), _lib.ptr(coords0), _lib.ptr(target), _lib.ptr(mcol),
+                                           E, H, W, sp), "motion_im2col")
+        f1 = new(128); self._conv("fe0", [mcol], E, H, W, 1, 128, f1, act=1)
         f2 = new(64); self._conv("fe2", [f1], E, H, W, 3, 64, f2, act=1)
         # global context: glo = mean_hw(sigmoid(w(net)) * net) ; then the three 1x1 "glo" convs as one GEMV batch
         gsum = torch.zeros(E, 128, dtype=torch.float32, device=dev)
@@ -148,24 +156,47 @@ class UpdateOperatorTC:
         # heads
         h0 = new(256); self._conv("h0", [net2], E, H, W, 3, 256, h0, act=1)
         h2 = new(16); self._conv("h2", [h0], E, H, W, 3, 16, h2, act=0)
-        delta = h2[..., 0:2].float()
-        weight = torch.sigmoid(h2[..., 2:4].float())
-        if ii is None:
-            return net2, delta, weight
+        if post is None:
+            post = (torch.empty(E, H, W, 2, device=dev), torch.empty(E, H, W, 2, device=dev), None, None)
+        flow, conf, ba_t, ba_w = post
+        _lib.check(lib.nslam_flow_heads_post(_lib.ptr(h2), _lib.ptr(coords1), _lib.ptr(flow), _lib.ptr(conf),
+                                             _lib.ptr(ba_t), _lib.ptr(ba_w), E, H * W, sp), "flow_heads_post")
+        if agg is None:
+            return net2, flow, conf
         # GraphAgg
+        seg_ptr, seg_edges, K = agg
         a1 = new(128); self._conv("a1", [net2], E, H, W, 3, 128, a1, act=1)
-        if agg is not None:
-            ix, K = agg                                  # precomputed on the host: no device sync
-        else:
-            _, ix = torch.unique(ii, return_inverse=True)
-            K = int(ix.max().item()) + 1
-        s = torch.zeros(K, H, W, 128, dtype=torch.float32, device=dev).index_add_(0, ix, a1.float())
-        cnt = torch.zeros(K, dtype=torch.float32, device=dev).index_add_(0, ix, torch.ones_like(ix, dtype=torch.float32))
-        am = (s / cnt.view(-1, 1, 1, 1)).half()
+        am = torch.empty(K, H, W, 128, **h16)
+        _lib.check(lib.nslam_segment_mean(_lib.ptr(a1), _lib.ptr(seg_ptr), _lib.ptr(seg_edges), _lib.ptr(am), K, H * W, sp),
+                   "segment_mean")
         a2 = torch.empty(K, H, W, 128, **h16); self._conv("a2", [am], K, H, W, 3, 128, a2, act=1)
         e16 = torch.empty(K, H, W, 16, **h16); self._conv("eta", [a2], K, H, W, 3, 16, e16, act=0)
-        eta = 0.01 * F.softplus(e16[..., 0].float())
         upmask = torch.empty(K, H, W, 576, **h16)
         for wp, b, c0, n in self.P["um"]:
             conv_tc([a2], wp, b, K, H, W, 1, 0, n, out0=upmask[..., c0:], out0_channels=576, num_sms=self.num_sms)
-        return net2, delta, weight, eta, upmask
+        return net2, flow, conf, e16, upmask
+
+    def call_reference_convention(self, net, inp, corr, motion, ii=None):
+        """UpdateModule.forward's own argument/return convention (droid_net.py:118-150) on top of the fused
+        operator — used by the parity tests: motion [E,4,ht,wd] (|.| < 64) is turned into the coordinate
+        tensors it is derived from in the frontend; returns net, delta, weight (, eta, upmask NHWC)."""
+        import numpy as np
+        E, H, W, _ = net.shape
+        dev = net.device
+        yy, xx = torch.meshgrid(torch.arange(H, device=dev).float(), torch.arange(W, device=dev).float(), indexing="ij")
+        coords0 = torch.stack([xx, yy], -1).contiguous()
+        m = motion.float().permute(0, 2, 3, 1)
+        coords1 = (coords0[None] + m[..., 0:2]).contiguous()
+        target = (coords1 + m[..., 2:4]).contiguous()
+        agg = None
+        if ii is not None:
+            ux, inv = np.unique(ii.cpu().numpy(), return_inverse=True)
+            order = np.argsort(inv, kind="stable").astype(np.int32)
+            ptr = np.zeros(len(ux) + 1, np.int32); np.cumsum(np.bincount(inv, minlength=len(ux)), out=ptr[1:])
+            agg = (torch.as_tensor(ptr, device=dev), torch.as_tensor(order, device=dev), len(ux))
+        out = self(net, inp, corr, coords1, coords0, target=target, agg=agg)
+        delta = out[1] - coords1
+        if ii is None:
+            return out[0], delta, out[2]
+        eta = 0.01 * torch.nn.functional.softplus(out[3][..., 0].float())
+        return out[0], delta, out[2], eta, out[4]

@@ -1,0 +1,158 @@
+// A19 — small fused kernels around the update operator (what PyTorch would run as ~25 elementwise /
+// indexing launches per update(): reference slam/visual_frontends/visual_frontend.py:371-470 and
+// networks/droid_net.py:59-75,118-150).
+//
+//   nslam_motion_im2col   motion = clamp([coords1 - coords0 | target - coords1], +-64) and its 7x7
+//                         im2col (49 taps x 4 channels, zero padded, fp16) in one pass: the 7x7
+//                         flow-encoder conv then runs as a 1x1 tensor-core GEMM (K = 196 -> 200).
+//   nslam_flow_heads_post delta/weight heads -> new flow target = coords1 + delta, confidence =
+//                         sigmoid(.), written both in the frontend's [E,ht,wd,2] state and in the
+//                         BA's planar [E,2,ht,wd] input buffers.
+//   nslam_segment_mean    GraphAgg's scatter_mean over edges that share the source keyframe
+//                         (droid_net.py:67), fp32 accumulation in edge order, fp16 out.
+//   nslam_eta_damping     eta = 0.01 softplus(.) -> damping[ux]; BA damping = 0.2 damping[kx] + EP.
+// All HBM-bound, one pass over their tensors.
+#include "common.cuh"
+
+namespace nslam {
+
+constexpr int MI_C = 200;    // im2col row: 196 real values + 4 zeros (TMA rows must be 16-byte multiples)
+
+// one thread per (pixel, tap): 4 motion channels of the tap's source pixel -> 8 bytes
+__global__ void motion_im2col_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0,
+                                     const float* __restrict__ target, __half* __restrict__ out,
+                                     int E, int ht, int wd) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)E * ht * wd * 50;
+  if (id >= total) return;
+  const int tap = (int)(id % 50);
+  const size_t pix = id / 50;
+  const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
+  const int e = (int)(pix / ((size_t)wd * ht));
+  uint2 v = make_uint2(0u, 0u);
+  if (tap < 49) {
+    const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
+    if (yy >= 0 && yy < ht && xx >= 0 && xx < wd) {
+      const size_t q = ((size_t)e * ht + yy) * wd + xx;
+      const float2 c1 = reinterpret_cast<const float2*>(coords1)[q];
+      const float2 c0 = reinterpret_cast<const float2*>(coords0)[(size_t)yy * wd + xx];
+      const float2 tg = target ? reinterpret_cast<const float2*>(target)[q] : c1;
+      const float m0 = fminf(fmaxf(c1.x - c0.x, -64.f), 64.f), m1 = fminf(fmaxf(c1.y - c0.y, -64.f), 64.f);
+      const float m2 = fminf(fmaxf(tg.x - c1.x, -64.f), 64.f), m3 = fminf(fmaxf(tg.y - c1.y, -64.f), 64.f);
+      const __half2 a = __floats2half2_rn(m0, m1), b = __floats2half2_rn(m2, m3);
+      v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+  }
+  *reinterpret_cast<uint2*>(out + pix * MI_C + tap * 4) = v;
+}
+
+// h2 [E,ht,wd,16] fp16: cols 0,1 = delta, cols 2,3 = weight logits
+__global__ void flow_heads_post_kernel(const __half* __restrict__ h2, const float* __restrict__ coords1,
+                                       float* __restrict__ flow, float* __restrict__ conf,
+                                       float* __restrict__ ba_target, float* __restrict__ ba_weight,
+                                       int E, int hw) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (id >= (size_t)E * hw) return;
+  const uint2 raw = *reinterpret_cast<const uint2*>(h2 + id * 16);
+  const __half2 d = *reinterpret_cast<const __half2*>(&raw.x), w = *reinterpret_cast<const __half2*>(&raw.y);
+  const float2 c1 = reinterpret_cast<const float2*>(coords1)[id];
+  const float2 f = make_float2(c1.x + __low2float(d), c1.y + __high2float(d));
+  const float2 s = make_float2(1.f / (1.f + __expf(-__low2float(w))), 1.f / (1.f + __expf(-__high2float(w))));
+  reinterpret_cast<float2*>(flow)[id] = f;
+  reinterpret_cast<float2*>(conf)[id] = s;
+  if (ba_target) {
+    const size_t e = id / hw, p = id % hw;
+    ba_target[(e * 2 + 0) * hw + p] = f.x; ba_target[(e * 2 + 1) * hw + p] = f.y;
+    ba_weight[(e * 2 + 0) * hw + p] = s.x; ba_weight[(e * 2 + 1) * hw + p] = s.y;
+  }
+}
+
+// out[k, p, :] = mean_{e in seg k} a[e, p, :]   (128 channels; one thread = 8 channels of one pixel)
+__global__ void segment_mean_kernel(const __half* __restrict__ a, const int* __restrict__ seg_ptr,
+                                    const int* __restrict__ seg_edges, __half* __restrict__ out, int K, int hw) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (id >= (size_t)K * hw * 16) return;
+  const int c8 = (int)(id % 16);
+  const size_t p = (id / 16) % hw;
+  const int k = (int)(id / ((size_t)16 * hw));
+  const int s0 = seg_ptr[k], s1 = seg_ptr[k + 1];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = s0; s < s1; s++) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(a + ((size_t)seg_edges[s] * hw + p) * 128 + c8 * 8);
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] += __half2float(h[j]);
+  }
+  const float inv = 1.f / (float)max(s1 - s0, 1);
+  __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) o[j] = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
+  *reinterpret_cast<uint4*>(out + ((size_t)k * hw + p) * 128 + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// e16 [K,hw,16] fp16 (col 0 = eta logit) -> damping[ux[k]] = 0.01 softplus ; then (second launch)
+// ba_damp[j] = 0.2 damping[kx[j]] + EP
+__global__ void eta_kernel(const __half* __restrict__ e16, const long long* __restrict__ ux,
+                           float* __restrict__ damping, int K, int hw) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (id >= (size_t)K * hw) return;
+  const float x = __half2float(e16[id * 16]);
+  const float sp = x > 20.f ? x : log1pf(expf(x));           // F.softplus (threshold 20)
+  damping[(size_t)ux[id / hw] * hw + id % hw] = 0.01f * sp;
+}
+__global__ void ba_damp_kernel(const float* __restrict__ damping, const long long* __restrict__ kx,
+                               float* __restrict__ out, int K, int hw, float ep) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (id >= (size_t)K * hw) return;
+  out[id] = 0.2f * damping[(size_t)kx[id / hw] * hw + id % hw] + ep;
+}
+
+}  // namespace nslam
+
+extern "C" {
+
+int nslam_motion_im2col(const float* coords1, const float* coords0, const float* target, void* out,
+                        int E, int ht, int wd, void* stream) {
+  const size_t total = (size_t)E * ht * wd * 50;
+  if (total == 0) return 0;
+  nslam::motion_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      coords1, coords0, target, (__half*)out, E, ht, wd);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+int nslam_flow_heads_post(const void* h2, const float* coords1, float* flow, float* conf, float* ba_target,
+                          float* ba_weight, int E, int hw, void* stream) {
+  const size_t total = (size_t)E * hw;
+  if (total == 0) return 0;
+  nslam::flow_heads_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)h2, coords1, flow, conf, ba_target, ba_weight, E, hw);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+int nslam_segment_mean(const void* a, const int* seg_ptr, const int* seg_edges, void* out, int K, int hw,
+                       void* stream) {
+  const size_t total = (size_t)K * hw * 16;
+  if (total == 0) return 0;
+  nslam::segment_mean_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, seg_ptr, seg_edges, (__half*)out, K, hw);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+int nslam_eta_damping(const void* e16, const long long* ux, float* damping, int K, const long long* kx_ba,
+                      float* ba_damp, int Kba, int hw, float ep, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K > 0) {
+    nslam::eta_kernel<<<(unsigned)(((size_t)K * hw + 255) / 256), 256, 0, st>>>((const __half*)e16, ux, damping, K, hw);
+    NSLAM_CHECK_LAUNCH();
+  }
+  if (Kba > 0 && ba_damp) {
+    nslam::ba_damp_kernel<<<(unsigned)(((size_t)Kba * hw + 255) / 256), 256, 0, st>>>(damping, kx_ba, ba_damp, Kba, hw, ep);
+    NSLAM_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -20,24 +20,32 @@ template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 
-constexpr int UX = 32;  // coarse pixels per CTA
+constexpr int UX = 32;        // coarse pixels per CTA
+constexpr int UROW = 576 + 8; // smem row (one coarse pixel) for channels-last masks: +8 halfs keeps the
+                              // 4 pixels a warp touches on distinct banks
 
-// grid: (ceil(wd/UX), ht, K)  block: 256
-template <typename T>
+// grid: (ceil(wd/UX), ht, K)  block: 256.  Up to two data planes share one softmax (inverse depth
+// and its covariance are upsampled with the same mask, visual_frontend.py:444-446).
+template <typename T, bool NHWC>
 __global__ void __launch_bounds__(256)
-cvx_upsample_kernel(const float* __restrict__ data, const T* __restrict__ mask,
-                    float* __restrict__ out, int ht, int wd, float pw, int mask_nhwc) {
+cvx_upsample_kernel(const float* __restrict__ data, const float* __restrict__ data2, const T* __restrict__ mask,
+                    float* __restrict__ out, float* __restrict__ out2, const long long* __restrict__ index,
+                    int ht, int wd, float pw) {
   extern __shared__ unsigned char smraw[];
-  T* ms = reinterpret_cast<T*>(smraw);  // [576][UX]
-  __shared__ float nb[3][UX + 2];
+  T* ms = reinterpret_cast<T*>(smraw);  // NHWC: [UX][UROW]   NCHW: [576][UX]
+  __shared__ float nb[2][3][UX + 2];
   const int k = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * UX;
   const int hw = ht * wd;
-  if (mask_nhwc) {
-    // channels-last mask [K,ht,wd,576] (what the tensor-core update operator produces)
+  const size_t kd = index ? (size_t)index[k] : (size_t)k;     // row of data / out this mask plane applies to
+  if (NHWC) {
+    // channels-last mask [K,ht,wd,576] (what the tensor-core update operator produces): 16-byte copies
     const T* mk = mask + ((size_t)k * hw + (size_t)y * wd + x0) * 576;
-    for (int id = threadIdx.x; id < 576 * UX; id += 256) {
-      const int xx = id / 576, c = id % 576;
-      ms[c * UX + xx] = (x0 + xx < wd) ? mk[(size_t)xx * 576 + c] : T(0);
+    constexpr int V = 16 / sizeof(T), NV = 576 / V;
+    for (int id = threadIdx.x; id < NV * UX; id += 256) {
+      const int xx = id / NV, c = (id % NV) * V;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (x0 + xx < wd) v = *reinterpret_cast<const uint4*>(mk + (size_t)xx * 576 + c);
+      *reinterpret_cast<uint4*>(ms + xx * UROW + c) = v;
     }
   } else {
     const T* mk = mask + (size_t)k * 576 * hw + (size_t)y * wd + x0;
@@ -46,10 +54,11 @@ cvx_upsample_kernel(const float* __restrict__ data, const T* __restrict__ mask,
       ms[id] = (x0 + xx < wd) ? mk[(size_t)c * hw + xx] : T(0);
     }
   }
-  for (int id = threadIdx.x; id < 3 * (UX + 2); id += 256) {
-    const int r = id / (UX + 2), xx = id % (UX + 2);
+  for (int id = threadIdx.x; id < 2 * 3 * (UX + 2); id += 256) {
+    const int pl = id / (3 * (UX + 2)), r = (id / (UX + 2)) % 3, xx = id % (UX + 2);
     const int yy = y + r - 1, xg = x0 + xx - 1;
-    nb[r][xx] = (yy >= 0 && yy < ht && xg >= 0 && xg < wd) ? data[(size_t)k * hw + yy * wd + xg] : 0.f;
+    const float* src = pl ? data2 : data;
+    nb[pl][r][xx] = (src && yy >= 0 && yy < ht && xg >= 0 && xg < wd) ? src[kd * hw + yy * wd + xg] : 0.f;
   }
   __syncthreads();
   // 8 x (8*UX) outputs; thread -> (sy, X)
@@ -64,48 +73,63 @@ cvx_upsample_kernel(const float* __restrict__ data, const T* __restrict__ mask,
     for (int n = 0; n < 9; n++) {
       const int dy = n / 3 - 1, dx = n % 3 - 1;
       const bool inb = (y + dy >= 0) && (y + dy < ht) && (x + dx >= 0) && (x + dx < wd);
-      m[n] = inb ? to_f<T>(ms[(n * 64 + sy * 8 + sx) * UX + xx]) : -INFINITY;
+      const int c = n * 64 + sy * 8 + sx;
+      m[n] = inb ? to_f<T>(NHWC ? ms[xx * UROW + c] : ms[c * UX + xx]) : -INFINITY;
       mx = fmaxf(mx, m[n]);
     }
     float e[9], sum = 0.f;
 #pragma unroll
     for (int n = 0; n < 9; n++) { e[n] = expf(m[n] - mx); sum += e[n]; }
-    float acc = 0.f;
+    float acc = 0.f, acc2 = 0.f;
 #pragma unroll
     for (int n = 0; n < 9; n++) {
       float wgt = e[n] / sum;
       if (sizeof(T) == 2) wgt = __half2float(__float2half_rn(wgt));
       if (pw != 1.0f) wgt = powf(wgt, pw);
-      acc += wgt * nb[n / 3][xx + n % 3];
+      acc += wgt * nb[0][n / 3][xx + n % 3];
+      acc2 += wgt * nb[1][n / 3][xx + n % 3];
     }
-    out[((size_t)k * 8 * ht + (size_t)y * 8 + sy) * W8 + (size_t)x0 * 8 + X] = acc;
+    const size_t o = (kd * 8 * ht + (size_t)y * 8 + sy) * W8 + (size_t)x0 * 8 + X;
+    out[o] = acc;
+    if (out2) out2[o] = acc2;
   }
+}
+
+template <typename T, bool NHWC>
+static int launch_upsample(const float* data, const float* data2, const void* mask, float* out, float* out2,
+                           const long long* index, int K, int ht, int wd, float pw, cudaStream_t st) {
+  dim3 grid((wd + UX - 1) / UX, ht, K);
+  const size_t smem = (NHWC ? (size_t)UX * UROW : (size_t)576 * UX) * sizeof(T);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(cvx_upsample_kernel<T, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cvx_upsample_kernel<T, NHWC><<<grid, 256, smem, st>>>(data, data2, (const T*)mask, out, out2, index, ht, wd, pw);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
 }
 
 }  // namespace nslam
 
-extern "C" int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out,
-                                  int K, int ht, int wd, float pw, int mask_nhwc, void* stream) {
+/* data2/out2 may be NULL (single plane) */
+extern "C" int nslam_cvx_upsample2(const float* data, const float* data2, const void* mask, int mask_dtype,
+                                   float* out, float* out2, const long long* index, int K, int ht, int wd,
+                                   float pw, int mask_nhwc, void* stream) {
   using namespace nslam;
   if (K == 0) return 0;
-  dim3 grid((wd + UX - 1) / UX, ht, K);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mask_dtype == 0) {
-    const size_t smem = 576 * UX * sizeof(__half);
-    cvx_upsample_kernel<__half><<<grid, 256, smem, st>>>(data, (const __half*)mask, out, ht, wd, pw, mask_nhwc);
-  } else if (mask_dtype == 1) {
-    const size_t smem = 576 * UX * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(cvx_upsample_kernel<float>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      configured = true;
-    }
-    cvx_upsample_kernel<float><<<grid, 256, smem, st>>>(data, (const float*)mask, out, ht, wd, pw, mask_nhwc);
-  } else {
-    return (int)cudaErrorInvalidValue;
-  }
-  NSLAM_CHECK_LAUNCH();
-  return 0;
+  if (mask_dtype == 0)
+    return mask_nhwc ? launch_upsample<__half, true>(data, data2, mask, out, out2, index, K, ht, wd, pw, st)
+                     : launch_upsample<__half, false>(data, data2, mask, out, out2, index, K, ht, wd, pw, st);
+  if (mask_dtype == 1)
+    return mask_nhwc ? launch_upsample<float, true>(data, data2, mask, out, out2, index, K, ht, wd, pw, st)
+                     : launch_upsample<float, false>(data, data2, mask, out, out2, index, K, ht, wd, pw, st);
+  return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, float* out,
+                                  int K, int ht, int wd, float pw, int mask_nhwc, void* stream) {
+  return nslam_cvx_upsample2(data, nullptr, mask, mask_dtype, out, nullptr, nullptr, K, ht, wd, pw, mask_nhwc, stream);
 }

@@ -221,6 +221,20 @@ def cvx_upsample(data, mask, pow=1.0, mask_nhwc=False):
     return out.unsqueeze(-1)
 
 
+def cvx_upsample2(data, data2, mask, out, out2, pow=1.0, index=None):
+    """two planes (inverse depth + depth covariance) through one softmax of a channels-last mask
+    [K,ht,wd,576].  data*/out* are fp32 contiguous [*,ht,wd] / [*,8ht,8wd]; plane k of the mask is applied to
+    row index[k] of data/out (int64 device tensor; identity when None).  Writes out/out2 in place."""
+    lib = _lib.load()
+    K, ht, wd = mask.shape[0], data.shape[-2], data.shape[-1]
+    assert mask.is_contiguous() and mask.shape[-1] == 576
+    for t in (data, data2, out, out2):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    _lib.check(lib.nslam_cvx_upsample2(_lib.ptr(data), _lib.ptr(data2), _lib.ptr(mask), _DT[mask.dtype],
+                                       _lib.ptr(out), _lib.ptr(out2), _lib.ptr(index), K, ht, wd, float(pow), 1,
+                                       _lib.stream_ptr()), "cvx_upsample2")
+
+
 # ------------------------------------------------------------------------------------------ BA
 class BAProblem:
     """Device buffers + graph tables of one BA window; owns everything the kernels touch."""

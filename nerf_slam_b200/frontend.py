@@ -245,15 +245,33 @@ class RaftVisualFrontend:
         c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
         return torch.tanh(c[..., :128]), torch.relu(c[..., 128:])
 
-    def _run_update_net(self, net, inp, corr_nhwc, motion, ii=None, agg=None):
-        """update operator on NHWC tensors: net/inp [E,ht,wd,128], corr [E,ht,wd,CORR_PAD], motion [E,4,ht,wd]
-        -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32 (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576]).
-        agg = (ix, K): host-precomputed inverse index of unique(ii) (keeps the call free of device syncs)."""
+    @staticmethod
+    def _agg_tables(ii_host, device):
+        """CSR of the edges per source keyframe for GraphAgg (host-built: no device sync)"""
+        ux, inv = np.unique(np.asarray(ii_host), return_inverse=True)
+        order = np.argsort(inv, kind="stable").astype(np.int32)
+        ptr = np.zeros(len(ux) + 1, np.int32)
+        np.cumsum(np.bincount(inv, minlength=len(ux)), out=ptr[1:])
+        return (torch.as_tensor(ptr, device=device), torch.as_tensor(order, device=device), len(ux))
+
+    def _run_update_net(self, net, inp, corr_nhwc, coords1, target, ii_host=None):
+        """update operator on NHWC tensors: net/inp [E,ht,wd,128], corr [E,ht,wd,CORR_PAD], coords1/target
+        [E,ht,wd,2] (target None -> zero residual) -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32
+        (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576]) — the reference's UpdateModule return convention
+        (droid_net.py:118-150).  ii_host: numpy source indices of the edges (enables GraphAgg)."""
         if self.update_tc is not None:
-            return self.update_tc(net, inp, corr_nhwc, motion, ii, agg=agg)
+            agg = None if ii_host is None else self._agg_tables(ii_host, self.device)
+            out = self.update_tc(net, inp, corr_nhwc, coords1.contiguous(), self.coords0, target=target, agg=agg)
+            delta = out[1] - coords1
+            if ii_host is None:
+                return out[0], delta, out[2]
+            eta = 0.01 * torch.nn.functional.softplus(out[3][..., 0].float())
+            return out[0], delta, out[2], eta, out[4]
+        tgt = coords1 if target is None else target
+        motion = torch.cat([coords1 - self.coords0, tgt - coords1], dim=-1).permute(0, 3, 1, 2).clamp(-64.0, 64.0)
         nchw = lambda t: t.permute(0, 3, 1, 2)
-        out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None],
-                              None if motion is None else motion[None], ii, ii)
+        ii = None if ii_host is None else torch.as_tensor(np.asarray(ii_host), device=self.device)
+        out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None], motion[None], ii, ii)
         net2 = out[0][0].permute(0, 2, 3, 1).contiguous()
         if ii is None:
             return net2, out[1][0].float(), out[2][0].float()
@@ -333,7 +351,7 @@ class RaftVisualFrontend:
         corr = db.corr_lookup_pyramid(pyr, self._coords0_b, 3, nhwc_stride=CORR_PAD, coords_nhwc=True)
         net = self.contexts_imgs[:, 0].index_select(0, idx)
         inp = self.cst_contexts_imgs[:, 0].index_select(0, idx)
-        _, delta, _ = self._run_update_net(net, inp, corr, None)
+        _, delta, _ = self._run_update_net(net, inp, corr, self._coords0_b, None)
         self.last_motion.copy_(delta.float().norm(dim=-1).mean())
 
     def _frame_front(self, imgs_k):
@@ -585,6 +603,7 @@ class RaftVisualFrontend:
         st.kf0, st.EP = kf0, EP
         ux, inv = np.unique(ii_h, return_inverse=True)
         st.ux = torch.as_tensor(ux, device=dev); st.ix = torch.as_tensor(inv, device=dev); st.K = len(ux)
+        st.agg = self._agg_tables(ii_h, dev)
         st.inp = self.cst_contexts_imgs[self.ii, 0].contiguous()
         if use_inactive:
             m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
@@ -612,19 +631,27 @@ class RaftVisualFrontend:
     def _update_body(self, st, itrs, compute_covariances):
         """device-only part of update() (visual_frontend.py:371-470); no host<->device traffic, no syncs"""
         coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
-        motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
-        motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
         corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
-        net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, st.inp, corr, motion,
-                                                                   self.ii, agg=(st.ix, st.K))
-        self.gru_hidden_states.copy_(net)
-        torch.add(coords1, delta, out=self.gru_estimated_flow)
-        self.gru_estimated_flow_weight.copy_(weight)
-        self.damping[st.ux] = damping
-        st.target[st.n_in:].copy_(self.gru_estimated_flow.permute(0, 3, 1, 2))
-        st.weight[st.n_in:].copy_(self.gru_estimated_flow_weight.permute(0, 3, 1, 2))
-        torch.mul(self.damping[st.kx_ba], 0.2, out=st.damp)
-        st.damp.add_(st.EP)
+        if self.update_tc is not None:
+            # flow/confidence land directly in the frontend state AND in the BA's planar input buffers
+            net, _, _, e16, upmask = self.update_tc(
+                self.gru_hidden_states, st.inp, corr, coords1, self.coords0, target=self.gru_estimated_flow, agg=st.agg,
+                post=(self.gru_estimated_flow, self.gru_estimated_flow_weight, st.target[st.n_in:], st.weight[st.n_in:]))
+            self.gru_hidden_states.copy_(net)
+            _lib.check(_lib.load().nslam_eta_damping(_lib.ptr(e16), _lib.ptr(st.ux), _lib.ptr(self.damping), st.K,
+                                                     _lib.ptr(st.kx_ba), _lib.ptr(st.damp), int(st.kx_ba.numel()),
+                                                     self.ht * self.wd, float(st.EP), _lib.stream_ptr()), "eta_damping")
+        else:
+            net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, st.inp, corr, coords1,
+                                                                       self.gru_estimated_flow, self.ii_h)
+            self.gru_hidden_states.copy_(net)
+            torch.add(coords1, delta, out=self.gru_estimated_flow)
+            self.gru_estimated_flow_weight.copy_(weight)
+            self.damping[st.ux] = damping
+            st.target[st.n_in:].copy_(self.gru_estimated_flow.permute(0, 3, 1, 2))
+            st.weight[st.n_in:].copy_(self.gru_estimated_flow_weight.permute(0, 3, 1, 2))
+            torch.mul(self.damping[st.kx_ba], 0.2, out=st.damp)
+            st.damp.add_(st.EP)
         dx, linv, status = st.prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
                                                 prior_idx=0 if st.has_prior else -1,
                                                 prior_pose=self.prior_pose if st.has_prior else None,
@@ -635,9 +662,10 @@ class RaftVisualFrontend:
             self.world_T_body_cov[st.kf0:st.kf1] = sg
             self.cam0_idepths_cov[st.kx_prob] = z_cov
             self.cam0_depths_cov[st.kx_prob] = d_cov
-        self.cam0_idepths_up[st.ux] = db.cvx_upsample(self.cam0_idepths[st.ux].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
-        self.cam0_depths_cov_up[st.ux] = db.cvx_upsample(self.cam0_depths_cov[st.ux].unsqueeze(-1), upmask, pow=1.0,
-                                                         mask_nhwc=True).squeeze(-1)
+        # inverse depths and depth covariances of the K source keyframes through one softmax, gathered /
+        # scattered by keyframe index inside the kernel
+        db.cvx_upsample2(self.cam0_idepths, self.cam0_depths_cov, upmask, self.cam0_idepths_up, self.cam0_depths_cov_up,
+                         index=st.ux)
 
     @torch.no_grad()
     def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
@@ -712,8 +740,6 @@ class RaftVisualFrontend:
         corr_op = AltCorrBlock(fm)
         for _ in range(steps):
             coords1, _ = self.reproject(self.ii, self.jj)
-            motion = torch.cat([coords1 - self.coords0, self.gru_estimated_flow - coords1], dim=-1)
-            motion = motion.permute(0, 3, 1, 2).clamp(-64.0, 64.0)
             s = 8
             for i in range(0, int(self.jj_h.max()) + 1, s):
                 v = (self.ii_h >= i) & (self.ii_h < i + s)
@@ -725,7 +751,8 @@ class RaftVisualFrontend:
                 corr = corr_op(coords1[vd][None], cams * iis, cams * jjs + (iis == jjs).long())[0]      # [e,196,ht,wd] fp32
                 corr = torch.nn.functional.pad(corr.permute(0, 2, 3, 1), (0, CORR_PAD - 196)).half().contiguous()
                 net, delta, weight, damping, upmask = self._run_update_net(
-                    self.gru_hidden_states[vd], self.cst_contexts_imgs[iis, 0], corr, motion[vd], iis)
+                    self.gru_hidden_states[vd], self.cst_contexts_imgs[iis, 0], corr, coords1[vd].contiguous(),
+                    self.gru_estimated_flow[vd].contiguous(), self.ii_h[v])
                 self.gru_hidden_states[vd] = net
                 self.gru_estimated_flow[vd] = coords1[vd] + delta
                 self.gru_estimated_flow_weight[vd] = weight

@@ -7,31 +7,18 @@ so the reference's `droid.pth` loads unchanged:
   UpdateModule   networks/droid_net.py:78-150                                           [A5]
 
 Inference-only (the demo runs with autograd disabled, examples/slam_demo.py:198).  Parameters are
-plain tensors; `conv2d` is the single place where a convolution is executed, so that swapping the
-library convolution for the hand-written tcgen05 implicit-GEMM kernel (csrc/conv_igemm.cu) is one
-switch (`set_conv_backend`).  Activations are channels-last fp16 (what the tensor cores want);
-torch_scatter.scatter_mean of the reference is an index_add here.
+plain tensors; `conv2d` is the single place where a library convolution is executed (encoders, and
+the per-layer reference form of the update operator that the fused tensor-core operator in conv.py is
+tested against).  Activations are channels-last fp16; torch_scatter.scatter_mean of the reference is
+an index_add here.
 """
 from collections import OrderedDict
 
 import torch
 import torch.nn.functional as F
 
-_CONV_BACKEND = {"name": "cudnn"}
-
-
-def set_conv_backend(name):
-    assert name in ("cudnn", "tcgen05")
-    _CONV_BACKEND["name"] = name
-
-
 def conv2d(x, w, b, stride=1, padding=0, act=None):
     """x [N,C,H,W] (channels_last fp16/fp32), w [O,C,kh,kw], b [O]; act in {None,'relu','sigmoid','tanh'}"""
-    if _CONV_BACKEND["name"] == "tcgen05":
-        from . import conv as _conv
-        y = _conv.conv2d_tc(x, w, b, stride, padding, act)
-        if y is not None:
-            return y
     y = F.conv2d(x, w, b, stride=stride, padding=padding)
     if act == "relu":
         y = F.relu(y, inplace=True)
@@ -89,6 +76,28 @@ def _inorm(x):
     return F.instance_norm(x)
 
 
+def _cl(y):
+    return y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
+
+
+def _inorm_stats(y):
+    """per-(image, channel) sum / sum of squares of a channels-last fp16 tensor (csrc/inorm.cu)"""
+    from . import _lib
+    B, C, H, W = y.shape
+    st = torch.empty(B, C, 2, dtype=torch.float32, device=y.device)
+    _lib.check(_lib.load().nslam_inorm_stats(_lib.ptr(y), _lib.ptr(st), B, H * W, C, _lib.stream_ptr()), "inorm_stats")
+    return st
+
+
+def _inorm_apply(y, st, relu=True, res=None, res_st=None):
+    """in place: y <- relu?(IN(y)); with res: y <- relu(res' + y), res' = IN(res) if res_st is given"""
+    from . import _lib
+    B, C, H, W = y.shape
+    _lib.check(_lib.load().nslam_inorm_apply(_lib.ptr(y), _lib.ptr(st), _lib.ptr(res), _lib.ptr(res_st), _lib.ptr(y),
+                                             B, H * W, C, 1e-5, int(relu), _lib.stream_ptr()), "inorm_apply")
+    return y
+
+
 class BasicEncoder(_Params):
     """7x7/2 conv -> 3 stages x 2 residual blocks (32, 64/2, 128/2) -> 1x1 conv.  [A1]"""
     DIM = 32
@@ -119,6 +128,8 @@ class BasicEncoder(_Params):
         x = x.reshape(b * n, c, h, w).contiguous(memory_format=torch.channels_last)
         wt, bs = self.w("conv1")
         x = x.to(wt.dtype)
+        if self.norm is _inorm and x.is_cuda and wt.dtype == torch.float16:
+            return self._forward_fused_norm(x).view(b, n, -1, h // 8, w // 8)
         x = F.relu(self.norm(conv2d(x, wt, bs, stride=2, padding=3)), inplace=True)
         for name, st in self.blocks:
             y = F.relu(self.norm(conv2d(x, *self.w(name + ".conv1"), stride=st, padding=1)), inplace=True)
@@ -128,6 +139,25 @@ class BasicEncoder(_Params):
             x = F.relu(x + y, inplace=True)
         x = conv2d(x, *self.w("conv2"))
         return x.view(b, n, x.shape[1], x.shape[2], x.shape[3])
+
+
+    def _forward_fused_norm(self, x):
+        """same network with the instance norms, ReLUs and residual adds on the fused NHWC kernels
+        (csrc/inorm.cu): per conv one statistics pass + one apply pass instead of ~8 library launches"""
+        wt, bs = self.w("conv1")
+        x = _cl(conv2d(x, wt, bs, stride=2, padding=3))
+        _inorm_apply(x, _inorm_stats(x))
+        for name, st in self.blocks:
+            y = _cl(conv2d(x, *self.w(name + ".conv1"), stride=st, padding=1))
+            _inorm_apply(y, _inorm_stats(y))
+            z = _cl(conv2d(y, *self.w(name + ".conv2"), stride=1, padding=1))
+            if st != 1:
+                d = _cl(conv2d(x, *self.w(name + ".downsample.0"), stride=st, padding=0))
+                _inorm_apply(z, _inorm_stats(z), res=d, res_st=_inorm_stats(d))
+            else:
+                _inorm_apply(z, _inorm_stats(z), res=x)
+            x = z
+        return conv2d(x, *self.w("conv2"))
 
 
 class UpdateModule(_Params):

@@ -108,7 +108,7 @@ def test_update_operator_tc_vs_library_path(with_agg):
     corr = corr.half().to(DEV)
     motion = (torch.randn(E, 4, H, W, generator=g) * 3).to(DEV)
     ii = torch.tensor([0, 0, 1, 2, 2], device=DEV) if with_agg else None
-    got = op(net, inp, corr, motion, ii)
+    got = op.call_reference_convention(net, inp, corr, motion, ii)
     nchw = lambda t: t.permute(0, 3, 1, 2)
     ref = um(nchw(net)[None], nchw(inp)[None], nchw(corr[..., :196])[None], motion[None], ii, ii)
     torch.cuda.synchronize()

@@ -50,8 +50,8 @@ def test_update_operator_tc_vs_reference_python():
     op = UpdateOperatorTC(um, DEV)
     nhwc = lambda x: torch.from_numpy(x[0]).permute(0, 2, 3, 1).contiguous()
     corr = torch.zeros(3, 8, 12, CORR_PAD); corr[..., :196] = nhwc(d["corr"])
-    o = op(nhwc(d["net"]).half().to(DEV), nhwc(d["inp"]).half().to(DEV), corr.half().to(DEV),
-           torch.from_numpy(d["flow"][0]).to(DEV), torch.from_numpy(d["ii"]).to(DEV))
+    o = op.call_reference_convention(nhwc(d["net"]).half().to(DEV), nhwc(d["inp"]).half().to(DEV), corr.half().to(DEV),
+                                     torch.from_numpy(d["flow"][0]).to(DEV), torch.from_numpy(d["ii"]).to(DEV))
     ref_net = torch.from_numpy(d["out_net"][0]).permute(0, 2, 3, 1)
     assert float((o[0].float().cpu() - ref_net).abs().max()) < 3e-2
     assert float((o[1].cpu() - torch.from_numpy(d["delta"][0])).abs().max()) < 8e-2        # px

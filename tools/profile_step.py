@@ -27,10 +27,9 @@ coords1, _ = fe.reproject(fe.ii, fe.jj)
 T(lambda: fe.reproject(fe.ii, fe.jj), name="reproject")
 T(lambda: fe.corr_pool.lookup(fe.slots_d, coords1, nhwc=True), name="corr_lookup(nhwc)")
 corr = fe.corr_pool.lookup(fe.slots_d, coords1, nhwc=True)
-motion = torch.cat([coords1 - fe.coords0, fe.gru_estimated_flow - coords1], dim=-1).permute(0, 3, 1, 2).clamp(-64, 64)
 inp = fe.cst_contexts_imgs[fe.ii, 0]
-T(lambda: fe._run_update_net(fe.gru_hidden_states, inp, corr, motion, fe.ii), name=f"update operator ({fe.conv_backend}) E={E}")
-net, delta, weight, damping, upmask = fe._run_update_net(fe.gru_hidden_states, inp, corr, motion, fe.ii)
+T(lambda: fe._run_update_net(fe.gru_hidden_states, inp, corr, coords1, fe.gru_estimated_flow, fe.ii_h), name=f"update operator ({fe.conv_backend}) E={E}")
+net, delta, weight, damping, upmask = fe._run_update_net(fe.gru_hidden_states, inp, corr, coords1, fe.gru_estimated_flow, fe.ii_h)
 ii, jj = fe.ii_h, fe.jj_h
 target = fe.gru_estimated_flow.permute(0, 3, 1, 2).contiguous(); wgt = fe.gru_estimated_flow_weight.permute(0, 3, 1, 2).contiguous()
 dmp = .2 * fe.damping[torch.as_tensor(np.unique(ii), device=fe.device)].contiguous() + 1e-7
