@@ -50,6 +50,8 @@ typedef struct nslam_ngp_batch {
   int* counters;     /* [4]: samples, rays kept */
   float* loss;       /* [1] */
   int max_rays, max_samples;
+  void* enc;         /* __half [max_samples,32]  hash encodings kept by the tensor-core forward (or NULL) */
+  void* denc;        /* __half [max_samples,32]  loss-scaled encoding gradients for the scatter kernel (or NULL) */
 } nslam_ngp_batch;
 
 int nslam_ngp_train_step(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
@@ -76,9 +78,13 @@ int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up,
  * accumulates weight gradients in TMEM across all tiles of a CTA. */
 int nslam_ngp_pack_mlp(const float* mlp, void* packed, void* stream);
 int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
-                         int n, int max_samples, float* rgbsigma, int num_sms, void* stream);
+                         int n, int max_samples, float* rgbsigma, void* enc_out, int num_sms, void* stream);
+/* enc_in (from forward_tc's enc_out) or NULL = re-gather; denc_scratch or NULL = scatter inside the kernel.
+ * With denc_scratch the hash-grid scatter runs as its own full-occupancy kernel (one thread per
+ * sample x level) after the MLP backward. */
 int nslam_ngp_backward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
-                          const float* dout, float loss_scale, int num_sms, void* stream);
+                          const float* dout, float loss_scale, const void* enc_in, void* denc_scratch,
+                          int max_samples, int num_sms, void* stream);
 int nslam_ngp_train_step_tc(const nslam_ngp_model* m, const nslam_ngp_images* im, const nslam_ngp_batch* b,
                             const void* packed, int n_rays, unsigned seed, float lambda_depth, float bg_r,
                             float bg_g, float bg_b, float loss_scale, int num_sms, void* stream);

@@ -17,23 +17,25 @@
 // * 4-stage mbarrier ring, one thread issues tcgen05.mma (M128, N, K16), fp32 accumulators in
 //   TMEM, double buffered so the epilogue of tile t overlaps the MMAs of tile t+1;
 // * persistent CTAs (grid = #SMs) walk the (image, tile) list;
-// * epilogue (4 warps, thread = pixel): tcgen05.ld -> +bias (+ per-image global-context vector)
-//   -> activation / GRU gating -> fp16 -> swizzled smem -> TMA store (clips partial tiles).
+// * epilogue (8 warps, thread = pixel, the two warps of a TMEM lane quarter split the columns):
+//   tcgen05.ld -> +bias (+ per-image global-context vector) -> activation / GRU gating -> fp16 ->
+//   swizzled smem -> TMA store (clips partial tiles).  Kernel templated on the epilogue mode.
 //
 // Epilogue modes:
 //   0 ACT   y = act(acc + bias [+ gctx[n]])                          act: 0 none 1 relu 2 sigmoid 3 tanh
 //   1 ZR    N = 256: z = sigmoid(acc[0:128]+..), r = sigmoid(acc[128:256]+..);
 //           out0 = z, out1 = r * net          (ConvGRU z,r gates, gru.py:27-29)
 //   2 Q     q = tanh(acc + ..); out0 = (1 - z) * net + z * q         (gru.py:29-31)
-//   3 GLO   y = sigmoid(acc + bias) * net; column sums over the image atomically added to
-//           gsum[n][c] (fp32)  -> glo = mean (gru.py:23-25); nothing is stored
+//   3 GLO   y = sigmoid(acc + bias) * net; per-tile column sums (warp transpose-reduce -> shared
+//           accumulator) added to gsum[n][c] (fp32)  -> glo = mean (gru.py:23-25); nothing is stored
 // Roofline: tensor pipe; FLOPs = 2 * pixels * taps * Cin * Cout.
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace nslam {
 
-constexpr int CG_THREADS = 192;
+constexpr int CG_EPI_WARPS = 8;
+constexpr int CG_THREADS = 64 + 32 * CG_EPI_WARPS;     // TMA warp, MMA warp, 8 epilogue warps
 template <int N> struct CgStages { static constexpr int value = (N >= 256) ? 3 : 4; };
 constexpr int CG_TH = 8, CG_TW = 16;
 
@@ -94,7 +96,73 @@ struct CgSmem {
   static constexpr int TOTAL = BAR + 256;
 };
 
-template <int N>
+// transpose-reduce: on entry lane l holds v[0..31] (32 columns of ITS pixel); on exit every lane
+// returns the sum over the warp's 32 pixels of column `lane` (31 shuffles instead of 32 x 5)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const int half = n >> 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// one 32-column chunk of the epilogue: x = acc + bias (+ gctx) -> mode-specific map -> v[]
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32], const float* __restrict__ sb,
+                                          const float* __restrict__ g, int c0, int act, bool valid,
+                                          const uint4 (&an)[4], const uint4 (&az)[4]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g) g4 = __ldg(reinterpret_cast<const float4*>(g + c0 + i));
+    v[i + 0] = __uint_as_float(r[i + 0]) + b4.x + g4.x; v[i + 1] = __uint_as_float(r[i + 1]) + b4.y + g4.y;
+    v[i + 2] = __uint_as_float(r[i + 2]) + b4.z + g4.z; v[i + 3] = __uint_as_float(r[i + 3]) + b4.w + g4.w;
+  }
+  if (MODE == 0) {
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
+    } else if (act != 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = act_apply(v[i], act);
+    }
+  } else if (MODE == 1) {
+    if (c0 < 128) {                       // z
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+    } else {                              // r * net
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const __half* hv = reinterpret_cast<const __half*>(&an[i >> 3]);
+        v[i] = __half2float(hv[i & 7]) / (1.f + __expf(-v[i]));
+      }
+    }
+  } else if (MODE == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const __half* hn = reinterpret_cast<const __half*>(&an[i >> 3]);
+      const __half* hz = reinterpret_cast<const __half*>(&az[i >> 3]);
+      const float z = __half2float(hz[i & 7]), nt = __half2float(hn[i & 7]);
+      v[i] = (1.f - z) * nt + z * tanhf(v[i]);
+    }
+  } else {                                // MODE 3: sigmoid(acc) * net
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const __half* hn = reinterpret_cast<const __half*>(&an[i >> 3]);
+      v[i] = valid ? __half2float(hn[i & 7]) / (1.f + __expf(-v[i])) : 0.f;
+    }
+  }
+}
+
+template <int N, int MODE>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   using SM = CgSmem<N>;
@@ -110,6 +178,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   uint64_t* tm_empty = tm_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
   float* sbias = reinterpret_cast<float*>(sm + SM::BIAS);
+  float* sacc = sbias + N;                       // mode 3: per-CTA column sums of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -120,11 +189,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; s++) tc::tma_prefetch_desc(&maps.src[s]);
     for (int s = 0; s < CG_STAGES; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], 4); }
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], CG_EPI_WARPS); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<TCOLS>(tmem_slot);
-  for (int i = threadIdx.x; i < N; i += CG_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < N; i += CG_THREADS) { sbias[i] = p.bias ? p.bias[i] : 0.f; sacc[i] = 0.f; }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -178,11 +247,16 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
       }
     }
   } else {
-    // ===================== epilogue =====================
+    // ===================== epilogue: 8 warps; warp pair (w, w+4) shares a TMEM lane quarter and
+    // splits the N columns in halves (N >= 64), thread = output pixel =====================
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int hh = row / CG_TW, ww = row % CG_TW;
-    const int etid = (warp - 2) * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    constexpr int NG = (N >= 64) ? N / 2 : N;       // columns per group
+    const int cbeg = (N >= 64) ? grp * NG : 0;
+    const bool works = (N >= 64) || grp == 0;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
       const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
@@ -194,94 +268,60 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
       tc::mbar_wait(&tm_full[as], aph);
       tc::tc_fence_after();
       // staging buffers free again once the previous tile's TMA stores have read them
-      if (etid == 0) tma_store_wait_read();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (MODE != 3 && etid == 0) tma_store_wait_read();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const float* g = p.gctx ? p.gctx + (size_t)n * N : nullptr;
+      if (works) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        if (N >= 32) {
+        for (int c0 = cbeg; c0 < cbeg + NG; c0 += 32) {
+          uint32_t r[32];
           tc::tmem_ld_32x32(taddr + c0, r);
-        } else {
-          // N == 16: only 16 columns are valid; load 32 (allocated) and ignore the rest
-          tc::tmem_ld_32x32(taddr + c0, r);
-        }
-        tc::tmem_ld_wait();
-        float v[32];
+          // operand loads of the gating modes overlap the TMEM read
+          uint4 an[4] = {}, az[4] = {};
+          if (MODE == 1) {
+            if (c0 >= 128 && valid) {
+              const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + (c0 - 128));
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const int c = c0 + i;
-          float x = __uint_as_float(r[i]) + ((c < N) ? sbias[c] : 0.f);
-          if (g && c < N) x += g[c];
-          v[i] = x;
-        }
-        if (p.mode == 0) {
+              for (int i = 0; i < 4; i++) an[i] = np[i];
+            }
+          } else if (MODE == 2 || MODE == 3) {
+            if (valid) {
+              const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + c0);
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = act_apply(v[i], p.act);
-        } else if (p.mode == 1) {
-          // cols [0,128) -> z ; [128,256) -> r * net
-          if (c0 < 128) {
+              for (int i = 0; i < 4; i++) an[i] = np[i];
+              if (MODE == 2) {
+                const uint4* zp = reinterpret_cast<const uint4*>(p.zbuf + pix * 128 + c0);
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+                for (int i = 0; i < 4; i++) az[i] = zp[i];
+              }
+            }
+          }
+          tc::tmem_ld_wait();
+          float v[32];
+          epi_chunk<MODE>(r, v, sbias, g, c0, p.act, valid, an, az);
+          if (MODE == 3) {
+            const float cs = warp_colsum32(v, lane);
+            atomicAdd(&sacc[c0 + lane], cs);
           } else {
-            const __half* np = p.net + pix * 128 + (c0 - 128);
+            // fp16, into the staging tile of this 64-channel group
+            const int t64 = c0 / 64;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              uint4 raw = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
-              const __half* hv = reinterpret_cast<const __half*>(&raw);
+              if (c0 + i >= N) break;
+              __half2 h2[4];
 #pragma unroll
-              for (int j = 0; j < 8; j++) v[i + j] = __half2float(hv[j]) / (1.f + __expf(-v[i + j]));
-            }
-          }
-        } else if (p.mode == 2) {
-          const __half* np = p.net + pix * 128 + c0;
-          const __half* zp = p.zbuf + pix * 128 + c0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 rn = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
-            uint4 rz = valid ? *reinterpret_cast<const uint4*>(zp + i) : make_uint4(0, 0, 0, 0);
-            const __half* hn = reinterpret_cast<const __half*>(&rn);
-            const __half* hz = reinterpret_cast<const __half*>(&rz);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float z = __half2float(hz[j]), nt = __half2float(hn[j]);
-              v[i + j] = (1.f - z) * nt + z * tanhf(v[i + j]);
-            }
-          }
-        } else {  // mode 3: sigmoid(acc) * net, column sums
-          const __half* np = p.net + pix * 128 + c0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 rn = valid ? *reinterpret_cast<const uint4*>(np + i) : make_uint4(0, 0, 0, 0);
-            const __half* hn = reinterpret_cast<const __half*>(&rn);
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[i + j] = valid ? __half2float(hn[j]) / (1.f + __expf(-v[i + j])) : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            float s = warp_sum(v[i]);
-            if (lane == 0) atomicAdd(p.gsum + (size_t)n * 128 + c0 + i, s);
-          }
-        }
-        if (p.mode != 3) {
-          // fp16, into the 128B-swizzled staging tile of this 64-channel group
-          const int t64 = c0 / 64;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            if (c0 + i >= N) break;
-            __half2 h2[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-            if (N >= 64) {
-              // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
-              unsigned char* st = sm + SM::OUT + t64 * 16384 + row * 128;
-              const int chunk = ((c0 % 64) + i) / 8;
-              *reinterpret_cast<uint4*>(st + ((chunk ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
-            } else {
-              // narrow outputs: dense rows of N halfs, un-swizzled tensor map
-              unsigned char* st = sm + SM::OUT + row * (N * 2);
-              *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+              for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+              if (N >= 64) {
+                // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
+                unsigned char* st = sm + SM::OUT + t64 * 16384 + row * 128;
+                const int chunk = ((c0 % 64) + i) / 8;
+                *reinterpret_cast<uint4*>(st + ((chunk ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
+              } else {
+                // narrow outputs: dense rows of N halfs, un-swizzled tensor map
+                unsigned char* st = sm + SM::OUT + row * (N * 2);
+                *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+              }
             }
           }
         }
@@ -289,11 +329,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
-      if (p.mode != 3) {
+      if (MODE != 3) {
         tc::fence_proxy_async();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
-          if (p.mode == 1) {
+          if (MODE == 1) {
             tma_store_4d(&maps.out[0], sm + SM::OUT + 0 * 16384, 0, w0, h0, n);
             tma_store_4d(&maps.out[0], sm + SM::OUT + 1 * 16384, 64, w0, h0, n);
             tma_store_4d(&maps.out[1], sm + SM::OUT + 2 * 16384, 0, w0, h0, n);
@@ -304,29 +344,57 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
           }
           tma_store_commit();
         }
+      } else {
+        // flush this tile's column sums (the next tile usually belongs to another image)
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (etid < N) {
+          const float sv = sacc[etid];
+          sacc[etid] = 0.f;
+          if (sv != 0.f) atomicAdd(p.gsum + (size_t)n * 128 + etid, sv);
+        }
       }
     }
-    if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (MODE != 3 && etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<TCOLS>(tmem_base);
 }
 
-template <int N>
-static int launch_conv(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
+template <int N, int MODE>
+static int launch_conv_m(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
   const int smem = CgSmem<N>::TOTAL + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int ntiles = p.B * p.tiles_h * p.tiles_w;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  conv_igemm_kernel<N><<<grid, CG_THREADS, smem, st>>>(maps, p);
+  conv_igemm_kernel<N, MODE><<<grid, CG_THREADS, smem, st>>>(maps, p);
   NSLAM_CHECK_LAUNCH();
   return 0;
+}
+
+// only the (N, mode) pairs the update operator uses are instantiated
+static int launch_conv(int N, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
+  if (p.mode == 0) {
+    switch (N) {
+      case 16: return launch_conv_m<16, 0>(maps, p, num_sms, st);
+      case 32: return launch_conv_m<32, 0>(maps, p, num_sms, st);
+      case 64: return launch_conv_m<64, 0>(maps, p, num_sms, st);
+      case 128: return launch_conv_m<128, 0>(maps, p, num_sms, st);
+      case 256: return launch_conv_m<256, 0>(maps, p, num_sms, st);
+    }
+  } else if (p.mode == 1 && N == 256) {
+    return launch_conv_m<256, 1>(maps, p, num_sms, st);
+  } else if (p.mode == 2 && N == 128) {
+    return launch_conv_m<128, 2>(maps, p, num_sms, st);
+  } else if (p.mode == 3 && N == 128) {
+    return launch_conv_m<128, 3>(maps, p, num_sms, st);
+  }
+  return (int)cudaErrorInvalidValue;
 }
 
 }  // namespace nslam
@@ -377,14 +445,7 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
       if (r) return r;
     }
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (N) {
-    case 16: return launch_conv<16>(maps, p, num_sms, st);
-    case 64: return launch_conv<64>(maps, p, num_sms, st);
-    case 128: return launch_conv<128>(maps, p, num_sms, st);
-    case 256: return launch_conv<256>(maps, p, num_sms, st);
-    default: return (int)cudaErrorInvalidValue;
-  }
+  return launch_conv(N, maps, p, num_sms, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -69,7 +69,7 @@ __device__ __forceinline__ void issue_layer(uint32_t a_addr, uint32_t b_addr, ui
 __global__ void __launch_bounds__(128)
 forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ counters, int n_fixed,
                   const __half2* __restrict__ grid, LevelInfo lv, const unsigned char* __restrict__ packed,
-                  float* __restrict__ rgbsigma) {
+                  float* __restrict__ rgbsigma, __half* __restrict__ enc_out) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + FwdSmem::BAR);
@@ -110,6 +110,12 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
       for (int c = 0; c < 4; c++) store_row_chunk(arow, tid, c, enc + 8 * c);
 #pragma unroll
       for (int c = 4; c < 8; c++) store_row_chunk(arow, tid, c, z8);
+      if (enc_out && act) {
+        // keep the fp16 encoding for the backward pass (saves its 128 gathers per sample)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          reinterpret_cast<uint4*>(enc_out + (size_t)s * ENC_DIM)[c] = *reinterpret_cast<const uint4*>(arow + ((c ^ (tid & 7)) << 4));
+      }
     }
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -335,7 +341,8 @@ __global__ void __launch_bounds__(128, 1)
 backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ counters,
                    const __half2* __restrict__ grid, LevelInfo lv, const unsigned char* __restrict__ packed_fwd,
                    const unsigned char* __restrict__ packed_bwd, const float* __restrict__ dout,
-                   float* __restrict__ mlp_grad, float* __restrict__ grid_grad, float loss_scale) {
+                   float* __restrict__ mlp_grad, float* __restrict__ grid_grad, float loss_scale,
+                   const __half* __restrict__ enc_in, __half* __restrict__ denc_out) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BwdSmem::BAR);
@@ -377,12 +384,22 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     uint32_t m1[2], m3[2], m4[2];
     // ---------------- forward recompute, keeping the layer inputs
     {
-      float enc[ENC_DIM];
-      hash_encode(c7, grid, lv, enc);
       const float z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       unsigned char* a0 = act + 0 * 16384 + tid * 128;
+      if (enc_in) {
+        // encoding saved by the forward pass: 64 contiguous bytes per sample
 #pragma unroll
-      for (int c = 0; c < 4; c++) store_row_chunk(a0, tid, c, enc + 8 * c);
+        for (int c = 0; c < 4; c++) {
+          uint4 e4 = make_uint4(0, 0, 0, 0);
+          if (actv) e4 = reinterpret_cast<const uint4*>(enc_in + (size_t)s * ENC_DIM)[c];
+          *reinterpret_cast<uint4*>(a0 + ((c ^ (tid & 7)) << 4)) = e4;
+        }
+      } else {
+        float enc[ENC_DIM];
+        hash_encode(c7, grid, lv, enc);
+#pragma unroll
+        for (int c = 0; c < 4; c++) store_row_chunk(a0, tid, c, enc + 8 * c);
+      }
 #pragma unroll
       for (int c = 4; c < 8; c++) store_row_chunk(a0, tid, c, z8);
     }
@@ -511,7 +528,18 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
       uint32_t r[32];
       tc::tmem_ld_32x32(taddr + TM_ACC, r);             // d/d enc [32], still loss-scaled
       tc::tmem_ld_wait();
-      if (actv) {
+      if (denc_out) {
+        // hand the (loss-scaled, fp16) encoding gradient to the scatter kernel
+        if (actv) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            __half2 h2[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]));
+            reinterpret_cast<uint4*>(denc_out + (size_t)s * ENC_DIM)[c] = *reinterpret_cast<const uint4*>(h2);
+          }
+        }
+      } else if (actv) {
 #pragma unroll 2
         for (int l = 0; l < N_LEVELS; l++) {
           const float ga = __uint_as_float(r[2 * l]) * inv_scale, gb = __uint_as_float(r[2 * l + 1]) * inv_scale;
@@ -563,6 +591,34 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+
+// hash-grid gradient scatter: one thread per (sample, level) -> 8 float2 atomics.  Split from the MLP
+// backward so that the atomics run at full occupancy instead of behind 4 warps per SM.
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(const float* __restrict__ coords, const int* __restrict__ counters, const __half* __restrict__ denc,
+                    LevelInfo lv, float* __restrict__ grid_grad, float inv_scale) {
+  const int n = counters[0];
+  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < (size_t)n * N_LEVELS; id += (size_t)gridDim.x * blockDim.x) {
+    const int l = (int)(id % N_LEVELS);
+    const size_t s = id / N_LEVELS;
+    const float2 gd = __half22float2(reinterpret_cast<const __half2*>(denc)[s * N_LEVELS + l]);
+    const float ga = gd.x * inv_scale, gb = gd.y * inv_scale;
+    if (ga == 0.f && gb == 0.f) continue;
+    const float sc = lv.scale[l];
+    const float px = fmaf(coords[s * 7 + 0], sc, 0.5f), py = fmaf(coords[s * 7 + 1], sc, 0.5f), pz = fmaf(coords[s * 7 + 2], sc, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    float2* gg = reinterpret_cast<float2*>(grid_grad) + lv.offset[l];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+      const float w = (dx ? wx : 1.f - wx) * (dy ? wy : 1.f - wy) * (dz ? wz : 1.f - wz);
+      atomicAdd(gg + grid_index(ix + dx, iy + dy, iz + dz, lv.res[l], lv.size[l], lv.dense[l]), make_float2(w * ga, w * gb));
+    }
+  }
+}
+
 }  // namespace ngp
 
 extern "C" {
@@ -577,7 +633,7 @@ int nslam_ngp_pack_mlp(const float* mlp, void* packed, void* stream) {
 
 /* tensor-core variant of nslam_ngp_forward: coords [n,7] (n < 0: read counters[0]) -> rgbsigma [n,4] */
 int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const float* coords, const int* counters,
-                         int n, int max_samples, float* rgbsigma, int num_sms, void* stream) {
+                         int n, int max_samples, float* rgbsigma, void* enc_out, int num_sms, void* stream) {
   using namespace ngp;
   LevelInfo lv;
   for (int l = 0; l < N_LEVELS; l++) {
@@ -596,7 +652,7 @@ int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const flo
   int grid = (cap + 127) / 128;
   if (grid > 4 * num_sms) grid = 4 * num_sms;
   forward_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(coords, counters, n, (const __half2*)m->grid_half, lv,
-                                                              (const unsigned char*)packed, rgbsigma);
+                                                              (const unsigned char*)packed, rgbsigma, (__half*)enc_out);
   cudaError_t e = cudaGetLastError();
   return (int)e;
 }
@@ -605,7 +661,7 @@ int nslam_ngp_forward_tc(const nslam_ngp_model* m, const void* packed, const flo
  * mlp_grad / grid_grad accumulate (fp32 atomics); `dout` as produced by the loss kernel. */
 int nslam_ngp_backward_tc(const nslam_ngp_model* m, const void* packed,
                           const float* coords, const int* counters, const float* dout, float loss_scale,
-                          int num_sms, void* stream) {
+                          const void* enc_in, void* denc_scratch, int max_samples, int num_sms, void* stream) {
   using namespace ngp;
   LevelInfo lv;
   for (int l = 0; l < N_LEVELS; l++) {
@@ -619,10 +675,22 @@ int nslam_ngp_backward_tc(const nslam_ngp_model* m, const void* packed,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  backward_tc_kernel<<<num_sms, 128, smem, (cudaStream_t)stream>>>(coords, counters, (const __half2*)m->grid_half, lv,
-                                                                 (const unsigned char*)packed, (const unsigned char*)packed + PW_TOTAL,
-                                                                 dout, m->mlp_grad, m->grid_grad, loss_scale);
-  return (int)cudaGetLastError();
+  cudaStream_t st = (cudaStream_t)stream;
+  backward_tc_kernel<<<num_sms, 128, smem, st>>>(coords, counters, (const __half2*)m->grid_half, lv,
+                                                 (const unsigned char*)packed, (const unsigned char*)packed + PW_TOTAL,
+                                                 dout, m->mlp_grad, m->grid_grad, loss_scale, (const __half*)enc_in,
+                                                 (__half*)denc_scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (denc_scratch) {
+    // one thread per (sample, level); the sample count lives on the device -> grid-stride over the capacity
+    size_t want = ((size_t)max_samples * N_LEVELS + 255) / 256;
+    const size_t cap = (size_t)num_sms * 32;
+    grid_scatter_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(coords, counters, (const __half*)denc_scratch, lv,
+                                                                            m->grid_grad, 1.f / loss_scale);
+    e = cudaGetLastError();
+  }
+  return (int)e;
 }
 
 /* one training step with the network on tensor cores: sample -> forward_tc -> loss -> backward_tc
@@ -632,11 +700,12 @@ int nslam_ngp_train_step_tc(const nslam_ngp_model* m, const nslam_ngp_images* im
                             float bg_g, float bg_b, float loss_scale, int num_sms, void* stream) {
   int r = nslam_ngp_sample_phase(m, im, b, n_rays, seed, stream);
   if (r) return r;
-  r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, num_sms, stream);
+  r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, b->enc, num_sms, stream);
   if (r) return r;
   r = nslam_ngp_loss_phase(b, n_rays, lambda_depth, bg_r, bg_g, bg_b, stream);
   if (r) return r;
-  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, num_sms, stream);
+  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, b->enc, b->denc, b->max_samples,
+                               num_sms, stream);
 }
 
 /* tests: loss + gradients on caller-provided rays/samples through the tensor-core kernels */
@@ -647,11 +716,12 @@ int nslam_ngp_loss_backward_tc(const nslam_ngp_model* m, const nslam_ngp_batch* 
   int h[4] = {n_samples, n_rays, n_rays, 0};
   cudaMemcpyAsync(b->counters, h, sizeof(h), cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(b->loss, 0, sizeof(float), st);
-  int r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, num_sms, stream);
+  int r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, b->enc, num_sms, stream);
   if (r) return r;
   r = nslam_ngp_loss_phase(b, n_rays, lambda_depth, bg_r, bg_g, bg_b, stream);
   if (r) return r;
-  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, num_sms, stream);
+  return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, b->enc, b->denc, b->max_samples,
+                               num_sms, stream);
 }
 
 }  // extern "C"

@@ -64,7 +64,8 @@ class NgpImages(ctypes.Structure):
 
 class NgpBatch(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("rays", "coords", "tdist", "rgbsigma", "dout", "counters", "loss")] + \
-               [(n, ctypes.c_int) for n in ("max_rays", "max_samples")]
+               [(n, ctypes.c_int) for n in ("max_rays", "max_samples")] + \
+               [(n, ctypes.c_void_p) for n in ("enc", "denc")]
 
 
 def level_table(aabb_scale):
@@ -211,7 +212,9 @@ class Testbed:
         self._bufs = dict(rays=torch.zeros(self.max_rays, 16, **f), coords=torch.zeros(self.max_samples, 7, **f),
                           tdist=torch.zeros(self.max_samples, **f), rgbsigma=torch.zeros(self.max_samples, 4, **f),
                           dout=torch.zeros(self.max_samples, 4, **f),
-                          counters=torch.zeros(4, dtype=torch.int32, device=dev), loss=torch.zeros(1, **f))
+                          counters=torch.zeros(4, dtype=torch.int32, device=dev), loss=torch.zeros(1, **f),
+                          enc=torch.zeros(self.max_samples, 32, dtype=torch.float16, device=dev),
+                          denc=torch.zeros(self.max_samples, 32, dtype=torch.float16, device=dev))
         for k, v in self._bufs.items():
             setattr(b, k, v.data_ptr())
         b.max_rays, b.max_samples = self.max_rays, self.max_samples
