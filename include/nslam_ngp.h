@@ -62,8 +62,12 @@ int nslam_ngp_adam(const nslam_ngp_model* m, int step, float lr, float beta1, fl
 int nslam_ngp_forward(const nslam_ngp_model* m, const float* coords, int n, float* rgbsigma, void* stream);
 int nslam_ngp_loss_backward(const nslam_ngp_model* m, const nslam_ngp_batch* b, int n_rays, int n_samples,
                             float lambda_depth, float bg_r, float bg_g, float bg_b, int num_sms, void* stream);
+/* packed != NULL: the density MLP of the refresh runs on tensor cores (nslam_ngp_density_sample_tc) */
 int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_images* im, int n_per_cascade,
-                                  unsigned seed, float decay, float min_thickness, void* stream);
+                                  unsigned seed, float decay, float min_thickness, const void* packed, int num_sms,
+                                  void* stream);
+int nslam_ngp_density_sample_tc(const nslam_ngp_model* m, const void* packed, int n_per_cascade, unsigned seed,
+                                float decay, int num_sms, void* stream);
 int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, const float* cam18_host,
                           int x0, int y0, int tw, int th, int max_per_ray, float bg_r, float bg_g,
                           float bg_b, float* out_rgbd, void* stream);

@@ -15,7 +15,8 @@
 // four epilogue warps read the accumulators with tcgen05.ld, scale by 1/16, round to fp16 and
 // build pyramid levels 1..3 from the SAME registers (an 8x16 target tile contains complete
 // 2x2/4x4/8x8 pooling cells; the fp16 rounding chain of the reference is reproduced), stage the
-// four tiles in shared memory and write every level once with 16-byte coalesced stores.
+// four tiles in shared memory and write every level once: levels 0/1 with one TMA store per tile
+// ({16,8,128} box straight from the staging buffer), levels 2/3 with cooperative stores.
 // HBM traffic = algorithmic: features in once (L2 resident), each volume byte written once.
 #include "common.cuh"
 #include "tc.cuh"
@@ -25,8 +26,8 @@ namespace nslam {
 constexpr int CV_STAGES = 3;
 constexpr int CV_THREADS = 320;            // TMA warp, MMA warp, 2 epilogue groups of 4 warps
 constexpr int CV_TH = 8, CV_TW = 16;       // target tile
-constexpr int CV_L0_STRIDE = 272;          // bytes per staged row, 256 + 16 pad (conflict-free 128-bit)
-constexpr int CV_L1_STRIDE = 80;           // 64 + 16
+constexpr int CV_L0_STRIDE = 256;          // bytes per staged row: dense [8][16] halfs = the TMA store box
+constexpr int CV_L1_STRIDE = 64;           // dense [4][8]
 constexpr int CV_L2_STRIDE = 16;
 constexpr int CV_L3_STRIDE = 4;
 constexpr int CV_STAGE_BYTES = 128 * (CV_L0_STRIDE + CV_L1_STRIDE + CV_L2_STRIDE + CV_L3_STRIDE);
@@ -52,7 +53,14 @@ struct CvParams {
   int NH, NW;      // target tiles
   int MT;          // 128-pixel source strips per edge
   int nwork;       // E * MT work items, walked persistently
+  int tma_l0, tma_l1;  // levels 0/1 stored by TMA (their row pitch is a multiple of 16 bytes)
 };
+
+__device__ __forceinline__ void cv_tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(tc::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 __device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
 
@@ -100,8 +108,8 @@ __device__ __forceinline__ void cv_store_level(const unsigned char* stage, int r
 // B-tile ring, the TMEM accumulator stages and the two epilogue groups run across work items
 // without draining (global tile counter t: ring slot = t % STAGES, epilogue group = t & 1).
 __global__ void __launch_bounds__(CV_THREADS, 1)
-corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                      const __grid_constant__ CUtensorMap tmB, CvParams p) {
+corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, CvParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -205,7 +213,8 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
         tc::mbar_wait(&tm_full[grp], use & 1);
         use++;
         tc::tc_fence_after();
-        // this group's staging buffers are free once its previous tile's stores were issued
+        // this group's staging buffers are free once its previous tile's stores have read them
+        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 3, 128;" ::: "memory");
         __half l1[4][8];
@@ -253,20 +262,30 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           l3[wr] = __float2half_rn(s * 0.25f);
         }
         *reinterpret_cast<uint32_t*>(st3) = *reinterpret_cast<const uint32_t*>(l3);
+        tc::fence_proxy_async();
         if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
         else asm volatile("bar.sync 4, 128;" ::: "memory");
-        // cooperative, coalesced stores of the four tiles
+        // levels 0 and 1 (94 % of the bytes): one TMA store each (the box clips partial tiles);
+        // the two small levels (and odd row pitches) by cooperative stores
         const int h0 = (n / p.NW) * CV_TH, w0 = (n % p.NW) * CV_TW;
-        cv_store_level<16, 8>(stg + CvSmem::L0, CV_L0_STRIDE, p.out[0], e, p.HW, m0, p.H2, p.W2, h0,
-                              w0, etid);
-        cv_store_level<8, 4>(stg + CvSmem::L1, CV_L1_STRIDE, p.out[1], e, p.HW, m0, p.H2 >> 1,
-                             p.W2 >> 1, h0 >> 1, w0 >> 1, etid);
+        if (etid == 0) {
+          if (p.tma_l0) cv_tma_store_4d(&tmO0, stg + CvSmem::L0, w0, h0, m0, e);
+          if (p.tma_l1) cv_tma_store_4d(&tmO1, stg + CvSmem::L1, w0 >> 1, h0 >> 1, m0, e);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (!p.tma_l0)
+          cv_store_level<16, 8>(stg + CvSmem::L0, CV_L0_STRIDE, p.out[0], e, p.HW, m0, p.H2, p.W2, h0,
+                                w0, etid);
+        if (!p.tma_l1)
+          cv_store_level<8, 4>(stg + CvSmem::L1, CV_L1_STRIDE, p.out[1], e, p.HW, m0, p.H2 >> 1,
+                               p.W2 >> 1, h0 >> 1, w0 >> 1, etid);
         cv_store_level<4, 2>(stg + CvSmem::L2, CV_L2_STRIDE, p.out[2], e, p.HW, m0, p.H2 >> 2,
                              p.W2 >> 2, h0 >> 2, w0 >> 2, etid);
         cv_store_level<2, 1>(stg + CvSmem::L3, CV_L3_STRIDE, p.out[3], e, p.HW, m0, p.H2 >> 3,
                              p.W2 >> 3, h0 >> 3, w0 >> 3, etid);
       }
     }
+    if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -336,6 +355,20 @@ int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, cons
   p.ii = ii; p.jj = jj; p.HW = HW; p.H2 = H; p.W2 = W;
   p.NH = (H + CV_TH - 1) / CV_TH; p.NW = (W + CV_TW - 1) / CV_TW;
   p.MT = (HW + 127) / 128; p.nwork = E * p.MT;
+  // output tensor maps for levels 0/1: {W_l, H_l, HW, E}, box {16>>l, 8>>l, 128, 1}, no swizzle
+  CUtensorMap tmO[2];
+  int use_tma[2] = {0, 0};
+  for (int l = 0; l < 2; l++) {
+    const int Hl = H >> l, Wl = W >> l;
+    if (Hl == 0 || Wl == 0 || (Wl * 2) % 16 != 0 || ((size_t)Hl * Wl * 2) % 16 != 0) { tmO[l] = tmA; continue; }
+    uint64_t dims[4] = {(uint64_t)Wl, (uint64_t)Hl, (uint64_t)HW, (uint64_t)E};
+    uint64_t strides[3] = {(uint64_t)Wl * 2, (uint64_t)Hl * Wl * 2, (uint64_t)HW * Hl * Wl * 2};
+    uint32_t box[4] = {(uint32_t)(CV_TW >> l), (uint32_t)(CV_TH >> l), 128, 1};
+    int r = tc::make_tmap_f16(&tmO[l], p.out[l], 4, dims, strides, box, false, nullptr, /*swizzle128=*/false);
+    if (r) return r;
+    use_tma[l] = 1;
+  }
+  p.tma_l0 = use_tma[0]; p.tma_l1 = use_tma[1];
   const int smem = CvSmem::TOTAL + 1024;
   static bool configured = false;
   if (!configured) {
@@ -348,7 +381,7 @@ int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, cons
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.nwork < sms ? p.nwork : sms;
-  corr_volume_tc_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  corr_volume_tc_kernel<<<grid, CV_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, tmO[0], tmO[1], p);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }

@@ -619,6 +619,104 @@ grid_scatter_kernel(const float* __restrict__ coords, const int* __restrict__ co
   }
 }
 
+
+// occupancy-grid refresh on tensor cores: cell -> jittered point -> hash encode -> density MLP (layers 1-2)
+// -> EMA-max into density[].  Same sampling rule as ngp::density_sample_kernel (csrc/ngp_train.cu).
+__global__ void __launch_bounds__(128)
+density_tc_kernel(const __half2* __restrict__ grid, LevelInfo lv, const unsigned char* __restrict__ packed,
+                  float aabb_lo, float inv_extent, int cascades, int n_per_cascade, uint32_t seed, float decay,
+                  float* __restrict__ density) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + FwdSmem::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int total = n_per_cascade * cascades;
+  const int ntiles = (total + 127) / 128;
+  for (int i = tid; i < PW3 / 16; i += 128)          // W1 and W2 images only
+    reinterpret_cast<uint4*>(sm + FwdSmem::W)[i] = reinterpret_cast<const uint4*>(packed)[i];
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
+  NGP_TC_SYNC();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_addr = tc::smem_u32(sm + FwdSmem::A), w_addr = tc::smem_u32(sm + FwdSmem::W);
+  unsigned char* arow = sm + FwdSmem::A + tid * 128;
+  const int NC = GRID * GRID * GRID;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i = tile * 128 + tid;
+    bool actv = i < total;
+    size_t gi = 0;
+    float s = 1.f, x01[3] = {0.5f, 0.5f, 0.5f};
+    if (actv) {
+      const int mip = i / n_per_cascade, j = i % n_per_cascade;
+      const uint32_t cell = (n_per_cascade >= NC) ? (uint32_t)j : (pcg(pcg(seed) ^ (uint32_t)i) % NC);
+      gi = (size_t)mip * NC + cell;
+      actv = density[gi] >= 0.f;                     // never visible from a training camera -> skip
+      const int ix = cell % GRID, iy = (cell / GRID) % GRID, iz = cell / (GRID * GRID);
+      s = scalbnf(1.f, mip);
+      const float p[3] = {((ix + rnd01(seed, i, 11)) / GRID - 0.5f) * s + 0.5f,
+                          ((iy + rnd01(seed, i, 12)) / GRID - 0.5f) * s + 0.5f,
+                          ((iz + rnd01(seed, i, 13)) / GRID - 0.5f) * s + 0.5f};
+#pragma unroll
+      for (int k = 0; k < 3; k++) x01[k] = (p[k] - aabb_lo) * inv_extent;
+    }
+    {
+      float enc[ENC_DIM];
+      if (actv) {
+        hash_encode(x01, grid, lv, enc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < ENC_DIM; k++) enc[k] = 0.f;
+      }
+      const float z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 4; c++) store_row_chunk(arow, tid, c, enc + 8 * c);
+#pragma unroll
+      for (int c = 4; c < 8; c++) store_row_chunk(arow, tid, c, z8);
+    }
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<64>(a_addr, w_addr + PW1, tmem, 2, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+      float v[8];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        tc::tmem_ld_32x32(taddr + h * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) v[j] = fmaxf(__uint_as_float(r[c * 8 + j]), 0.f);
+          store_row_chunk(arow, tid, h * 4 + c, v);
+        }
+      }
+    }
+    NGP_TC_SYNC();
+    if (tid == 0) issue_layer<16>(a_addr, w_addr + PW2, tmem, 4, bar);
+    tc::mbar_wait(bar, phase & 1); phase++;
+    tc::tc_fence_after();
+    {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(taddr, r);
+      tc::tmem_ld_wait();
+      if (actv) {
+        const float thick = __expf(__uint_as_float(r[0])) * MIN_STEP * s;   // optical thickness of one minimal step
+        density[gi] = fmaxf(density[gi] * decay, thick);
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
 }  // namespace ngp
 
 extern "C" {
@@ -722,6 +820,32 @@ int nslam_ngp_loss_backward_tc(const nslam_ngp_model* m, const nslam_ngp_batch* 
   if (r) return r;
   return nslam_ngp_backward_tc(m, packed, b->coords, b->counters, b->dout, loss_scale, b->enc, b->denc, b->max_samples,
                                num_sms, stream);
+}
+
+/* density MLP on tensor cores for the occupancy-grid refresh (phase of nslam_ngp_update_density_grid) */
+int nslam_ngp_density_sample_tc(const nslam_ngp_model* m, const void* packed, int n_per_cascade, unsigned seed,
+                                float decay, int num_sms, void* stream) {
+  using namespace ngp;
+  LevelInfo lv;
+  for (int l = 0; l < N_LEVELS; l++) {
+    lv.scale[l] = m->scale[l]; lv.res[l] = m->res[l]; lv.size[l] = m->size[l];
+    lv.offset[l] = m->offset[l]; lv.dense[l] = m->dense[l];
+  }
+  const int smem = FwdSmem::TOTAL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(density_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int total = n_per_cascade * m->cascades;
+  if (total == 0) return 0;
+  int grid = (total + 127) / 128;
+  if (grid > 4 * num_sms) grid = 4 * num_sms;
+  density_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __half2*)m->grid_half, lv, (const unsigned char*)packed,
+                                                              0.5f - 0.5f * m->aabb_scale, 1.f / m->aabb_scale, m->cascades,
+                                                              n_per_cascade, seed, decay, m->density);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

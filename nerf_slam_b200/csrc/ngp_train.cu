@@ -897,7 +897,8 @@ int nslam_ngp_loss_backward(const nslam_ngp_model* m, const nslam_ngp_batch* b, 
 
 /* occupancy grid: mark visibility, sample densities (EMA-max), rebuild the bitfield */
 int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_images* im, int n_per_cascade,
-                                  unsigned seed, float decay, float min_thickness, void* stream) {
+                                  unsigned seed, float decay, float min_thickness, const void* packed, int num_sms,
+                                  void* stream) {
   using namespace ngp;
   int r = ensure_attrs();
   if (r) return r;
@@ -908,9 +909,14 @@ int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_imag
                                                                       im->n_active, m->cascades, m->density);
   NGP_CHECK_LAUNCH();
   const int n = n_per_cascade * m->cascades;
-  density_sample_kernel<<<(n + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>((const __half2*)m->grid_half, make_lv(m), m->mlp,
-                                                                     make_scene(m), n_per_cascade, seed, decay, m->density);
-  NGP_CHECK_LAUNCH();
+  if (packed) {
+    r = nslam_ngp_density_sample_tc(m, packed, n_per_cascade, seed, decay, num_sms, stream);
+    if (r) return r;
+  } else {
+    density_sample_kernel<<<(n + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>((const __half2*)m->grid_half, make_lv(m), m->mlp,
+                                                                       make_scene(m), n_per_cascade, seed, decay, m->density);
+    NGP_CHECK_LAUNCH();
+  }
   cudaMemsetAsync(m->stats, 0, 2 * sizeof(float), st);
   density_mean_kernel<<<592, 256, 0, st>>>(m->density, total, m->stats);
   NGP_CHECK_LAUNCH();

@@ -268,7 +268,8 @@ class Testbed:
         _lib.check(lib.nslam_ngp_update_density_grid(ctypes.byref(self.model), ctypes.byref(im), n,
                                                      (self.seed * 7919 + self.training_step) & 0xFFFFFFFF,
                                                      self.nerf.training.density_grid_decay, 0.01,
-                                                     _lib.stream_ptr()), "ngp_update_density_grid")
+                                                     _lib.ptr(self.packed) if self.mlp_backend == "tcgen05" else None,
+                                                     self.num_sms, _lib.stream_ptr()), "ngp_update_density_grid")
 
     def train_step(self):
         """one optimisation step; no host synchronisation"""
