@@ -30,8 +30,20 @@ inorm_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int 
 #pragma unroll
     for (int j = 0; j < 8; j++) { const float v = __half2float(h[j]); s[j] += v; q[j] = fmaf(v, v, q[j]); }
   }
+  // lanes that own the same channel group (lane % CG equal) are reduced by shuffles first, so that each
+  // warp issues one shared-memory atomic per channel instead of one per thread
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < 8; j++) { atomicAdd(&acc[(cg * 8 + j) * 2], s[j]); atomicAdd(&acc[(cg * 8 + j) * 2 + 1], q[j]); }
+  for (int j = 0; j < 8; j++) {
+    for (int o = 16; o >= CG; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+    }
+  }
+  if (lane < CG || CG >= 32) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { atomicAdd(&acc[(cg * 8 + j) * 2], s[j]); atomicAdd(&acc[(cg * 8 + j) * 2 + 1], q[j]); }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(stats + (size_t)b * C * 2 + i, acc[i]);
 }

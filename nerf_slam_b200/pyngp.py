@@ -159,6 +159,7 @@ class Testbed:
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self._measured = None
         self.grad_hook = None        # e.g. dist.allreduce_grads for data-parallel training
+        self._ctr_event = None; self._ctr_host = None; self._loss_host = None; self._ctr_rays = 0
         # "tcgen05": MLP forward/backward on tensor cores (csrc/ngp_tc.cu); "simt": fp32 CUDA-core kernels
         self.mlp_backend = "tcgen05"
         self.loss_scale = 1024.0
@@ -297,16 +298,36 @@ class Testbed:
         _lib.check(lib.nslam_ngp_adam(ctypes.byref(self.model), self.training_step, self.lr * decay, self.beta1,
                                       self.beta2, self.eps, self.l2, _lib.stream_ptr()), "ngp_adam")
         self.pack_weights()
-        # adapt the ray count so that a batch holds ~max_samples samples (uses the LAST completed step's
-        # counters without blocking: read asynchronously every 16 steps)
-        if self.training_step % 16 == 0:
-            c = self._bufs["counters"].cpu()
-            used, kept = int(c[0]), max(int(c[1]), 1)
+        # adapt the ray count so that a batch holds ~max_samples samples.  The device counters are copied to
+        # pinned memory every 16 steps and consumed whenever that copy has completed: the host never waits.
+        if self._ctr_event is not None and self._ctr_event.query():
+            used, kept = int(self._ctr_host[0]), max(int(self._ctr_host[1]), 1)
+            self.loss = float(self._loss_host[0])
+            self._ctr_event = None
             self._measured = (used, kept)
             target = int(0.9 * self.max_samples)
-            new = int(self.rays_per_batch * target / max(used, 1))
+            new = int(self._ctr_rays * target / max(used, 1))
             self.rays_per_batch = int(min(self.max_rays, max(256, (new // 128) * 128)))
+        if self.training_step % 16 == 0 and self._ctr_event is None:
+            if self._ctr_host is None:
+                self._ctr_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+                self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self._ctr_host.copy_(self._bufs["counters"], non_blocking=True)
+            self._loss_host.copy_(self._bufs["loss"], non_blocking=True)
+            self._ctr_rays = self.rays_per_batch
+            self._ctr_event = torch.cuda.Event()
+            self._ctr_event.record()
+
+    def sync_stats(self):
+        """block until the last asynchronous counter/loss readback has landed (tests, reporting)"""
+        torch.cuda.current_stream().synchronize()
+        if self._ctr_event is not None:
+            self._ctr_event.synchronize()
+            self.loss = float(self._loss_host[0])
+            self._measured = (int(self._ctr_host[0]), max(int(self._ctr_host[1]), 1))
+        else:
             self.loss = float(self._bufs["loss"].item())
+        return self.loss
 
     def frame(self):
         """Testbed.frame(): one training step when shall_train and data is present (fusion/nerf_fusion.py:299)"""

@@ -80,8 +80,9 @@ def test_segment_mean():
     order = np.argsort(inv, kind="stable").astype(np.int32)
     ptr = np.zeros(len(ux) + 1, np.int32); np.cumsum(np.bincount(inv), out=ptr[1:])
     out = torch.empty(len(ux), HW, 128, dtype=torch.float16, device=DEV)
-    _lib.check(lib.nslam_segment_mean(_lib.ptr(a), _lib.ptr(torch.as_tensor(ptr, device=DEV)), _lib.ptr(torch.as_tensor(order, device=DEV)),
-                                      _lib.ptr(out), len(ux), HW, _lib.stream_ptr()), "segmean")
+    ptr_d, order_d = torch.as_tensor(ptr, device=DEV), torch.as_tensor(order, device=DEV)     # keep alive across the launch
+    _lib.check(lib.nslam_segment_mean(_lib.ptr(a), _lib.ptr(ptr_d), _lib.ptr(order_d), _lib.ptr(out), len(ux), HW,
+                                      _lib.stream_ptr()), "segmean")
     for k, u in enumerate(ux):
         ref = a[torch.as_tensor(ii == u, device=DEV)].float().mean(0)
         assert float((out[k].float() - ref).abs().max()) < 2e-3

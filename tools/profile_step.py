@@ -53,4 +53,5 @@ torch.cuda.synchronize()
 tb = job2.nf.ngp
 for _ in range(40): tb.train_step()
 T(tb.train_step, n=32, name=f"nerf train_step rays={tb.rays_per_batch}")
+tb.sync_stats()
 print("nerf samples/rays last:", tb._measured, "loss", tb.loss)
