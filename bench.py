@@ -118,7 +118,10 @@ class SlamNerfJob:
         if self.is_nerf:
             from nerf_slam_b200.nerf_fusion import NerfFusion
             self.nf = NerfFusion("nerf", args, self.dev)
-            self.nerf_stream = torch.cuda.Stream() if world == 1 else torch.cuda.current_stream()
+            self.nerf_stream = torch.cuda.Stream(priority=0) if world == 1 else torch.cuda.current_stream()
+        # SLAM is the latency-critical chain (host decisions wait on it): its kernels run on a HIGH-priority
+        # stream so that NeRF training on the same GPU only fills the gaps
+        self.slam_stream = torch.cuda.Stream(priority=-1) if (self.is_slam and world == 1) else torch.cuda.current_stream()
         self.handoff = None
         self.nerf_group = None
         if world > 1:
@@ -154,18 +157,19 @@ class SlamNerfJob:
         if self.is_slam:
             if e2e:
                 self.h2d += packet["images"].numel()
-            _, _, viz = self.fe.forward(packet)
-            if self.world == 1:
-                if viz is not None and "cam0_poses" in viz:
-                    ev = torch.cuda.Event(); ev.record()
-                    with torch.cuda.stream(self.nerf_stream):
-                        self.nerf_stream.wait_event(ev)
-                        self.nf.process_slam([None, viz])
-            else:
-                self._send(viz)
-            if e2e:
-                result = self.fe.cam0_T_world[max(self.fe.kf_idx - 1, 0)].cpu()      # D2H of the step's result
-                self.d2h += 7 * 4
+            with torch.cuda.stream(self.slam_stream):
+                _, _, viz = self.fe.forward(packet)
+                if self.world == 1:
+                    if viz is not None and "cam0_poses" in viz:
+                        ev = torch.cuda.Event(); ev.record()
+                        with torch.cuda.stream(self.nerf_stream):
+                            self.nerf_stream.wait_event(ev)
+                            self.nf.process_slam([None, viz])
+                else:
+                    self._send(viz)
+                if e2e:
+                    result = self.fe.cam0_T_world[max(self.fe.kf_idx - 1, 0)].cpu()      # D2H of the step's result
+                    self.d2h += 7 * 4
         elif self.world > 1:
             self._recv()
         if self.is_nerf:
@@ -249,8 +253,9 @@ def run_ours(a):
         e0.record()
         for p in frames[a.warmup:]:
             job.step(p, e2e)
-        if job.is_nerf and world == 1:
+        if world == 1:
             torch.cuda.current_stream().wait_stream(job.nerf_stream)
+            torch.cuda.current_stream().wait_stream(job.slam_stream)
         e1.record()
         barrier()
         if prof:

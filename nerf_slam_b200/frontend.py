@@ -156,7 +156,8 @@ class RaftVisualFrontend:
         self._static = None
         self._img_static = None
         self._graph_pool = torch.cuda.graph_pool_handle() if self.use_cuda_graphs else None
-        self._capture_stream = torch.cuda.Stream() if self.use_cuda_graphs else None
+        # kernel nodes inherit the priority of the stream they were captured on: keep the SLAM chain high
+        self._capture_stream = torch.cuda.Stream(priority=-1) if self.use_cuda_graphs else None
 
     def stop_condition(self):
         return self.stop
@@ -497,23 +498,27 @@ class RaftVisualFrontend:
         mask = np.asarray(mask, dtype=bool)
         if mask.shape[0] == 0:
             return
-        md = torch.as_tensor(mask, device=self.device)
+        # integer index tensors built on the host: boolean-mask indexing would sync the device (nonzero)
+        if not mask.any():
+            return
+        rm_d = torch.as_tensor(np.nonzero(mask)[0], device=self.device)
         if store:
             self.ii_inactive_h = np.concatenate([self.ii_inactive_h, self.ii_h[mask]])
             self.jj_inactive_h = np.concatenate([self.jj_inactive_h, self.jj_h[mask]])
-            self.gru_estimated_flow_inactive = torch.cat([self.gru_estimated_flow_inactive, self.gru_estimated_flow[md]], 0)
+            self.gru_estimated_flow_inactive = torch.cat([self.gru_estimated_flow_inactive,
+                                                          self.gru_estimated_flow.index_select(0, rm_d)], 0)
             self.gru_estimated_flow_weight_inactive = torch.cat(
-                [self.gru_estimated_flow_weight_inactive, self.gru_estimated_flow_weight[md]], 0)
+                [self.gru_estimated_flow_weight_inactive, self.gru_estimated_flow_weight.index_select(0, rm_d)], 0)
         if self.corr_impl == "volume":
             self.corr_pool.release(self.slots_h[mask].tolist())
         keep = ~mask
         self.ii_h, self.jj_h, self.age_h, self.slots_h = self.ii_h[keep], self.jj_h[keep], self.age_h[keep], self.slots_h[keep]
         self._sync_edges()
-        kd = ~md
+        kd = torch.as_tensor(np.nonzero(keep)[0], device=self.device)
         if self.gru_hidden_states is not None:
-            self.gru_hidden_states = self.gru_hidden_states[kd]
-        self.gru_estimated_flow = self.gru_estimated_flow[kd]
-        self.gru_estimated_flow_weight = self.gru_estimated_flow_weight[kd]
+            self.gru_hidden_states = self.gru_hidden_states.index_select(0, kd)
+        self.gru_estimated_flow = self.gru_estimated_flow.index_select(0, kd)
+        self.gru_estimated_flow_weight = self.gru_estimated_flow_weight.index_select(0, kd)
 
     def rm_keyframe(self, kf):
         """visual_frontend.py:530-574"""
@@ -526,10 +531,10 @@ class RaftVisualFrontend:
         self.ii_inactive_h[self.ii_inactive_h >= kf] -= 1
         self.jj_inactive_h[self.jj_inactive_h >= kf] -= 1
         if m.any():
-            md = torch.as_tensor(~m, device=self.device)
+            md = torch.as_tensor(np.nonzero(~m)[0], device=self.device)
             self.ii_inactive_h, self.jj_inactive_h = self.ii_inactive_h[~m], self.jj_inactive_h[~m]
-            self.gru_estimated_flow_inactive = self.gru_estimated_flow_inactive[md]
-            self.gru_estimated_flow_weight_inactive = self.gru_estimated_flow_weight_inactive[md]
+            self.gru_estimated_flow_inactive = self.gru_estimated_flow_inactive.index_select(0, md)
+            self.gru_estimated_flow_weight_inactive = self.gru_estimated_flow_weight_inactive.index_select(0, md)
         m = (self.ii_h == kf) | (self.jj_h == kf)
         self.ii_h[self.ii_h >= kf] -= 1
         self.jj_h[self.jj_h >= kf] -= 1
@@ -607,9 +612,9 @@ class RaftVisualFrontend:
         st.inp = self.cst_contexts_imgs[self.ii, 0].contiguous()
         if use_inactive:
             m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
-            md = torch.as_tensor(m, device=dev)
+            md = torch.as_tensor(np.nonzero(m)[0], device=dev)     # integer indices: no device->host sync
             ii = np.concatenate([self.ii_inactive_h[m], ii_h]); jj = np.concatenate([self.jj_inactive_h[m], jj_h])
-            tin = self.gru_estimated_flow_inactive[md]; win = self.gru_estimated_flow_weight_inactive[md]
+            tin = self.gru_estimated_flow_inactive.index_select(0, md); win = self.gru_estimated_flow_weight_inactive.index_select(0, md)
         else:
             ii, jj = ii_h, jj_h
             tin = win = torch.zeros(0, ht, wd, 2, device=dev)

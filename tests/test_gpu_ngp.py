@@ -74,7 +74,7 @@ def _grad_err(got, ref, backend):
 
 
 @pytest.mark.parametrize("backend,R,per,tol", [("simt", 24, 11, 3e-3), ("tcgen05", 24, 11, 1e-1), ("tcgen05", 300, 13, 1e-1),
-                                               ("tcgen05", 8, 16, 3e-3)])
+                                               ("tcgen05", 8, 16, 1e-1)])
 def test_loss_and_gradients_match_autograd(backend, R, per, tol):
     """simt: fp32 CUDA-core kernels, tight tolerance.  tcgen05: fp16 operands (weights, activations,
     loss-scaled deltas), fp32 accumulation in TMEM -> gradients within 2 % of the largest entry."""
