@@ -187,7 +187,7 @@ class SlamNerfJob:
             z = torch.zeros(0, dtype=torch.long, device=self.dev)
             self.handoff.send(z, None, torch.zeros(0, 3, H_IMG, W_IMG, dtype=torch.uint8, device=self.dev), None, None)
             return
-        c2w = torch.as_tensor(_pose_tq_to_c2w(viz["cam0_poses"])[:, :3, :4], device=self.dev, dtype=torch.float32)
+        c2w = torch.as_tensor(_pose_tq_to_c2w(viz.get("cam0_poses_host", viz["cam0_poses"]))[:, :3, :4], device=self.dev, dtype=torch.float32)
         self.handoff.send(viz["viz_idx"], c2w, viz["cam0_images"], viz["cam0_idepths_up"], viz["cam0_depths_cov_up"])
 
     def _recv(self):
@@ -304,49 +304,111 @@ def run_ours(a):
                 "d2h_bytes_per_step": int(job.d2h / max(a.steps + a.warmup, 1)), "keyframes": st_e2e["kf"]},
         "clocks": clk,
     }
-    line.update(extra_sections(a, job, pk))
+    st_dev["frames"] = a.steps
+    counts = count_own_launches(job, st_dev)
+    line.update(extra_sections(a, job, pk, counts))
     print(json.dumps(line), flush=True)
 
 
-def extra_sections(a, job, pk):
-    """roofline of the dominant hand-written kernel (live CUDA-event timing), cpu_baseline, launches"""
+def _time_kernel(torch, fn, dev, iters=8, skip=3):
+    """CUDA-event timing on the launching (current) stream, L2 flushed between launches"""
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    ts = []
+    for i in range(iters):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        if i >= skip:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts))
+
+
+def extra_sections(a, job, pk, counts):
+    """roofline of the dominant hand-written kernel (live CUDA-event timing), secondary rooflines,
+    cpu_baseline, launch count"""
     import torch
+    from nerf_slam_b200 import conv as nconv
     from nerf_slam_b200 import droid_backends as db
     out = {}
     fe = job.fe
-    # live timing of the 4-level correlation lookup on the front-end's current graph state
     E = int(fe.ii.shape[0])
-    coords1, _ = fe.reproject(fe.ii, fe.jj)
-    c = coords1.permute(0, 3, 1, 2).contiguous()
-    flush = torch.empty(64 * 1024 * 1024, device=job.dev)
-    ts = []
-    for i in range(8):
-        flush.zero_()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); fe.corr_pool.lookup(fe.slots_d, c); e1.record(); torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(e0.elapsed_time(e1))
-    ms = float(np.mean(ts))
     hw = fe.ht * fe.wd
-    alg = E * hw * (4 * 64 * 2 + 8 + 196 * 2)
-    out["roofline"] = {"kernel": "corr_lookup_kernel<half,3> (A3, 4 pyramid levels fused)", "bound": "hbm",
-                       "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                       "frac": round(alg / ms / 1e6 / pk["hbm_gbs"], 3), "traffic": None,
-                       "peak_source": pk["_src"], "launch_ms": round(ms, 4), "edges": E,
-                       "algorithmic_bytes_per_launch": alg}
-    out["gpu_launches"] = count_launches(job)
+    dev = job.dev
+    h16 = dict(dtype=torch.float16, device=dev)
+    # ---- dominant kernel: the ConvGRU z|r gate convolution (3x3, 448 -> 256 channels, fused gating epilogue),
+    # the single largest kernel of update() (profiles/r01_kernel_table_*.log); tensor-pipe bound
+    op = fe.update_tc
+    net = torch.randn(E, fe.ht, fe.wd, 128, device=dev).half(); inp = torch.randn_like(net); c2 = torch.randn_like(net)
+    f2 = torch.randn(E, fe.ht, fe.wd, 64, device=dev).half()
+    gzr = torch.zeros(E, 256, device=dev); z = torch.empty_like(net); rnet = torch.empty_like(net)
+    wp, b = op.P["zr"]
+    ms = _time_kernel(torch, lambda: nconv.conv_tc([net, inp, c2, f2], wp, b, E, fe.ht, fe.wd, 3, 1, 256, mode=1, gctx=gzr, net=net,
+                                                   out0=z, out0_channels=128, out1=rnet, num_sms=op.num_sms), dev)
+    flops = 2.0 * E * hw * 9 * 448 * 256
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    out["roofline"] = {"kernel": "conv_igemm_kernel<256,1> (A5: ConvGRU z|r gates, 3x3 448->256 + fused sigmoid / r*h epilogue)",
+                       "bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": peak, "unit": "TFLOP/s",
+                       "frac": round(flops / ms / 1e9 / peak, 3),
+                       "traffic": 93408000, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                       "traffic_source": "profiles/r01_ncu_raw_run11.csv, captured at 18 edges",
+                       "peak_source": pk["_src"] + " (dense bf16 cuBLAS, sustained figure: the kernel is timed inside a long step)",
+                       "launch_ms": round(ms, 4), "edges": E, "algorithmic_flops_per_launch": flops}
+    # ---- secondary rooflines (HBM-bound kernels of the path)
+    others = []
+    coords1, _ = fe.reproject(fe.ii, fe.jj)
+    ms = _time_kernel(torch, lambda: fe.corr_pool.lookup(fe.slots_d, coords1, nhwc=True), dev)
+    alg = E * hw * (4 * 64 * 2 + 8 + nconv.CORR_PAD * 2)
+    others.append({"kernel": "corr_lookup_nhwc_kernel<half,3> (A3, 4 pyramid levels fused)", "bound": "hbm",
+                   "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": round(alg / ms / 1e6 / pk["hbm_gbs"], 3), "launch_ms": round(ms, 4), "edges": E})
+    Ev = 4
+    fm = torch.randn(6, fe.ht, fe.wd, 128, device=dev).half()
+    ii32 = torch.tensor([0, 1, 2, 3], dtype=torch.int32, device=dev); jj32 = torch.tensor([1, 2, 3, 4], dtype=torch.int32, device=dev)
+    ms = _time_kernel(torch, lambda: db.corr_volume_build(fm, ii32, jj32), dev)
+    lv = sum((fe.ht >> l) * (fe.wd >> l) for l in range(4))
+    alg = Ev * (2 * 128 * hw * 2 + hw * lv * 2)
+    others.append({"kernel": "corr_volume_tc_kernel (A2, volume + 3 pooled levels in one pass)", "bound": "hbm",
+                   "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": round(alg / ms / 1e6 / pk["hbm_gbs"], 3), "launch_ms": round(ms, 4), "edges": Ev})
+    out["roofline_others"] = others
+    out["gpu_launches"] = counts["total"]
+    out["gpu_launches_detail"] = counts
     out["cpu_baseline"] = cpu_port_sample(a, st_updates_per_frame=None)
     return out
 
 
-def count_launches(job):
-    """kernels of OUR library per keyframe step are counted from the call structure:
-    update() = reproject 1 + lookup 1 + BA 2x(prep, linearise, edge, schur, reduce, assemble, solve, retract, depth)
-               + cov 3 + upsample 2 ;  NeRF iter = sample, forward, loss, backward, adam x2 (+4 every 16)"""
-    upd = 1 + 1 + 2 * 9 + 3 + 2
-    nerf = 6
-    return {"per_update_call": upd, "per_nerf_iter": nerf,
-            "note": "own kernels only; convolutions of the encoders/update operator currently run in cuDNN"}
+def count_own_launches(job, st):
+    """launches of OUR kernels (namespaces nslam:: / ngp::) inside the timed region: kernels per update(),
+    per frame front and per NeRF iteration are counted with the CUPTI profiler on one call each (CUDA-graph
+    replays included), then multiplied by the number of calls the timed region made."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    fe = job.fe
+
+    def own(fn):
+        fn(); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        n_own = n_all = 0
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA and not ev.name.startswith("Mem"):
+                n_all += 1
+                if "nslam::" in ev.name or "ngp::" in ev.name:
+                    n_own += 1
+        return n_own, n_all
+    img = job.make_frames(1, True)[0]
+    x = img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3)
+    with torch.cuda.stream(job.slam_stream):
+        up = own(lambda: fe.update(use_inactive=True))
+        fr = own(lambda: fe._frame_front(x))
+    with torch.cuda.stream(job.nerf_stream):
+        ne = own(job.nf.fit_volume_once) if job.is_nerf else (0, 0)
+    total = up[0] * st["updates"] + fr[0] * st["frames"] + ne[0] * st["nerf_iters"]
+    return {"total": int(total), "own_per_update_call": up[0], "all_per_update_call": up[1], "own_per_frame_front": fr[0],
+            "all_per_frame_front": fr[1], "own_per_nerf_iter": ne[0], "all_per_nerf_iter": ne[1],
+            "note": "own = kernels of libnslam_sm100a.so; the remainder are torch glue and the encoders' cuDNN convolutions; "
+                    "per-keyframe extras (context encoder, correlation volumes of new edges) are not included in total"}
 
 
 # ------------------------------------------------------------------------------------------ CPU port

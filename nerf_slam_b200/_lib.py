@@ -134,3 +134,17 @@ def ptr(t):
     if t is None:
         return c_void_p(0)
     return c_void_p(t.data_ptr())
+
+
+def h2d(a, device, dtype=None):
+    """numpy array (or list) -> device tensor through PINNED memory with a non-blocking copy.
+    `torch.as_tensor(ndarray, device=...)` copies from pageable memory, which makes the CUDA runtime
+    synchronise the stream before every copy (one hidden device sync per small index upload)."""
+    import numpy as np
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if t.numel() == 0:
+        return torch.empty(t.shape, dtype=t.dtype, device=device)
+    return t.pin_memory().to(device, non_blocking=True)

@@ -125,7 +125,7 @@ class BAGraphHost:
     def to_device(self, device):
         import torch
         flat, offs = self.packed()
-        buf = torch.from_numpy(flat).to(device, non_blocking=True)
+        buf = torch.from_numpy(flat).pin_memory().to(device, non_blocking=True)
         g = _lib.BAGraph()
         for name in ("E", "P", "K", "kf0", "NR", "NPAIR", "RMAX", "NHC", "NVC"):
             setattr(g, name, getattr(self, name))

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from . import droid_backends as db
 
 
@@ -81,8 +82,8 @@ class CorrPool:
         if n == 0:
             return
         dev = self.device
-        ii = torch.as_tensor(np.asarray(fi, np.int32), device=dev)
-        jj = torch.as_tensor(np.asarray(fj, np.int32), device=dev)
+        ii = _lib.h2d(np.asarray(fi, np.int32), dev)
+        jj = _lib.h2d(np.asarray(fj, np.int32), dev)
         s = sorted(slots)
         contiguous = s == list(range(s[0], s[0] + n)) and list(slots) == s
         if contiguous:

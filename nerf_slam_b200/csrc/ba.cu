@@ -334,9 +334,7 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
   extern __shared__ double sA[];
   double* A = SMEM ? sA : work;
   double* y = work + (size_t)n * n;  // rhs / solution
-  __shared__ int fail;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) fail = 0;
   for (int id = tid; id < n * n; id += nt) {
     const int r = id / n, c = id % n;
     double a = (double)Hin[id];
@@ -353,48 +351,48 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
     y[id] = r;
   }
   __syncthreads();
-  // right-looking Cholesky, lower triangle, column by column
+  // Right-looking Cholesky on the LOWER triangle, ONE barrier per column: every thread reads the pivot
+  // itself (uniform failure test), the scaled column is written as a ROW of the unused UPPER triangle
+  // (U[j][i] = L[i][j], diagonal in diag[]), so column j of A is read-only during step j and the
+  // trailing update (2-D thread mapping, no integer divisions) needs no intermediate barrier.
+  double* diag = y + n;                       // [n] = L[j][j]
+  const int tx = tid & 15, ty = tid >> 4;     // 16 x 16
+  bool failed = false;
   for (int j = 0; j < n; j++) {
-    if (tid == 0) {
-      const double d = A[(size_t)j * n + j];
-      if (!(d > 0.0)) fail = 1;
-      else A[(size_t)j * n + j] = sqrt(d);
-    }
-    __syncthreads();
-    if (fail) break;
-    const double dj = A[(size_t)j * n + j];
-    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)i * n + j] /= dj;
-    __syncthreads();
-    // trailing update: A[i][c] -= L[i][j] L[c][j] for j < c <= i
-    const int m = n - j - 1;
-    for (int id = tid; id < m * m; id += nt) {
-      const int i = j + 1 + id / m, c = j + 1 + id % m;
-      if (c <= i) A[(size_t)i * n + c] -= A[(size_t)i * n + j] * A[(size_t)c * n + j];
+    const double d = A[(size_t)j * n + j];
+    if (!(d > 0.0)) { failed = true; break; }
+    const double rs = 1.0 / sqrt(d);
+    if (tid == 0) diag[j] = d * rs;
+    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)j * n + i] = A[(size_t)i * n + j] * rs;   // U[j][i]
+    for (int i = j + 1 + ty; i < n; i += 16) {
+      const double li = A[(size_t)i * n + j] * rs;
+      for (int c = j + 1 + tx; c <= i; c += 16) A[(size_t)i * n + c] -= li * (A[(size_t)c * n + j] * rs);
     }
     __syncthreads();
   }
-  if (fail) {
+  if (failed) {
     for (int id = tid; id < n; id += nt) dx[id] = 0.f;
     if (Linv) for (int id = tid; id < n * n; id += nt) Linv[id] = 0.f;
     if (tid == 0 && status) *status = 1;
     return;
   }
+  // L[i][c] (c < i) = A[c*n + i];  L[i][i] = diag[i]
   // forward/back substitution by one warp (n is small): L z = y, L^T x = z
   if (tid < 32) {
     for (int i = 0; i < n; i++) {
       double s = 0.0;
-      for (int c = tid; c < i; c += 32) s += A[(size_t)i * n + c] * y[c];
+      for (int c = tid; c < i; c += 32) s += A[(size_t)c * n + i] * y[c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
+      if (tid == 0) y[i] = (y[i] - s) / diag[i];
       __syncwarp();
     }
     for (int i = n - 1; i >= 0; i--) {
       double s = 0.0;
-      for (int c = i + 1 + tid; c < n; c += 32) s += A[(size_t)c * n + i] * y[c];
+      for (int c = i + 1 + tid; c < n; c += 32) s += A[(size_t)i * n + c] * y[c];     // L[c][i] = U[i][c]
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
+      if (tid == 0) y[i] = (y[i] - s) / diag[i];
       __syncwarp();
     }
   }
@@ -402,21 +400,19 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
   for (int id = tid; id < n; id += nt) dx[id] = (float)y[id];
   if (tid == 0 && status) *status = 0;
   if (Linv) {
-    // column c of L^-1: solve L x = e_c (one thread per column, fp64 scratch behind y)
-    double* Li = work + (size_t)n * n + 2 * (size_t)n;
+    // column c of L^-1: solve L x = e_c.  One thread per column; x overwrites the (now free) LOWER
+    // triangle of A column by column: X[i][c] lives at A[i*n + c] (i >= c), which step j > c never reads
+    // as part of L (L is in the upper triangle).
     for (int c = tid; c < n; c += nt) {
       for (int i = 0; i < n; i++) {
+        if (i < c) { Linv[(size_t)i * n + c] = 0.f; continue; }
         double s = (i == c) ? 1.0 : 0.0;
-        for (int k = c; k < i; k++) s -= A[(size_t)i * n + k] * Li[(size_t)k * n + c];
-        const double x = (i < c) ? 0.0 : s / A[(size_t)i * n + i];
-        Li[(size_t)i * n + c] = x;
+        for (int k = c; k < i; k++) s -= A[(size_t)k * n + i] * A[(size_t)k * n + c];   // L[i][k] * X[k][c]
+        const double x = s / diag[i];
+        A[(size_t)i * n + c] = x;
         Linv[(size_t)i * n + c] = (float)x;
       }
     }
-  }
-  if (SMEM) {
-    __syncthreads();
-    for (int id = tid; id < n * n; id += nt) work[id] = A[id];
   }
 }
 

@@ -198,7 +198,7 @@ class RaftVisualFrontend:
         self.intr0 = self.cam0_intrinsics[0]      # the kernels only ever see the first keyframe's intrinsics
         self.corr_pool = CorrPool(int(getattr(self.args, "corr_slots", 2 * self.max_factors)), ht, wd, dev)
         self._reset_graph()
-        self.viz_idx = torch.zeros(B, device=dev, dtype=torch.bool)
+        self.viz_idx = np.zeros(B, dtype=bool)          # host-side dirty flags (a device mask would need a sync to read)
 
     def _reset_graph(self):
         dev, ht, wd = self.device, self.ht, self.wd
@@ -218,9 +218,9 @@ class RaftVisualFrontend:
 
     def _sync_edges(self):
         self._static = None            # edge set changed: static part / CUDA graph of update() is stale
-        self.ii = torch.as_tensor(self.ii_h, device=self.device)
-        self.jj = torch.as_tensor(self.jj_h, device=self.device)
-        self.slots_d = torch.as_tensor(self.slots_h.astype(np.int32), device=self.device)
+        self.ii = _lib.h2d(self.ii_h, self.device)
+        self.jj = _lib.h2d(self.jj_h, self.device)
+        self.slots_d = _lib.h2d(self.slots_h.astype(np.int32), self.device)
 
     # ------------------------------------------------------------------ per-frame entry
     def _normalize_imgs(self, images):
@@ -229,14 +229,14 @@ class RaftVisualFrontend:
 
     def _store_frame(self, idx, batch, imgs_k):
         dev = self.device
-        self.gt_poses[idx] = torch.as_tensor(np.asarray(batch["poses"][0]), device=dev, dtype=torch.float32)
+        self.gt_poses[idx] = _lib.h2d(np.asarray(batch["poses"][0]), dev, torch.float32)
         if batch["depths"][0] is not None:
             d = torch.as_tensor(np.asarray(batch["depths"][0]), device=dev).float()
             self.gt_depths[idx] = d.permute(2, 0, 1)
         self.cam0_timestamps[idx] = float(batch["t_cams"][0])
         self.cam0_images[idx] = imgs_k[0, 0, :3]
         cm = batch["calibs"][0].camera_model.numpy()
-        self.cam0_intrinsics[idx] = (1.0 / self.dsf) * torch.as_tensor(np.asarray(cm), device=dev, dtype=torch.float32)
+        self.cam0_intrinsics[idx] = (1.0 / self.dsf) * _lib.h2d(np.asarray(cm), dev, torch.float32)
 
     def _feature_encoder(self, imgs_norm):
         return self.feature_net(imgs_norm)[0]          # [cams,128,ht,wd] fp16
@@ -253,7 +253,7 @@ class RaftVisualFrontend:
         order = np.argsort(inv, kind="stable").astype(np.int32)
         ptr = np.zeros(len(ux) + 1, np.int32)
         np.cumsum(np.bincount(inv, minlength=len(ux)), out=ptr[1:])
-        return (torch.as_tensor(ptr, device=device), torch.as_tensor(order, device=device), len(ux))
+        return (_lib.h2d(ptr, device), _lib.h2d(order, device), len(ux))
 
     def _run_update_net(self, net, inp, corr_nhwc, coords1, target, ii_host=None):
         """update operator on NHWC tensors: net/inp [E,ht,wd,128], corr [E,ht,wd,CORR_PAD], coords1/target
@@ -271,7 +271,7 @@ class RaftVisualFrontend:
         tgt = coords1 if target is None else target
         motion = torch.cat([coords1 - self.coords0, tgt - coords1], dim=-1).permute(0, 3, 1, 2).clamp(-64.0, 64.0)
         nchw = lambda t: t.permute(0, 3, 1, 2)
-        ii = None if ii_host is None else torch.as_tensor(np.asarray(ii_host), device=self.device)
+        ii = None if ii_host is None else _lib.h2d(np.asarray(ii_host), self.device)
         out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None], motion[None], ii, ii)
         net2 = out[0][0].permute(0, 2, 3, 1).contiguous()
         if ii is None:
@@ -401,8 +401,8 @@ class RaftVisualFrontend:
 
     def distance(self, ii, jj, beta=0.3, bidirectional=True):
         """visual_frontend.py:778-799"""
-        ii = torch.as_tensor(np.asarray(ii), device=self.device, dtype=torch.long).reshape(-1)
-        jj = torch.as_tensor(np.asarray(jj), device=self.device, dtype=torch.long).reshape(-1)
+        ii = _lib.h2d(np.asarray(ii).reshape(-1), self.device, torch.long)
+        jj = _lib.h2d(np.asarray(jj).reshape(-1), self.device, torch.long)
         if bidirectional:
             poses = self.cam0_T_world[:self.kf_idx + 1].clone()
             d1 = db.frame_distance(poses, self.cam0_idepths, self.cam0_intrinsics[0], ii, jj, beta)
@@ -486,7 +486,7 @@ class RaftVisualFrontend:
         self.age_h = np.concatenate([self.age_h, np.zeros(new, np.int64)])
         self.slots_h = np.concatenate([self.slots_h, slots])
         self._sync_edges()
-        iid = torch.as_tensor(ii, device=self.device)
+        iid = _lib.h2d(ii, self.device)
         hid = self.contexts_imgs[iid, 0]
         self.gru_hidden_states = hid if self.gru_hidden_states is None else torch.cat([self.gru_hidden_states, hid], 0)
         target, _ = self.reproject(ii, jj)
@@ -501,7 +501,7 @@ class RaftVisualFrontend:
         # integer index tensors built on the host: boolean-mask indexing would sync the device (nonzero)
         if not mask.any():
             return
-        rm_d = torch.as_tensor(np.nonzero(mask)[0], device=self.device)
+        rm_d = _lib.h2d(np.nonzero(mask)[0], self.device)
         if store:
             self.ii_inactive_h = np.concatenate([self.ii_inactive_h, self.ii_h[mask]])
             self.jj_inactive_h = np.concatenate([self.jj_inactive_h, self.jj_h[mask]])
@@ -514,7 +514,7 @@ class RaftVisualFrontend:
         keep = ~mask
         self.ii_h, self.jj_h, self.age_h, self.slots_h = self.ii_h[keep], self.jj_h[keep], self.age_h[keep], self.slots_h[keep]
         self._sync_edges()
-        kd = torch.as_tensor(np.nonzero(keep)[0], device=self.device)
+        kd = _lib.h2d(np.nonzero(keep)[0], self.device)
         if self.gru_hidden_states is not None:
             self.gru_hidden_states = self.gru_hidden_states.index_select(0, kd)
         self.gru_estimated_flow = self.gru_estimated_flow.index_select(0, kd)
@@ -531,7 +531,7 @@ class RaftVisualFrontend:
         self.ii_inactive_h[self.ii_inactive_h >= kf] -= 1
         self.jj_inactive_h[self.jj_inactive_h >= kf] -= 1
         if m.any():
-            md = torch.as_tensor(np.nonzero(~m)[0], device=self.device)
+            md = _lib.h2d(np.nonzero(~m)[0], self.device)
             self.ii_inactive_h, self.jj_inactive_h = self.ii_inactive_h[~m], self.jj_inactive_h[~m]
             self.gru_estimated_flow_inactive = self.gru_estimated_flow_inactive.index_select(0, md)
             self.gru_estimated_flow_weight_inactive = self.gru_estimated_flow_weight_inactive.index_select(0, md)
@@ -542,8 +542,8 @@ class RaftVisualFrontend:
 
     def reproject(self, ii, jj):
         """visual_frontend.py:909-918 -> coords [E,ht,wd,2], valid"""
-        ii = torch.as_tensor(np.asarray(ii) if not torch.is_tensor(ii) else ii, device=self.device, dtype=torch.long).reshape(-1)
-        jj = torch.as_tensor(np.asarray(jj) if not torch.is_tensor(jj) else jj, device=self.device, dtype=torch.long).reshape(-1)
+        ii = ii.to(self.device, torch.long).reshape(-1) if torch.is_tensor(ii) else _lib.h2d(np.asarray(ii).reshape(-1), self.device, torch.long)
+        jj = jj.to(self.device, torch.long).reshape(-1) if torch.is_tensor(jj) else _lib.h2d(np.asarray(jj).reshape(-1), self.device, torch.long)
         return db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, ii, jj)
 
     # ------------------------------------------------------------------ init / steady state
@@ -607,12 +607,12 @@ class RaftVisualFrontend:
         kf0 = max(0, int(ii_h.min()))
         st.kf0, st.EP = kf0, EP
         ux, inv = np.unique(ii_h, return_inverse=True)
-        st.ux = torch.as_tensor(ux, device=dev); st.ix = torch.as_tensor(inv, device=dev); st.K = len(ux)
+        st.ux = _lib.h2d(ux, dev); st.ix = _lib.h2d(inv, dev); st.K = len(ux)
         st.agg = self._agg_tables(ii_h, dev)
         st.inp = self.cst_contexts_imgs[self.ii, 0].contiguous()
         if use_inactive:
             m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
-            md = torch.as_tensor(np.nonzero(m)[0], device=dev)     # integer indices: no device->host sync
+            md = _lib.h2d(np.nonzero(m)[0], dev)                   # integer indices: no device->host sync
             ii = np.concatenate([self.ii_inactive_h[m], ii_h]); jj = np.concatenate([self.jj_inactive_h[m], jj_h])
             tin = self.gru_estimated_flow_inactive.index_select(0, md); win = self.gru_estimated_flow_weight_inactive.index_select(0, md)
         else:
@@ -623,13 +623,13 @@ class RaftVisualFrontend:
         st.target = torch.empty(Eba, 2, ht, wd, device=dev); st.weight = torch.empty(Eba, 2, ht, wd, device=dev)
         st.target[:st.n_in] = tin.permute(0, 3, 1, 2); st.weight[:st.n_in] = win.permute(0, 3, 1, 2)
         kxb = np.unique(ii)
-        st.kx_ba = torch.as_tensor(kxb, device=dev)
+        st.kx_ba = _lib.h2d(kxb, dev)
         st.damp = torch.empty(len(kxb), ht, wd, device=dev)
         kf1 = int(max(ii.max(), jj.max())) + 1
         st.kf1 = kf1
         st.prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
                                self.cam0_idepths_sensed, st.target, st.weight, st.damp, ii, jj, kf0, kf1)
-        st.kx_prob = torch.as_tensor(st.prob.gh.tables["kx"].astype(np.int64), device=dev)
+        st.kx_prob = _lib.h2d(st.prob.gh.tables["kx"].astype(np.int64), dev)
         st.has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
         return st
 
@@ -719,7 +719,7 @@ class RaftVisualFrontend:
                                              want_linv=compute_covariances, clamp_min=1e-3)
         if compute_covariances and linv is not None:
             sg, z_cov, d_cov = prob.covariances(linv)
-            kx = torch.as_tensor(prob.gh.tables["kx"].astype(np.int64), device=self.device)
+            kx = _lib.h2d(prob.gh.tables["kx"].astype(np.int64), self.device)
             self.world_T_body_cov[kf0:kf1] = sg
             self.cam0_idepths_cov[kx] = z_cov
             self.cam0_depths_cov[kx] = d_cov
@@ -794,9 +794,10 @@ class RaftVisualFrontend:
     def get_viz_out(self, batch):
         """visual_frontend.py:1337-1391.  Tensors stay on the device: the NeRF side receives them
         through NCCL / peer copies (nerf_slam_b200.dist), never through the CPU."""
-        idx, = torch.where(self.viz_idx)
-        if len(idx) == 0:
+        idx_h = np.nonzero(self.viz_idx)[0]
+        if len(idx_h) == 0:
             return {"is_last_frame": True} if batch["is_last_frame"] else None
+        idx = _lib.h2d(idx_h, self.device)
         sel = lambda t: torch.index_select(t, 0, idx)
         out = {"cam0_poses": sel(self.cam0_T_world), "gt_poses": sel(self.gt_poses), "gt_depths": sel(self.gt_depths),
                "world_T_body": sel(self.world_T_body), "world_T_body_cov": sel(self.world_T_body_cov),
@@ -804,7 +805,9 @@ class RaftVisualFrontend:
                "cam0_idepths_sensed": sel(self.cam0_idepths_sensed), "cam0_idepths_cov": sel(self.cam0_idepths_cov),
                "cam0_depths_cov": sel(self.cam0_depths_cov), "cam0_depths_cov_up": sel(self.cam0_depths_cov_up),
                "cam0_images": sel(self.cam0_images), "cam0_intrinsics": sel(self.cam0_intrinsics),
-               "calibs": batch["calibs"], "viz_idx": idx, "kf_idx": self.kf_idx,
+               "calibs": batch["calibs"], "viz_idx": idx, "viz_idx_host": idx_h.tolist(), "kf_idx": self.kf_idx,
                "kf_idx_to_f_idx": dict(self.kf_idx_to_f_idx), "is_last_frame": batch["is_last_frame"]}
+        # host copy of the (tiny) pose block, read on THIS stream: consumers on other streams then need no sync
+        out["cam0_poses_host"] = out["cam0_poses"].double().cpu().numpy()
         self.viz_idx[:] = False
         return out

@@ -14,7 +14,7 @@ from . import pyngp as ngp
 
 def _pose_tq_to_c2w(tq):
     """cam_T_world [n,7] (t, q_xyzw) -> world_T_cam 4x4 (fp64 on the host; n is small)"""
-    tq = tq.detach().double().cpu().numpy()
+    tq = tq.detach().double().cpu().numpy() if torch.is_tensor(tq) else np.asarray(tq, np.float64)
     out = np.zeros((tq.shape[0], 4, 4))
     for k, v in enumerate(tq):
         x, y, z, w = v[3:]
@@ -75,14 +75,15 @@ class NerfFusion:
             idepths_up = -torch.ones_like(idepths_up)
         elif self.mask_type != "ours":
             raise NotImplementedError(f"Unknown mask type: {self.mask_type}")
-        c2w = _pose_tq_to_c2w(slam["cam0_poses"])          # scale 1.0, offset 0 (:167-170)
+        c2w = _pose_tq_to_c2w(slam.get("cam0_poses_host", slam["cam0_poses"]))          # scale 1.0, offset 0 (:167-170)
+        ids = slam["viz_idx_host"] if "viz_idx_host" in slam else viz_idx.tolist()
         intr = calib.camera_model.numpy()
         dev = self.ngp.device
         self.ngp.nerf.training.update_training_images_device(
-            viz_idx.tolist(), c2w[:, :3, :4], images.to(dev), idepths_up.to(dev), depths_cov_up.to(dev),
+            ids, c2w[:, :3, :4], images.to(dev), idepths_up.to(dev), depths_cov_up.to(dev),
             intr[:2], intr[2:])
         if "gt_depths" in slam:
-            for k, fid in enumerate(viz_idx.tolist()):
+            for k, fid in enumerate(ids):
                 self.ref_frames[fid] = (k, slam)           # lazily materialised by eval_gt_traj
         return False
 

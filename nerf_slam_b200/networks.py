@@ -143,16 +143,18 @@ class BasicEncoder(_Params):
 
     def _forward_fused_norm(self, x):
         """same network with the instance norms, ReLUs and residual adds on the fused NHWC kernels
-        (csrc/inorm.cu): per conv one statistics pass + one apply pass instead of ~8 library launches"""
-        wt, bs = self.w("conv1")
-        x = _cl(conv2d(x, wt, bs, stride=2, padding=3))
+        (csrc/inorm.cu): per conv one statistics pass + one apply pass instead of ~8 library launches.
+        A per-channel bias in front of an instance norm cancels exactly (the norm subtracts the channel mean),
+        so those convolutions run without their bias (saves one elementwise launch each)."""
+        wt, _ = self.w("conv1")
+        x = _cl(conv2d(x, wt, None, stride=2, padding=3))
         _inorm_apply(x, _inorm_stats(x))
         for name, st in self.blocks:
-            y = _cl(conv2d(x, *self.w(name + ".conv1"), stride=st, padding=1))
+            y = _cl(conv2d(x, self.w(name + ".conv1")[0], None, stride=st, padding=1))
             _inorm_apply(y, _inorm_stats(y))
-            z = _cl(conv2d(y, *self.w(name + ".conv2"), stride=1, padding=1))
+            z = _cl(conv2d(y, self.w(name + ".conv2")[0], None, stride=1, padding=1))
             if st != 1:
-                d = _cl(conv2d(x, *self.w(name + ".downsample.0"), stride=st, padding=0))
+                d = _cl(conv2d(x, self.w(name + ".downsample.0")[0], None, stride=st, padding=0))
                 _inorm_apply(z, _inorm_stats(z), res=d, res_st=_inorm_stats(d))
             else:
                 _inorm_apply(z, _inorm_stats(z), res=x)

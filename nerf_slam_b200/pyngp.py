@@ -249,9 +249,9 @@ class Testbed:
         for i in ids:
             if int(i) not in self.active_set:
                 self.active_set.append(int(i))
-        self.cams.copy_(torch.from_numpy(self.cams_h))
+        self.cams.copy_(torch.from_numpy(self.cams_h).pin_memory(), non_blocking=True)
         n = len(self.active_set)
-        self.active[:n] = torch.as_tensor(self.active_set, dtype=torch.int32)
+        self.active[:n].copy_(torch.as_tensor(self.active_set, dtype=torch.int32).pin_memory(), non_blocking=True)
         self.nerf.training.n_images_for_training = n
 
     def _images(self):
