@@ -124,9 +124,33 @@ def check(err, what):
         raise RuntimeError(msg)
 
 
+_fixed_stream = None
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream.  The lookup costs ~14 us of host time; hot loops that issue
+    dozens of launches on one stream wrap themselves in `fixed_stream()` so that it is done once."""
+    if _fixed_stream is not None:
+        return _fixed_stream
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class fixed_stream:
+    """context manager: resolve the current stream once for all C-ABI calls inside (the caller guarantees
+    that the current stream does not change within the block)"""
+
+    def __enter__(self):
+        global _fixed_stream
+        import torch
+        self._prev = _fixed_stream
+        _fixed_stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self
+
+    def __exit__(self, *exc):
+        global _fixed_stream
+        _fixed_stream = self._prev
+        return False
 
 
 def ptr(t):

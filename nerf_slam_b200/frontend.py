@@ -26,6 +26,7 @@ import torch
 from . import droid_backends as db
 from . import _lib
 from .corr import CorrPool, AltCorrBlock
+from .graph import proximity_edges
 from .networks import BasicEncoder, UpdateModule, load_droid_weights
 
 
@@ -155,6 +156,9 @@ class RaftVisualFrontend:
             self.use_cuda_graphs = False       # the library path syncs inside GraphAgg (torch.unique)
         self._static = None
         self._img_static = None
+        # update(): replaying a captured graph saves host time per call but costs a re-capture (~2 ms of host
+        # time with an idle stream) whenever the edge set changes, i.e. once per keyframe
+        self.use_update_graphs = self.use_cuda_graphs and bool(getattr(args, "update_graphs", True))
         self._graph_pool = torch.cuda.graph_pool_handle() if self.use_cuda_graphs else None
         # kernel nodes inherit the priority of the stream they were captured on: keep the SLAM chain high
         self._capture_stream = torch.cuda.Stream(priority=-1) if self.use_cuda_graphs else None
@@ -342,6 +346,10 @@ class RaftVisualFrontend:
         """device-only: static image buffer -> fnet -> motion filter (1 update iteration on
         (last keyframe -> current frame), visual_frontend.py:976-1007) -> self.last_motion"""
         from .conv import CORR_PAD
+        with _lib.fixed_stream():
+            self._frame_front_impl(CORR_PAD)
+
+    def _frame_front_impl(self, CORR_PAD):
         imgs_norm = self._normalize_imgs(self._img_static)
         feats = self._feature_encoder(imgs_norm)                       # [cams,128,ht,wd]
         self._feats_cur.copy_(feats)
@@ -418,44 +426,11 @@ class RaftVisualFrontend:
         ii, jj = np.meshgrid(ix, jx, indexing="ij")
         ii, jj = ii.reshape(-1), jj.reshape(-1)
         d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
-        d[(ii - rad) < jj] = np.inf
-        d[d > 100] = np.inf
-        W = t - kf1
-
-        def suppress(i, j):
-            for di in range(-nms, nms + 1):
-                for dj in range(-nms, nms + 1):
-                    if abs(di) + abs(dj) <= max(min(abs(i - j) - 2, nms), 0):
-                        i1, j1 = i + di, j + dj
-                        if (kf0 <= i1 < t) and (kf1 <= j1 < t):
-                            d[(i1 - kf0) * W + (j1 - kf1)] = np.inf
-
         ii1 = np.concatenate([self.ii_h, self.ii_bad_h, self.ii_inactive_h])
         jj1 = np.concatenate([self.jj_h, self.jj_bad_h, self.jj_inactive_h])
-        for i, j in zip(ii1, jj1):
-            suppress(int(i), int(j))
-        es = []
-        for i in range(kf0, t):
-            if self.stereo:
-                es.append((i, i))
-                d[(i - kf0) * W + (i - kf1)] = np.inf
-            for j in range(max(i - rad - 1, 0), i):
-                es.append((i, j)); es.append((j, i))
-                d[(i - kf0) * W + (j - kf1)] = np.inf
-        # torch.argsort on the reference side: unstable sort of fp32; ties are resolved here by
-        # index order (stable), which is what torch's CPU sort yields for equal keys in practice
-        order = np.argsort(d, kind="stable")
-        for k in order:
-            if d[k] > thresh:
-                continue
-            if len(es) > self.max_factors:
-                break
-            i, j = int(ii[k]), int(jj[k])
-            es.append((i, j)); es.append((j, i))
-            suppress(i, j)
-        if not es:
+        es = proximity_edges(d, ii, jj, ii1, jj1, kf0, kf1, t, rad, nms, thresh, self.max_factors, self.stereo)
+        if es.shape[0] == 0:
             return
-        es = np.asarray(es, dtype=np.int64)
         self.add_factors(es[:, 0], es[:, 1], remove)
 
     def _filter_repeated_edges(self, ii, jj):
@@ -635,6 +610,10 @@ class RaftVisualFrontend:
 
     def _update_body(self, st, itrs, compute_covariances):
         """device-only part of update() (visual_frontend.py:371-470); no host<->device traffic, no syncs"""
+        with _lib.fixed_stream():
+            self._update_body_impl(st, itrs, compute_covariances)
+
+    def _update_body_impl(self, st, itrs, compute_covariances):
         coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
         corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
         if self.update_tc is not None:
@@ -682,7 +661,7 @@ class RaftVisualFrontend:
             st.use_inactive = use_inactive
             self._static = st
         cc = self.compute_covariances
-        if self.use_cuda_graphs and st.calls >= 1:
+        if self.use_update_graphs and st.calls >= 1:
             if st.graph is None:
                 g = torch.cuda.CUDAGraph()
                 cs = self._capture_stream

@@ -274,6 +274,10 @@ class Testbed:
 
     def train_step(self):
         """one optimisation step; no host synchronisation"""
+        with _lib.fixed_stream():
+            self._train_step_impl()
+
+    def _train_step_impl(self):
         lib = _lib.load()
         if self._t0 is None:
             self._t0 = time.perf_counter()

@@ -1,0 +1,36 @@
+"""edge selection (A18): the vectorised host logic must pick bit-identical edges, in the same order,
+as the loop-for-loop restatement of the reference (oracle/graph.py)"""
+import numpy as np
+import pytest
+
+from nerf_slam_b200.graph import proximity_edges
+from oracle.graph import add_proximity_factors_edges
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_proximity_edges_bit_exact(seed):
+    rng = np.random.default_rng(seed)
+    t = int(rng.integers(3, 26))
+    kf0 = int(rng.integers(0, t)); kf1 = int(rng.integers(0, t))
+    if seed % 3 == 0:                      # the frontend's steady-state call: kf0 = kf_idx - 4, kf1 = max(kf_idx + 1 - window, 0)
+        kf0 = max(t - 5, 0); kf1 = max(t - 25, 0)
+    rad = int(rng.integers(1, 4)); nms = int(rng.integers(0, 3))
+    stereo = bool(rng.integers(0, 2)); max_factors = int(rng.integers(4, 80))
+    thresh = float(rng.uniform(5, 40))
+    n = (t - kf0) * (t - kf1)
+    d = rng.uniform(0, 60, n).astype(np.float32)
+    d[rng.random(n) < 0.05] = 150.0                                     # > 100 -> inf
+    d[rng.random(n) < 0.1] = np.float32(7.5)                            # ties
+    ne = int(rng.integers(0, 30))
+    ii1 = rng.integers(0, t, ne); jj1 = rng.integers(0, t, ne)
+    ix, jx = np.meshgrid(np.arange(kf0, t), np.arange(kf1, t), indexing="ij")
+    ref = add_proximity_factors_edges(d, kf0, kf1, t, ii1, jj1, rad, nms, thresh, max_factors, stereo)
+    got = proximity_edges(d.copy(), ix.reshape(-1), jx.reshape(-1), ii1, jj1, kf0, kf1, t, rad, nms, thresh, max_factors, stereo)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_proximity_edges_empty_and_single():
+    d = np.zeros(1, np.float32)
+    got = proximity_edges(d.copy(), np.array([0]), np.array([0]), np.zeros(0, np.int64), np.zeros(0, np.int64), 0, 0, 1, 2, 2, 16.0, 48, False)
+    ref = add_proximity_factors_edges(d, 0, 0, 1, [], [], 2, 2, 16.0, 48, False)
+    assert np.array_equal(got, ref)
