@@ -123,6 +123,8 @@ class SlamNerfJob:
         # SLAM is the latency-critical chain (host decisions wait on it): its kernels run on a HIGH-priority
         # stream so that NeRF training on the same GPU only fills the gaps
         self.slam_stream = torch.cuda.Stream(priority=-1) if (self.is_slam and world == 1) else torch.cuda.current_stream()
+        self._res_ring = [torch.zeros(7).pin_memory() for _ in range(4)]
+        self._res_events = [torch.cuda.Event() for _ in range(4)]
         self.handoff = None
         self.nerf_group = None
         if world > 1:
@@ -169,7 +171,13 @@ class SlamNerfJob:
                 else:
                     self._send(viz)
                 if e2e:
-                    result = self.fe.cam0_T_world[max(self.fe.kf_idx - 1, 0)].cpu()      # D2H of the step's result
+                    # D2H of the step's result (latest keyframe pose): asynchronous copy into a pinned ring, consumed
+                    # one step later -> the host never stalls on it; `drain_results` waits for the last ones before
+                    # the timed region ends
+                    slot = self.k % len(self._res_ring)
+                    self._res_ring[slot].copy_(self.fe.cam0_T_world[max(self.fe.kf_idx - 1, 0)], non_blocking=True)
+                    self._res_events[slot].record()
+                    result = slot
                     self.d2h += 7 * 4
         elif self.world > 1:
             self._recv()
@@ -198,6 +206,12 @@ class SlamNerfJob:
             intr = self.room.calib.camera_model.numpy()
             self.nf.ngp.nerf.training.update_training_images_device(idx.tolist(), c2w.double().cpu().numpy(), img, idep, cov,
                                                                     intr[:2], intr[2:])
+
+    def drain_results(self):
+        """all asynchronous result read-backs of the e2e arm have landed on the host"""
+        for ev in self._res_events:
+            ev.synchronize()
+        return [r.clone() for r in self._res_ring]
 
     def sync(self):
         self.torch.cuda.synchronize()
@@ -254,6 +268,8 @@ def run_ours(a):
         e0.record()
         for p in frames[a.warmup:]:
             job.step(p, e2e)
+        if e2e and job.is_slam:
+            job.drain_results()
         if world == 1:
             torch.cuda.current_stream().wait_stream(job.nerf_stream)
             torch.cuda.current_stream().wait_stream(job.slam_stream)

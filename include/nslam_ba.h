@@ -121,6 +121,9 @@ int nslam_ba_gn_iterations(const nslam_ba_graph* g, const nslam_ba_buffers* b, i
                            double* work, float* dx, float* Linv, float* prior_err, int* status,
                            float clamp_min, void* stream);
 
+/* pixels per CTA tile of the BA kernels: nslam_ba_buffers.T = ceil(ht*wd / tile) */
+int nslam_ba_tile_pixels(void);
+
 #ifdef __cplusplus
 }
 #endif

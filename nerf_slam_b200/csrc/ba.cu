@@ -24,7 +24,7 @@
 
 namespace nslam {
 
-constexpr int TILE = 256;  // pixels per CTA tile (one pixel per thread)
+constexpr int TILE = 128;  // pixels per CTA tile (one pixel per thread); 640x480/8: 38 tiles x K maps fills the 148 SMs twice
 constexpr int AUX = 80;    // floats per edge in edge_aux
 
 // ------------------------------------------------------------------------------------------
@@ -232,7 +232,7 @@ __global__ void ba_edge_blocks_kernel(nslam_ba_graph g, nslam_ba_buffers b) {
 
 // ------------------------------------------------------------------------------------------
 // A9: Schur products for depth map k on one pixel tile: S_ab = sum_p Q e_a e_b^T, v_a = sum_p Q w e_a
-// grid (T, K), 256 threads, dynamic smem: (6*RMAX) rows x (TILE+1) floats + 2*TILE
+// grid (T, K), TILE threads, dynamic smem: (6*RMAX) rows x (TILE+1) floats + 2*TILE
 __global__ void __launch_bounds__(TILE)
 ba_schur_kernel(nslam_ba_graph g, nslam_ba_buffers b) {
   extern __shared__ float sm[];
@@ -404,11 +404,19 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
     // triangle of A column by column: X[i][c] lives at A[i*n + c] (i >= c), which step j > c never reads
     // as part of L (L is in the upper triangle).
     for (int c = tid; c < n; c += nt) {
-      for (int i = 0; i < n; i++) {
-        if (i < c) { Linv[(size_t)i * n + c] = 0.f; continue; }
-        double s = (i == c) ? 1.0 : 0.0;
-        for (int k = c; k < i; k++) s -= A[(size_t)k * n + i] * A[(size_t)k * n + c];   // L[i][k] * X[k][c]
-        const double x = s / diag[i];
+      for (int i = 0; i < c; i++) Linv[(size_t)i * n + c] = 0.f;
+      for (int i = c; i < n; i++) {
+        // four independent accumulators: the fp64 dependency chain, not the loads, bounds this loop
+        double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = c;
+        for (; k + 3 < i; k += 4) {
+          s0 -= A[(size_t)k * n + i] * A[(size_t)k * n + c];                      // L[i][k] * X[k][c]
+          s1 -= A[(size_t)(k + 1) * n + i] * A[(size_t)(k + 1) * n + c];
+          s2 -= A[(size_t)(k + 2) * n + i] * A[(size_t)(k + 2) * n + c];
+          s3 -= A[(size_t)(k + 3) * n + i] * A[(size_t)(k + 3) * n + c];
+        }
+        for (; k < i; k++) s0 -= A[(size_t)k * n + i] * A[(size_t)k * n + c];
+        const double x = ((s0 + s1) + (s2 + s3)) / diag[i];
         A[(size_t)i * n + c] = x;
         Linv[(size_t)i * n + c] = (float)x;
       }
@@ -699,6 +707,9 @@ int nslam_ba_solve(const float* Hin, const float* vin, int P, int prior_pose_idx
   NSLAM_CHECK_LAUNCH();
   return 0;
 }
+
+/* pixels per CTA tile of the BA kernels: callers size `part`/`spart` with T = ceil(ht*wd / tile) */
+int nslam_ba_tile_pixels(void) { return nslam::TILE; }
 
 int nslam_ba_retract(float* world_T_body, float* cam_T_world, const float* cam_T_body,
                      const float* dx, int kf0, int P, void* stream) {

@@ -247,7 +247,8 @@ class BAProblem:
         ht, wd = disps.shape[1:]
         hw = ht * wd
         self.ht, self.wd, self.hw = ht, wd, hw
-        T = (hw + 255) // 256
+        tile = _lib.load().nslam_ba_tile_pixels()
+        T = (hw + tile - 1) // tile
         f = dict(dtype=torch.float32, device=dev)
         n = 6 * gh.P
         self.H = torch.empty(n, n, **f)
@@ -368,7 +369,8 @@ def solve_depth(dx, disps, Q, E, w, ii, jj, t0, t1):
     ht, wd = disps.shape[1:]
     b = _lib.BABuffers()
     b.disps = disps.data_ptr(); b.Q = Q.data_ptr(); b.Emat = E.data_ptr(); b.w = w.data_ptr()
-    b.ht, b.wd, b.T = ht, wd, (ht * wd + 255) // 256
+    tile = _lib.load().nslam_ba_tile_pixels()
+    b.ht, b.wd, b.T = ht, wd, (ht * wd + tile - 1) // tile
     lib = _lib.load()
     dx = dx.float().contiguous()
     _lib.check(lib.nslam_ba_depth(ctypes.byref(g), ctypes.byref(b), _lib.ptr(dx), 0.0,
