@@ -83,13 +83,21 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// smem: A stages [S][16384] | B stages [S][N*128] | out staging [NOUT64][16384] | bias/gctx | barriers
-template <int N>
+// smem: A stages | B stages | out staging [NOUT64][16384] | bias / column sums | barriers
+//   plain : A stage = one 8x16-pixel tile (16 KB) per (tap, channel block), B stage = its weight block
+//   HALO  : (3x3, pad 1) A stage = one COLUMN-SHIFTED copy of the tile with a 1-pixel vertical halo
+//           (box {64c,16w,10h} = 20 KB, loaded once per (channel block, dx)); the three taps dy = 0,1,2 of that
+//           column read it at descriptor offsets dy * 16 rows * 128 B = dy * 2048 B (swizzle-atom aligned).
+//           A traffic per channel block: 3 x 20 KB instead of 9 x 16 KB.  Weight blocks have their own ring.
+template <int N, bool HALO>
 struct CgSmem {
   static constexpr int STAGES = CgStages<N>::value;
+  static constexpr int A_STAGE = HALO ? 20480 : 16384;
+  static constexpr int A_STAGES = HALO ? ((N >= 256) ? 3 : 4) : STAGES;
+  static constexpr int B_STAGES = HALO ? ((N >= 256) ? 3 : 4) : STAGES;
   static constexpr int A = 0;
-  static constexpr int B = STAGES * 16384;
-  static constexpr int OUT = B + STAGES * N * 128;
+  static constexpr int B = A_STAGES * A_STAGE;
+  static constexpr int OUT = B + B_STAGES * N * 128;
   static constexpr int NOUT64 = (N >= 64) ? N / 64 : 1;    // 64-channel staging tiles
   static constexpr int BIAS = OUT + NOUT64 * 16384;
   static constexpr int BAR = BIAS + 2 * N * 4;
@@ -162,23 +170,27 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32
   }
 }
 
-template <int N, int MODE>
+template <int N, int MODE, bool HALO>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
-  using SM = CgSmem<N>;
+  using SM = CgSmem<N, HALO>;
   constexpr int CG_STAGES = SM::STAGES;
+  constexpr int AS = SM::A_STAGES, BS = SM::B_STAGES;
   constexpr int TCOLS = (N <= 32) ? 64 : (N <= 64 ? 128 : (N <= 128 ? 256 : 512));   // 2 accumulator stages
   constexpr int ACC_STRIDE = TCOLS / 2;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::BAR);
-  uint64_t* full_b = bars;
-  uint64_t* empty_b = bars + CG_STAGES;
-  uint64_t* tm_full = bars + 2 * CG_STAGES;
+  uint64_t* full_b = bars;                       // plain: one ring; HALO: the weight-block ring
+  uint64_t* empty_b = bars + BS;
+  uint64_t* full_a = bars + 2 * BS;              // HALO only: the shifted-tile ring
+  uint64_t* empty_a = full_a + AS;
+  uint64_t* tm_full = empty_a + AS;
   uint64_t* tm_empty = tm_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
   float* sbias = reinterpret_cast<float*>(sm + SM::BIAS);
   float* sacc = sbias + N;                       // mode 3: per-CTA column sums of the current tile
+  static_assert((4 * 4 + 4) * 8 + 8 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -188,7 +200,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; s++) tc::tma_prefetch_desc(&maps.src[s]);
-    for (int s = 0; s < CG_STAGES; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < BS; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < AS; s++) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], CG_EPI_WARPS); }
     tc::fence_barrier_init();
   }
@@ -202,21 +215,59 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
-        const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
-        for (int tap = 0; tap < taps; tap++) {
-          const int dy = tap / p.KW - p.pad, dx = tap % p.KW - p.pad;
-          int cbg = 0;
-          for (int s = 0; s < p.n_src; s++) {
-            for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
-              const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
-              tc::mbar_wait(&empty_b[st], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&full_b[st], 16384 + N * 128);
-              tc::tma_load_4d(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n);
-              bulk_copy_g2s(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
-                            N * 128, &full_b[st]);
+      if (HALO) {
+        // unit = (channel block, dx): one shifted halo tile + the three weight blocks of its taps (dy = 0..2).
+        // The tile of the NEXT unit is requested before this unit's weight blocks so that two units are in flight.
+        uint32_t ia = 0, ib = 0;
+        auto load_a = [&](int s, int cb, int dx, int w0, int h0, int n) {
+          const int sa = ia % AS, pa = (ia / AS) & 1;
+          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+          tc::mbar_arrive_expect_tx(&full_a[sa], SM::A_STAGE);
+          tc::tma_load_4d(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + dx - 1, h0 - 1, n);
+          ia++;
+        };
+        const int units = p.cb_total * 3;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+          const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+          // (source, block) of global channel block g
+          auto src_of = [&](int g, int& sidx, int& cb) { sidx = 0; cb = g; while (cb >= p.src_cb[sidx]) { cb -= p.src_cb[sidx]; sidx++; } };
+          int s0, c0;
+          src_of(0, s0, c0);
+          load_a(s0, c0, 0, w0, h0, n);
+          for (int u = 0; u < units; u++) {
+            const int cbg = u / 3, dx = u % 3;
+            if (u + 1 < units) {
+              int s1, c1;
+              src_of((u + 1) / 3, s1, c1);
+              load_a(s1, c1, (u + 1) % 3, w0, h0, n);
+            }
+            for (int dy = 0; dy < 3; dy++, ib++) {
+              const int sb = ib % BS, pb = (ib / BS) & 1;
+              tc::mbar_wait(&empty_b[sb], pb ^ 1);
+              tc::mbar_arrive_expect_tx(&full_b[sb], N * 128);
+              bulk_copy_g2s(sm + SM::B + sb * (N * 128), p.wpacked + (size_t)((dy * 3 + dx) * p.cb_total + cbg) * N * 64,
+                            N * 128, &full_b[sb]);
+            }
+          }
+        }
+      } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+          const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+          for (int tap = 0; tap < taps; tap++) {
+            const int dy = tap / p.KW - p.pad, dx = tap % p.KW - p.pad;
+            int cbg = 0;
+            for (int s = 0; s < p.n_src; s++) {
+              for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
+                const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
+                tc::mbar_wait(&empty_b[st], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full_b[st], 16384 + N * 128);
+                tc::tma_load_4d(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n);
+                bulk_copy_g2s(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
+                              N * 128, &full_b[st]);
+              }
             }
           }
         }
@@ -226,22 +277,44 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, 0);
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, ia = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
         const int as = tcount & 1, aph = (tcount >> 1) & 1;
         tc::mbar_wait(&tm_empty[as], aph ^ 1);
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int kb = 0; kb < nkb; kb++, it++) {
-          const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
-          tc::mbar_wait(&full_b[st], ph);
-          tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(sm + SM::A + st * 16384);
-          const uint32_t b_addr = tc::smem_u32(sm + SM::B + st * (N * 128));
+        if (HALO) {
+          const int units = p.cb_total * 3;
+          for (int u = 0; u < units; u++, ia++) {
+            const int sa = ia % AS, pa = (ia / AS) & 1;
+            tc::mbar_wait(&full_a[sa], pa);
+            const uint32_t a_base = tc::smem_u32(sm + SM::A + sa * SM::A_STAGE);
+            for (int dy = 0; dy < 3; dy++, it++) {
+              const int sb = it % BS, pb = (it / BS) & 1;
+              tc::mbar_wait(&full_b[sb], pb);
+              tc::tc_fence_after();
+              const uint32_t a_addr = a_base + dy * (CG_TW * 128);          // 16 pixel rows further down: +2048 B
+              const uint32_t b_addr = tc::smem_u32(sm + SM::B + sb * (N * 128));
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
-                         (kb | k) ? 1u : 0u);
-          tc::umma_commit(&empty_b[st]);
+              for (int k = 0; k < 4; k++)
+                tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
+                             (u | dy | k) ? 1u : 0u);
+              tc::umma_commit(&empty_b[sb]);
+            }
+            tc::umma_commit(&empty_a[sa]);
+          }
+        } else {
+          for (int kb = 0; kb < nkb; kb++, it++) {
+            const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
+            tc::mbar_wait(&full_b[st], ph);
+            tc::tc_fence_after();
+            const uint32_t a_addr = tc::smem_u32(sm + SM::A + st * 16384);
+            const uint32_t b_addr = tc::smem_u32(sm + SM::B + st * (N * 128));
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
+                           (kb | k) ? 1u : 0u);
+            tc::umma_commit(&empty_b[st]);
+          }
         }
         tc::umma_commit(&tm_full[as]);
       }
@@ -361,38 +434,42 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   if (warp == 1) tc::tmem_dealloc<TCOLS>(tmem_base);
 }
 
-template <int N, int MODE>
-static int launch_conv_m(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
-  const int smem = CgSmem<N>::TOTAL + 1024;
+template <int N, int MODE, bool HALO>
+static int launch_conv_mh(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
+  const int smem = CgSmem<N, HALO>::TOTAL + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int ntiles = p.B * p.tiles_h * p.tiles_w;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  conv_igemm_kernel<N, MODE><<<grid, CG_THREADS, smem, st>>>(maps, p);
+  conv_igemm_kernel<N, MODE, HALO><<<grid, CG_THREADS, smem, st>>>(maps, p);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }
+template <int N, int MODE>
+static int launch_conv_m(const ConvMaps& maps, const ConvParams& p, bool halo, int num_sms, cudaStream_t st) {
+  return halo ? launch_conv_mh<N, MODE, true>(maps, p, num_sms, st) : launch_conv_mh<N, MODE, false>(maps, p, num_sms, st);
+}
 
 // only the (N, mode) pairs the update operator uses are instantiated
-static int launch_conv(int N, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st) {
+static int launch_conv(int N, const ConvMaps& maps, const ConvParams& p, bool halo, int num_sms, cudaStream_t st) {
   if (p.mode == 0) {
     switch (N) {
-      case 16: return launch_conv_m<16, 0>(maps, p, num_sms, st);
-      case 32: return launch_conv_m<32, 0>(maps, p, num_sms, st);
-      case 64: return launch_conv_m<64, 0>(maps, p, num_sms, st);
-      case 128: return launch_conv_m<128, 0>(maps, p, num_sms, st);
-      case 256: return launch_conv_m<256, 0>(maps, p, num_sms, st);
+      case 16: return launch_conv_m<16, 0>(maps, p, halo, num_sms, st);
+      case 32: return launch_conv_m<32, 0>(maps, p, halo, num_sms, st);
+      case 64: return launch_conv_m<64, 0>(maps, p, halo, num_sms, st);
+      case 128: return launch_conv_m<128, 0>(maps, p, halo, num_sms, st);
+      case 256: return launch_conv_m<256, 0>(maps, p, halo, num_sms, st);
     }
   } else if (p.mode == 1 && N == 256) {
-    return launch_conv_m<256, 1>(maps, p, num_sms, st);
+    return launch_conv_m<256, 1>(maps, p, halo, num_sms, st);
   } else if (p.mode == 2 && N == 128) {
-    return launch_conv_m<128, 2>(maps, p, num_sms, st);
+    return launch_conv_m<128, 2>(maps, p, halo, num_sms, st);
   } else if (p.mode == 3 && N == 128) {
-    return launch_conv_m<128, 3>(maps, p, num_sms, st);
+    return launch_conv_mh<128, 3, false>(maps, p, num_sms, st);
   }
   return (int)cudaErrorInvalidValue;
 }
@@ -420,6 +497,8 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
   p.n_src = n_src; p.KH = KH; p.KW = KW; p.pad = pad; p.N = N; p.mode = mode; p.act = act;
   p.wpacked = (const __half*)wpacked; p.bias = bias; p.gctx = gctx; p.net = (const __half*)net;
   p.zbuf = (const __half*)zbuf; p.gsum = gsum;
+  // 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap
+  const bool halo = (KH == 3 && KW == 3 && pad == 1 && mode != 3);
   int cbt = 0;
   for (int s = 0; s < n_src; s++) {
     const int C = src_channels[s];
@@ -428,7 +507,7 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
     cbt += p.src_cb[s];
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {64, CG_TW, CG_TH, 1};
+    uint32_t box[4] = {64, CG_TW, (uint32_t)(halo ? CG_TH + 2 : CG_TH), 1};
     int r = tc::make_tmap_f16(&maps.src[s], srcs[s], 4, dims, strides, box);
     if (r) return r;
   }
@@ -445,7 +524,7 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
       if (r) return r;
     }
   }
-  return launch_conv(N, maps, p, num_sms, (cudaStream_t)stream);
+  return launch_conv(N, maps, p, halo, num_sms, (cudaStream_t)stream);
 }
 
 }  // extern "C"
