@@ -351,48 +351,107 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
     y[id] = r;
   }
   __syncthreads();
-  // Right-looking Cholesky on the LOWER triangle, ONE barrier per column: every thread reads the pivot
-  // itself (uniform failure test), the scaled column is written as a ROW of the unused UPPER triangle
-  // (U[j][i] = L[i][j], diagonal in diag[]), so column j of A is read-only during step j and the
-  // trailing update (2-D thread mapping, no integer divisions) needs no intermediate barrier.
-  double* diag = y + n;                       // [n] = L[j][j]
+  // Blocked right-looking Cholesky with the natural 6x6 pose blocks (n = 6P), lower triangle, in place:
+  //   per block column: every panel thread factors the 6x6 diagonal block itself (registers; identical
+  //   arithmetic in all threads -> a uniform failure test, no broadcast barrier), solves its own row of the
+  //   panel against it, barrier, rank-6 trailing update with a 2-D thread mapping, barrier.
+  //   P x 2 barriers instead of n x 3 and 6 FMAs per trailing element per barrier.
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+  double* diag = y + n;                       // [n] 1 / L[j][j]
   const int tx = tid & 15, ty = tid >> 4;     // 16 x 16
-  bool failed = false;
-  for (int j = 0; j < n; j++) {
-    const double d = A[(size_t)j * n + j];
-    if (!(d > 0.0)) { failed = true; break; }
-    const double rs = 1.0 / sqrt(d);
-    if (tid == 0) diag[j] = d * rs;
-    for (int i = j + 1 + tid; i < n; i += nt) A[(size_t)j * n + i] = A[(size_t)i * n + j] * rs;   // U[j][i]
-    for (int i = j + 1 + ty; i < n; i += 16) {
-      const double li = A[(size_t)i * n + j] * rs;
-      for (int c = j + 1 + tx; c <= i; c += 16) A[(size_t)i * n + c] -= li * (A[(size_t)c * n + j] * rs);
+  const int P = n / 6;
+  __syncthreads();
+  for (int jb = 0; jb < P; jb++) {
+    const int j0 = 6 * jb;
+    // ---- diagonal block: Ljj (lower) and the reciprocals of its diagonal, redundantly per thread
+    double Lb[6][6], rd[6];
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) Lb[r][c] = A[(size_t)(j0 + r) * n + j0 + c];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double d = Lb[c][c];
+#pragma unroll
+      for (int k = 0; k < c; k++) d -= Lb[c][k] * Lb[c][k];
+      if (!(d > 0.0)) bad = true;
+      const double l = sqrt(d);
+      rd[c] = 1.0 / l;
+      Lb[c][c] = l;
+#pragma unroll
+      for (int r = c + 1; r < 6; r++) {
+        double v = Lb[r][c];
+#pragma unroll
+        for (int k = 0; k < c; k++) v -= Lb[r][k] * Lb[c][k];
+        Lb[r][c] = v * rd[c];
+      }
+    }
+    if (bad) { s_fail = 1; }
+    // ---- panel rows i > j0 + 5: row_i(L) = row_i(A) * Ljj^-T   (thread per row)
+    for (int i = j0 + 6 + tid; i < n; i += nt) {
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        double v = A[(size_t)i * n + j0 + c];
+#pragma unroll
+        for (int k = 0; k < c; k++) v -= x[k] * Lb[c][k];
+        x[c] = v * rd[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) A[(size_t)i * n + j0 + c] = x[c];
+    }
+    __syncthreads();                          // panel complete, diagonal block of A still unfactored in memory
+    if (s_fail) break;
+    {                                         // threads 0..20 write Ljj (lower) and the reciprocal diagonal
+      int idx = 0;                            // (statically unrolled: Lb must stay in registers)
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++, idx++)
+          if (tid == idx) {
+            A[(size_t)(j0 + r) * n + j0 + c] = Lb[r][c];
+            if (r == c) diag[j0 + r] = rd[r];
+          }
+    }
+    // ---- trailing update: A[i][c] -= sum_k L[i][j0+k] L[c][j0+k],  j0+6 <= c <= i
+    for (int i = j0 + 6 + ty; i < n; i += 16) {
+      double li[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) li[k] = A[(size_t)i * n + j0 + k];
+      for (int c = j0 + 6 + tx; c <= i; c += 16) {
+        double acc = A[(size_t)i * n + c];
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc -= li[k] * A[(size_t)c * n + j0 + k];
+        A[(size_t)i * n + c] = acc;
+      }
     }
     __syncthreads();
   }
-  if (failed) {
+  if (s_fail) {
     for (int id = tid; id < n; id += nt) dx[id] = 0.f;
     if (Linv) for (int id = tid; id < n * n; id += nt) Linv[id] = 0.f;
     if (tid == 0 && status) *status = 1;
     return;
   }
-  // L[i][c] (c < i) = A[c*n + i];  L[i][i] = diag[i]
+  // L is now in the lower triangle of A (diagonal included); diag[] holds 1 / L[i][i].
   // forward/back substitution by one warp (n is small): L z = y, L^T x = z
   if (tid < 32) {
     for (int i = 0; i < n; i++) {
-      double s = 0.0;
-      for (int c = tid; c < i; c += 32) s += A[(size_t)c * n + i] * y[c];
+      double sacc = 0.0;
+      for (int c = tid; c < i; c += 32) sacc += A[(size_t)i * n + c] * y[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (tid == 0) y[i] = (y[i] - s) / diag[i];
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (tid == 0) y[i] = (y[i] - sacc) * diag[i];
       __syncwarp();
     }
     for (int i = n - 1; i >= 0; i--) {
-      double s = 0.0;
-      for (int c = i + 1 + tid; c < n; c += 32) s += A[(size_t)i * n + c] * y[c];     // L[c][i] = U[i][c]
+      double sacc = 0.0;
+      for (int c = i + 1 + tid; c < n; c += 32) sacc += A[(size_t)c * n + i] * y[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (tid == 0) y[i] = (y[i] - s) / diag[i];
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (tid == 0) y[i] = (y[i] - sacc) * diag[i];
       __syncwarp();
     }
   }
@@ -400,24 +459,25 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
   for (int id = tid; id < n; id += nt) dx[id] = (float)y[id];
   if (tid == 0 && status) *status = 0;
   if (Linv) {
-    // column c of L^-1: solve L x = e_c.  One thread per column; x overwrites the (now free) LOWER
-    // triangle of A column by column: X[i][c] lives at A[i*n + c] (i >= c), which step j > c never reads
-    // as part of L (L is in the upper triangle).
+    // column c of X = L^-1: forward substitution, one thread per column, X stored in the UPPER triangle
+    // (X[i][c] at A[c*n + i], i >= c; the diagonal entry X[c][c] = 1/L[c][c] stays in diag[])
     for (int c = tid; c < n; c += nt) {
       for (int i = 0; i < c; i++) Linv[(size_t)i * n + c] = 0.f;
-      for (int i = c; i < n; i++) {
+      const double xcc = diag[c];
+      Linv[(size_t)c * n + c] = (float)xcc;
+      for (int i = c + 1; i < n; i++) {
         // four independent accumulators: the fp64 dependency chain, not the loads, bounds this loop
-        double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int k = c;
+        double s0 = -A[(size_t)i * n + c] * xcc, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // k = c term
+        int k = c + 1;
         for (; k + 3 < i; k += 4) {
-          s0 -= A[(size_t)k * n + i] * A[(size_t)k * n + c];                      // L[i][k] * X[k][c]
-          s1 -= A[(size_t)(k + 1) * n + i] * A[(size_t)(k + 1) * n + c];
-          s2 -= A[(size_t)(k + 2) * n + i] * A[(size_t)(k + 2) * n + c];
-          s3 -= A[(size_t)(k + 3) * n + i] * A[(size_t)(k + 3) * n + c];
+          s0 -= A[(size_t)i * n + k] * A[(size_t)c * n + k];                      // L[i][k] * X[k][c]
+          s1 -= A[(size_t)i * n + k + 1] * A[(size_t)c * n + k + 1];
+          s2 -= A[(size_t)i * n + k + 2] * A[(size_t)c * n + k + 2];
+          s3 -= A[(size_t)i * n + k + 3] * A[(size_t)c * n + k + 3];
         }
-        for (; k < i; k++) s0 -= A[(size_t)k * n + i] * A[(size_t)k * n + c];
-        const double x = ((s0 + s1) + (s2 + s3)) / diag[i];
-        A[(size_t)i * n + c] = x;
+        for (; k < i; k++) s0 -= A[(size_t)i * n + k] * A[(size_t)c * n + k];
+        const double x = ((s0 + s1) + (s2 + s3)) * diag[i];
+        A[(size_t)c * n + i] = x;
         Linv[(size_t)i * n + c] = (float)x;
       }
     }
