@@ -19,6 +19,18 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
                      int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
                      void* out0, int out0_channels, void* out1, int num_sms, void* stream);
 
+/* extended form: mode 4 = encoder layer (BasicEncoder, networks/modules/extractor.py:118-198):
+ *   stats [B][N][2] fp32 (zeroed by the caller) or NULL: per-image channel sum / sum of squares of the fp16
+ *   outputs, consumed by nslam_inorm_apply; sub = 2: stride-2 convolution (out0 is [B,ceil(H/2),ceil(W/2),C]). */
+int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_src, int B, int H, int W,
+                        int KH, int KW, int pad, int N, const void* wpacked, const float* bias, int mode,
+                        int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
+                        void* out0, int out0_channels, void* out1, float* stats, int sub, int num_sms,
+                        void* stream);
+/* im2col of the encoders' 7x7 / stride-2 / 3-channel first layer: x [B,3,H,W] fp32 -> [B,H/2,W/2,152] fp16,
+ * K index = (ky*7 + kx)*3 + c (147 real columns) -> the layer runs as a 1x1 GEMM (extractor.py:139). */
+int nslam_im2col7_s2(const float* x, void* out, int B, int H, int W, void* stream);
+
 /* ---- fused glue around the update operator (csrc/update_glue.cu); all DEVICE pointers -------------
  * motion_im2col: motion = clamp([coords1-coords0 | target-coords1], +-64) (visual_frontend.py:392-394)
  *   laid out as the 7x7 im2col [E,ht,wd,200] fp16 (tap-major, 4 channels per tap, cols 196..199 zero) so
@@ -44,7 +56,7 @@ int nslam_eta_damping(const void* e16, const long long* ux, float* damping, int 
  * norm_fn='instance' (networks/modules/extractor.py:6-60,118-198): biased variance, eps 1e-5, fp32
  * statistics, fp16 rounding after the normalisation and after the residual add like the library path.
  * stats [B,C,2] = per-(image, channel) sum and sum of squares. */
-int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, void* stream);
+int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, int zero_first, void* stream);
 int nslam_inorm_apply(const void* x, const float* stats, const void* res, const float* res_stats, void* out,
                       int B, int HW, int C, float eps, int relu, void* stream);
 

@@ -52,7 +52,10 @@ _SIGNATURES = {
     "nslam_flow_heads_post": [_P, _P, _P, _P, _P, _P, c_int, c_int, _P],
     "nslam_segment_mean": [_P, _P, _P, _P, c_int, c_int, _P],
     "nslam_eta_damping": [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_float, _P],
-    "nslam_inorm_stats": [_P, _P, c_int, c_int, c_int, _P],
+    "nslam_conv_igemm_ex": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
+                            _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],
+    "nslam_im2col7_s2": [_P, _P, c_int, c_int, c_int, _P],
+    "nslam_inorm_stats": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "nslam_inorm_apply": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P],
     "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],
     "nslam_ba_tile_pixels": [],

@@ -200,3 +200,102 @@ class UpdateOperatorTC:
             return out[0], delta, out[2]
         eta = 0.01 * torch.nn.functional.softplus(out[3][..., 0].float())
         return out[0], delta, out[2], eta, out[4]
+
+
+def conv_enc(srcs, wpacked, bias, B, H, W, k, N, out, act=0, stats=None, sub=1, num_sms=148):
+    """encoder layer on the tensor-core kernel (mode 4): NHWC fp16 in/out, optional channel statistics for the
+    instance norm that follows, optional stride 2 (out is then [B,ceil(H/2),ceil(W/2),N])"""
+    lib = _lib.load()
+    n = len(srcs)
+    ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    chans = (ctypes.c_int * n)(*[s.shape[-1] for s in srcs])
+    _lib.check(lib.nslam_conv_igemm_ex(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(chans, ctypes.c_void_p), n,
+                                       B, H, W, k, k, k // 2, N, _lib.ptr(wpacked), _lib.ptr(bias), 4, act,
+                                       None, None, None, None, _lib.ptr(out), out.shape[-1], None, _lib.ptr(stats), sub,
+                                       num_sms, _lib.stream_ptr()), "conv_igemm_ex")
+
+
+class EncoderTC:
+    """BasicEncoder.forward (networks/modules/extractor.py:183-198, ResidualBlock :6-55) on the tensor-core
+    convolution kernel, NHWC fp16 end to end:
+      7x7/s2 first layer = im2col (csrc/update_glue.cu) + 1x1 GEMM; every other layer = conv_igemm mode 4;
+      stride-2 layers are evaluated at stride 1 and store / count only the even pixels;
+      norm_fn='instance': the convolutions accumulate the channel statistics in their epilogue, one fused apply
+      pass does norm + ReLU (+ residual [+ its own norm] + ReLU); biases in front of a norm are dropped (they cancel);
+      norm_fn='none' (context encoder): bias + ReLU in the conv epilogue, residual add + ReLU in the apply pass."""
+
+    def __init__(self, enc, device):
+        from . import networks as nw
+        self.inorm = enc.norm is nw._inorm
+        self.dev = device
+        self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        sd = {k: v.to(device).float() for k, v in enc.state_dict().items()}
+        f32 = lambda t: t.float().contiguous()
+        bias = (lambda k: None) if self.inorm else (lambda k: f32(sd[k + ".bias"]))
+        P = {}
+        w1 = torch.zeros(32, 152, 1, 1, device=device)
+        w1[:, :147, 0, 0] = sd["conv1.weight"].permute(0, 2, 3, 1).reshape(32, 147)       # K index = (ky*7+kx)*3 + c
+        P["conv1"] = (pack_weights(w1, [152]), bias("conv1"), 32)
+        self.blocks = []
+        for name, st in enc.blocks:
+            cin = sd[name + ".conv1.weight"].shape[1]; cout = sd[name + ".conv1.weight"].shape[0]
+            P[name + ".conv1"] = (pack_weights(sd[name + ".conv1.weight"], [cin]), bias(name + ".conv1"), cout)
+            P[name + ".conv2"] = (pack_weights(sd[name + ".conv2.weight"], [cout]), bias(name + ".conv2"), cout)
+            if st != 1:
+                P[name + ".down"] = (pack_weights(sd[name + ".downsample.0.weight"], [cin]), bias(name + ".downsample.0"), cout)
+            self.blocks.append((name, st, cin, cout))
+        cout = sd["conv2.weight"].shape[0]
+        P["conv2"] = (pack_weights(sd["conv2.weight"], [sd["conv2.weight"].shape[1]]), f32(sd["conv2.bias"]), cout)
+        self.P = P
+
+    def __call__(self, x):
+        """x [B,3,H,W] fp32 normalised image -> [B,C,H/8,W/8] fp16 (NCHW view of NHWC storage)"""
+        from . import networks as nw
+        lib = _lib.load()
+        B, _, H, W = x.shape
+        dev = x.device
+        h16 = dict(dtype=torch.float16, device=dev)
+        x = x.float().contiguous()
+        arena = torch.zeros(16, B * 128 * 2, dtype=torch.float32, device=dev) if self.inorm else None
+        slot = [0]
+
+        def st_buf(C):
+            if arena is None:
+                return None
+            v = arena[slot[0]][:B * C * 2].view(B, C, 2)
+            slot[0] += 1
+            return v
+
+        def nchw(t):                      # NHWC storage viewed as the NCHW-shaped channels-last tensor inorm_apply expects
+            return t.permute(0, 3, 1, 2)
+        act = 0 if self.inorm else 1
+        h, w = H // 2, W // 2
+        col = torch.empty(B, h, w, 152, **h16)
+        _lib.check(lib.nslam_im2col7_s2(_lib.ptr(x), _lib.ptr(col), B, H, W, _lib.stream_ptr()), "im2col7")
+        wp, b, n = self.P["conv1"]
+        cur = torch.empty(B, h, w, n, **h16); s0 = st_buf(n)
+        conv_enc([col], wp, b, B, h, w, 1, n, cur, act=act, stats=s0, num_sms=self.num_sms)
+        if self.inorm:
+            nw._inorm_apply(nchw(cur), s0)
+        for name, st, cin, cout in self.blocks:
+            ho, wo = (h + st - 1) // st, (w + st - 1) // st
+            wp, b, _ = self.P[name + ".conv1"]
+            y = torch.empty(B, ho, wo, cout, **h16); s1 = st_buf(cout)
+            conv_enc([cur], wp, b, B, h, w, 3, cout, y, act=act, stats=s1, sub=st, num_sms=self.num_sms)
+            if self.inorm:
+                nw._inorm_apply(nchw(y), s1)
+            wp, b, _ = self.P[name + ".conv2"]
+            z = torch.empty(B, ho, wo, cout, **h16); s2 = st_buf(cout)
+            conv_enc([y], wp, b, B, ho, wo, 3, cout, z, act=act, stats=s2, num_sms=self.num_sms)
+            res, sr = cur, None
+            if st != 1:
+                wp, b, _ = self.P[name + ".down"]
+                res = torch.empty(B, ho, wo, cout, **h16); sr = st_buf(cout)
+                conv_enc([cur], wp, b, B, h, w, 1, cout, res, act=0, stats=sr, sub=st, num_sms=self.num_sms)
+            # out = relu(res' + relu(norm?(z)));  z already carries its ReLU when there is no norm
+            nw._inorm_apply(nchw(z), s2, relu=self.inorm, res=nchw(res), res_st=sr)
+            cur, h, w = z, ho, wo
+        wp, b, n = self.P["conv2"]
+        out = torch.empty(B, h, w, n, **h16)
+        conv_enc([cur], wp, b, B, h, w, 1, n, out, act=0, num_sms=self.num_sms)
+        return out.permute(0, 3, 1, 2)

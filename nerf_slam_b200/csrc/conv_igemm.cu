@@ -28,6 +28,10 @@
 //   2 Q     q = tanh(acc + ..); out0 = (1 - z) * net + z * q         (gru.py:29-31)
 //   3 GLO   y = sigmoid(acc + bias) * net; per-tile column sums (warp transpose-reduce -> shared
 //           accumulator) added to gsum[n][c] (fp32)  -> glo = mean (gru.py:23-25); nothing is stored
+//   4 ENC   encoder layers (BasicEncoder, extractor.py): y = act(acc + bias) like mode 0, plus (a) optional
+//           per-(image, channel) sum / sum of squares of the fp16 outputs for the instance norm that follows
+//           and (b) optional stride-2 output: the conv is evaluated at stride 1 and only even rows/columns
+//           are stored and counted (a 3x3/s2 conv reads every input pixel anyway).
 // Roofline: tensor pipe; FLOPs = 2 * pixels * taps * Cin * Cout.
 #include "common.cuh"
 #include "tc.cuh"
@@ -54,6 +58,8 @@ struct ConvParams {
   const __half* net;       // [B,H,W,128] (modes 1,2,3)
   const __half* zbuf;      // [B,H,W,128] (mode 2)
   float* gsum;             // [B][128] (mode 3)
+  float* stats;            // [B][N][2] per-image channel sum / sum of squares of the fp16 outputs (mode 4) or null
+  int sub;                 // mode 4: 1 = store every pixel, 2 = store (and count) even rows/cols only (stride-2 conv)
 };
 
 struct ConvMaps {
@@ -100,7 +106,7 @@ struct CgSmem {
   static constexpr int OUT = B + B_STAGES * N * 128;
   static constexpr int NOUT64 = (N >= 64) ? N / 64 : 1;    // 64-channel staging tiles
   static constexpr int BIAS = OUT + NOUT64 * 16384;
-  static constexpr int BAR = BIAS + 2 * N * 4;
+  static constexpr int BAR = BIAS + 3 * N * 4;     // bias | column sums | column sums of squares
   static constexpr int TOTAL = BAR + 256;
 };
 
@@ -134,7 +140,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32
     v[i + 0] = __uint_as_float(r[i + 0]) + b4.x + g4.x; v[i + 1] = __uint_as_float(r[i + 1]) + b4.y + g4.y;
     v[i + 2] = __uint_as_float(r[i + 2]) + b4.z + g4.z; v[i + 3] = __uint_as_float(r[i + 3]) + b4.w + g4.w;
   }
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 4) {
     if (act == 1) {
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
@@ -206,7 +212,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<TCOLS>(tmem_slot);
-  for (int i = threadIdx.x; i < N; i += CG_THREADS) { sbias[i] = p.bias ? p.bias[i] : 0.f; sacc[i] = 0.f; }
+  for (int i = threadIdx.x; i < N; i += CG_THREADS) { sbias[i] = p.bias ? p.bias[i] : 0.f; sacc[i] = 0.f; sacc[N + i] = 0.f; }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -337,6 +343,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
       const int h = h0 + hh, w = w0 + ww;
       const bool valid = (h < p.H) && (w < p.W);
       const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+      // mode 4 with sub == 2: only even rows/cols are kept; they are compacted to a 4x8 staging tile
+      const bool kept = (MODE != 4) || (p.sub == 1) || (((hh | ww) & 1) == 0);
+      const int srow = (MODE == 4 && p.sub == 2) ? (hh >> 1) * (CG_TW / 2) + (ww >> 1) : row;
       const int as = tcount & 1, aph = (tcount >> 1) & 1;
       tc::mbar_wait(&tm_full[as], aph);
       tc::tc_fence_after();
@@ -379,22 +388,36 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
           } else {
             // fp16, into the staging tile of this 64-channel group
             const int t64 = c0 / 64;
+            if (kept) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (c0 + i >= N) break;
-              __half2 h2[4];
+              for (int i = 0; i < 32; i += 8) {
+                if (c0 + i >= N) break;
+                __half2 h2[4];
 #pragma unroll
-              for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-              if (N >= 64) {
-                // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
-                unsigned char* st = sm + SM::OUT + t64 * 16384 + row * 128;
-                const int chunk = ((c0 % 64) + i) / 8;
-                *reinterpret_cast<uint4*>(st + ((chunk ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
-              } else {
-                // narrow outputs: dense rows of N halfs, un-swizzled tensor map
-                unsigned char* st = sm + SM::OUT + row * (N * 2);
-                *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+                for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                if (N >= 64) {
+                  // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
+                  unsigned char* st = sm + SM::OUT + t64 * 16384 + srow * 128;
+                  const int chunk = ((c0 % 64) + i) / 8;
+                  *reinterpret_cast<uint4*>(st + ((chunk ^ (srow & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
+                } else {
+                  // narrow outputs: dense rows of N halfs, un-swizzled tensor map
+                  unsigned char* st = sm + SM::OUT + srow * (N * 2);
+                  *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+                }
               }
+            }
+            if (MODE == 4 && p.stats) {
+              // statistics of what the next layer will read: the fp16-rounded values of the kept, in-image pixels
+              float q2[32];
+              const bool cnt = kept && valid;
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                const float hv = cnt ? __half2float(__float2half_rn(v[i])) : 0.f;
+                v[i] = hv; q2[i] = hv * hv;
+              }
+              const float cs = warp_colsum32(v, lane), cq = warp_colsum32(q2, lane);
+              if (c0 + lane < N) { atomicAdd(&sacc[c0 + lane], cs); atomicAdd(&sacc[N + c0 + lane], cq); }
             }
           }
         }
@@ -411,11 +434,22 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
             tma_store_4d(&maps.out[0], sm + SM::OUT + 1 * 16384, 64, w0, h0, n);
             tma_store_4d(&maps.out[1], sm + SM::OUT + 2 * 16384, 0, w0, h0, n);
             tma_store_4d(&maps.out[1], sm + SM::OUT + 3 * 16384, 64, w0, h0, n);
+          } else if (MODE == 4 && p.sub == 2) {
+            for (int t = 0; t < SM::NOUT64; t++)
+              tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, t * 64, w0 >> 1, h0 >> 1, n);
           } else {
             for (int t = 0; t < SM::NOUT64; t++)
               tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, t * 64, w0, h0, n);
           }
           tma_store_commit();
+        }
+        if (MODE == 4 && p.stats) {
+          // flush this tile's channel statistics (shared accumulators were completed before bar.sync 2)
+          for (int i = etid; i < 2 * N; i += 32 * CG_EPI_WARPS) {
+            const float sv = sacc[i];
+            sacc[i] = 0.f;
+            if (sv != 0.f) atomicAdd(p.stats + ((size_t)n * N + (i % N)) * 2 + (i / N), sv);
+          }
         }
       } else {
         // flush this tile's column sums (the next tile usually belongs to another image)
@@ -470,6 +504,13 @@ static int launch_conv(int N, const ConvMaps& maps, const ConvParams& p, bool ha
     return launch_conv_m<128, 2>(maps, p, halo, num_sms, st);
   } else if (p.mode == 3 && N == 128) {
     return launch_conv_mh<128, 3, false>(maps, p, num_sms, st);
+  } else if (p.mode == 4) {
+    switch (N) {
+      case 32: return launch_conv_m<32, 4>(maps, p, halo, num_sms, st);
+      case 64: return launch_conv_m<64, 4>(maps, p, halo, num_sms, st);
+      case 128: return launch_conv_m<128, 4>(maps, p, halo, num_sms, st);
+      case 256: return launch_conv_m<256, 4>(maps, p, halo, num_sms, st);
+    }
   }
   return (int)cudaErrorInvalidValue;
 }
@@ -484,10 +525,10 @@ extern "C" {
  *   wpacked: produced by nslam_conv_pack_weights; bias [N] fp32 or NULL
  *   out0 (and out1 for mode 1): [B,H,W,out_channels] fp16; N = 16,32,64,128,256 columns per launch
  *   mode/act/gctx/net/zbuf/gsum: see the epilogue modes above. */
-int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src, int B, int H, int W,
-                     int KH, int KW, int pad, int N, const void* wpacked, const float* bias, int mode,
-                     int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
-                     void* out0, int out0_channels, void* out1, int num_sms, void* stream) {
+int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_src, int B, int H, int W,
+                        int KH, int KW, int pad, int N, const void* wpacked, const float* bias, int mode,
+                        int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
+                        void* out0, int out0_channels, void* out1, float* stats, int sub, int num_sms, void* stream) {
   using namespace nslam;
   if (n_src < 1 || n_src > 4 || B <= 0) return (int)cudaErrorInvalidValue;
   ConvMaps maps;
@@ -496,7 +537,8 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
   p.tiles_h = (H + CG_TH - 1) / CG_TH; p.tiles_w = (W + CG_TW - 1) / CG_TW;
   p.n_src = n_src; p.KH = KH; p.KW = KW; p.pad = pad; p.N = N; p.mode = mode; p.act = act;
   p.wpacked = (const __half*)wpacked; p.bias = bias; p.gctx = gctx; p.net = (const __half*)net;
-  p.zbuf = (const __half*)zbuf; p.gsum = gsum;
+  p.zbuf = (const __half*)zbuf; p.gsum = gsum; p.stats = stats; p.sub = (mode == 4 && sub == 2) ? 2 : 1;
+  if (mode == 4 && sub != 1 && sub != 2) return (int)cudaErrorInvalidValue;
   // 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap
   const bool halo = (KH == 3 && KW == 3 && pad == 1 && mode != 3);
   int cbt = 0;
@@ -517,14 +559,23 @@ int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src
     const int nout = (mode == 1) ? 2 : 1;
     for (int o = 0; o < nout; o++) {
       const int C = (mode == 1) ? 128 : out0_channels;
-      uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-      uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-      uint32_t box[4] = {(uint32_t)(C < 64 ? C : 64), CG_TW, CG_TH, 1};
+      const int Wo = (W + p.sub - 1) / p.sub, Ho = (H + p.sub - 1) / p.sub;     // stride-2 layers store every other pixel
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+      uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wo * C * 2, (uint64_t)Ho * Wo * C * 2};
+      uint32_t box[4] = {(uint32_t)(C < 64 ? C : 64), (uint32_t)(CG_TW / p.sub), (uint32_t)(CG_TH / p.sub), 1};
       int r = tc::make_tmap_f16(&maps.out[o], outs[o], 4, dims, strides, box, false, nullptr, /*swizzle128=*/N >= 64);
       if (r) return r;
     }
   }
   return launch_conv(N, maps, p, halo, num_sms, (cudaStream_t)stream);
+}
+
+int nslam_conv_igemm(const void* const* srcs, const int* src_channels, int n_src, int B, int H, int W,
+                     int KH, int KW, int pad, int N, const void* wpacked, const float* bias, int mode,
+                     int act, const float* gctx, const void* net, const void* zbuf, float* gsum,
+                     void* out0, int out0_channels, void* out1, int num_sms, void* stream) {
+  return nslam_conv_igemm_ex(srcs, src_channels, n_src, B, H, W, KH, KW, pad, N, wpacked, bias, mode, act, gctx, net, zbuf,
+                             gsum, out0, out0_channels, out1, nullptr, 1, num_sms, stream);
 }
 
 }  // extern "C"

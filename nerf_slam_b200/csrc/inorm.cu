@@ -70,12 +70,14 @@ inorm_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = cg * 8 + j;
-    const float2 st = *reinterpret_cast<const float2*>(stats + ((size_t)b * C + c) * 2);
-    const float mean = st.x * inv_n;
-    const float var = fmaxf(st.y * inv_n - mean * mean, 0.f);
-    float y = (__half2float(h[j]) - mean) * rsqrtf(var + eps);
-    // the library path rounds the normalised tensor to fp16 before the ReLU / add
-    y = __half2float(__float2half_rn(y));
+    float y = __half2float(h[j]);
+    if (stats) {                                                  // NULL: no normalisation (context encoder)
+      const float2 st = *reinterpret_cast<const float2*>(stats + ((size_t)b * C + c) * 2);
+      const float mean = st.x * inv_n;
+      const float var = fmaxf(st.y * inv_n - mean * mean, 0.f);
+      // the library path rounds the normalised tensor to fp16 before the ReLU / add
+      y = __half2float(__float2half_rn((y - mean) * rsqrtf(var + eps)));
+    }
     if (relu) y = fmaxf(y, 0.f);
     if (res) {
       float r = __half2float(hr[j]);
@@ -96,11 +98,12 @@ inorm_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats
 
 extern "C" {
 
-/* x [B,HW,C] fp16 NHWC (C multiple of 8, <= 128); stats [B,C,2] fp32 is zeroed here */
-int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, void* stream) {
+/* x [B,HW,C] fp16 NHWC (C multiple of 8, <= 128); stats [B,C,2] fp32 is zeroed here unless the caller
+ * passes zero_first = 0 (it then provides an already-zeroed buffer, e.g. a slice of one arena per forward) */
+int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, int zero_first, void* stream) {
   if (C % 8 != 0 || C > 128 || 256 % (C / 8) != 0) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(float), st);
+  if (zero_first) cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(float), st);
   dim3 grid((HW + nslam::IN_PIX - 1) / nslam::IN_PIX, B);
   nslam::inorm_stats_kernel<<<grid, 256, 0, st>>>((const __half*)x, stats, HW, C);
   NSLAM_CHECK_LAUNCH();
@@ -108,7 +111,7 @@ int nslam_inorm_stats(const void* x, float* stats, int B, int HW, int C, void* s
 }
 
 /* out = relu?(IN(x)) ; with res: out = relu(res' + relu?(IN(x))), res' = IN(res) when res_stats != NULL.
- * out may alias x. */
+ * stats == NULL: IN(x) := x (plain residual add + ReLU of the un-normalised context encoder).  out may alias x. */
 int nslam_inorm_apply(const void* x, const float* stats, const void* res, const float* res_stats, void* out,
                       int B, int HW, int C, float eps, int relu, void* stream) {
   if (C % 8 != 0) return (int)cudaErrorInvalidValue;

@@ -156,3 +156,48 @@ int nslam_eta_damping(const void* e16, const long long* ux, float* damping, int 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// A1: im2col of the encoders' first layer (7x7, stride 2, pad 3, 3 input channels -> K = 147, padded to
+// 152 so that rows are 16-byte multiples): the layer then runs as a 1x1 tensor-core GEMM.
+//   x [B,3,H,W] fp32 (normalised image, NCHW)  ->  out [B,H/2,W/2,152] fp16, K index = (ky*7 + kx)*3 + c
+namespace nslam {
+constexpr int I7_K = 147, I7_KP = 152, I7_PIX = 32;
+
+__global__ void __launch_bounds__(256)
+im2col7_s2_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) __half tile[I7_PIX * I7_KP];
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t npix = (size_t)B * Ho * Wo;
+  const size_t p0 = (size_t)blockIdx.x * I7_PIX;
+  for (int idx = threadIdx.x; idx < I7_PIX * I7_KP; idx += 256) {
+    const int px = idx / I7_KP, k = idx % I7_KP;
+    const size_t pid = p0 + px;
+    float v = 0.f;
+    if (k < I7_K && pid < npix) {
+      const int ox = (int)(pid % Wo), oy = (int)((pid / Wo) % Ho), b = (int)(pid / ((size_t)Wo * Ho));
+      const int tap = k / 3, c = k % 3;
+      const int iy = 2 * oy + tap / 7 - 3, ix = 2 * ox + tap % 7 - 3;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)b * 3 + c) * H + iy) * W + ix];
+    }
+    tile[idx] = __float2half_rn(v);
+  }
+  __syncthreads();
+  constexpr int V = I7_KP / 8;                 // 19 x 16 bytes per pixel
+  for (int idx = threadIdx.x; idx < I7_PIX * V; idx += 256) {
+    const int px = idx / V, j = idx % V;
+    const size_t pid = p0 + px;
+    if (pid < npix) reinterpret_cast<uint4*>(out + pid * I7_KP)[j] = reinterpret_cast<const uint4*>(tile + px * I7_KP)[j];
+  }
+}
+}  // namespace nslam
+
+extern "C" int nslam_im2col7_s2(const float* x, void* out, int B, int H, int W, void* stream) {
+  if (H % 2 || W % 2) return (int)cudaErrorInvalidValue;
+  const size_t npix = (size_t)B * (H / 2) * (W / 2);
+  if (npix == 0) return 0;
+  nslam::im2col7_s2_kernel<<<(unsigned)((npix + nslam::I7_PIX - 1) / nslam::I7_PIX), 256, 0, (cudaStream_t)stream>>>(
+      x, (__half*)out, B, H, W);
+  NSLAM_CHECK_LAUNCH();
+  return 0;
+}

@@ -139,10 +139,18 @@ class RaftVisualFrontend:
         # update operator: hand-written tcgen05 implicit-GEMM convolutions (default) or the cuDNN
         # library path (args.conv_backend == "cudnn"; kept as the A/B reference for the parity tests)
         self.conv_backend = getattr(args, "conv_backend", "tcgen05")
+        # the encoders' library convolutions: let cuDNN time its algorithms once per shape (its heuristic picks a
+        # CUDA-core kernel for the 32-channel layers); set args.cudnn_benchmark = False to disable
+        if getattr(args, "cudnn_benchmark", True):
+            torch.backends.cudnn.benchmark = True
         self.update_tc = None
+        self.feature_tc = self.context_tc = None
         if self.conv_backend == "tcgen05":
-            from .conv import UpdateOperatorTC
+            from .conv import EncoderTC, UpdateOperatorTC
             self.update_tc = UpdateOperatorTC(self.update_net, device)
+            if getattr(args, "encoder_backend", "tcgen05") == "tcgen05":
+                self.feature_tc = EncoderTC(self.feature_net, device)
+                self.context_tc = EncoderTC(self.context_net, device)
 
         # prior sigmas (visual_frontend.py:142-153)
         self.g_prior_cov = torch.block_diag(0.01 ** 2 * torch.eye(3), 0.01 ** 2 * torch.eye(3)).to(device)
@@ -243,11 +251,16 @@ class RaftVisualFrontend:
         self.cam0_intrinsics[idx] = (1.0 / self.dsf) * _lib.h2d(np.asarray(cm), dev, torch.float32)
 
     def _feature_encoder(self, imgs_norm):
+        if self.feature_tc is not None:
+            return self.feature_tc(imgs_norm[0])       # tensor-core path, [cams,128,ht,wd] fp16 (NHWC storage)
         return self.feature_net(imgs_norm)[0]          # [cams,128,ht,wd] fp16
 
     def _context_encoder(self, imgs_norm):
         """-> (tanh(context), relu(gru input)), both channels-last [cams,ht,wd,128]"""
-        c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
+        if self.context_tc is not None:
+            c = self.context_tc(imgs_norm[0]).permute(0, 2, 3, 1)
+        else:
+            c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
         return torch.tanh(c[..., :128]), torch.relu(c[..., 128:])
 
     @staticmethod

@@ -80,12 +80,14 @@ def _cl(y):
     return y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
 
 
-def _inorm_stats(y):
-    """per-(image, channel) sum / sum of squares of a channels-last fp16 tensor (csrc/inorm.cu)"""
+def _inorm_stats(y, out=None):
+    """per-(image, channel) sum / sum of squares of a channels-last fp16 tensor (csrc/inorm.cu).
+    out: already-zeroed [B,C,2] fp32 view (one arena zeroed once per forward) or None to allocate + zero here"""
     from . import _lib
     B, C, H, W = y.shape
-    st = torch.empty(B, C, 2, dtype=torch.float32, device=y.device)
-    _lib.check(_lib.load().nslam_inorm_stats(_lib.ptr(y), _lib.ptr(st), B, H * W, C, _lib.stream_ptr()), "inorm_stats")
+    st = out if out is not None else torch.empty(B, C, 2, dtype=torch.float32, device=y.device)
+    _lib.check(_lib.load().nslam_inorm_stats(_lib.ptr(y), _lib.ptr(st), B, H * W, C, 0 if out is not None else 1,
+                                             _lib.stream_ptr()), "inorm_stats")
     return st
 
 
@@ -146,18 +148,26 @@ class BasicEncoder(_Params):
         (csrc/inorm.cu): per conv one statistics pass + one apply pass instead of ~8 library launches.
         A per-channel bias in front of an instance norm cancels exactly (the norm subtracts the channel mean),
         so those convolutions run without their bias (saves one elementwise launch each)."""
+        B = x.shape[0]
+        arena = torch.zeros(16, B, 128, 2, dtype=torch.float32, device=x.device)      # one memset for all norm layers
+        slot = [0]
+
+        def stats(t):
+            v = arena[slot[0]].view(-1)[:B * t.shape[1] * 2].view(B, t.shape[1], 2)
+            slot[0] += 1
+            return _inorm_stats(t, out=v)
         wt, _ = self.w("conv1")
         x = _cl(conv2d(x, wt, None, stride=2, padding=3))
-        _inorm_apply(x, _inorm_stats(x))
+        _inorm_apply(x, stats(x))
         for name, st in self.blocks:
             y = _cl(conv2d(x, self.w(name + ".conv1")[0], None, stride=st, padding=1))
-            _inorm_apply(y, _inorm_stats(y))
+            _inorm_apply(y, stats(y))
             z = _cl(conv2d(y, self.w(name + ".conv2")[0], None, stride=1, padding=1))
             if st != 1:
                 d = _cl(conv2d(x, self.w(name + ".downsample.0")[0], None, stride=st, padding=0))
-                _inorm_apply(z, _inorm_stats(z), res=d, res_st=_inorm_stats(d))
+                _inorm_apply(z, stats(z), res=d, res_st=stats(d))
             else:
-                _inorm_apply(z, _inorm_stats(z), res=x)
+                _inorm_apply(z, stats(z), res=x)
             x = z
         return conv2d(x, *self.w("conv2"))
 

@@ -119,3 +119,23 @@ def test_update_operator_tc_vs_library_path(with_agg):
     if with_agg:
         assert close(got[3], ref[3][0], 2e-3)                           # eta
         assert close(got[4], ref[4][0].permute(0, 2, 3, 1), 8e-2)       # upmask logits
+
+
+@pytest.mark.parametrize("norm,out_dim", [("instance", 128), ("none", 256)])
+def test_encoder_tc_vs_library_path(norm, out_dim):
+    """BasicEncoder on the tensor-core kernel (im2col first layer, statistics in the conv epilogue, stride-2
+    stores) vs the same network through the library convolutions; two images, sizes that leave partial tiles"""
+    from nerf_slam_b200.conv import EncoderTC
+    from nerf_slam_b200.networks import BasicEncoder, load_droid_weights
+    enc = BasicEncoder(out_dim, norm, torch.Generator().manual_seed(5))
+    if os.path.exists(WEIGHTS):
+        enc.load_state_dict(load_droid_weights(WEIGHTS), "feature_net." if norm == "instance" else "context_net.")
+    enc.to(device=DEV, dtype=torch.float16)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 2, 3, 120, 152, generator=g).to(DEV)
+    ref = enc(x)[0].float()
+    got = EncoderTC(enc, DEV)(x[0]).float()
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (2, out_dim, 15, 19)
+    err = float((got - ref).abs().max())
+    assert err < 5e-2 * max(1.0, float(ref.abs().max())), err

@@ -71,3 +71,10 @@ def test_encoders_vs_reference_python():
     x = torch.from_numpy(d["img"]).to(DEV)
     assert float((f(x).float().cpu() - torch.from_numpy(d["fnet"])).abs().max()) < 5e-2
     assert float((c(x).float().cpu() - torch.from_numpy(d["cnet"])).abs().max()) < 5e-2
+    # the same networks on the tensor-core convolution kernel (im2col first layer, fused statistics, stride-2 stores)
+    from nerf_slam_b200.conv import EncoderTC
+    ft, ct = EncoderTC(f, DEV), EncoderTC(c, DEV)
+    xb = x.reshape(-1, *x.shape[-3:])
+    got_f = ft(xb).float().cpu().reshape(d["fnet"].shape); got_c = ct(xb).float().cpu().reshape(d["cnet"].shape)
+    assert float((got_f - torch.from_numpy(d["fnet"])).abs().max()) < 5e-2
+    assert float((got_c - torch.from_numpy(d["cnet"])).abs().max()) < 5e-2
