@@ -52,7 +52,8 @@ struct CvParams {
   int HW, H2, W2;
   int NH, NW;      // target tiles
   int MT;          // 128-pixel source strips per edge
-  int nwork;       // E * MT work items, walked persistently
+  int nwork;       // E * MT * split work items, walked persistently
+  int split;       // target-tile chunks per (edge, strip): keeps all SMs busy when E * MT < #SMs
   int tma_l0, tma_l1;  // levels 0/1 stored by TMA (their row pitch is a multiple of 16 bytes)
 };
 
@@ -145,13 +146,15 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       uint32_t t = 0, wi = 0;
       for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, wi++) {
-        const int e = w / p.MT, m0 = (w % p.MT) * 128;
+        const int ws = w / p.split, ck = w % p.split;
+        const int e = ws / p.MT, m0 = (ws % p.MT) * 128;
+        const int n_lo = ck * NT / p.split, n_hi = (ck + 1) * NT / p.split;
         const int fi = p.ii[e], fj = p.jj[e];
         tc::mbar_wait(a_empty, (wi & 1) ^ 1);          // MMAs of the previous strip are done with A
         tc::mbar_arrive_expect_tx(a_full, 32768);
         tc::tma_load_3d(sm + CvSmem::A, &tmA, a_full, 0, m0, fi);
         tc::tma_load_3d(sm + CvSmem::A + 16384, &tmA, a_full, 64, m0, fi);
-        for (int n = 0; n < NT; n++, t++) {
+        for (int n = n_lo; n < n_hi; n++, t++) {
           const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
           tc::mbar_wait(&empty_b[s], ph ^ 1);
           const int h0 = (n / p.NW) * CV_TH, w0 = (n % p.NW) * CV_TW;
@@ -169,8 +172,10 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t a_addr = tc::smem_u32(sm + CvSmem::A);
       uint32_t t = 0, wi = 0;
       for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, wi++) {
+        const int ck = w % p.split;
+        const int n_lo = ck * NT / p.split, n_hi = (ck + 1) * NT / p.split;
         tc::mbar_wait(a_full, wi & 1);
-        for (int n = 0; n < NT; n++, t++) {
+        for (int n = n_lo; n < n_hi; n++, t++) {
           const int s = t % CV_STAGES, ph = (t / CV_STAGES) & 1;
           const int as = t & 1, aph = (t >> 1) & 1;
           tc::mbar_wait(&tm_empty[as], aph ^ 1);
@@ -207,8 +212,10 @@ corr_volume_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t taddr = tmem_base + grp * 128 + ((uint32_t)(q * 32) << 16);
     uint32_t t = 0, use = 0;
     for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
-      const int e = w / p.MT, m0 = (w % p.MT) * 128;
-      for (int n = 0; n < NT; n++, t++) {
+      const int ws = w / p.split, ck = w % p.split;
+      const int e = ws / p.MT, m0 = (ws % p.MT) * 128;
+      const int n_lo = ck * NT / p.split, n_hi = (ck + 1) * NT / p.split;
+      for (int n = n_lo; n < n_hi; n++, t++) {
         if ((int)(t & 1) != grp) continue;
         tc::mbar_wait(&tm_full[grp], use & 1);
         use++;
@@ -354,7 +361,17 @@ int nslam_corr_volume_build(const void* fmaps, int NF, int H, int W, int C, cons
   p.out[0] = (__half*)out0; p.out[1] = (__half*)out1; p.out[2] = (__half*)out2; p.out[3] = (__half*)out3;
   p.ii = ii; p.jj = jj; p.HW = HW; p.H2 = H; p.W2 = W;
   p.NH = (H + CV_TH - 1) / CV_TH; p.NW = (W + CV_TW - 1) / CV_TW;
-  p.MT = (HW + 127) / 128; p.nwork = E * p.MT;
+  p.MT = (HW + 127) / 128;
+  int dev0 = 0, sms0 = 148;
+  cudaGetDevice(&dev0);
+  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+  // few edges (the per-frame motion filter builds ONE volume): split the target tiles of a strip over
+  // several CTAs so that E * MT * split >= #SMs (the A strip is re-loaded per chunk: 32 KB, L2-resident)
+  p.split = (sms0 + E * p.MT - 1) / (E * p.MT);
+  if (p.split > 8) p.split = 8;
+  if (p.split > p.NH * p.NW) p.split = p.NH * p.NW;
+  if (p.split < 1) p.split = 1;
+  p.nwork = E * p.MT * p.split;
   // output tensor maps for levels 0/1: {W_l, H_l, HW, E}, box {16>>l, 8>>l, 128, 1}, no swizzle
   CUtensorMap tmO[2];
   int use_tma[2] = {0, 0};

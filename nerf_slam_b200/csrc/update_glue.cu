@@ -18,32 +18,44 @@ namespace nslam {
 
 constexpr int MI_C = 200;    // im2col row: 196 real values + 4 zeros (TMA rows must be 16-byte multiples)
 
-// one thread per (pixel, tap): 4 motion channels of the tap's source pixel -> 8 bytes
-__global__ void motion_im2col_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0,
-                                     const float* __restrict__ target, __half* __restrict__ out,
-                                     int E, int ht, int wd) {
-  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t total = (size_t)E * ht * wd * 50;
-  if (id >= total) return;
-  const int tap = (int)(id % 50);
-  const size_t pix = id / 50;
-  const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
-  const int e = (int)(pix / ((size_t)wd * ht));
-  uint2 v = make_uint2(0u, 0u);
-  if (tap < 49) {
-    const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
-    if (yy >= 0 && yy < ht && xx >= 0 && xx < wd) {
-      const size_t q = ((size_t)e * ht + yy) * wd + xx;
-      const float2 c1 = reinterpret_cast<const float2*>(coords1)[q];
-      const float2 c0 = reinterpret_cast<const float2*>(coords0)[(size_t)yy * wd + xx];
-      const float2 tg = target ? reinterpret_cast<const float2*>(target)[q] : c1;
-      const float m0 = fminf(fmaxf(c1.x - c0.x, -64.f), 64.f), m1 = fminf(fmaxf(c1.y - c0.y, -64.f), 64.f);
-      const float m2 = fminf(fmaxf(tg.x - c1.x, -64.f), 64.f), m3 = fminf(fmaxf(tg.y - c1.y, -64.f), 64.f);
-      const __half2 a = __floats2half2_rn(m0, m1), b = __floats2half2_rn(m2, m3);
-      v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b);
+// CTA = 32 consecutive pixels: the 32 x 200 fp16 im2col rows are assembled in shared memory (one thread per
+// (pixel, tap): 4 motion channels of the tap's source pixel) and written out with coalesced 16-byte stores
+constexpr int MI_PIX = 32;
+__global__ void __launch_bounds__(256)
+motion_im2col_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0,
+                     const float* __restrict__ target, __half* __restrict__ out,
+                     int E, int ht, int wd) {
+  __shared__ __align__(16) __half tile[MI_PIX * MI_C];
+  const size_t npix = (size_t)E * ht * wd;
+  const size_t p0 = (size_t)blockIdx.x * MI_PIX;
+  for (int idx = threadIdx.x; idx < MI_PIX * 50; idx += 256) {
+    const int px = idx / 50, tap = idx % 50;
+    const size_t pix = p0 + px;
+    uint2 v = make_uint2(0u, 0u);
+    if (tap < 49 && pix < npix) {
+      const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
+      const size_t e = pix / ((size_t)wd * ht);
+      const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
+      if (yy >= 0 && yy < ht && xx >= 0 && xx < wd) {
+        const size_t q = (e * ht + yy) * wd + xx;
+        const float2 c1 = reinterpret_cast<const float2*>(coords1)[q];
+        const float2 c0 = reinterpret_cast<const float2*>(coords0)[(size_t)yy * wd + xx];
+        const float2 tg = target ? reinterpret_cast<const float2*>(target)[q] : c1;
+        const float m0 = fminf(fmaxf(c1.x - c0.x, -64.f), 64.f), m1 = fminf(fmaxf(c1.y - c0.y, -64.f), 64.f);
+        const float m2 = fminf(fmaxf(tg.x - c1.x, -64.f), 64.f), m3 = fminf(fmaxf(tg.y - c1.y, -64.f), 64.f);
+        const __half2 a = __floats2half2_rn(m0, m1), b = __floats2half2_rn(m2, m3);
+        v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b);
+      }
     }
+    *reinterpret_cast<uint2*>(tile + px * MI_C + tap * 4) = v;
   }
-  *reinterpret_cast<uint2*>(out + pix * MI_C + tap * 4) = v;
+  __syncthreads();
+  constexpr int V = MI_C / 8;                  // 25 x 16 bytes per pixel
+  for (int idx = threadIdx.x; idx < MI_PIX * V; idx += 256) {
+    const int px = idx / V, j = idx % V;
+    const size_t pix = p0 + px;
+    if (pix < npix) reinterpret_cast<uint4*>(out + pix * MI_C)[j] = reinterpret_cast<const uint4*>(tile + px * MI_C)[j];
+  }
 }
 
 // h2 [E,ht,wd,16] fp16: cols 0,1 = delta, cols 2,3 = weight logits
@@ -113,9 +125,9 @@ extern "C" {
 
 int nslam_motion_im2col(const float* coords1, const float* coords0, const float* target, void* out,
                         int E, int ht, int wd, void* stream) {
-  const size_t total = (size_t)E * ht * wd * 50;
-  if (total == 0) return 0;
-  nslam::motion_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  const size_t npix = (size_t)E * ht * wd;
+  if (npix == 0) return 0;
+  nslam::motion_im2col_kernel<<<(unsigned)((npix + nslam::MI_PIX - 1) / nslam::MI_PIX), 256, 0, (cudaStream_t)stream>>>(
       coords1, coords0, target, (__half*)out, E, ht, wd);
   NSLAM_CHECK_LAUNCH();
   return 0;
