@@ -281,11 +281,13 @@ def run_ours(a):
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=job.dev)
+        n_it = torch.tensor([(job.nf.total_iters - it0) if job.is_nerf else 0], device=job.dev, dtype=torch.float32)
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_it, op=dist.ReduceOp.SUM)          # NeRF iterations of all trainer ranks
         stats = dict(kf=(job.fe.kf_idx - kf0) if job.is_slam else 0, updates=(job.fe.stats["updates"] - up0) if job.is_slam else 0,
-                     nerf_iters=(job.nf.total_iters - it0) if job.is_nerf else 0, wall_s=wall)
+                     nerf_iters=int(n_it.item()), wall_s=wall)
         return float(t.item()), stats
 
     clocks = ClockSampler(local)
@@ -420,8 +422,10 @@ def count_own_launches(job, st):
     with torch.cuda.stream(job.slam_stream):
         up = own(lambda: fe.update(use_inactive=True))
         fr = own(lambda: fe._frame_front(x))
-    with torch.cuda.stream(job.nerf_stream):
-        ne = own(job.nf.fit_volume_once) if job.is_nerf else (0, 0)
+    ne = (0, 0)
+    if job.is_nerf:
+        with torch.cuda.stream(job.nerf_stream):
+            ne = own(job.nf.fit_volume_once)
     total = up[0] * st["updates"] + fr[0] * st["frames"] + ne[0] * st["nerf_iters"]
     return {"total": int(total), "own_per_update_call": up[0], "all_per_update_call": up[1], "own_per_frame_front": fr[0],
             "all_per_frame_front": fr[1], "own_per_nerf_iter": ne[0], "all_per_nerf_iter": ne[1],

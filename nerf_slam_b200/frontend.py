@@ -79,6 +79,38 @@ def coords_grid(ht, wd, device):
     return torch.stack([x, y], dim=-1)
 
 
+class _Timers:
+    """optional wall-clock section timers of the HOST thread (NSLAM_TIMERS=1); no device syncs are added"""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get("NSLAM_TIMERS", "0") == "1"
+        self.t = {}
+
+    def section(self, name):
+        return _Section(self, name)
+
+    def report(self):
+        return {k: (round(v[0] * 1e3, 2), v[1]) for k, v in sorted(self.t.items(), key=lambda kv: -kv[1][0])}
+
+
+class _Section:
+    def __init__(self, timers, name):
+        self.tm, self.name = timers, name
+
+    def __enter__(self):
+        if self.tm.on:
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if self.tm.on:
+            import time
+            e = self.tm.t.setdefault(self.name, [0.0, 0])
+            e[0] += time.perf_counter() - self.t0; e[1] += 1
+        return False
+
+
 class RaftVisualFrontend:
     def __init__(self, world_T_body_t0, body_T_cam0, args, device="cuda:0"):
         self.args = args
@@ -143,6 +175,7 @@ class RaftVisualFrontend:
         # CUDA-core kernel for the 32-channel layers); set args.cudnn_benchmark = False to disable
         if getattr(args, "cudnn_benchmark", True):
             torch.backends.cudnn.benchmark = True
+        self.timers = _Timers()
         self.update_tc = None
         self.feature_tc = self.context_tc = None
         if self.conv_backend == "tcgen05":
@@ -322,8 +355,11 @@ class RaftVisualFrontend:
             return x0, factors, viz_out
 
         assert k > 0 and self.kf_idx < self.buffer
-        feats = self._frame_front(imgs_k)              # feature encoder + motion filter (CUDA graph)
-        if not (self.last_motion.item() > self.motion_filter_thresh):
+        with self.timers.section("frame.front issue"):
+            feats = self._frame_front(imgs_k)          # feature encoder + motion filter (CUDA graph)
+        with self.timers.section("frame.motion item (device wait)"):
+            enough = self.last_motion.item() > self.motion_filter_thresh
+        if not enough:
             if batch["is_last_frame"]:
                 self.kf_idx -= 1
                 self.terminate()
@@ -438,13 +474,16 @@ class RaftVisualFrontend:
         ix = np.arange(kf0, t); jx = np.arange(kf1, t)
         ii, jj = np.meshgrid(ix, jx, indexing="ij")
         ii, jj = ii.reshape(-1), jj.reshape(-1)
-        d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
+        with self.timers.section("prox.distance + cpu (device wait)"):
+            d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
         ii1 = np.concatenate([self.ii_h, self.ii_bad_h, self.ii_inactive_h])
         jj1 = np.concatenate([self.jj_h, self.jj_bad_h, self.jj_inactive_h])
-        es = proximity_edges(d, ii, jj, ii1, jj1, kf0, kf1, t, rad, nms, thresh, self.max_factors, self.stereo)
+        with self.timers.section("prox.selection (host)"):
+            es = proximity_edges(d, ii, jj, ii1, jj1, kf0, kf1, t, rad, nms, thresh, self.max_factors, self.stereo)
         if es.shape[0] == 0:
             return
-        self.add_factors(es[:, 0], es[:, 1], remove)
+        with self.timers.section("prox.add_factors"):
+            self.add_factors(es[:, 0], es[:, 1], remove)
 
     def _filter_repeated_edges(self, ii, jj):
         eset = set(zip(self.ii_h.tolist(), self.jj_h.tolist())) | \
@@ -557,20 +596,27 @@ class RaftVisualFrontend:
 
     def _update(self):
         """visual_frontend.py:577-638"""
-        if self.gru_hidden_states is not None:
-            self.rm_factors(self.age_h > self.max_age, store=True)
-        self.add_proximity_factors(kf0=self.kf_idx - 4, kf1=max(self.kf_idx + 1 - self.frontend_window, 0),
-                                   rad=self.frontend_radius, nms=self.frontend_nms,
-                                   thresh=self.frontend_thresh, beta=self.beta, remove=True)
+        T = self.timers.section
+        with T("kf.rm_factors(age)"):
+            if self.gru_hidden_states is not None:
+                self.rm_factors(self.age_h > self.max_age, store=True)
+        with T("kf.add_proximity_factors"):
+            self.add_proximity_factors(kf0=self.kf_idx - 4, kf1=max(self.kf_idx + 1 - self.frontend_window, 0),
+                                       rad=self.frontend_radius, nms=self.frontend_nms,
+                                       thresh=self.frontend_thresh, beta=self.beta, remove=True)
         k = self.kf_idx
         self.cam0_idepths[k] = torch.where(self.cam0_idepths_sensed[k] > 0, self.cam0_idepths_sensed[k], self.cam0_idepths[k])
-        for _ in range(self.iters1):
-            self.update(use_inactive=True)
-        d = self.distance([k - 2], [k - 1], beta=self.beta, bidirectional=True)
-        if d.item() < self.keyframe_thresh:
+        with T("kf.updates iters1 (host issue)"):
+            for _ in range(self.iters1):
+                self.update(use_inactive=True)
+        with T("kf.distance + item (device wait)"):
+            d = self.distance([k - 2], [k - 1], beta=self.beta, bidirectional=True)
+            dv = d.item()
+        if dv < self.keyframe_thresh:
             return False
-        for _ in range(self.iters2):
-            self.update(use_inactive=True)
+        with T("kf.updates iters2 (host issue)"):
+            for _ in range(self.iters2):
+                self.update(use_inactive=True)
         nk = k + 1
         if nk < self.buffer:
             self.cam0_T_world[nk] = self.cam0_T_world[k]
@@ -670,12 +716,14 @@ class RaftVisualFrontend:
         part; from the second call on the device work is replayed from a CUDA graph."""
         st = self._static
         if st is None or st.use_inactive != use_inactive:
-            st = self._prepare_static(use_inactive, EP)
+            with self.timers.section("update.prepare_static"):
+                st = self._prepare_static(use_inactive, EP)
             st.use_inactive = use_inactive
             self._static = st
         cc = self.compute_covariances
         if self.use_update_graphs and st.calls >= 1:
             if st.graph is None:
+              with self.timers.section("update.graph capture"):
                 g = torch.cuda.CUDAGraph()
                 cs = self._capture_stream
                 cs.wait_stream(torch.cuda.current_stream())

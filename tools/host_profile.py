@@ -14,13 +14,16 @@ for p in frames[:8]:
     job.step(p, False)
 torch.cuda.synchronize()
 pr = cProfile.Profile()
+fe.timers.t.clear()
 t0 = time.perf_counter()
-pr.enable()
+if os.environ.get("NSLAM_CPROFILE", "1") == "1":
+    pr.enable()
 for p in frames[8:]:
     job.step(p, False)
 torch.cuda.synchronize()
 pr.disable()
 dt = time.perf_counter() - t0
+print("host section timers (ms total, calls):", fe.timers.report())
 print(f"64 frames in {dt * 1e3:.1f} ms -> {dt / 64 * 1e3:.2f} ms/frame, kf now {fe.kf_idx}, updates {fe.stats['updates']}")
 for key in ("cumulative", "tottime"):
     s = io.StringIO()
