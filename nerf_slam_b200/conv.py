@@ -63,6 +63,16 @@ def conv_tc(srcs, wpacked, bias, B, H, W, KH, pad, N, mode=0, act=0, gctx=None, 
                                     int(out0_channels or 0), _lib.ptr(out1), num_sms, _lib.stream_ptr()), "conv_igemm")
 
 
+def _sm_budget(device, env):
+    """number of SMs a family of PERSISTENT kernels may occupy (grid size).  SLAM and NeRF run on two streams
+    of one GPU; their persistent CTAs do not pre-empt each other, so a static split (e.g. NSLAM_SLAM_SMS=108,
+    NSLAM_NERF_SMS=40) keeps the latency-critical SLAM kernels from waiting for a NeRF CTA to retire."""
+    import os
+    n = torch.cuda.get_device_properties(device).multi_processor_count
+    v = int(os.environ.get(env, "0"))
+    return max(1, min(n, v)) if v > 0 else n
+
+
 CORR_PAD = 200      # 196 correlation channels padded to a multiple of 8 (TMA stride rule), zero tail
 MOTION_COLS = 200   # 7x7x4 im2col of the motion input (196) padded the same way
 
@@ -77,7 +87,7 @@ class UpdateOperatorTC:
         """params: networks.UpdateModule (its state_dict tensors)"""
         sd = {k: v.to(device).float() for k, v in params.state_dict().items()}
         self.dev = device
-        self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.num_sms = _sm_budget(device, "NSLAM_SLAM_SMS")
         f32 = lambda t: t.float().contiguous()
         P = {}
         P["ce0"] = (pack_weights(sd["corr_encoder.0.weight"], [196]), f32(sd["corr_encoder.0.bias"]))
@@ -228,7 +238,7 @@ class EncoderTC:
         from . import networks as nw
         self.inorm = enc.norm is nw._inorm
         self.dev = device
-        self.num_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.num_sms = _sm_budget(device, "NSLAM_SLAM_SMS")
         sd = {k: v.to(device).float() for k, v in enc.state_dict().items()}
         f32 = lambda t: t.float().contiguous()
         bias = (lambda k: None) if self.inorm else (lambda k: f32(sd[k + ".bias"]))

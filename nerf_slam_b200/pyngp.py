@@ -156,7 +156,8 @@ class Testbed:
         self.rgba = None
         self.lr, self.beta1, self.beta2, self.eps, self.l2 = 1e-2, 0.9, 0.99, 1e-15, 1e-6
         self._t0 = None
-        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        from .conv import _sm_budget
+        self.num_sms = _sm_budget(self.device, "NSLAM_NERF_SMS")
         self._measured = None
         self.grad_hook = None        # e.g. dist.allreduce_grads for data-parallel training
         self._ctr_event = None; self._ctr_host = None; self._loss_host = None; self._ctr_rays = 0
