@@ -92,7 +92,8 @@ def make_args(buffer):
     return types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False, eval=False, mask_type="ours",
                                  weights=w if os.path.exists(w) else None, corr_slots=112,
                                  update_graphs=os.environ.get("NSLAM_UPDATE_GRAPHS", "1") == "1",
-                                 encoder_backend=os.environ.get("NSLAM_ENCODER", "tcgen05"))
+                                 encoder_backend=os.environ.get("NSLAM_ENCODER", "tcgen05"),
+                                 op_step=os.environ.get("NSLAM_OP_STEP", "1") == "1")
 
 
 class SlamNerfJob:
@@ -121,6 +122,10 @@ class SlamNerfJob:
             from nerf_slam_b200.nerf_fusion import NerfFusion
             self.nf = NerfFusion("nerf", args, self.dev)
             self.nerf_stream = torch.cuda.Stream(priority=0) if world == 1 else torch.cuda.current_stream()
+            if world == 1 and "NSLAM_NERF_SMS" not in os.environ:
+                # sharing the GPU with SLAM: the persistent NeRF kernels stay on 40 of the 148 SMs so that the
+                # latency-critical SLAM kernels never wait for a NeRF CTA to retire (profiles/r01_sm_split_run20.log)
+                self.nf.ngp.num_sms = min(self.nf.ngp.num_sms, 40)
         # SLAM is the latency-critical chain (host decisions wait on it): its kernels run on a HIGH-priority
         # stream so that NeRF training on the same GPU only fills the gaps
         self.slam_stream = torch.cuda.Stream(priority=-1) if (self.is_slam and world == 1) else torch.cuda.current_stream()
@@ -510,7 +515,7 @@ def run_reference(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--steps", type=int, default=192)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nerf-iters", type=int, default=2)

@@ -51,6 +51,33 @@ int nslam_segment_mean(const void* a, const int* seg_ptr, const int* seg_edges, 
 int nslam_eta_damping(const void* e16, const long long* ux, float* damping, int K, const long long* kx_ba,
                       float* ba_damp, int Kba, int hw, float ep, void* stream);
 
+/* ---- the whole update operator in one host call (csrc/update_step.cu) -------------------------------------
+ * UpdateModule.forward + GraphAgg (networks/droid_net.py:59-75,118-150) on a fixed edge set: every pointer is a
+ * DEVICE pointer, the struct itself lives on the host.  Weight slots follow conv.py::UpdateOperatorTC (packed by
+ * pack_weights).  net_out may alias net (in-place hidden-state update).  K == 0: skip GraphAgg. */
+enum { NSLAM_W_CE0 = 0, NSLAM_W_CE2, NSLAM_W_FE0, NSLAM_W_FE2, NSLAM_W_GLO, NSLAM_W_ZR, NSLAM_W_Q, NSLAM_W_H0, NSLAM_W_H2,
+       NSLAM_W_A1, NSLAM_W_A2, NSLAM_W_ETA, NSLAM_W_UM0, NSLAM_W_UM1, NSLAM_W_UM2, NSLAM_W_COUNT };
+typedef struct nslam_update_ctx {
+  int E, K, H, W, num_sms, corr_channels, Kba;
+  float ep;
+  /* inputs */
+  const void* net; const void* inp; const void* corr;          /* [E,H,W,128] x2, [E,H,W,corr_channels] fp16 */
+  const float* coords1; const float* coords0; const float* target;   /* [E,H,W,2], [H,W,2], [E,H,W,2] or NULL */
+  const int* seg_ptr; const int* seg_edges;                     /* GraphAgg CSR: [K+1], [E] */
+  /* outputs */
+  void* net_out;                                                /* [E,H,W,128] fp16 */
+  float* flow; float* conf; float* ba_target; float* ba_weight; /* [E,H,W,2] x2, planar [E,2,H,W] x2 (or NULL) */
+  void* upmask;                                                 /* [K,H,W,576] fp16 */
+  const long long* ux; float* damping; const long long* kx_ba; float* ba_damp;   /* eta -> damping (or damping NULL) */
+  /* weights */
+  const void* wp[NSLAM_W_COUNT]; const float* bias[NSLAM_W_COUNT];
+  const float* glo_w; const float* glo_b;                        /* [384,128], [384] fp32 */
+  /* workspace (fp16 unless noted) */
+  void* c1; void* c2; void* mcol; void* f1; void* f2; float* gsum; float* gzr; float* gq;
+  void* z; void* rnet; void* h0; void* h2; void* a1; void* am; void* a2; void* e16;
+} nslam_update_ctx;
+int nslam_update_op_step(const nslam_update_ctx* ctx, void* stream);
+
 /* ---- instance norm of the feature encoder (csrc/inorm.cu), NHWC fp16 ----------------------------------
  * Replaces F.instance_norm + ReLU (+ residual add + ReLU) of BasicEncoder/ResidualBlock with
  * norm_fn='instance' (networks/modules/extractor.py:6-60,118-198): biased variance, eps 1e-5, fp32

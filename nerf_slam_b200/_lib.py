@@ -33,6 +33,20 @@ class BABuffers(ctypes.Structure):
                [(n, c_int) for n in ("ht", "wd", "T")]
 
 
+N_UPDATE_WEIGHTS = 15      # NSLAM_W_COUNT (include/nslam_nn.h)
+
+
+class UpdateCtx(ctypes.Structure):
+    """mirror of `nslam_update_ctx` (include/nslam_nn.h)"""
+    _fields_ = [(n, c_int) for n in ("E", "K", "H", "W", "num_sms", "corr_channels", "Kba")] + [("ep", c_float)] + \
+               [(n, c_void_p) for n in ("net", "inp", "corr", "coords1", "coords0", "target", "seg_ptr", "seg_edges",
+                                        "net_out", "flow", "conf", "ba_target", "ba_weight", "upmask",
+                                        "ux", "damping", "kx_ba", "ba_damp")] + \
+               [("wp", c_void_p * N_UPDATE_WEIGHTS), ("bias", c_void_p * N_UPDATE_WEIGHTS)] + \
+               [(n, c_void_p) for n in ("glo_w", "glo_b", "c1", "c2", "mcol", "f1", "f2", "gsum", "gzr", "gq",
+                                        "z", "rnet", "h0", "h2", "a1", "am", "a2", "e16")]
+
+
 _P = c_void_p
 _SIGNATURES = {
     # name: argtypes (all return int)
@@ -55,6 +69,7 @@ _SIGNATURES = {
     "nslam_conv_igemm_ex": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
                             _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, _P],
     "nslam_im2col7_s2": [_P, _P, c_int, c_int, c_int, _P],
+    "nslam_update_op_step": [ctypes.POINTER(UpdateCtx), _P],
     "nslam_inorm_stats": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "nslam_inorm_apply": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P],
     "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],

@@ -186,6 +186,36 @@ class UpdateOperatorTC:
             conv_tc([a2], wp, b, K, H, W, 1, 0, n, out0=upmask[..., c0:], out0_channels=576, num_sms=self.num_sms)
         return net2, flow, conf, e16, upmask
 
+    W_ORDER = ("ce0", "ce2", "fe0", "fe2", "glo", "zr", "q", "h0", "h2", "a1", "a2", "eta", "um0", "um1", "um2")
+
+    def make_step(self, E, K, H, W, device):
+        """-> (ctx, keep): a `nslam_update_ctx` for a fixed (E, K) with all intermediates in ONE workspace
+        tensor; the caller fills the input/output pointers and calls `step(ctx)`.  `keep` holds the tensors the
+        ctx points into."""
+        ctx = _lib.UpdateCtx()
+        ctx.E, ctx.K, ctx.H, ctx.W, ctx.num_sms, ctx.corr_channels = E, K, H, W, self.num_sms, CORR_PAD
+        um = {f"um{i}": (wp, b) for i, (wp, b, c0, n) in enumerate(self.P["um"])}
+        for i, name in enumerate(self.W_ORDER):
+            wp, b = (um[name] if name in um else self.P[name][:2])
+            ctx.wp[i] = wp.data_ptr(); ctx.bias[i] = b.data_ptr() if b is not None else None
+        ctx.glo_w, ctx.glo_b = self.glo_w.data_ptr(), self.glo_b.data_ptr()
+        hw = H * W
+        sizes = dict(c1=E * hw * 128 * 2, c2=E * hw * 128 * 2, mcol=E * hw * MOTION_COLS * 2, f1=E * hw * 128 * 2,
+                     f2=E * hw * 64 * 2, gsum=E * 128 * 4, gzr=E * 256 * 4, gq=E * 128 * 4, z=E * hw * 128 * 2,
+                     rnet=E * hw * 128 * 2, h0=E * hw * 256 * 2, h2=E * hw * 16 * 2, a1=E * hw * 128 * 2,
+                     am=max(K, 1) * hw * 128 * 2, a2=max(K, 1) * hw * 128 * 2, e16=max(K, 1) * hw * 16 * 2)
+        total = sum((v + 255) // 256 * 256 for v in sizes.values())
+        ws = torch.empty(total, dtype=torch.uint8, device=device)
+        off = 0
+        for name, v in sizes.items():
+            setattr(ctx, name, ws.data_ptr() + off)
+            off += (v + 255) // 256 * 256
+        return ctx, ws
+
+    @staticmethod
+    def step(ctx):
+        _lib.check(_lib.load().nslam_update_op_step(ctypes.byref(ctx), _lib.stream_ptr()), "update_op_step")
+
     def call_reference_convention(self, net, inp, corr, motion, ii=None):
         """UpdateModule.forward's own argument/return convention (droid_net.py:118-150) on top of the fused
         operator — used by the parity tests: motion [E,4,ht,wd] (|.| < 64) is turned into the coordinate

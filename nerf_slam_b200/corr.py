@@ -94,7 +94,7 @@ class CorrPool:
                 outs = [lv[sl:sl + 1] for lv in self.levels]
                 db.corr_volume_build_into(fmaps_nhwc, ii[k:k + 1], jj[k:k + 1], outs)
 
-    def lookup(self, slots_dev, coords, nhwc=False):
+    def lookup(self, slots_dev, coords, nhwc=False, out=None):
         """slots_dev int32 [E] device.
         nhwc=False: coords [E,2,ht,wd] -> [E,196,ht,wd] fp16 (reference layout)
         nhwc=True : coords [E,ht,wd,2] (what reproject returns) -> [E,ht,wd,CORR_PAD] fp16, zero-padded
@@ -102,7 +102,7 @@ class CorrPool:
         if nhwc:
             from .conv import CORR_PAD
             return db.corr_lookup_pyramid(self.levels, coords.contiguous(), self.radius, slots=slots_dev,
-                                          nhwc_stride=CORR_PAD, coords_nhwc=True)
+                                          nhwc_stride=CORR_PAD, coords_nhwc=True, out=out)
         return db.corr_lookup_pyramid(self.levels, coords, self.radius, slots=slots_dev)
 
 

@@ -99,12 +99,15 @@ template <int N, bool HALO>
 struct CgSmem {
   static constexpr int STAGES = CgStages<N>::value;
   static constexpr int A_STAGE = HALO ? 20480 : 16384;
-  static constexpr int A_STAGES = HALO ? ((N >= 256) ? 3 : 4) : STAGES;
-  static constexpr int B_STAGES = HALO ? ((N >= 256) ? 3 : 4) : STAGES;
+  // the loops are latency-bound on the weight blocks (one 1-D bulk copy per tap and channel block, ~1.5 us
+  // round trip): keep as many of them in flight as shared memory allows
+  static constexpr int A_STAGES = HALO ? 3 : STAGES;
+  static constexpr int B_STAGES = HALO ? ((N >= 256) ? 4 : 8) : STAGES;
   static constexpr int A = 0;
   static constexpr int B = A_STAGES * A_STAGE;
   static constexpr int OUT = B + B_STAGES * N * 128;
-  static constexpr int NOUT64 = (N >= 64) ? N / 64 : 1;    // 64-channel staging tiles
+  static constexpr int PASSES = (N >= 256) ? 2 : 1;        // N = 256: the epilogue stages / stores 128 columns at a time
+  static constexpr int NOUT64 = (N >= 64) ? (N / PASSES) / 64 : 1;    // 64-channel staging tiles
   static constexpr int BIAS = OUT + NOUT64 * 16384;
   static constexpr int BAR = BIAS + 3 * N * 4;     // bias | column sums | column sums of squares
   static constexpr int TOTAL = BAR + 256;
@@ -354,97 +357,112 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const float* g = p.gctx ? p.gctx + (size_t)n * N : nullptr;
-      if (works) {
+      constexpr int PASSES = SM::PASSES, CPP = N / PASSES;          // columns staged per pass
+      constexpr int GC = (N >= 64) ? CPP / 2 : N;                   // columns per warp group per pass
 #pragma unroll 1
-        for (int c0 = cbeg; c0 < cbeg + NG; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(taddr + c0, r);
-          // operand loads of the gating modes overlap the TMEM read
-          uint4 an[4] = {}, az[4] = {};
-          if (MODE == 1) {
-            if (c0 >= 128 && valid) {
-              const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + (c0 - 128));
+      for (int pass = 0; pass < PASSES; pass++) {
+        if (pass > 0) {
+          // the staging tiles are reused: wait until the previous pass' TMA stores have read them
+          if (etid == 0) tma_store_wait_read();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        const int cbeg = pass * CPP + ((N >= 64) ? grp * GC : 0);
+        if (works) {
+#pragma unroll 1
+          for (int c0 = cbeg; c0 < cbeg + GC; c0 += 32) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(taddr + c0, r);
+            // operand loads of the gating modes overlap the TMEM read
+            uint4 an[4] = {}, az[4] = {};
+            if (MODE == 1) {
+              if (c0 >= 128 && valid) {
+                const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + (c0 - 128));
 #pragma unroll
-              for (int i = 0; i < 4; i++) an[i] = np[i];
-            }
-          } else if (MODE == 2 || MODE == 3) {
-            if (valid) {
-              const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + c0);
-#pragma unroll
-              for (int i = 0; i < 4; i++) an[i] = np[i];
-              if (MODE == 2) {
-                const uint4* zp = reinterpret_cast<const uint4*>(p.zbuf + pix * 128 + c0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) az[i] = zp[i];
+                for (int i = 0; i < 4; i++) an[i] = np[i];
               }
-            }
-          }
-          tc::tmem_ld_wait();
-          float v[32];
-          epi_chunk<MODE>(r, v, sbias, g, c0, p.act, valid, an, az);
-          if (MODE == 3) {
-            const float cs = warp_colsum32(v, lane);
-            atomicAdd(&sacc[c0 + lane], cs);
-          } else {
-            // fp16, into the staging tile of this 64-channel group
-            const int t64 = c0 / 64;
-            if (kept) {
+            } else if (MODE == 2 || MODE == 3) {
+              if (valid) {
+                const uint4* np = reinterpret_cast<const uint4*>(p.net + pix * 128 + c0);
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (c0 + i >= N) break;
-                __half2 h2[4];
+                for (int i = 0; i < 4; i++) an[i] = np[i];
+                if (MODE == 2) {
+                  const uint4* zp = reinterpret_cast<const uint4*>(p.zbuf + pix * 128 + c0);
 #pragma unroll
-                for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-                if (N >= 64) {
-                  // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
-                  unsigned char* st = sm + SM::OUT + t64 * 16384 + srow * 128;
-                  const int chunk = ((c0 % 64) + i) / 8;
-                  *reinterpret_cast<uint4*>(st + ((chunk ^ (srow & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
-                } else {
-                  // narrow outputs: dense rows of N halfs, un-swizzled tensor map
-                  unsigned char* st = sm + SM::OUT + srow * (N * 2);
-                  *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+                  for (int i = 0; i < 4; i++) az[i] = zp[i];
                 }
               }
             }
-            if (MODE == 4 && p.stats) {
-              // statistics of what the next layer will read: the fp16-rounded values of the kept, in-image pixels
-              float q2[32];
-              const bool cnt = kept && valid;
+            tc::tmem_ld_wait();
+            float v[32];
+            epi_chunk<MODE>(r, v, sbias, g, c0, p.act, valid, an, az);
+            if (MODE == 3) {
+              const float cs = warp_colsum32(v, lane);
+              atomicAdd(&sacc[c0 + lane], cs);
+            } else {
+              // fp16, into the staging tile of this 64-channel group (tile index within the pass)
+              const int t64 = (c0 - pass * CPP) / 64;
+              if (kept) {
 #pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float hv = cnt ? __half2float(__float2half_rn(v[i])) : 0.f;
-                v[i] = hv; q2[i] = hv * hv;
+                for (int i = 0; i < 32; i += 8) {
+                  if (c0 + i >= N) break;
+                  __half2 h2[4];
+#pragma unroll
+                  for (int j = 0; j < 4; j++) h2[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                  if (N >= 64) {
+                    // 128B-swizzled staging tile (matches the SWIZZLE_128B output tensor map)
+                    unsigned char* st = sm + SM::OUT + t64 * 16384 + srow * 128;
+                    const int chunk = ((c0 % 64) + i) / 8;
+                    *reinterpret_cast<uint4*>(st + ((chunk ^ (srow & 7)) * 16)) = *reinterpret_cast<const uint4*>(h2);
+                  } else {
+                    // narrow outputs: dense rows of N halfs, un-swizzled tensor map
+                    unsigned char* st = sm + SM::OUT + srow * (N * 2);
+                    *reinterpret_cast<uint4*>(st + (c0 + i) * 2) = *reinterpret_cast<const uint4*>(h2);
+                  }
+                }
               }
-              const float cs = warp_colsum32(v, lane), cq = warp_colsum32(q2, lane);
-              if (c0 + lane < N) { atomicAdd(&sacc[c0 + lane], cs); atomicAdd(&sacc[N + c0 + lane], cq); }
+              if (MODE == 4 && p.stats) {
+                // statistics of what the next layer will read: the fp16-rounded values of the kept, in-image pixels
+                float q2[32];
+                const bool cnt = kept && valid;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  const float hv = cnt ? __half2float(__float2half_rn(v[i])) : 0.f;
+                  v[i] = hv; q2[i] = hv * hv;
+                }
+                const float cs = warp_colsum32(v, lane), cq = warp_colsum32(q2, lane);
+                if (c0 + lane < N) { atomicAdd(&sacc[c0 + lane], cs); atomicAdd(&sacc[N + c0 + lane], cq); }
+              }
             }
           }
         }
-      }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
-      if (MODE != 3) {
-        tc::fence_proxy_async();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (etid == 0) {
-          if (MODE == 1) {
-            tma_store_4d(&maps.out[0], sm + SM::OUT + 0 * 16384, 0, w0, h0, n);
-            tma_store_4d(&maps.out[0], sm + SM::OUT + 1 * 16384, 64, w0, h0, n);
-            tma_store_4d(&maps.out[1], sm + SM::OUT + 2 * 16384, 0, w0, h0, n);
-            tma_store_4d(&maps.out[1], sm + SM::OUT + 3 * 16384, 64, w0, h0, n);
-          } else if (MODE == 4 && p.sub == 2) {
-            for (int t = 0; t < SM::NOUT64; t++)
-              tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, t * 64, w0 >> 1, h0 >> 1, n);
-          } else {
-            for (int t = 0; t < SM::NOUT64; t++)
-              tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, t * 64, w0, h0, n);
-          }
-          tma_store_commit();
+        if (pass == PASSES - 1) {
+          // the accumulator stage may be overwritten by the next tile's MMAs
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
         }
+        if (MODE != 3) {
+          tc::fence_proxy_async();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (etid == 0) {
+            if (MODE == 1) {
+              // pass 0: z (columns 0..127) -> out0 ; pass 1: r * net (columns 128..255) -> out1
+              tma_store_4d(&maps.out[pass], sm + SM::OUT + 0 * 16384, 0, w0, h0, n);
+              tma_store_4d(&maps.out[pass], sm + SM::OUT + 1 * 16384, 64, w0, h0, n);
+            } else if (MODE == 4 && p.sub == 2) {
+              for (int t = 0; t < SM::NOUT64; t++)
+                tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, pass * CPP + t * 64, w0 >> 1, h0 >> 1, n);
+            } else {
+              for (int t = 0; t < SM::NOUT64; t++)
+                tma_store_4d(&maps.out[0], sm + SM::OUT + t * 16384, pass * CPP + t * 64, w0, h0, n);
+            }
+            tma_store_commit();
+          }
+        }
+      }
+      if (MODE != 3) {
         if (MODE == 4 && p.stats) {
-          // flush this tile's channel statistics (shared accumulators were completed before bar.sync 2)
+          // flush this tile's channel statistics (shared accumulators were completed before the last bar.sync 2)
           for (int i = etid; i < 2 * N; i += 32 * CG_EPI_WARPS) {
             const float sv = sacc[i];
             sacc[i] = 0.f;

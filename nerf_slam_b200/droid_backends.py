@@ -56,7 +56,7 @@ def corr_index_backward(volume, coords, corr_grad, radius):
                               "inference hot path (SURVEY.md §8, out of scope)")
 
 
-def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coords_nhwc=False):
+def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coords_nhwc=False, out=None):
     """fused 4-level version of CorrBlock.__call__ (networks/modules/corr.py:40-50):
     volumes: list of [n,h1,w1,h2>>l,w2>>l]; coords [n,2,h1,w1] (level-0 pixels) ->
     [n, L*(2r+1)^2, h1, w1]"""
@@ -67,7 +67,9 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coor
     n = coords.shape[0]
     dt = volumes[0].dtype
     rd = 2 * radius + 1
-    if nhwc_stride:
+    if out is not None:
+        assert out.is_contiguous() and out.dtype == dt and out.numel() == n * h1 * w1 * (nhwc_stride or L * rd * rd)
+    elif nhwc_stride:
         out = torch.empty(n, h1, w1, nhwc_stride, dtype=dt, device=coords.device)
     else:
         out = torch.empty(n, L * rd * rd, h1, w1, dtype=dt, device=coords.device)
@@ -186,7 +188,7 @@ def depth_filter(poses, disps, intrinsics, ix, thresh):
     return counter
 
 
-def reproject(poses, disps, intrinsics, ii, jj, want_valid=True):
+def reproject(poses, disps, intrinsics, ii, jj, want_valid=True, out=None):
     """A6 (pops.projective_transform, networks/geom/projective_ops.py:98-145, jacobian=False):
     poses [N,7], disps [N,h,w], intrinsics [N,4] or [4] -> coords [E,h,w,2], valid [E,h,w,1]"""
     ii, jj = _i64(ii).contiguous(), _i64(jj).contiguous()
@@ -195,7 +197,8 @@ def reproject(poses, disps, intrinsics, ii, jj, want_valid=True):
     E = ii.shape[0]
     ht, wd = disps.shape[1:]
     stride = 4 if intrinsics.dim() == 2 else 0
-    coords = torch.empty(E, ht, wd, 2, dtype=torch.float32, device=poses.device)
+    coords = out if out is not None else torch.empty(E, ht, wd, 2, dtype=torch.float32, device=poses.device)
+    assert coords.is_contiguous() and coords.numel() == E * ht * wd * 2
     valid = torch.empty(E, ht, wd, 1, dtype=torch.float32, device=poses.device) if want_valid else None
     _lib.check(lib.nslam_reproject(_lib.ptr(poses), _lib.ptr(disps), _lib.ptr(intrinsics), stride,
                                    _lib.ptr(ii), _lib.ptr(jj), E, ht, wd, _lib.ptr(coords),

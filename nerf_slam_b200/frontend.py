@@ -27,6 +27,7 @@ from . import droid_backends as db
 from . import _lib
 from .corr import CorrPool, AltCorrBlock
 from .graph import proximity_edges
+from .conv import CORR_PAD as CORR_PAD_
 from .networks import BasicEncoder, UpdateModule, load_droid_weights
 
 
@@ -200,6 +201,8 @@ class RaftVisualFrontend:
         # update(): replaying a captured graph saves host time per call but costs a re-capture (~2 ms of host
         # time with an idle stream) whenever the edge set changes, i.e. once per keyframe
         self.use_update_graphs = self.use_cuda_graphs and bool(getattr(args, "update_graphs", True))
+        # the update operator as one C call per update() (csrc/update_step.cu) instead of ~45 ctypes/torch calls
+        self.use_op_step = bool(getattr(args, "op_step", True))
         self._graph_pool = torch.cuda.graph_pool_handle() if self.use_cuda_graphs else None
         # kernel nodes inherit the priority of the stream they were captured on: keep the SLAM chain high
         self._capture_stream = torch.cuda.Stream(priority=-1) if self.use_cuda_graphs else None
@@ -643,6 +646,7 @@ class RaftVisualFrontend:
         ux, inv = np.unique(ii_h, return_inverse=True)
         st.ux = _lib.h2d(ux, dev); st.ix = _lib.h2d(inv, dev); st.K = len(ux)
         st.agg = self._agg_tables(ii_h, dev)
+        st.op_ctx = None
         st.inp = self.cst_contexts_imgs[self.ii, 0].contiguous()
         if use_inactive:
             m = (self.ii_inactive_h >= kf0 - 3) & (self.jj_inactive_h >= kf0 - 3)
@@ -665,6 +669,23 @@ class RaftVisualFrontend:
                                self.cam0_idepths_sensed, st.target, st.weight, st.damp, ii, jj, kf0, kf1)
         st.kx_prob = _lib.h2d(st.prob.gh.tables["kx"].astype(np.int64), dev)
         st.has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
+        if self.update_tc is not None and self.use_op_step:
+            # the whole update operator as one host call on fixed buffers (csrc/update_step.cu)
+            E = int(self.ii.shape[0])
+            c, st.op_ws = self.update_tc.make_step(E, st.K, ht, wd, dev)
+            st.coords1 = torch.empty(E, ht, wd, 2, device=dev)
+            st.corr = torch.zeros(E, ht, wd, CORR_PAD_, dtype=torch.float16, device=dev)
+            st.upmask = torch.empty(st.K, ht, wd, 576, dtype=torch.float16, device=dev)
+            c.net = c.net_out = self.gru_hidden_states.data_ptr()
+            c.inp, c.corr, c.coords1, c.coords0 = st.inp.data_ptr(), st.corr.data_ptr(), st.coords1.data_ptr(), self.coords0.data_ptr()
+            c.target = c.flow = self.gru_estimated_flow.data_ptr()
+            c.conf = self.gru_estimated_flow_weight.data_ptr()
+            c.ba_target, c.ba_weight = st.target[st.n_in:].data_ptr(), st.weight[st.n_in:].data_ptr()
+            c.seg_ptr, c.seg_edges = st.agg[0].data_ptr(), st.agg[1].data_ptr()
+            c.upmask = st.upmask.data_ptr()
+            c.ux, c.damping, c.kx_ba, c.ba_damp = st.ux.data_ptr(), self.damping.data_ptr(), st.kx_ba.data_ptr(), st.damp.data_ptr()
+            c.Kba, c.ep = int(st.kx_ba.numel()), float(EP)
+            st.op_ctx = c
         return st
 
     def _update_body(self, st, itrs, compute_covariances):
@@ -673,9 +694,19 @@ class RaftVisualFrontend:
             self._update_body_impl(st, itrs, compute_covariances)
 
     def _update_body_impl(self, st, itrs, compute_covariances):
-        coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
-        corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
-        if self.update_tc is not None:
+        if st.op_ctx is not None:
+            db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False,
+                         out=st.coords1)
+            self.corr_pool.lookup(self.slots_d, st.coords1, nhwc=True, out=st.corr)
+            self.update_tc.step(st.op_ctx)          # hidden state, flow, confidence, BA inputs, damping: all in place
+            upmask = st.upmask
+            coords1 = None
+        else:
+            coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
+            corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
+        if st.op_ctx is not None:
+            pass
+        elif self.update_tc is not None:
             # flow/confidence land directly in the frontend state AND in the BA's planar input buffers
             net, _, _, e16, upmask = self.update_tc(
                 self.gru_hidden_states, st.inp, corr, coords1, self.coords0, target=self.gru_estimated_flow, agg=st.agg,

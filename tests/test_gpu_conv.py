@@ -139,3 +139,54 @@ def test_encoder_tc_vs_library_path(norm, out_dim):
     assert got.shape == ref.shape == (2, out_dim, 15, 19)
     err = float((got - ref).abs().max())
     assert err < 5e-2 * max(1.0, float(ref.abs().max())), err
+
+
+def test_update_op_step_matches_python_sequencing():
+    """nslam_update_op_step (one C call, fixed workspace, in-place hidden state) must reproduce
+    UpdateOperatorTC.__call__ (the same kernels issued one by one from Python) bit for bit"""
+    from nerf_slam_b200 import _lib
+    from nerf_slam_b200.conv import CORR_PAD, UpdateOperatorTC
+    from nerf_slam_b200.networks import UpdateModule, load_droid_weights
+    um = UpdateModule(torch.Generator().manual_seed(3))
+    if os.path.exists(WEIGHTS):
+        um.load_state_dict(load_droid_weights(WEIGHTS), "update_net.")
+    um.to(device=DEV, dtype=torch.float16)
+    op = UpdateOperatorTC(um, DEV)
+    g = torch.Generator().manual_seed(14)
+    E, H, W = 6, 30, 40
+    net = torch.tanh(torch.randn(E, H, W, 128, generator=g)).half().to(DEV)
+    inp = torch.relu(torch.randn(E, H, W, 128, generator=g)).half().to(DEV)
+    corr = torch.zeros(E, H, W, CORR_PAD); corr[..., :196] = torch.randn(E, H, W, 196, generator=g) * 2
+    corr = corr.half().to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    coords0 = torch.stack([xx, yy], -1).contiguous().to(DEV)
+    coords1 = (coords0[None] + torch.randn(E, H, W, 2, generator=g).to(DEV) * 3).contiguous()
+    target = (coords1 + torch.randn(E, H, W, 2, generator=g).to(DEV) * 2).contiguous()
+    ii = np.array([0, 0, 1, 2, 2, 2])
+    ux, inv = np.unique(ii, return_inverse=True)
+    order = np.argsort(inv, kind="stable").astype(np.int32)
+    ptr = np.zeros(len(ux) + 1, np.int32); np.cumsum(np.bincount(inv), out=ptr[1:])
+    seg_ptr, seg_edges, K = torch.as_tensor(ptr, device=DEV), torch.as_tensor(order, device=DEV), len(ux)
+    ref = op(net, inp, corr, coords1, coords0, target=target, agg=(seg_ptr, seg_edges, K))
+    ref = [t.clone() for t in ref]
+    # one-call path
+    ctx, ws = op.make_step(E, K, H, W, DEV)
+    net2 = net.clone(); flow = target.clone(); conf = torch.empty_like(flow)
+    bt = torch.empty(E, 2, H, W, device=DEV); bw = torch.empty_like(bt)
+    upmask = torch.empty(K, H, W, 576, dtype=torch.float16, device=DEV)
+    uxd = torch.as_tensor(ux, device=DEV); damping = torch.zeros(8, H, W, device=DEV); bad = torch.empty(K, H, W, device=DEV)
+    ctx.net = ctx.net_out = net2.data_ptr(); ctx.inp = inp.data_ptr(); ctx.corr = corr.data_ptr()
+    ctx.coords1, ctx.coords0 = coords1.data_ptr(), coords0.data_ptr()
+    ctx.target = ctx.flow = flow.data_ptr(); ctx.conf = conf.data_ptr()
+    ctx.ba_target, ctx.ba_weight = bt.data_ptr(), bw.data_ptr()
+    ctx.seg_ptr, ctx.seg_edges = seg_ptr.data_ptr(), seg_edges.data_ptr()
+    ctx.upmask = upmask.data_ptr()
+    ctx.ux, ctx.damping, ctx.kx_ba, ctx.ba_damp, ctx.Kba, ctx.ep = uxd.data_ptr(), damping.data_ptr(), uxd.data_ptr(), bad.data_ptr(), K, 1e-7
+    op.step(ctx)
+    torch.cuda.synchronize()
+    assert torch.equal(net2, ref[0]) and torch.equal(flow, ref[1]) and torch.equal(conf, ref[2])
+    assert torch.equal(upmask, ref[4])
+    assert torch.equal(bt, ref[1].permute(0, 3, 1, 2)) and torch.equal(bw, ref[2].permute(0, 3, 1, 2))
+    eta = 0.01 * torch.nn.functional.softplus(ref[3][..., 0].float())
+    assert torch.allclose(damping[uxd], eta, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(bad, 0.2 * eta + 1e-7, rtol=1e-5, atol=1e-9)
