@@ -91,7 +91,7 @@ def make_args(buffer):
     w = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
     return types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False, eval=False, mask_type="ours",
                                  weights=w if os.path.exists(w) else None, corr_slots=112,
-                                 update_graphs=os.environ.get("NSLAM_UPDATE_GRAPHS", "1") == "1",
+                                 update_graphs=os.environ.get("NSLAM_UPDATE_GRAPHS", "0") == "1",
                                  encoder_backend=os.environ.get("NSLAM_ENCODER", "tcgen05"),
                                  op_step=os.environ.get("NSLAM_OP_STEP", "1") == "1")
 

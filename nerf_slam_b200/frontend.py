@@ -199,8 +199,9 @@ class RaftVisualFrontend:
         self._static = None
         self._img_static = None
         # update(): replaying a captured graph saves host time per call but costs a re-capture (~2 ms of host
-        # time with an idle stream) whenever the edge set changes, i.e. once per keyframe
-        self.use_update_graphs = self.use_cuda_graphs and bool(getattr(args, "update_graphs", True))
+        # time with an idle stream) whenever the edge set changes, i.e. once per keyframe.  With the operator as
+        # one C call (use_op_step) the eager path issues ~10 host calls per update and is the default.
+        self.use_update_graphs = self.use_cuda_graphs and bool(getattr(args, "update_graphs", False))
         # the update operator as one C call per update() (csrc/update_step.cu) instead of ~45 ctypes/torch calls
         self.use_op_step = bool(getattr(args, "op_step", True))
         self._graph_pool = torch.cuda.graph_pool_handle() if self.use_cuda_graphs else None

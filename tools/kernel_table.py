@@ -36,7 +36,7 @@ torch.cuda.synchronize()
 print("edges", len(fe.ii_h), "kf", fe.kf_idx)
 for _ in range(3):
     fe.update(use_inactive=True)
-table(lambda: fe.update(use_inactive=True), 4, "update() [graph replay]")
+table(lambda: fe.update(use_inactive=True), 4, "update()")
 img = job.make_frames(1, True)[0]
 x = img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3)
 for _ in range(3):
