@@ -224,6 +224,8 @@ class SlamNerfJob:
 
 
 def run_ours(a):
+    # NCCL's version banner / debug lines go to a file, not to stdout (rank 0 prints exactly ONE JSON line)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nslam_nccl_%h_%p.log")
     import torch
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -317,7 +319,7 @@ def run_ours(a):
     line = {
         "metric": "SLAM+NeRF frames/sec on 640x480 synthetic stream", "value": round(fps, 2), "unit": "frames/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_dev / a.steps, 3),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (nets, corr) / f32 (BA, NeRF MLP)",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands + f32 accumulate (encoders, update operator, correlation, NeRF MLP) / f32 (BA, losses, Adam) / f64 (BA solve)",
         "data": "synthetic (procedural box room, seeded)",
         "config": {"workload": "configs[1]: Replica-office0-shaped synthetic 640x480, buffer=100, --slam --fusion=nerf",
                    "weights": "droid.pth" if job.args.weights else "random-init (seeded)", "nerf_iters_per_frame": a.nerf_iters,

@@ -23,6 +23,8 @@ torch.cuda.synchronize()
 print("edges", len(fe.ii_h), "kf", fe.kf_idx, "rays", tb.rays_per_batch, flush=True)
 torch.cuda.profiler.start()
 fe.update(use_inactive=True)
+fe.use_cuda_graphs = False
+fe._frame_front_body()
 tb.training_step = 17            # not a density-grid step
 tb.train_step()
 torch.cuda.synchronize()
