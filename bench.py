@@ -226,6 +226,11 @@ class SlamNerfJob:
 def run_ours(a):
     # NCCL's version banner / debug lines go to a file, not to stdout (rank 0 prints exactly ONE JSON line)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nslam_nccl_%h_%p.log")
+    # ... and whatever a library still writes to fd 1 (NCCL's version banner does) is diverted to stderr until
+    # the result line is printed
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -334,6 +339,8 @@ def run_ours(a):
     st_dev["frames"] = a.steps
     counts = count_own_launches(job, st_dev)
     line.update(extra_sections(a, job, pk, counts))
+    sys.stdout.flush()
+    os.dup2(_saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
