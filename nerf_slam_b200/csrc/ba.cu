@@ -436,26 +436,48 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
     return;
   }
   // L is now in the lower triangle of A (diagonal included); diag[] holds 1 / L[i][i].
-  // forward/back substitution by one warp (n is small): L z = y, L^T x = z
-  if (tid < 32) {
-    for (int i = 0; i < n; i++) {
-      double sacc = 0.0;
-      for (int c = tid; c < i; c += 32) sacc += A[(size_t)i * n + c] * y[c];
+  // blocked forward / back substitution (6x6 pose blocks): thread 0 solves the diagonal block, all threads
+  // eliminate it from the remaining rows: 2 barriers per block instead of one warp-serial step per row
+  for (int jb = 0; jb < P; jb++) {                       // L z = y
+    const int j0 = 6 * jb;
+    if (tid == 0) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (tid == 0) y[i] = (y[i] - sacc) * diag[i];
-      __syncwarp();
-    }
-    for (int i = n - 1; i >= 0; i--) {
-      double sacc = 0.0;
-      for (int c = i + 1 + tid; c < n; c += 32) sacc += A[(size_t)c * n + i] * y[c];
+      for (int c = 0; c < 6; c++) {
+        double v = y[j0 + c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (tid == 0) y[i] = (y[i] - sacc) * diag[i];
-      __syncwarp();
+        for (int k = 0; k < c; k++) v -= A[(size_t)(j0 + c) * n + j0 + k] * y[j0 + k];
+        y[j0 + c] = v * diag[j0 + c];
+      }
     }
+    __syncthreads();
+    for (int i = j0 + 6 + tid; i < n; i += nt) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc += A[(size_t)i * n + j0 + k] * y[j0 + k];
+      y[i] -= acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  for (int jb = P - 1; jb >= 0; jb--) {                  // L^T x = z
+    const int j0 = 6 * jb;
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 5; c >= 0; c--) {
+        double v = y[j0 + c];
+#pragma unroll
+        for (int k = c + 1; k < 6; k++) v -= A[(size_t)(j0 + k) * n + j0 + c] * y[j0 + k];
+        y[j0 + c] = v * diag[j0 + c];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < j0; i += nt) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc += A[(size_t)(j0 + k) * n + i] * y[j0 + k];
+      y[i] -= acc;
+    }
+    __syncthreads();
+  }
   for (int id = tid; id < n; id += nt) dx[id] = (float)y[id];
   if (tid == 0 && status) *status = 0;
   if (Linv) {

@@ -28,26 +28,36 @@ motion_im2col_kernel(const float* __restrict__ coords1, const float* __restrict_
   __shared__ __align__(16) __half tile[MI_PIX * MI_C];
   const size_t npix = (size_t)E * ht * wd;
   const size_t p0 = (size_t)blockIdx.x * MI_PIX;
-  for (int idx = threadIdx.x; idx < MI_PIX * 50; idx += 256) {
-    const int px = idx / 50, tap = idx % 50;
+  // work item = (pixel, ky): the 7 taps of one window row read 7 horizontally adjacent source pixels
+  for (int idx = threadIdx.x; idx < MI_PIX * 8; idx += 256) {
+    const int px = idx >> 3, ky = idx & 7;
     const size_t pix = p0 + px;
-    uint2 v = make_uint2(0u, 0u);
-    if (tap < 49 && pix < npix) {
-      const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
-      const size_t e = pix / ((size_t)wd * ht);
-      const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
-      if (yy >= 0 && yy < ht && xx >= 0 && xx < wd) {
-        const size_t q = (e * ht + yy) * wd + xx;
-        const float2 c1 = reinterpret_cast<const float2*>(coords1)[q];
-        const float2 c0 = reinterpret_cast<const float2*>(coords0)[(size_t)yy * wd + xx];
-        const float2 tg = target ? reinterpret_cast<const float2*>(target)[q] : c1;
+    if (ky == 7) {                                              // columns 196..199: zero tail
+      *reinterpret_cast<uint2*>(tile + px * MI_C + 196) = make_uint2(0u, 0u);
+      continue;
+    }
+    const bool pok = pix < npix;
+    const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
+    const size_t e = pix / ((size_t)wd * ht);
+    const int yy = y + ky - 3;
+    const bool rowok = pok && yy >= 0 && yy < ht;
+    const size_t rowq = (e * ht + (rowok ? yy : 0)) * wd;
+    const size_t row0 = (size_t)(rowok ? yy : 0) * wd;
+#pragma unroll
+    for (int kx = 0; kx < 7; kx++) {
+      const int xx = x + kx - 3;
+      uint2 v = make_uint2(0u, 0u);
+      if (rowok && xx >= 0 && xx < wd) {
+        const float2 c1 = reinterpret_cast<const float2*>(coords1)[rowq + xx];
+        const float2 c0 = reinterpret_cast<const float2*>(coords0)[row0 + xx];
+        const float2 tg = target ? reinterpret_cast<const float2*>(target)[rowq + xx] : c1;
         const float m0 = fminf(fmaxf(c1.x - c0.x, -64.f), 64.f), m1 = fminf(fmaxf(c1.y - c0.y, -64.f), 64.f);
         const float m2 = fminf(fmaxf(tg.x - c1.x, -64.f), 64.f), m3 = fminf(fmaxf(tg.y - c1.y, -64.f), 64.f);
         const __half2 a = __floats2half2_rn(m0, m1), b = __floats2half2_rn(m2, m3);
         v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b);
       }
+      *reinterpret_cast<uint2*>(tile + px * MI_C + (ky * 7 + kx) * 4) = v;
     }
-    *reinterpret_cast<uint2*>(tile + px * MI_C + tap * 4) = v;
   }
   __syncthreads();
   constexpr int V = MI_C / 8;                  // 25 x 16 bytes per pixel
@@ -182,18 +192,28 @@ im2col7_s2_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, 
   const int Ho = H / 2, Wo = W / 2;
   const size_t npix = (size_t)B * Ho * Wo;
   const size_t p0 = (size_t)blockIdx.x * I7_PIX;
-  for (int idx = threadIdx.x; idx < I7_PIX * I7_KP; idx += 256) {
-    const int px = idx / I7_KP, k = idx % I7_KP;
+  // work item = (pixel, ky, channel): 7 horizontally adjacent input values -> 7 smem stores (stride 3 halfs)
+  for (int idx = threadIdx.x; idx < I7_PIX * 21; idx += 256) {
+    const int px = idx / 21, r = idx % 21, ky = r / 3, c = r % 3;
     const size_t pid = p0 + px;
-    float v = 0.f;
-    if (k < I7_K && pid < npix) {
+    __half* dst = tile + px * I7_KP + ky * 21 + c;
+    if (pid < npix) {
       const int ox = (int)(pid % Wo), oy = (int)((pid / Wo) % Ho), b = (int)(pid / ((size_t)Wo * Ho));
-      const int tap = k / 3, c = k % 3;
-      const int iy = 2 * oy + tap / 7 - 3, ix = 2 * ox + tap % 7 - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)b * 3 + c) * H + iy) * W + ix];
+      const int iy = 2 * oy + ky - 3, ix0 = 2 * ox - 3;
+      const float* src = x + (((size_t)b * 3 + c) * H + (iy >= 0 && iy < H ? iy : 0)) * W;
+      const bool rowok = iy >= 0 && iy < H;
+#pragma unroll
+      for (int kx = 0; kx < 7; kx++) {
+        const int ix = ix0 + kx;
+        dst[kx * 3] = __float2half_rn((rowok && ix >= 0 && ix < W) ? src[ix] : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int kx = 0; kx < 7; kx++) dst[kx * 3] = __float2half_rn(0.f);
     }
-    tile[idx] = __float2half_rn(v);
   }
+  for (int idx = threadIdx.x; idx < I7_PIX * (I7_KP - I7_K); idx += 256)        // zero the K padding
+    tile[(idx / (I7_KP - I7_K)) * I7_KP + I7_K + idx % (I7_KP - I7_K)] = __float2half_rn(0.f);
   __syncthreads();
   constexpr int V = I7_KP / 8;                 // 19 x 16 bytes per pixel
   for (int idx = threadIdx.x; idx < I7_PIX * V; idx += 256) {
