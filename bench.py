@@ -383,8 +383,8 @@ def extra_sections(a, job, pk, counts):
     out["roofline"] = {"kernel": "conv_igemm_kernel<256,1> (A5: ConvGRU z|r gates, 3x3 448->256 + fused sigmoid / r*h epilogue)",
                        "bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": peak, "unit": "TFLOP/s",
                        "frac": round(flops / ms / 1e9 / peak, 3),
-                       "traffic": 93408000, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                       "traffic_source": "profiles/r01_ncu_raw_run11.csv, captured at 18 edges",
+                       "traffic": 92820000, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                       "traffic_source": "profiles/r01_ncu_raw_run22.csv, captured at 18 edges (sm__pipe_tensor_cycles_active 68.2 %)",
                        "peak_source": pk["_src"] + " (dense bf16 cuBLAS, sustained figure: the kernel is timed inside a long step)",
                        "launch_ms": round(ms, 4), "edges": E, "algorithmic_flops_per_launch": flops}
     # ---- secondary rooflines (HBM-bound kernels of the path)
