@@ -37,8 +37,9 @@ motion_im2col_kernel(const float* __restrict__ coords1, const float* __restrict_
       continue;
     }
     const bool pok = pix < npix;
-    const int x = (int)(pix % wd), y = (int)((pix / wd) % ht);
-    const size_t e = pix / ((size_t)wd * ht);
+    const unsigned p32 = (unsigned)pix;                         // E * ht * wd < 2^31: 32-bit divisions
+    const int x = (int)(p32 % (unsigned)wd), y = (int)((p32 / (unsigned)wd) % (unsigned)ht);
+    const size_t e = p32 / ((unsigned)wd * (unsigned)ht);
     const int yy = y + ky - 3;
     const bool rowok = pok && yy >= 0 && yy < ht;
     const size_t rowq = (e * ht + (rowok ? yy : 0)) * wd;
@@ -198,7 +199,8 @@ im2col7_s2_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, 
     const size_t pid = p0 + px;
     __half* dst = tile + px * I7_KP + ky * 21 + c;
     if (pid < npix) {
-      const int ox = (int)(pid % Wo), oy = (int)((pid / Wo) % Ho), b = (int)(pid / ((size_t)Wo * Ho));
+      const unsigned p32 = (unsigned)pid;                        // B * Ho * Wo < 2^31: 32-bit divisions
+      const int ox = (int)(p32 % (unsigned)Wo), oy = (int)((p32 / (unsigned)Wo) % (unsigned)Ho), b = (int)(p32 / ((unsigned)Wo * (unsigned)Ho));
       const int iy = 2 * oy + ky - 3, ix0 = 2 * ox - 3;
       const float* src = x + (((size_t)b * 3 + c) * H + (iy >= 0 && iy < H ? iy : 0)) * W;
       const bool rowok = iy >= 0 && iy < H;
