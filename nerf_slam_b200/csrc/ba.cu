@@ -152,11 +152,24 @@ ba_linearize_kernel(nslam_ba_graph g, nslam_ba_buffers b) {
         Ei[n] += si;
       }
     }
-    block_sum<27>(acc, red);
-    if (threadIdx.x == 0) {
-      float* dst = b.part + ((size_t)e * b.T + tile) * 27;
+    // tile reduction of the 27 Gram / gradient entries: per-warp shuffle sums (27 independent chains), then 27
+    // threads add the per-warp partials and write the tile's partial directly (the next iteration's barriers
+    // protect `red`)
+    {
+      constexpr int NW = TILE / 32;
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-      for (int n = 0; n < 27; n++) dst[n] = acc[n];
+      for (int n = 0; n < 27; n++) {
+        const float v = warp_sum(acc[n]);
+        if (lane == 0) red[n * NW + wid] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < 27) {
+        float sred = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) sred += red[threadIdx.x * NW + w];
+        b.part[((size_t)e * b.T + tile) * 27 + threadIdx.x] = sred;
+      }
     }
   }
 
@@ -261,17 +274,32 @@ ba_schur_kernel(nslam_ba_graph g, nslam_ba_buffers b) {
   __syncthreads();
   const int D = 6 * R;
   const int poff = g.pair_off[k];
-  // S blocks: entry id = (ra*R + rb)*36 + m*6 + n  <->  X row (ra*6+m), X row (rb*6+n)
-  const int nent = R * R * 36;
-  for (int id = threadIdx.x; id < nent; id += TILE) {
-    const int blk = id / 36, mn = id % 36;
-    const int ra = blk / R, rb = blk % R;
-    const float* xa = Xs + (ra * 6 + mn / 6) * LD;
-    const float* xb = Xs + (rb * 6 + mn % 6) * LD;
-    float s = 0.f;
-#pragma unroll 8
-    for (int t = 0; t < TILE; t++) s += xa[t] * qs[t] * xb[t];
-    b.spart[((size_t)(poff + blk) * 36 + mn) * b.T + tile] = s;
+  // S blocks: entry (ra*R + rb)*36 + m*6 + n  <->  X row (ra*6+m), X row (rb*6+n).
+  // Only the block pairs ra <= rb are computed (S_ba = S_ab^T is written from the same registers) and one
+  // work item produces a whole block ROW (6 entries): 8 shared-memory loads per 6 FMAs instead of 18.
+  const int npairs = R * (R + 1) / 2;
+  for (int item = threadIdx.x; item < npairs * 6; item += TILE) {
+    const int pr = item / 6, m = item % 6;
+    int ra = 0, rem = pr;
+    while (rem >= R - ra) { rem -= R - ra; ra++; }
+    const int rb = ra + rem;
+    const float* xa = Xs + (ra * 6 + m) * LD;
+    const float* xb = Xs + (rb * 6) * LD;
+    float acc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int t = 0; t < TILE; t++) {
+      const float a = xa[t] * qs[t];
+#pragma unroll
+      for (int n = 0; n < 6; n++) acc6[n] = fmaf(a, xb[n * LD + t], acc6[n]);
+    }
+    float* dab = b.spart + ((size_t)(poff + ra * R + rb) * 36 + m * 6) * b.T + tile;
+#pragma unroll
+    for (int n = 0; n < 6; n++) dab[(size_t)n * b.T] = acc6[n];
+    if (ra != rb) {
+      float* dba = b.spart + ((size_t)(poff + rb * R + ra) * 36 + m) * b.T + tile;
+#pragma unroll
+      for (int n = 0; n < 6; n++) dba[(size_t)n * 6 * b.T] = acc6[n];
+    }
   }
   float* vpart = b.spart + (size_t)g.NPAIR * 36 * b.T;
   for (int id = threadIdx.x; id < D; id += TILE) {
