@@ -443,7 +443,7 @@ def count_own_launches(job, st):
     total = up[0] * st["updates"] + fr[0] * st["frames"] + ne[0] * st["nerf_iters"]
     return {"total": int(total), "own_per_update_call": up[0], "all_per_update_call": up[1], "own_per_frame_front": fr[0],
             "all_per_frame_front": fr[1], "own_per_nerf_iter": ne[0], "all_per_nerf_iter": ne[1],
-            "note": "own = kernels of libnslam_sm100a.so; the remainder are torch glue and the encoders' cuDNN convolutions; "
+            "note": "own = kernels of libnslam_sm100a.so; the remainder are torch glue (index/copy/normalise) kernels; "
                     "per-keyframe extras (context encoder, correlation volumes of new edges) are not included in total"}
 
 
