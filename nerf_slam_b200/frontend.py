@@ -744,8 +744,10 @@ class RaftVisualFrontend:
 
     @torch.no_grad()
     def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
-        """visual_frontend.py:371-470.  The first call after an edge-set change prepares the static
-        part; from the second call on the device work is replayed from a CUDA graph."""
+        """visual_frontend.py:371-470.  The first call after an edge-set change prepares the static part
+        (index tables, BA window, operator workspace); every call then issues ~10 host calls (reproject,
+        lookup, nslam_update_op_step, BA Gauss-Newton, covariances, upsample).  With args.update_graphs the
+        device work is instead captured once per edge set and replayed as a CUDA graph."""
         st = self._static
         if st is None or st.use_inactive != use_inactive:
             with self.timers.section("update.prepare_static"):
