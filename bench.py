@@ -516,7 +516,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "SLAM+NeRF frames/sec on 640x480 synthetic stream", "value": round(v, 4),
             "unit": "frames/s", "n_gpus": a.gpus, "steps": len(vals), "warmup": min(a.warmup, 1),
             "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": "configs[1] (bounded CPU sample, see cpu_baseline.sample)"},
+            "dtype": "f32", "data": "synthetic (procedural box room, seeded)",
+            "config": {"workload": "configs[1]: Replica-office0-shaped synthetic 640x480, buffer=100, --slam --fusion=nerf",
+                       "note": "CPU port of the reference path on a bounded sample of this workload, see cpu_baseline.sample"},
             "cpu_baseline": res, "e2e": {"value": round(v, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
