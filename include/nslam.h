@@ -84,7 +84,7 @@ int nslam_cvx_upsample(const float* data, const void* mask, int mask_dtype, floa
                        int ht, int wd, float pw, int mask_nhwc, void* stream);
 /* two planes through one softmax (inverse depths and their covariances share the mask,
  * visual_frontend.py:444-446); data2/out2 may be NULL.  index (int64 [K], or NULL = identity): mask plane
- * k is applied to row index[k] of data*/out* (the `x[kx] = cvx_upsample(y[kx], mask)` gather/scatter). */
+ * k is applied to row index[k] of the data and out planes (x[kx] = cvx_upsample(y[kx], mask) gather/scatter). */
 int nslam_cvx_upsample2(const float* data, const float* data2, const void* mask, int mask_dtype,
                         float* out, float* out2, const long long* index, int K, int ht, int wd, float pw,
                         int mask_nhwc, void* stream);
