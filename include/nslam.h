@@ -45,6 +45,12 @@ int nslam_corr_volume_build_simt(const void* fmaps, int NF, int H, int W, int C,
                                  const int* jj, int E, void* out0, void* out1, void* out2,
                                  void* out3, void* stream);
 
+/* EXPERIMENTAL (off unless NSLAM_CORRVOL_ROWS=1 on the Python side; hardware validation pending): the same
+ * operation with row-pair tiles — level 0 leaves the SM as 320 contiguous bytes per source pixel instead of
+ * 32-byte pieces (csrc/corr_volume_rows.cu).  C = 128, H even, W in {64, 80}; cudaErrorNotSupported otherwise. */
+int nslam_corr_volume_build_rows(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj,
+                                 int E, void* out0, void* out1, void* out2, void* out3, void* stream);
+
 /* droid_backends.altcorr_forward (src/droid.cpp:303-313; kernel src/altcorr_kernel.cu:27-149)
  * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,N,H1,W1,2] fp32, corr [B,N,(2r+1)^2,H1,W1]. */
 int nslam_altcorr_forward(const void* fmap1, const void* fmap2, int dtype, const float* coords,

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "nslam_corr_index_forward": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "nslam_corr_lookup_pyramid": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "nslam_corr_volume_build": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "nslam_corr_volume_build_rows": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_corr_volume_build_simt": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_altcorr_forward": [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "nslam_reproject": [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P],

@@ -85,6 +85,15 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coor
     return out
 
 
+def _corrvol_entry(lib, H, W, C):
+    """the row-pair kernel (csrc/corr_volume_rows.cu) is EXPERIMENTAL: opt-in with NSLAM_CORRVOL_ROWS=1 and only
+    for the shapes it supports; everything else runs the validated tiled kernel"""
+    import os
+    if os.environ.get("NSLAM_CORRVOL_ROWS", "0") == "1" and C == 128 and H % 2 == 0 and W in (64, 80):
+        return lib.nslam_corr_volume_build_rows
+    return lib.nslam_corr_volume_build
+
+
 def corr_volume_build(fmaps_nhwc, ii, jj, simt=False):
     """A2: fmaps [NF,H,W,C] fp16 channels-last, ii/jj int32 device frame indices ->
     4 pyramid levels [E,H,W,H>>l,W>>l] fp16 (CorrBlock.__init__, networks/modules/corr.py:23-38)"""
@@ -95,7 +104,7 @@ def corr_volume_build(fmaps_nhwc, ii, jj, simt=False):
     E = ii.shape[0]
     outs = [torch.empty(E, H, W, H >> l, W >> l, dtype=torch.float16, device=fmaps_nhwc.device)
             for l in range(4)]
-    fn = lib.nslam_corr_volume_build_simt if simt else lib.nslam_corr_volume_build
+    fn = lib.nslam_corr_volume_build_simt if simt else _corrvol_entry(lib, H, W, C)
     _lib.check(fn(_lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj), E,
                   *[_lib.ptr(o) for o in outs], _lib.stream_ptr()), "corr_volume_build")
     return outs
@@ -105,8 +114,8 @@ def corr_volume_build_into(fmaps_nhwc, ii, jj, outs):
     """as corr_volume_build but writes into caller-provided level tensors (arena slots)"""
     lib = _lib.load()
     NF, H, W, C = fmaps_nhwc.shape
-    _lib.check(lib.nslam_corr_volume_build(_lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj),
-                                           ii.shape[0], *[_lib.ptr(o) for o in outs], _lib.stream_ptr()),
+    _lib.check(_corrvol_entry(lib, H, W, C)(_lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj),
+                                            ii.shape[0], *[_lib.ptr(o) for o in outs], _lib.stream_ptr()),
                "corr_volume_build")
 
 

@@ -1,6 +1,8 @@
 """GPU parity tests: hand-written sm_100a kernels (through the C ABI) vs the CPU oracle on the same
 seeded inputs.  Tolerances are stated per test (SURVEY.md §8c / north_star: bit-exact for the
 fp16 lookup and integer work, fp32 tolerances elsewhere)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -330,3 +332,27 @@ def test_corr_lookup_nhwc_equals_reference_layout(db):
                                  slots=slots, nhwc_stride=200, coords_nhwc=True)        # [E,H,W,200]
     assert torch.equal(got[..., :196].permute(0, 3, 1, 2).float(), ref.float())
     assert float(got[..., 196:].abs().max()) == 0.0
+
+
+@pytest.mark.skipif(os.environ.get("NSLAM_CORRVOL_ROWS", "0") != "1",
+                    reason="experimental row-pair correlation kernel: enable with NSLAM_CORRVOL_ROWS=1")
+@pytest.mark.parametrize("H,W,E", [(60, 80, 3), (16, 64, 2), (30, 80, 1)])
+def test_corr_volume_rows_matches_tiled_kernel(H, W, E):
+    """csrc/corr_volume_rows.cu (two full target rows per MMA tile) must reproduce csrc/corr_volume.cu bit for
+    bit: same K order in the fp32 accumulation, same fp16 rounding chain of the pyramid"""
+    import ctypes
+    from nerf_slam_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(77)
+    NF = 4
+    fm = torch.randn(NF, H, W, 128, generator=g).half().to("cuda:0")
+    ii = torch.randint(0, NF, (E,), generator=g).int().to("cuda:0"); jj = torch.randint(0, NF, (E,), generator=g).int().to("cuda:0")
+    mk = lambda: [torch.zeros(E, H, W, H >> l, W >> l, dtype=torch.float16, device="cuda:0") for l in range(4)]
+    a, b = mk(), mk()
+    _lib.check(lib.nslam_corr_volume_build(_lib.ptr(fm), NF, H, W, 128, _lib.ptr(ii), _lib.ptr(jj), E,
+                                           *[_lib.ptr(o) for o in a], _lib.stream_ptr()), "tiled")
+    _lib.check(lib.nslam_corr_volume_build_rows(_lib.ptr(fm), NF, H, W, 128, _lib.ptr(ii), _lib.ptr(jj), E,
+                                                *[_lib.ptr(o) for o in b], _lib.stream_ptr()), "rows")
+    torch.cuda.synchronize()
+    for l in range(4):
+        assert torch.equal(a[l], b[l]), (l, float((a[l].float() - b[l].float()).abs().max()))
