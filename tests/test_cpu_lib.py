@@ -34,3 +34,18 @@ def test_ops_fail_loudly_without_cuda():
     with pytest.raises(RuntimeError):
         droid_backends.frame_distance(torch.zeros(2, 7), torch.zeros(2, 4, 4), torch.zeros(4),
                                       torch.zeros(1, dtype=torch.long), torch.ones(1, dtype=torch.long), 0.3)
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: the package must not import, load or reference it"""
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nerf_slam_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|from\s+\.\.?oracle)|oracle/_ref|oracle\._ref|build_ref", re.M)
+    bad = []
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):                      # (CUDA sources only mention the oracle in comments)
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                if pat.search(txt):
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad
