@@ -166,3 +166,52 @@ def test_frame_distance_f32_tree_close_to_f64(rng):
     a = geom.frame_distance(poses, disps, intr, ii, jj, 0.3, np.float32)
     b = geom.frame_distance(poses, disps, intr, ii, jj, 0.3, np.float64)
     assert np.allclose(a, b, rtol=1e-4)
+
+
+def test_row_pair_tiling_of_the_correlation_pyramid(rng):
+    """index/rounding emulation of csrc/corr_volume_rows.cu (tile = two full target rows; level 1 from the tile,
+    levels 2/3 from register carries across 2/4 consecutive row pairs, column halves per warp) against the
+    oracle pyramid: locks the offsets and the carry logic of that kernel on the CPU."""
+    from oracle import corr as ocorr
+    H, W, C, E = 12, 16, 8, 2                      # W % 16 == 0, H even; H/2 = 6 row pairs (last quad incomplete)
+    f1 = rng.normal(0, 1, (E, C, H, W)).astype(np.float16)
+    f2 = rng.normal(0, 1, (E, C, H, W)).astype(np.float16)
+    ref = ocorr.corr_volume_pyramid(f1, f2)
+    HW = H * W
+    out = [np.full((E, HW, (H >> l) * (W >> l)), np.nan, np.float16) for l in range(4)]
+    f16 = np.float16
+    pool = lambda a, b, c, d: f16((((np.float32(a) + np.float32(b)) + np.float32(c)) + np.float32(d)) * np.float32(0.25))
+    WH = W // 2
+    for e in range(E):
+        a = f1[e].reshape(C, HW).T.astype(np.float32)          # [HW, C]
+        b = f2[e].reshape(C, HW).T.astype(np.float32)
+        vol = (a @ b.T) * np.float32(0.0625)                   # fp32 accumulate, scaled
+        for m in range(HW):                                    # thread = source pixel
+            for hsel in range(2):                              # column half of the warp
+                c0 = hsel * WH
+                l1p = l2p = None
+                for rp in range(H // 2):
+                    h0 = vol[m, 2 * rp * W + c0:2 * rp * W + c0 + WH].astype(f16)
+                    h1 = vol[m, (2 * rp + 1) * W + c0:(2 * rp + 1) * W + c0 + WH].astype(f16)
+                    out[0][e, m, 2 * rp * W + c0:2 * rp * W + c0 + WH] = h0
+                    out[0][e, m, (2 * rp + 1) * W + c0:(2 * rp + 1) * W + c0 + WH] = h1
+                    l1 = np.array([pool(h0[2 * x], h0[2 * x + 1], h1[2 * x], h1[2 * x + 1]) for x in range(WH // 2)], f16)
+                    out[1][e, m, rp * (W // 2) + c0 // 2:rp * (W // 2) + c0 // 2 + WH // 2] = l1
+                    if rp & 1:
+                        l2 = np.array([pool(l1p[2 * y], l1p[2 * y + 1], l1[2 * y], l1[2 * y + 1]) for y in range(WH // 4)], f16)
+                        q2 = rp >> 1
+                        if q2 < (H >> 2):
+                            out[2][e, m, q2 * (W // 4) + c0 // 4:q2 * (W // 4) + c0 // 4 + WH // 4] = l2
+                        if (rp & 3) == 3:
+                            q3 = rp >> 2
+                            if q3 < (H >> 3):
+                                l3 = np.array([pool(l2p[2 * z], l2p[2 * z + 1], l2[2 * z], l2[2 * z + 1]) for z in range(WH // 8)], f16)
+                                out[3][e, m, q3 * (W // 8) + c0 // 8:q3 * (W // 8) + c0 // 8 + WH // 8] = l3
+                        else:
+                            l2p = l2
+                    else:
+                        l1p = l1
+    for l in range(4):
+        got = out[l].reshape(E, H, W, H >> l, W >> l).astype(np.float32)
+        assert not np.isnan(got).any(), l
+        assert np.abs(got - ref[l].astype(np.float32)).max() <= 2e-2, l       # same tolerance as the GPU parity test
