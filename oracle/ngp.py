@@ -144,3 +144,72 @@ def init_params(aabb_scale, seed=0, dtype=torch.float32):
         s = math.sqrt(6.0 / (i + o))       # xavier uniform (tcnn default for FullyFusedMLP)
         P[name] = (torch.rand(i, o, generator=g, dtype=dtype) * 2 - 1) * s
     return P
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Ray march through the cascaded occupancy grid (the sampler of a training / render step).
+# Restates nerf_slam_b200/csrc/ngp_train.cu::march_warp in its SERIAL meaning (fp32 arithmetic, numpy scalars):
+#   step lattice t_{k+1} = t_k + dt(t_k), dt(t) = clamp(t * cone, MIN_STEP, MAX_STEP), independent of occupancy;
+#   a sample is emitted at every lattice point that lies inside the box and in an occupied cell of its cascade
+#   (cascade from the step size and the position, as in instant-ngp), up to max_n samples / 4096 lattice points.
+# The published instant-ngp marcher skips ahead to the next voxel boundary when a cell is empty and then snaps to
+# the same lattice; both visit the same lattice and differ only where the cascade changes inside a skipped voxel.
+GRID = 128
+MAX_STEPS = 1024
+MIN_STEP = np.float32(np.float32(1.73205080757) / np.float32(MAX_STEPS))
+MAX_STEP = np.float32(MIN_STEP * np.float32(128.0) * np.float32(8.0))
+MAX_LATTICE = 4096
+
+
+def calc_dt(t, cone):
+    return np.float32(min(max(np.float32(t) * np.float32(cone), MIN_STEP), MAX_STEP))
+
+
+def _mip_from_pos(p, cascades):
+    m = max(abs(p[0] - np.float32(0.5)), abs(p[1] - np.float32(0.5)), abs(p[2] - np.float32(0.5)))
+    e = math.frexp(float(m))[1] if m != 0 else 0
+    return min(max(e + 1, 0), cascades - 1)
+
+
+def mip_from_dt(dt, p, cascades):
+    mip = _mip_from_pos(p, cascades)
+    d = np.float32(dt) * np.float32(2 * GRID)
+    if d < 1.0:
+        return mip
+    e = math.frexp(float(d))[1]
+    return min(max(max(e, mip), 0), cascades - 1)
+
+
+def occupied(p, mip, bits):
+    """bits: uint8 bitfield [cascades * GRID^3 / 8]"""
+    s = np.float32(2.0 ** (-mip))
+    idx = [int(math.floor(float(((np.float32(p[a]) - np.float32(0.5)) * s + np.float32(0.5)) * np.float32(GRID)))) for a in range(3)]
+    if min(idx) < 0 or max(idx) >= GRID:
+        return False
+    i = idx[0] + GRID * (idx[1] + GRID * idx[2]) + mip * GRID ** 3
+    return bool((bits[i >> 3] >> (i & 7)) & 1)
+
+
+def march_lattice(o, d, aabb_lo, aabb_hi, near, cone, cascades, bits, jitter, max_n):
+    """-> list of (t, dt) of the emitted samples; o, d float32 [3] (d unit length)"""
+    o = np.asarray(o, np.float32); d = np.asarray(d, np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.float32(1.0) / d
+    tmin, tmax = np.float32(-1e30), np.float32(1e30)
+    for a in range(3):
+        t0, t1 = (np.float32(aabb_lo) - o[a]) * inv[a], (np.float32(aabb_hi) - o[a]) * inv[a]
+        tmin = max(tmin, min(t0, t1)); tmax = min(tmax, max(t0, t1))
+    if tmax <= max(tmin, np.float32(0.0)):
+        return []
+    t = np.float32(max(tmin, np.float32(near)) + np.float32(1e-6))
+    t = np.float32(t + calc_dt(t, cone) * np.float32(jitter))
+    out = []
+    for _ in range(MAX_LATTICE):
+        if not (t < tmax) or len(out) >= max_n:
+            break
+        dt = calc_dt(t, cone)
+        p = [np.float32(np.float32(d[a]) * t + o[a]) for a in range(3)]     # fmaf(d, t, o) up to one rounding
+        if occupied(p, mip_from_dt(dt, p, cascades), bits):
+            out.append((t, dt))
+        t = np.float32(t + dt)
+    return out

@@ -215,3 +215,63 @@ def test_row_pair_tiling_of_the_correlation_pyramid(rng):
         got = out[l].reshape(E, H, W, H >> l, W >> l).astype(np.float32)
         assert not np.isnan(got).any(), l
         assert np.abs(got - ref[l].astype(np.float32)).max() <= 2e-2, l       # same tolerance as the GPU parity test
+
+
+def test_warp_chunked_march_equals_serial_lattice_march(rng):
+    """the kernel tests 32 lattice points per iteration (ballot), truncates at max_n with the n-th set bit and replays
+    the kept masks; emulated here in Python against the serial oracle (oracle/ngp.py::march_lattice)"""
+    from oracle import ngp as ongp
+    cascades = 3
+    ncell = ongp.GRID ** 3 * cascades
+    for trial in range(6):
+        bits = (rng.random(ncell // 8) < [0.02, 0.3, 1.0][trial % 3]).astype(np.uint8) * rng.integers(1, 256, ncell // 8).astype(np.uint8)
+        o = rng.uniform(0.3, 0.7, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32); d /= np.linalg.norm(d)
+        max_n = [1024, 37, 5][trial % 3]
+        jitter = float(rng.random())
+        ref = ongp.march_lattice(o, d, -1.5, 2.5, 0.05, 1.0 / 256, cascades, bits, jitter, max_n)
+        # ---- warp emulation
+        inv = np.float32(1.0) / d
+        tmin, tmax = np.float32(-1e30), np.float32(1e30)
+        for a in range(3):
+            t0, t1 = (np.float32(-1.5) - o[a]) * inv[a], (np.float32(2.5) - o[a]) * inv[a]
+            tmin = max(tmin, min(t0, t1)); tmax = min(tmax, max(t0, t1))
+        tbase = np.float32(max(tmin, np.float32(0.05)) + np.float32(1e-6))
+        tbase = np.float32(tbase + ongp.calc_dt(tbase, 1.0 / 256) * np.float32(jitter))
+        n, masks, bases = 0, [], []
+        for ci in range(128):
+            if not (tbase < tmax) or n >= max_n:
+                break
+            ts = []
+            t = tbase
+            for lane in range(32):
+                ts.append(t); t = np.float32(t + ongp.calc_dt(t, 1.0 / 256))
+            m = 0
+            for lane in range(32):
+                tl = ts[lane]
+                if tl < tmax:
+                    dt = ongp.calc_dt(tl, 1.0 / 256)
+                    p = [np.float32(d[a] * tl + o[a]) for a in range(3)]
+                    if ongp.occupied(p, ongp.mip_from_dt(dt, p, cascades), bits):
+                        m |= 1 << lane
+            c = bin(m).count("1")
+            if n + c > max_n:                                   # keep the first max_n - n set bits (__fns)
+                keep, mm, cnt = max_n - n, 0, 0
+                for lane in range(32):
+                    if (m >> lane) & 1:
+                        if cnt == keep:
+                            break
+                        mm |= 1 << lane; cnt += 1
+                m = mm
+            n += bin(m).count("1")
+            masks.append(m); bases.append(tbase)
+            tbase = np.float32(ts[31] + ongp.calc_dt(ts[31], 1.0 / 256))
+        got = []
+        for m, tb in zip(masks, bases):
+            t = tb
+            for lane in range(32):
+                if (m >> lane) & 1:
+                    got.append((t, ongp.calc_dt(t, 1.0 / 256)))
+                t = np.float32(t + ongp.calc_dt(t, 1.0 / 256))
+        assert len(got) == len(ref) == n
+        assert all(a[0] == b[0] and a[1] == b[1] for a, b in zip(got, ref))
