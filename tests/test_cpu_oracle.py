@@ -275,3 +275,64 @@ def test_warp_chunked_march_equals_serial_lattice_march(rng):
                 t = np.float32(t + ongp.calc_dt(t, 1.0 / 256))
         assert len(got) == len(ref) == n
         assert all(a[0] == b[0] and a[1] == b[1] for a, b in zip(got, ref))
+
+
+def test_blocked_cholesky_solve_and_inverse_algorithm(rng):
+    """numpy emulation of csrc/ba.cu::ba_solve_kernel: Cholesky blocked by the 6x6 pose blocks (diagonal block
+    factored first, panel rows solved against it, rank-6 trailing update), blocked forward/back substitution and
+    the column-wise triangular inverse (stored in the upper triangle) — against numpy.linalg"""
+    P = 7
+    n = 6 * P
+    M = rng.normal(size=(n, n))
+    H = M @ M.T + n * np.eye(n)
+    v = rng.normal(size=n)
+    A = H.copy()
+    diag = np.zeros(n)
+    for jb in range(P):
+        j0 = 6 * jb
+        Lb = np.tril(A[j0:j0 + 6, j0:j0 + 6]).copy()
+        rd = np.zeros(6)
+        for c in range(6):
+            dd = Lb[c, c] - Lb[c, :c] @ Lb[c, :c]
+            assert dd > 0
+            l = np.sqrt(dd); rd[c] = 1.0 / l; Lb[c, c] = l
+            for r in range(c + 1, 6):
+                Lb[r, c] = (Lb[r, c] - Lb[r, :c] @ Lb[c, :c]) * rd[c]
+        for i in range(j0 + 6, n):                               # panel: row_i(L) = row_i(A) Ljj^-T
+            x = np.zeros(6)
+            for c in range(6):
+                x[c] = (A[i, j0 + c] - x[:c] @ Lb[c, :c]) * rd[c]
+            A[i, j0:j0 + 6] = x
+        A[j0:j0 + 6, j0:j0 + 6] = np.tril(Lb) + np.triu(A[j0:j0 + 6, j0:j0 + 6], 1)
+        diag[j0:j0 + 6] = rd
+        for i in range(j0 + 6, n):                               # trailing update (lower triangle)
+            for c in range(j0 + 6, i + 1):
+                A[i, c] -= A[i, j0:j0 + 6] @ A[c, j0:j0 + 6]
+    L = np.tril(A)
+    assert np.allclose(L, np.linalg.cholesky(H), rtol=1e-10, atol=1e-10)
+    y = v.copy()
+    for jb in range(P):                                          # L z = y
+        j0 = 6 * jb
+        for c in range(6):
+            y[j0 + c] = (y[j0 + c] - A[j0 + c, j0:j0 + c] @ y[j0:j0 + c]) * diag[j0 + c]
+        for i in range(j0 + 6, n):
+            y[i] -= A[i, j0:j0 + 6] @ y[j0:j0 + 6]
+    for jb in range(P - 1, -1, -1):                              # L^T x = z
+        j0 = 6 * jb
+        for c in range(5, -1, -1):
+            y[j0 + c] = (y[j0 + c] - A[j0 + c + 1:j0 + 6, j0 + c] @ y[j0 + c + 1:j0 + 6]) * diag[j0 + c]
+        for i in range(j0):
+            y[i] -= A[j0:j0 + 6, i] @ y[j0:j0 + 6]
+    assert np.allclose(y, np.linalg.solve(H, v), rtol=1e-9, atol=1e-10)
+    Linv = np.zeros((n, n))
+    for c in range(n):                                           # X = L^-1, column by column, X in the upper triangle
+        xcc = diag[c]
+        Linv[c, c] = xcc
+        for i in range(c + 1, n):
+            s = -A[i, c] * xcc
+            for k in range(c + 1, i):
+                s -= A[i, k] * A[c, k]                           # L[i][k] * X[k][c]
+            x = s * diag[i]
+            A[c, i] = x
+            Linv[i, c] = x
+    assert np.allclose(Linv, np.linalg.inv(np.linalg.cholesky(H)), rtol=1e-8, atol=1e-10)
