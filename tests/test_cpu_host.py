@@ -66,3 +66,56 @@ def test_pose_tq_to_c2w_is_inverse_of_cam_T_world():
                           [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
             T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t[k]
         assert np.allclose(c2w[k] @ T, np.eye(4), atol=1e-9)
+
+
+def test_halo_tile_schedule_reproduces_the_convolution():
+    """index emulation of csrc/conv_igemm.cu (HALO path): per (channel block, dx) one column-shifted tile with a
+    1-pixel vertical halo, the three taps dy read it 16*dy rows further down, weights come from the packed image in
+    (tap, source, block) order with the 128-byte swizzle undone — must equal F.conv2d on the concatenated input"""
+    import torch.nn.functional as F
+    from nerf_slam_b200.conv import pack_weights
+    g = torch.Generator().manual_seed(5)
+    B, H, W, N = 1, 11, 21, 16                                  # partial tiles in both directions
+    chans = [128, 72]                                           # second source: 2 blocks, the last one 8 channels wide
+    srcs = [torch.randn(B, H, W, c, generator=g) for c in chans]
+    w = torch.randn(N, sum(chans), 3, 3, generator=g) * 0.1
+    packed = pack_weights(w, chans).float().view(-1, N, 8, 8)   # [block][n][chunk position][8]
+    rows = torch.arange(N)
+    cbs = [(c + 63) // 64 for c in chans]
+    cb_total = sum(cbs)
+
+    def weight_block(tap, cbg):                                 # un-swizzled [N, 64]
+        blk = packed[tap * cb_total + cbg]
+        out = torch.empty(N, 8, 8)
+        for j in range(8):
+            out[rows, j] = blk[rows, j ^ (rows & 7)]
+        return out.reshape(N, 64)
+
+    ref = F.conv2d(torch.cat(srcs, -1).permute(0, 3, 1, 2).half().float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
+    got = torch.zeros(B, H, W, N)
+    TH, TW = 8, 16
+    for h0 in range(0, H, TH):
+        for w0 in range(0, W, TW):
+            acc = torch.zeros(TH * TW, N)
+            cbg = 0
+            for s, c in enumerate(chans):
+                for cb in range(cbs[s]):
+                    for dx in range(3):
+                        # TMA box {64c, 16w, 10h} at (cb*64, w0+dx-1, h0-1): zero fill outside the image / channel range
+                        tile = torch.zeros(TH + 2, TW, 64)
+                        for hy in range(TH + 2):
+                            for wx in range(TW):
+                                y, x = h0 - 1 + hy, w0 + dx - 1 + wx
+                                if 0 <= y < H and 0 <= x < W:
+                                    ce = min(c, cb * 64 + 64)
+                                    tile[hy, wx, :ce - cb * 64] = srcs[s][0, y, x, cb * 64:ce].half().float()
+                        flat = tile.reshape(-1, 64)                              # smem rows: hy*16 + wx
+                        for dy in range(3):
+                            A = flat[dy * TW:dy * TW + TH * TW]                    # descriptor offset dy*16 rows
+                            acc += A @ weight_block(dy * 3 + dx, cbg).T
+                    cbg += 1
+            for r in range(TH * TW):
+                y, x = h0 + r // TW, w0 + r % TW
+                if y < H and x < W:
+                    got[0, y, x] = acc[r]
+    assert float((got - ref).abs().max()) < 2e-3
