@@ -213,3 +213,16 @@ def march_lattice(o, d, aabb_lo, aabb_hi, near, cone, cascades, bits, jitter, ma
             out.append((t, dt))
         t = np.float32(t + dt)
     return out
+
+
+def pcg(v):
+    """counter-based hash of nerf_slam_b200/csrc/ngp_common.cuh::pcg (uint32 arithmetic)"""
+    v &= 0xFFFFFFFF
+    s_ = (v * 747796405 + 2891336453) & 0xFFFFFFFF
+    w = (((s_ >> ((s_ >> 28) + 4)) ^ s_) * 277803737) & 0xFFFFFFFF
+    return ((w >> 22) ^ w) & 0xFFFFFFFF
+
+
+def rnd01(a, b, c):
+    """uniform [0,1) of ngp_common.cuh::rnd01(a, b, c)"""
+    return np.float32(np.float32(pcg(pcg(pcg(a) ^ (b & 0xFFFFFFFF)) ^ (c & 0xFFFFFFFF)) >> 8) * np.float32(1.0 / 16777216.0))

@@ -3,6 +3,7 @@ Tolerances: the hash table is read in fp16 by the kernels (oracle uses the same 
 values), MLP math is fp32 -> rgb/sigma rel 1e-4; gradients rel 2e-3 (fp16 storage of the
 recomputed activations in the backward tile)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -207,3 +208,46 @@ def test_forward_tc_matches_oracle():
     out2 = torch.zeros(n, 4, device=DEV)
     _lib.check(lib.nslam_ngp_forward(ctypes.byref(tb.model), _lib.ptr(coords), n, _lib.ptr(out2), _lib.stream_ptr()), "fwd")
     assert float((out[:, :3] - out2[:, :3]).abs().max()) < 1e-2
+
+
+@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS", "0") != "1",
+                    reason="written without GPU access at the end of round 1: enable with NSLAM_PENDING_TESTS=1, validate, then unconditional")
+def test_sample_rays_matches_the_march_oracle():
+    """every ray the sampler keeps must carry exactly the samples of oracle/ngp.py::march_lattice (bit-equal t and dt:
+    the kernel rebuilds the lattice with the same serial fp32 recurrence), in ray order, with positions
+    (o + t d - aabb_lo) / extent"""
+    from nerf_slam_b200 import _lib
+    tb = _testbed(seed=11)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    H, W = 48, 64
+    tb._ensure_store(H, W)
+    c2w = np.eye(4)[:3]; c2w[:, 3] = [0.5, 0.5, 0.5]
+    tb._set_camera(0, c2w, (60.0, 60.0), (W / 2 - 0.5, H / 2 - 0.5), (W, H))
+    tb._activate([0])
+    bits = (torch.rand(tb.bits.shape, generator=g) < 0.25).to(torch.uint8) * torch.randint(1, 256, tb.bits.shape, generator=g, dtype=torch.uint8)
+    tb.bits.copy_(bits.to(DEV))
+    R, seed = 96, 1234
+    im = tb._images()
+    _lib.check(lib.nslam_ngp_sample_phase(ctypes.byref(tb.model), ctypes.byref(im), ctypes.byref(tb.batch), R, seed,
+                                          _lib.stream_ptr()), "sample")
+    torch.cuda.synchronize()
+    rays = tb._bufs["rays"][:R].cpu(); ri = rays.view(torch.int32)
+    coords = tb._bufs["coords"].cpu().numpy(); tdist = tb._bufs["tdist"].cpu().numpy()
+    bits_h = bits.numpy()
+    lo, hi = 0.5 - 0.5 * tb.aabb_scale, 0.5 + 0.5 * tb.aabb_scale
+    checked = 0
+    for i in range(R):
+        n, base = int(ri[i, 13]), int(ri[i, 12])
+        if n == 0:
+            continue
+        o = rays[i, 0:3].numpy(); d = rays[i, 3:6].numpy()
+        jit = float(ongp.rnd01(seed, i, 4))                       # the kernel's per-ray jitter
+        ref = ongp.march_lattice(o, d, lo, hi, tb.nerf.training.near_distance, 1.0 / 256, tb.cascades, bits_h, jit, 1024)
+        assert len(ref) == n
+        for k, (t, dt) in enumerate(ref):
+            assert abs(float(t) - float(tdist[base + k])) <= 2e-6 and float(dt) == float(coords[base + k, 3])
+            pos = (o + d * np.float32(t) - lo) / (hi - lo)
+            assert np.allclose(coords[base + k, 0:3], pos, atol=2e-6)
+        checked += 1
+    assert checked > 0
