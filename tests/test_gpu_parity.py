@@ -356,3 +356,29 @@ def test_corr_volume_rows_matches_tiled_kernel(H, W, E):
     torch.cuda.synchronize()
     for l in range(4):
         assert torch.equal(a[l], b[l]), (l, float((a[l].float() - b[l].float()).abs().max()))
+
+
+@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS", "0") != "1",
+                    reason="written without GPU access at the end of round 1: enable with NSLAM_PENDING_TESTS=1, validate, then unconditional")
+def test_droid_backends_ba_all_in_one_loop(db):
+    """A15: droid_backends.ba (ba_cuda, src/droid_kernels.cu:1441-1568, motion_only=False) = per iteration
+    linearise -> (A - S) solve with `ep + lm*diag` damping -> depth back-substitution -> left pose retraction, all
+    in place.  Oracle: the same composition of oracle/ba.py + oracle/se3.py pieces, 2 iterations."""
+    p = _ba_problem(71, nframes=6)
+    lm, ep, iters = 1e-4, 0.1, 2
+    poses = T(p["poses"].copy()); disps = T(p["disps"].copy())
+    dx, dz = db.ba(poses, T(p["poses"].copy()), disps, T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]),
+                   T(p["weight"]), T(p["eta"]), T(p["ii"]), T(p["jj"]), p["kf0"], p["kf1"], iters, lm, ep, False)
+    rp = p["poses"].astype(np.float64).copy(); rd = p["disps"].astype(np.float64).copy()
+    for _ in range(iters):
+        r = oba.reduced_camera_matrix(rp.astype(np.float32), rd.astype(np.float32), p["intr"], p["ext"], p["sens"], p["target"],
+                                      p["weight"], p["eta"], p["ii"], p["jj"], p["kf0"], p["kf1"])
+        rdx, _ = oba.dense_solve(r["H"], r["v"], lm=lm, ep=ep)
+        rd, _ = oba.solve_depth(rdx, rd, r["Q"], r["E"], r["w"], p["ii"], p["jj"], p["kf0"], p["kf1"])
+        t, q = se3.retr_se3(rdx.astype(np.float64), rp[p["kf0"]:p["kf1"], :3], rp[p["kf0"]:p["kf1"], 3:])
+        rp[p["kf0"]:p["kf1"]] = np.concatenate([t, q], -1)
+    got_p = poses.cpu().numpy().astype(np.float64)
+    sgn = np.sign((got_p[:, 3:] * rp[:, 3:]).sum(-1, keepdims=True))
+    assert np.allclose(got_p[:, :3], rp[:, :3], atol=2e-4) and np.allclose(got_p[:, 3:] * sgn, rp[:, 3:], atol=2e-4)
+    assert np.allclose(disps.cpu().numpy(), rd, rtol=2e-3, atol=2e-4)
+    assert dx.shape == (p["kf1"] - p["kf0"], 6) and torch.isfinite(dx).all() and torch.isfinite(dz).all()
