@@ -404,6 +404,14 @@ def ba(poses, body_poses, disps, intrinsics, extrinsics, disps_sens, targets, we
     poses/disps in place, returns [dx, dz]."""
     _chk(poses, disps, intrinsics, disps_sens, targets, weights, ii, jj)
     ih, jh = _host_edges(ii, jj)
+    return ba_host_edges(poses, disps, intrinsics, extrinsics, disps_sens, targets, weights, eta, ih, jh,
+                         t0, t1, iterations, lm, ep, motion_only)
+
+
+def ba_host_edges(poses, disps, intrinsics, extrinsics, disps_sens, targets, weights, eta, ih, jh,
+                  t0, t1, iterations, lm, ep, motion_only):
+    """`ba` with the edge list already on the host (int64 numpy): no device->host copy, no sync"""
+    _chk(poses, disps, intrinsics, disps_sens, targets, weights)
     prob = BAProblem(poses, disps, intrinsics, extrinsics.contiguous(), disps_sens, targets, weights,
                      eta.contiguous(), ih, jh, t0, t1)
     lib = _lib.load()

@@ -1,0 +1,144 @@
+"""A deterministic factor-graph life cycle, written against the PUBLIC surface of `FactorGraph`
+(networks/factor_graph.py) only, so that the same driver runs the reference's class (to record the
+golden trace, `make_golden_factor_graph.py`) and this repo's class (to replay it, `tests/test_cpu_droid.py`).
+
+The sequence is the one `DroidFrontend` issues (networks/droid_frontend.py:35-121): neighbourhood
+factors + 8 updates + proximity factors + 8 updates at initialisation, then per keyframe: age-based
+retirement, proximity factors with `remove=True`, 4 (+2) updates, and — for some frames — `rm_keyframe`.
+`update()` itself (network + BA) is replaced by its bookkeeping side effects (age += 1, new confidences),
+because the trace pins the EDGE SET, which is the bit-exact part of the contract.
+"""
+import contextlib
+import types
+
+import numpy as np
+import torch
+
+HT8, WD8, CH = 16, 16, 4       # 1/8-resolution grid (4 pooling steps need >= 16) and channels of the fake video
+
+
+class FakeVideo:
+    """the attributes `FactorGraph` touches (networks/factor_graph.py:20-29,122-135,173-182,313,326,334)"""
+
+    def __init__(self, n, seed, stereo=False, slope=4.0):
+        g = torch.Generator().manual_seed(seed)
+        self.ht, self.wd = HT8 * 8, WD8 * 8
+        self.stereo = stereo
+        self.counter = types.SimpleNamespace(value=0)
+        self.ready = types.SimpleNamespace(value=0)
+        self.images = torch.zeros(n, 3, 2, 2)
+        self.tstamp = torch.arange(n).float()
+        self.poses = torch.zeros(n, 7)
+        self.poses[:, 0] = torch.arange(n).float()          # slot -> frame identity (moves with rm_keyframe)
+        self.disps = torch.ones(n, HT8, WD8)
+        self.disps_sens = torch.zeros(n, HT8, WD8)
+        self.intrinsics = torch.ones(n, 4)
+        self.dirty = torch.zeros(n, dtype=torch.bool)
+        rig = 2 if stereo else 1
+        self.fmaps = torch.randn(n, rig, CH, HT8, WD8, generator=g)
+        self.nets = torch.randn(n, CH, HT8, WD8, generator=g)
+        self.inps = torch.randn(n, CH, HT8, WD8, generator=g)
+        # pairwise "flow distance" of frame identities: grows with the index gap, plus seeded noise and ties
+        a = torch.arange(n).float()
+        base = slope * (a[:, None] - a[None, :]).abs()
+        noise = torch.rand(n, n, generator=g) * 14.0
+        d = base + 0.5 * (noise + noise.t())
+        d[torch.rand(n, n, generator=g) < 0.08] = 7.5        # exact ties
+        d[torch.rand(n, n, generator=g) < 0.03] = 150.0      # > 100 -> treated as inf
+        self.D = d.float()
+        y, x = torch.meshgrid(torch.arange(HT8).float(), torch.arange(WD8).float(), indexing="ij")
+        self.coords0 = torch.stack([x, y], dim=-1)
+
+    def get_lock(self):
+        return contextlib.nullcontext()
+
+    def _ids(self, ix):
+        return self.poses[torch.as_tensor(ix).long().reshape(-1), 0].long()
+
+    def reproject(self, ii, jj):
+        """coords that encode which frames the edge connects: the trace checks that every per-edge tensor
+        follows its edge through add / remove / shift"""
+        ii = torch.as_tensor(ii).long().reshape(-1); jj = torch.as_tensor(jj).long().reshape(-1)
+        off = (self._ids(ii) * 100 + self._ids(jj)).float()
+        c = self.coords0[None, None] + off.view(1, -1, 1, 1, 1)
+        return c, torch.ones_like(c[..., :1])
+
+    def distance(self, ii, jj, beta=0.3, bidirectional=True):
+        return self.D[self._ids(ii), self._ids(jj)].clone()
+
+
+def snapshot(graph, tag):
+    tolist = lambda t: [int(v) for v in torch.as_tensor(t).reshape(-1).tolist()]
+    flow = graph.gru_estimated_flow
+    wgt = graph.gru_estimated_flow_weight
+    hid = graph.gru_hidden_states
+    return {
+        "tag": tag,
+        "ii": tolist(graph.ii), "jj": tolist(graph.jj), "age": tolist(graph.age),
+        "ii_inac": tolist(graph.ii_inac), "jj_inac": tolist(graph.jj_inac),
+        "ii_bad": tolist(graph.ii_bad), "jj_bad": tolist(graph.jj_bad),
+        # per-edge tensors, reduced to one scalar per edge
+        "flow00": [float(v) for v in flow[0, :, 0, 0, 0].tolist()],
+        "weight00": [round(float(v), 6) for v in wgt[0, :, 0, 0, 0].tolist()],
+        "target_inac00": [float(v) for v in graph.target_inac[0, :, 0, 0, 0].tolist()],
+        "n_hidden": 0 if hid is None else int(hid.shape[1]),
+        "hidden00": [] if hid is None else [round(float(v), 5) for v in hid[0, :, 0, 0, 0].float().tolist()],
+    }
+
+
+def fake_update(graph, rng):
+    """the bookkeeping side effects of FactorGraph.update (networks/factor_graph.py:202-255)"""
+    E = int(graph.ii.shape[0])
+    w = torch.as_tensor(rng.random(E).astype(np.float32))
+    w[torch.as_tensor(rng.random(E) < 0.08)] = 1e-4         # low-confidence edges (filter_edges removes |i-j|>2 ones)
+    graph.gru_estimated_flow_weight = w.view(1, E, 1, 1, 1).expand(1, E, HT8, WD8, 2).contiguous().to(graph.gru_estimated_flow_weight.device)
+    graph.age += 1
+
+
+def run_scenario(make_graph, seed, n_frames=30, stereo=False, slope=4.0, max_factors=48, warmup=8, max_age=25, window=25,
+                 nms=1, radius=2, thresh=16.0, beta=0.3):
+    """-> list of snapshots.  make_graph(video, max_factors) -> FactorGraph(video, None, "cpu", "volume", max_factors);
+    slope = distance per frame of index gap (smaller -> more frames within `thresh` -> the max_factors regime)"""
+    rng = np.random.default_rng(seed)
+    video = FakeVideo(n_frames + 2, seed, stereo, slope)
+    graph = make_graph(video, max_factors)
+    trace = []
+    # ---- DroidFrontend.__initialize
+    video.counter.value = warmup
+    t1 = warmup
+    graph.add_neighborhood_factors(0, t1, r=3)
+    trace.append(snapshot(graph, "init.neighborhood"))
+    for _ in range(8):
+        fake_update(graph, rng)
+    graph.add_proximity_factors(0, 0, rad=2, nms=2, thresh=thresh, remove=False)
+    trace.append(snapshot(graph, "init.proximity"))
+    for _ in range(8):
+        fake_update(graph, rng)
+    graph.rm_factors(graph.ii < warmup - 4, store=True)
+    trace.append(snapshot(graph, "init.rm_old"))
+    # ---- DroidFrontend.__update per keyframe
+    step = 0
+    while video.counter.value < n_frames:
+        video.counter.value += 1
+        t1 += 1
+        step += 1
+        if graph.correlation_volumes is not None:
+            graph.rm_factors(graph.age > max_age, store=True)
+        trace.append(snapshot(graph, f"kf{step}.rm_age"))
+        graph.add_proximity_factors(t1 - 5, max(t1 - window, 0), rad=radius, nms=nms, thresh=thresh, beta=beta, remove=True)
+        trace.append(snapshot(graph, f"kf{step}.proximity"))
+        for _ in range(4):
+            fake_update(graph, rng)
+        if step % 7 == 3:
+            graph.filter_edges()
+            trace.append(snapshot(graph, f"kf{step}.filter_edges"))
+        if rng.random() < 0.3:
+            graph.rm_keyframe(t1 - 2)
+            video.counter.value -= 1
+            t1 -= 1
+            n_frames -= 1                                   # the stream is finite: a dropped frame is gone
+            trace.append(snapshot(graph, f"kf{step}.rm_keyframe"))
+        else:
+            for _ in range(2):
+                fake_update(graph, rng)
+    return trace

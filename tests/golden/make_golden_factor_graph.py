@@ -1,0 +1,66 @@
+"""Record golden edge-set traces from the REFERENCE's own `FactorGraph` (networks/factor_graph.py), imported
+from /root/reference and run on CPU — build container only (the reference tree does not travel).
+
+  python tests/golden/make_golden_factor_graph.py        ->  tests/golden/ref_factor_graph_traces.json
+
+Third-party imports of the reference that cannot be installed (lietorch, matplotlib, droid_backends,
+icecream) are stubbed as far as import resolution needs; none of them is executed by the graph-management
+methods.  `CorrBlock` is the reference's own (pure torch on CPU: matmul + avg_pool, corr.py:23-38,52-72).
+The driver is `factor_graph_scenario.run_scenario` (shared with the replay test).
+
+Ties: the reference orders candidate edges with `torch.argsort(d)` and retires edges with `torch.argsort(age)`
+(networks/factor_graph.py:366,107) — UNSTABLE sorts, so the order of equal keys is implementation-defined (torch's
+CPU sort permutes ties once n > 16; the CUDA sort has its own order) and equal ages are the normal case.  The
+recording pins the one reproducible choice, index order (`stable=True`), by wrapping `torch.argsort` for the
+duration of the run; this repo's implementation makes the same choice (numpy stable argsort).
+"""
+import json
+import os
+import sys
+import types
+import warnings
+
+import torch
+
+REF = os.environ.get("NSLAM_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+SCENARIOS = [dict(seed=s, n_frames=n, stereo=st, slope=sl, max_factors=mf) for s, n, st, sl, mf in
+             [(0, 30, False, 4.0, 48), (1, 34, False, 1.5, 48), (2, 26, True, 2.0, 48), (3, 40, False, 1.0, 48),
+              (4, 22, False, 1.5, 24), (5, 30, True, 1.0, 32)]]
+
+
+def _stub_modules():
+    lt = types.ModuleType("lietorch"); lt.SE3 = object; lt.Sim3 = object
+    mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); mpl.pyplot = plt
+    dbk = types.ModuleType("droid_backends")
+    ic = types.ModuleType("icecream"); ic.ic = lambda *a, **k: None
+    for name, m in (("lietorch", lt), ("matplotlib", mpl), ("matplotlib.pyplot", plt), ("droid_backends", dbk),
+                    ("icecream", ic)):
+        sys.modules.setdefault(name, m)
+
+
+def main():
+    _stub_modules()
+    sys.path.insert(0, REF)
+    sys.path.insert(0, HERE)
+    warnings.filterwarnings("ignore")
+    from networks.factor_graph import FactorGraph
+    from factor_graph_scenario import run_scenario
+    out = []
+    unstable_argsort = torch.argsort
+    torch.argsort = lambda x, *a, **k: unstable_argsort(x, *a, **{**k, "stable": True})
+    for sc in SCENARIOS:
+        make = lambda video, mf: FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=mf)
+        trace = run_scenario(make, **sc)
+        out.append({"scenario": sc, "trace": trace})
+        last = trace[-1]
+        print(sc, "snapshots", len(trace), "max edges", max(len(t["ii"]) for t in trace), "final edges", len(last["ii"]), "inactive", len(last["ii_inac"]), "bad", len(last["ii_bad"]))
+    torch.argsort = unstable_argsort
+    path = os.path.join(HERE, "ref_factor_graph_traces.json")
+    with open(path, "w") as f:
+        json.dump({"torch": torch.__version__, "scenarios": out}, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

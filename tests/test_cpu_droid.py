@@ -1,0 +1,175 @@
+"""DROID-style plugin surface (nerf_slam_b200/droid.py), host side: the factor-graph life cycle must reproduce,
+snapshot for snapshot, the traces recorded from the REFERENCE's own `FactorGraph`
+(tests/golden/ref_factor_graph_traces.json, made by tests/golden/make_golden_factor_graph.py from
+/root/reference/networks/factor_graph.py on CPU).  Edge sets, ages, inactive/bad lists: bit-exact; the per-edge
+tensors (flow, confidence, hidden state, stored inactive targets) must follow their edges."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import factor_graph_scenario as scn   # noqa: E402
+
+from nerf_slam_b200 import droid      # noqa: E402
+
+with open(os.path.join(HERE, "golden", "ref_factor_graph_traces.json")) as f:
+    GOLD = json.load(f)["scenarios"]
+
+
+class FakePool:
+    """CorrPool's slot accounting without the kernels (no GPU in the CPU suite)"""
+    instances = []
+
+    def __init__(self, capacity, ht, wd, device):
+        self.capacity = capacity
+        self.free = list(range(capacity - 1, -1, -1))
+        self.frames = {}
+        FakePool.instances.append(self)
+
+    def alloc(self, n):
+        assert n <= len(self.free)
+        return [self.free.pop() for _ in range(n)]
+
+    def release(self, slots):
+        for s in slots:
+            del self.frames[int(s)]
+        self.free.extend(int(s) for s in slots)
+
+    def build(self, f, fi, fj, slots):
+        assert f.dim() == 4 and f.is_contiguous()                  # [frames,h,w,C] channels-last
+        for a, b, s in zip(fi, fj, slots):
+            # feature value (0,0,0) identifies the frame the operand rows were gathered from
+            self.frames[int(s)] = (float(f[a, 0, 0, 0]), float(f[b, 0, 0, 0]))
+
+
+@pytest.fixture(autouse=True)
+def fake_pool(monkeypatch):
+    FakePool.instances.clear()
+    monkeypatch.setattr(droid, "_make_pool", lambda cap, ht, wd, dev: FakePool(cap, ht, wd, dev))
+
+
+def _make(video, max_factors=48):
+    return droid.FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=max_factors)
+
+
+@pytest.mark.parametrize("k", range(len(GOLD)))
+def test_factor_graph_replays_reference_trace(k):
+    sc, ref = GOLD[k]["scenario"], GOLD[k]["trace"]
+    got = scn.run_scenario(_make, **sc)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert g["tag"] == r["tag"]
+        for key in ("ii", "jj", "age", "ii_inac", "jj_inac", "ii_bad", "jj_bad", "n_hidden"):
+            assert g[key] == r[key], f"{sc} {g['tag']} {key}"
+        for key in ("flow00", "weight00", "target_inac00", "hidden00"):
+            assert np.allclose(g[key], r[key], rtol=0, atol=2e-5), f"{sc} {g['tag']} {key}"
+
+
+def test_traces_cover_the_max_factors_regime():
+    """at least some recorded scenarios must exercise add_factors' age-ordered retirement (remove=True)"""
+    hit = [max(len(r["ii"]) for r in g["trace"]) >= g["scenario"]["max_factors"] - 2 for g in GOLD]
+    assert sum(hit) >= 3
+
+
+def test_volume_slots_follow_their_edges():
+    """arena accounting under add / retire / rm_keyframe / growth: one live slot per active edge, each built from
+    the two frames of its edge"""
+    holder = {}
+
+    def make(video, max_factors):
+        holder["video"] = video
+        g = droid.FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=max_factors)
+        holder["graph"] = g
+        return g
+    scn.run_scenario(make, seed=7, n_frames=28, slope=1.5, max_factors=32)
+    g = holder["graph"]
+    store = g.correlation_volumes
+    pool = store.pool
+    assert len(store) == len(g.ii) == len(set(store.slots.tolist()))
+    assert pool.capacity - len(pool.free) == len(g.ii)
+    assert set(pool.frames) == set(store.slots.tolist())
+
+
+def test_volume_store_grows():
+    video = scn.FakeVideo(40, seed=3)
+    video.counter.value = 30
+    g = droid.FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=-1)
+    g.add_neighborhood_factors(0, 12, r=3)          # 60 edges < initial capacity
+    cap0 = g.correlation_volumes.pool.capacity
+    g.add_neighborhood_factors(0, 30, r=4)
+    assert g.correlation_volumes.pool.capacity > cap0
+    assert len(g.correlation_volumes) == len(g.ii) == len(set(g.correlation_volumes.slots.tolist()))
+    assert len(set(zip(g.ii.tolist(), g.jj.tolist()))) == len(g.ii)
+
+
+def test_reference_shaped_views_and_in_place_age():
+    video = scn.FakeVideo(12, seed=1)
+    video.counter.value = 8
+    g = _make(video)
+    g.add_neighborhood_factors(0, 8, r=2)
+    E = len(g.ii)
+    assert g.ii.dtype == torch.long and g.gru_estimated_flow.shape == (1, E, scn.HT8, scn.WD8, 2)
+    assert g.gru_hidden_states.shape == (1, E, scn.CH, scn.HT8, scn.WD8)
+    assert g.gru_contexts_input.shape == (1, E, scn.CH, scn.HT8, scn.WD8)      # the reference's hole, filled
+    # hidden state of edge k = context features of its source frame
+    k = 5
+    assert torch.equal(g.gru_hidden_states[0, k], video.nets[int(g.ii[k])])
+    assert torch.equal(g.gru_contexts_input[0, k], video.inps[int(g.ii[k])])
+    g.age += 1
+    g.age += 1
+    assert g.age.tolist() == [2] * E
+    g.rm_factors(g.ii < 2, store=True)
+    assert (g.ii >= 2).all() and len(g.ii_inac) > 0
+    g.clear_edges()
+    assert len(g.ii) == 0 and g.gru_hidden_states is None
+
+
+def test_ba_inputs_with_inactive_edges():
+    """FactorGraph.update's BA operands (networks/factor_graph.py:229-244): stored inactive edges inside the window
+    come first, damping is gathered for the sorted unique source frames"""
+    video = scn.FakeVideo(14, seed=2)
+    video.counter.value = 10
+    g = _make(video)
+    g.add_neighborhood_factors(0, 10, r=2)
+    g.rm_factors(g.ii < 5, store=True)
+    g.damping[:] = torch.arange(g.damping.shape[0]).float().view(-1, 1, 1)
+    t0 = 6
+    ii, jj, target, weight, damping = g._ba_inputs(t0, True, 1e-7)
+    m = (g.ii_inac.numpy() >= t0 - 3) & (g.jj_inac.numpy() >= t0 - 3)
+    n_in = int(m.sum())
+    assert n_in > 0 and len(ii) == n_in + len(g.ii)
+    assert ii[:n_in].tolist() == g.ii_inac.numpy()[m].tolist() and ii[n_in:].tolist() == g.ii.tolist()
+    assert target.shape == (len(ii), 2, scn.HT8, scn.WD8) and target.is_contiguous()
+    # flow of an edge (i,j) encodes 100*i + j at pixel (0,0), x component (FakeVideo.reproject)
+    assert target[:, 0, 0, 0].tolist() == [100.0 * a + b for a, b in zip(ii.tolist(), jj.tolist())]
+    ux = np.unique(ii)
+    assert torch.allclose(damping[:, 0, 0], torch.as_tensor(0.2 * ux + 1e-7, dtype=torch.float32))
+
+
+def test_depth_video_and_frontend_surface():
+    """names a user of the reference relies on exist with the reference's signatures"""
+    import inspect
+    fg = droid.FactorGraph
+    for name in ("update", "update_lowmem", "add_factors", "rm_factors", "rm_keyframe", "add_neighborhood_factors",
+                 "add_proximity_factors", "filter_edges", "clear_edges", "print_edges"):
+        assert callable(getattr(fg, name))
+    assert list(inspect.signature(fg.update).parameters)[1:] == ["t0", "t1", "itrs", "use_inactive", "EP", "motion_only"]
+    assert list(inspect.signature(fg.update_lowmem).parameters)[1:] == ["t0", "t1", "itrs", "use_inactive", "EP", "steps"]
+    assert list(inspect.signature(fg.__init__).parameters)[1:6] == ["video", "update_net", "device", "corr_impl", "max_factors"]
+    assert list(inspect.signature(droid.MotionFilter.track).parameters)[1:] == ["k", "timestamp", "image", "depth", "intrinsics"]
+    assert list(inspect.signature(droid.DroidFrontend.__init__).parameters)[1:] == ["droid_net", "video", "args"]
+    for name in ("reproject", "distance", "ba", "append", "normalize", "get_lock", "upsample"):
+        assert callable(getattr(droid.DepthVideo, name))
+    v = droid.DepthVideo((64, 96), buffer=4, device="cpu")
+    assert v.fmaps.shape == (4, 1, 128, 8, 12) and v.nets.shape == (4, 128, 8, 12) and v.poses[0].tolist() == [0, 0, 0, 0, 0, 0, 1]
+    f = torch.randn(1, 128, 8, 12).half()
+    v.append(0.5, torch.zeros(3, 64, 96, dtype=torch.uint8), None, 1.0, torch.full((64, 96), 2.0), torch.tensor([1., 2, 3, 4]),
+             f, f[0] * 2, f[0] * 3)
+    assert v.counter.value == 1 and torch.equal(v.fmaps[0], f) and torch.equal(v._nets[0], (f[0] * 2).permute(1, 2, 0))
+    assert torch.allclose(v.disps_sens[0], torch.full((8, 12), 0.5))

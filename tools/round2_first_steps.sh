@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: run what was written at the end of round 1 without GPU access.
-#   1. the gated tests (ray sampler vs march oracle, droid_backends.ba)
+#   1. the gated tests (ray sampler vs march oracle, droid_backends.ba, the DROID-style plugin surface droid.py)
 #   2. the experimental row-pair correlation-volume kernel: bit-exactness vs the tiled kernel, micro-benchmark of
 #      both, the whole GPU suite and the bench with it enabled
 mkdir -p gpurun_out
@@ -8,6 +8,8 @@ NSLAM_PENDING_TESTS=1 timeout 600 python -m pytest -q -m gpu \
   "tests/test_gpu_ngp.py::test_sample_rays_matches_the_march_oracle" \
   "tests/test_gpu_parity.py::test_droid_backends_ba_all_in_one_loop" > gpurun_out/pending_tests.log 2>&1
 echo "pending tests exit $?" > gpurun_out/summary.txt
+NSLAM_PENDING_TESTS=1 timeout 900 python -m pytest -q -m gpu tests/test_gpu_droid.py > gpurun_out/pending_droid.log 2>&1
+echo "pending droid.py tests exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 300 python -m pytest -q -m gpu tests/test_gpu_parity.py -k "corr_volume" > gpurun_out/corr_rows_tests.log 2>&1
 echo "corr rows tests exit $?" >> gpurun_out/summary.txt
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
@@ -16,5 +18,5 @@ NSLAM_CORRVOL_ROWS=1 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/
 echo "suite with rows kernel exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 400 python bench.py > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 echo "bench with rows kernel exit $?" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 5 gpurun_out/corr_rows_tests.log
+cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log
 head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
