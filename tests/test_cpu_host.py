@@ -119,3 +119,196 @@ def test_halo_tile_schedule_reproduces_the_convolution():
                 if y < H and x < W:
                     got[0, y, x] = acc[r]
     assert float((got - ref).abs().max()) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# csrc/conv_igemm2.cu (CTA pairs, tcgen05 cta_group::2): discrete-event emulation of the synchronisation protocol.
+# Every actor below follows the kernel's loops and index arithmetic line for line (stage = counter % depth,
+# parity = (counter / depth) & 1, "empty" waits use parity ^ 1); loads and MMAs complete asynchronously after random
+# delays; the scheduler interleaves the actors at random.  Checked: no deadlock, every MMA sees the tile / weight
+# half it expects in BOTH CTAs, no stage is overwritten while an issued MMA may still read it, no accumulator stage
+# is overwritten before both epilogues have drained it, every epilogue reads the accumulator of its own pair.
+class _MBar:
+    def __init__(self, count):
+        self.count, self.pending, self.tx, self.phase = count, count, 0, 0
+
+    def _maybe_flip(self):
+        if self.pending == 0 and self.tx == 0:
+            self.phase ^= 1
+            self.pending = self.count
+
+    def arrive(self, tx=0):
+        self.tx += tx
+        self.pending -= 1
+        assert self.pending >= 0, "more arrivals than the barrier was initialised for"
+        self._maybe_flip()
+
+    def complete_tx(self, nbytes):
+        self.tx -= nbytes
+        self._maybe_flip()
+
+    def passed(self, parity):            # mbarrier.try_wait.parity: true once the phase with this parity has completed
+        return self.phase != parity
+
+
+def _simulate_pair_protocol(seed, npairs_total, nclusters, units, AS, BS):
+    import random
+    rnd = random.Random(seed)
+    A_BYTES, B_HALF = 20480, 8192
+    EPI_WARPS = 8
+    log = []
+
+    class CTA:
+        def __init__(self):
+            self.full_b = [_MBar(1) for _ in range(BS)]; self.empty_b = [_MBar(1) for _ in range(BS)]
+            self.full_a = [_MBar(1) for _ in range(AS)]; self.empty_a = [_MBar(1) for _ in range(AS)]
+            self.tm_full = [_MBar(1) for _ in range(2)]; self.tm_empty = [_MBar(2 * EPI_WARPS) for _ in range(2)]
+            self.a = [None] * AS; self.b = [None] * BS          # stage contents (tags); None = never written
+            self.a_busy = [0] * AS; self.b_busy = [0] * BS      # MMAs issued on the stage and not yet completed
+            self.acc = [None, None]                             # accumulator tag per TMEM stage
+            self.acc_unread = [0, 0]                            # epilogue warps that still have to read the stage
+
+    for cid in range(nclusters):
+        ctas = [CTA(), CTA()]
+        leader = ctas[0]
+        events = []                                             # (time, seq, fn): asynchronous completions
+        now = [0]; seq = [0]
+
+        def later(fn, lo=1, hi=40):
+            seq[0] += 1
+            events.append((now[0] + rnd.randint(lo, hi), seq[0], fn))
+
+        pairs = list(range(cid, npairs_total, nclusters))
+
+        def producer(rank):
+            me = ctas[rank]
+            ia = ib = 0
+
+            def load_a(tag):
+                nonlocal ia
+                sa, pa = ia % AS, (ia // AS) & 1
+                while not me.empty_a[sa].passed(pa ^ 1):
+                    yield
+                if rank == 0:
+                    leader.full_a[sa].arrive(tx=2 * A_BYTES)
+
+                def done(sa=sa, tag=tag):
+                    assert me.a_busy[sa] == 0, "A stage overwritten while an MMA may still read it"
+                    me.a[sa] = tag
+                    leader.full_a[sa].complete_tx(A_BYTES)       # .cta_group::2: completes on the LEADER's barrier
+                later(done)
+                ia += 1
+            for pair in pairs:
+                yield from load_a((pair, 0, rank))
+                for u in range(units):
+                    if u + 1 < units:
+                        yield from load_a((pair, u + 1, rank))
+                    for dy in range(3):
+                        sb, pb = ib % BS, (ib // BS) & 1
+                        while not me.empty_b[sb].passed(pb ^ 1):
+                            yield
+                        if rank == 0:
+                            leader.full_b[sb].arrive(tx=2 * B_HALF)
+
+                        def done(sb=sb, tag=(pair, u, dy, rank)):
+                            assert me.b_busy[sb] == 0, "B stage overwritten while an MMA may still read it"
+                            me.b[sb] = tag
+                            leader.full_b[sb].complete_tx(B_HALF)
+                        later(done)
+                        ib += 1
+                        yield
+
+        def mma():
+            it = ia = tcount = 0
+            for pair in pairs:
+                acs, aph = tcount & 1, (tcount >> 1) & 1
+                while not leader.tm_empty[acs].passed(aph ^ 1):
+                    yield
+                for c in ctas:
+                    assert c.acc_unread[acs] == 0, "accumulator stage overwritten before its epilogue finished"
+                for u in range(units):
+                    sa, pa = ia % AS, (ia // AS) & 1
+                    while not leader.full_a[sa].passed(pa):
+                        yield
+                    for dy in range(3):
+                        sb, pb = it % BS, (it // BS) & 1
+                        while not leader.full_b[sb].passed(pb):
+                            yield
+                        for r, c in enumerate(ctas):             # one MMA reads both CTAs' stages
+                            assert c.a[sa] == (pair, u, r), (c.a[sa], pair, u, r)
+                            assert c.b[sb] == (pair, u, dy, r), (c.b[sb], pair, u, dy, r)
+                            c.a_busy[sa] += 1; c.b_busy[sb] += 1
+                            if u == 0 and dy == 0:
+                                c.acc[acs] = [pair, 0]           # accumulate flag 0: overwrite
+                            assert c.acc[acs][0] == pair
+                            c.acc[acs][1] += 1
+
+                        def b_done(sa=sa, sb=sb):                # commit: arrives once the MMAs issued so far completed
+                            for c in ctas:
+                                c.b_busy[sb] -= 1; c.a_busy[sa] -= 1
+                                c.empty_b[sb].arrive()           # multicast to both CTAs
+                        later(b_done, 5, 30)
+                        it += 1
+                        yield
+
+                    def a_done(sa=sa):
+                        for c in ctas:
+                            c.empty_a[sa].arrive()
+                    later(a_done, 31, 45)                        # after the MMAs' own completions (commit order)
+                    ia += 1
+
+                def full(acs=acs):
+                    for c in ctas:
+                        c.acc_unread[acs] = EPI_WARPS
+                        c.tm_full[acs].arrive()
+                later(full, 46, 60)
+                tcount += 1
+
+        def epilogue_warp(rank, w):
+            me = ctas[rank]
+            tcount = 0
+            for pair in pairs:
+                acs, aph = tcount & 1, (tcount >> 1) & 1
+                while not me.tm_full[acs].passed(aph):
+                    yield
+                assert me.acc[acs] == [pair, units * 3], (me.acc[acs], pair)
+                for _ in range(rnd.randint(0, 3)):
+                    yield
+                me.acc_unread[acs] -= 1
+                leader.tm_empty[acs].arrive()                    # remote arrive on the leader's barrier
+                log.append((cid, pair, rank, w))
+                tcount += 1
+                yield
+
+        actors = [producer(0), producer(1), mma()] + [epilogue_warp(r, w) for r in range(2) for w in range(EPI_WARPS)]
+        alive = list(actors)
+        idle_rounds = 0
+        while alive:
+            now[0] += 1
+            due = sorted(e for e in events if e[0] <= now[0])
+            for e in due:
+                events.remove(e)
+                e[2]()
+            progressed = bool(due)
+            rnd.shuffle(alive)
+            for a in list(alive):
+                if rnd.random() < 0.6:
+                    try:
+                        next(a)
+                    except StopIteration:
+                        alive.remove(a)
+                    progressed = True
+            idle_rounds = 0 if (progressed or events) else idle_rounds + 1
+            assert now[0] < 2_000_000 and idle_rounds < 50, "deadlock"
+        while events:                                            # drain completions after the last actor left
+            events.sort()
+            events.pop(0)[2]()
+    return log
+
+
+def test_cta_pair_convolution_protocol_emulation():
+    for seed, (npairs, nclusters, units) in enumerate([(7, 2, 6), (5, 5, 3), (9, 4, 21), (1, 1, 3), (12, 3, 9)]):
+        log = _simulate_pair_protocol(seed, npairs, nclusters, units, AS=3, BS=12 if seed % 2 else 6)
+        done = {(pair, rank) for _, pair, rank, _ in log}
+        assert done == {(p, r) for p in range(npairs) for r in range(2)}
+        assert len(log) == npairs * 2 * 8

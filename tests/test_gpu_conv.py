@@ -53,6 +53,17 @@ def test_conv_matches_torch(cfg, act):
     assert float((err - 1e-2 * ref.abs()).max()) < 1e-2, float(err.max())
 
 
+@pytest.mark.skipif(os.environ.get("NSLAM_CONV_CTA2") != "1", reason="CTA-pair kernel is opt-in (NSLAM_CONV_CTA2=1)")
+@pytest.mark.parametrize("cfg", [
+    dict(chs=[128, 64], k=3, N=128, B=1, H=20, W=40),          # 9 tiles: the last pair has one tile only
+    dict(chs=[128], k=3, N=256, B=1, H=8, W=16),               # a single tile: one pair, second half empty
+    dict(chs=[128, 128, 128, 64], k=3, N=128, B=5, H=60, W=80),    # 200 tiles on 74 pairs: several pairs per cluster
+])
+def test_conv_pairs_odd_and_multi_wave(cfg):
+    """csrc/conv_igemm2.cu (cta_group::2): tile counts that leave half a pair empty, and more pairs than clusters"""
+    test_conv_matches_torch(cfg, 1)
+
+
 def test_gru_fused_epilogues():
     """modes 3 (glo), 1 (z, r*net) and 2 (state update) against the ConvGRU equations (gru.py:19-32)"""
     from nerf_slam_b200.conv import conv_tc, pack_weights

@@ -12,11 +12,16 @@ NSLAM_PENDING_TESTS=1 timeout 900 python -m pytest -q -m gpu tests/test_gpu_droi
 echo "pending droid.py tests exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 300 python -m pytest -q -m gpu tests/test_gpu_parity.py -k "corr_volume" > gpurun_out/corr_rows_tests.log 2>&1
 echo "corr rows tests exit $?" >> gpurun_out/summary.txt
+# 3. the CTA-pair convolution kernel (csrc/conv_igemm2.cu, cta_group::2): parity, then the kernel table with it enabled
+NSLAM_CONV_CTA2=1 timeout 600 python -m pytest -q -m gpu tests/test_gpu_conv.py > gpurun_out/conv_pairs_tests.log 2>&1
+echo "conv pairs tests exit $?" >> gpurun_out/summary.txt
+NSLAM_CONV_CTA2=1 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_pairs.log 2>&1
+timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_default.log 2>&1
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
 NSLAM_CORRVOL_ROWS=1 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_rows.jsonl
 NSLAM_CORRVOL_ROWS=1 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/suite_with_rows.log 2>&1
 echo "suite with rows kernel exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 400 python bench.py > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 echo "bench with rows kernel exit $?" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log
+cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log; tail -n 8 gpurun_out/conv_pairs_tests.log; grep -h "conv_igemm" gpurun_out/kernel_table_pairs.log | head -8; grep -h "conv_igemm" gpurun_out/kernel_table_default.log | head -8
 head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
