@@ -17,6 +17,8 @@ NSLAM_CONV_CTA2=1 timeout 600 python -m pytest -q -m gpu tests/test_gpu_conv.py 
 echo "conv pairs tests exit $?" >> gpurun_out/summary.txt
 NSLAM_CONV_CTA2=1 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_pairs.log 2>&1
 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_default.log 2>&1
+# 4. hardware question for the next convolution redesign (one halo box for all nine taps): see tools/probes/
+timeout 200 python tools/probes/run_umma_probe.py > gpurun_out/umma_probe.log 2>&1
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
 NSLAM_CORRVOL_ROWS=1 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_rows.jsonl
 NSLAM_CORRVOL_ROWS=1 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/suite_with_rows.log 2>&1
@@ -24,4 +26,4 @@ echo "suite with rows kernel exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 400 python bench.py > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 echo "bench with rows kernel exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log; tail -n 8 gpurun_out/conv_pairs_tests.log; grep -h "conv_igemm" gpurun_out/kernel_table_pairs.log | head -8; grep -h "conv_igemm" gpurun_out/kernel_table_default.log | head -8
-head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
+cat gpurun_out/umma_probe.log | head -40; head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
