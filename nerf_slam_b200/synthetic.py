@@ -26,6 +26,12 @@ class PinholeCameraModel:
         self.fx, self.fy, self.cx, self.cy = fx, fy, cx, cy
         self.K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
 
+    def scale_intrinsics(self, scale_x, scale_y):
+        """datasets/dataset.py:85-95"""
+        self.fx *= scale_x; self.cx *= scale_x
+        self.fy *= scale_y; self.cy *= scale_y
+        self.K = np.array([[self.fx, 0, self.cx], [0, self.fy, self.cy], [0, 0, 1.0]])
+
     def numpy(self):
         return np.array([self.fx, self.fy, self.cx, self.cy])
 
