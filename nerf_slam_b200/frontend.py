@@ -112,6 +112,25 @@ class _Section:
         return False
 
 
+class EmptyValues:
+    """what the reference's forward() hands to its (no-op) back-end: an EMPTY gtsam.Values / NonlinearFactorGraph
+    (visual_frontend.py:248-249).  They must not be None — VioSLAM._frontend stops the pipeline on `x0 is None`
+    (slam/vio_slam.py:112-113) — but nothing is ever read from them; gtsam is not a dependency here."""
+
+    def size(self):
+        return 0
+
+    def __len__(self):
+        return 0
+
+    def __bool__(self):
+        return True
+
+
+class EmptyFactorGraph(EmptyValues):
+    pass
+
+
 class RaftVisualFrontend:
     def __init__(self, world_T_body_t0, body_T_cam0, args, device="cuda:0"):
         self.args = args
@@ -339,7 +358,7 @@ class RaftVisualFrontend:
     def forward(self, batch):
         """visual_frontend.py:240-365"""
         k = int(batch["k"][0])
-        x0, factors, viz_out = None, None, None
+        x0, factors, viz_out = EmptyValues(), EmptyFactorGraph(), None
         img = batch["images"]
         if not torch.is_tensor(img):
             img = torch.as_tensor(np.asarray(img))

@@ -75,3 +75,26 @@ def test_pose_convention_round_trip():
         # utils/utils.py:104-116 spelled out: columns 1,2 negated, position + 0.5, rows cycled (y, z, x)
         e = m.copy(); e[:3, 1] *= -1; e[:3, 2] *= -1; e[:3, 3] += 0.5
         assert np.allclose(g, e[[1, 2, 0, 3]], atol=1e-15)
+
+
+def test_demo_cli_has_the_reference_options_and_defaults(written):
+    """examples/slam_demo.py: option names and defaults of the reference's parse_args (examples/slam_demo.py:20-55)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("slam_demo", os.path.join(os.path.dirname(HERE), "examples", "slam_demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    a = demo.parse_args([])
+    ref_defaults = dict(parallel_run=False, multi_gpu=False, initial_k=0, final_k=-1, img_stride=1, stereo=False,
+                        weights="droid.pth", buffer=512, dataset_dir="/home/tonirv/Datasets/euroc/V1_01_easy",
+                        dataset_name="euroc", mask_type="ours", slam=False, fusion="", gui=False, width=0, height=0,
+                        network="", eval=False)
+    for k, v in ref_defaults.items():
+        assert getattr(a, k) == v, k
+    a = demo.parse_args(["--dataset_dir", written[(64, 48, 6)], "--dataset_name", "nerf", "--buffer", "100", "--slam",
+                         "--fusion", "nerf", "--screenshot_w", "320"])
+    assert a.slam and a.fusion == "nerf" and a.buffer == 100 and a.width == 320
+    data = demo.make_data(a)
+    assert len(data) == 5                 # --final_k=-1 drops the last of the 6 frames, as in the reference
+    assert np.allclose(a.world_T_imu_t0, data[0]["poses"][0])
+    with pytest.raises(NotImplementedError):
+        demo.make_data(demo.parse_args(["--dataset_name", "euroc"]))

@@ -312,3 +312,12 @@ def test_cta_pair_convolution_protocol_emulation():
         done = {(pair, rank) for _, pair, rank, _ in log}
         assert done == {(p, r) for p in range(npairs) for r in range(2)}
         assert len(log) == npairs * 2 * 8
+
+
+def test_forward_placeholders_are_not_none():
+    """RaftVisualFrontend.forward returns empty, non-None x0 / factors like the reference's empty gtsam containers
+    (visual_frontend.py:248-249): the reference's VioSLAM._frontend stops the pipeline on `x0 is None`
+    (slam/vio_slam.py:112-113)"""
+    from nerf_slam_b200.frontend import EmptyFactorGraph, EmptyValues
+    x0, f = EmptyValues(), EmptyFactorGraph()
+    assert x0 is not None and f is not None and bool(x0) and x0.size() == 0 and len(f) == 0
