@@ -17,6 +17,12 @@ NSLAM_CONV_CTA2=1 timeout 600 python -m pytest -q -m gpu tests/test_gpu_conv.py 
 echo "conv pairs tests exit $?" >> gpurun_out/summary.txt
 NSLAM_CONV_CTA2=1 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_pairs.log 2>&1
 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_default.log 2>&1
+# 3b. the reference's command line on this implementation (procedural stream, then the same stream from files)
+timeout 300 python examples/slam_demo.py --dataset_dir=synthetic --dataset_name=nerf --buffer=60 --slam --fusion=nerf --synthetic_frames 120 > gpurun_out/demo_synthetic.log 2>&1
+echo "slam_demo synthetic exit $?" >> gpurun_out/summary.txt
+python -c "from nerf_slam_b200 import datasets, synthetic; datasets.write_transforms_dataset(synthetic.SyntheticRoom(640, 480, 60), '/tmp/nslam_ds')" \
+  && timeout 300 python examples/slam_demo.py --dataset_dir=/tmp/nslam_ds --dataset_name=nerf --buffer=60 --slam --fusion=nerf --eval > gpurun_out/demo_files.log 2>&1
+echo "slam_demo files exit $?" >> gpurun_out/summary.txt
 # 4. hardware question for the next convolution redesign (one halo box for all nine taps): see tools/probes/
 timeout 200 python tools/probes/run_umma_probe.py > gpurun_out/umma_probe.log 2>&1
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
@@ -26,4 +32,4 @@ echo "suite with rows kernel exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 400 python bench.py > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 echo "bench with rows kernel exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log; tail -n 8 gpurun_out/conv_pairs_tests.log; grep -h "conv_igemm" gpurun_out/kernel_table_pairs.log | head -8; grep -h "conv_igemm" gpurun_out/kernel_table_default.log | head -8
-cat gpurun_out/umma_probe.log | head -40; head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
+tail -n 3 gpurun_out/demo_synthetic.log; tail -n 3 gpurun_out/demo_files.log; cat gpurun_out/umma_probe.log | head -40; head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
