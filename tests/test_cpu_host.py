@@ -321,3 +321,76 @@ def test_forward_placeholders_are_not_none():
     from nerf_slam_b200.frontend import EmptyFactorGraph, EmptyValues
     x0, f = EmptyValues(), EmptyFactorGraph()
     assert x0 is not None and f is not None and bool(x0) and x0.size() == 0 and len(f) == 0
+
+
+def test_cta_pair_operand_addressing_reproduces_the_convolution():
+    """data-path emulation of csrc/conv_igemm2.cu: CTA rank r of pair p computes tile 2p + r; the weight block of
+    (tap, channel block) is fetched as two 2-D boxes {64, N/2} at rows blk*N + r*N/2 of the packed image viewed as
+    [blocks*N, 64] (no TMA swizzle: the image already is the swizzled smem layout); one MMA of the pair multiplies each
+    CTA's 128 pixel rows with the N columns formed by CTA 0's half (columns 0..N/2-1) and CTA 1's half (N/2..N-1).
+    An odd tile count leaves rank 1 of the last pair with an out-of-range tile (zero-filled loads, clipped stores)."""
+    import torch.nn.functional as F
+    from nerf_slam_b200.conv import pack_weights
+    g = torch.Generator().manual_seed(11)
+    B, H, W, N = 1, 20, 40, 128                                 # 3 x 3 = 9 tiles -> 5 pairs, the last one half empty
+    chans = [64, 40]
+    srcs = [torch.randn(B, H, W, c, generator=g) for c in chans]
+    w = torch.randn(N, sum(chans), 3, 3, generator=g) * 0.1
+    image = pack_weights(w, chans).float().view(-1, 64)         # the 2-D tensor the weight tensor map describes
+    cbs = [(c + 63) // 64 for c in chans]
+    cb_total = sum(cbs)
+    assert image.shape[0] == 9 * cb_total * N
+    rows = torch.arange(N // 2)
+
+    def half_block(blk, rank):                                  # box {64, N/2} at row blk*N + rank*N/2, then un-swizzle
+        box = image[blk * N + rank * (N // 2): blk * N + (rank + 1) * (N // 2)].view(N // 2, 8, 8)
+        out = torch.empty(N // 2, 8, 8)
+        for j in range(8):
+            out[rows, j] = box[rows, j ^ (rows & 7)]            # row phase = (row within the half) & 7 == (row in block) & 7
+        return out.reshape(N // 2, 64)
+
+    ref = F.conv2d(torch.cat(srcs, -1).permute(0, 3, 1, 2).half().float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
+    got = torch.full((B, H, W, N), float("nan"))
+    TH, TW = 8, 16
+    tiles_h, tiles_w = (H + TH - 1) // TH, (W + TW - 1) // TW
+    ntiles = B * tiles_h * tiles_w
+    assert ntiles % 2 == 1
+    for pair in range((ntiles + 1) // 2):
+        acc = [torch.zeros(TH * TW, N), torch.zeros(TH * TW, N)]
+        geo = []
+        for rank in range(2):
+            tile = 2 * pair + rank
+            n, tt = tile // (tiles_h * tiles_w), tile % (tiles_h * tiles_w)
+            geo.append((tile, n, (tt // tiles_w) * TH, (tt % tiles_w) * TW))
+        cbg = 0
+        for s, c in enumerate(chans):
+            for cb in range(cbs[s]):
+                for dx in range(3):
+                    tiles = []
+                    for rank in range(2):
+                        tile, n, h0, w0 = geo[rank]
+                        t = torch.zeros(TH + 2, TW, 64)
+                        for hy in range(TH + 2):
+                            for wx in range(TW):
+                                y, x = h0 - 1 + hy, w0 + dx - 1 + wx
+                                if n < B and 0 <= y < H and 0 <= x < W:      # image index B: everything out of range
+                                    ce = min(c, cb * 64 + 64)
+                                    t[hy, wx, :ce - cb * 64] = srcs[s][n, y, x, cb * 64:ce].half().float()
+                        tiles.append(t.reshape(-1, 64))
+                    for dy in range(3):
+                        blk = (dy * 3 + dx) * cb_total + cbg
+                        Bfull = torch.cat([half_block(blk, 0), half_block(blk, 1)], 0)     # [N, 64]: CTA 0's half first
+                        for rank in range(2):
+                            acc[rank] += tiles[rank][dy * TW:dy * TW + TH * TW] @ Bfull.T
+                cbg += 1
+        for rank in range(2):
+            tile, n, h0, w0 = geo[rank]
+            if tile >= ntiles:
+                assert float(acc[rank].abs().max()) == 0.0           # nothing but zero fill reached the missing tile
+                continue
+            for r in range(TH * TW):
+                y, x = h0 + r // TW, w0 + r % TW
+                if y < H and x < W:
+                    got[n, y, x] = acc[rank][r]
+    assert not torch.isnan(got).any()
+    assert float((got - ref).abs().max()) < 2e-3
