@@ -59,12 +59,32 @@ class FakeVideo:
         """coords that encode which frames the edge connects: the trace checks that every per-edge tensor
         follows its edge through add / remove / shift"""
         ii = torch.as_tensor(ii).long().reshape(-1); jj = torch.as_tensor(jj).long().reshape(-1)
-        off = (self._ids(ii) * 100 + self._ids(jj)).float()
+        off = (self._ids(ii) * 100 + self._ids(jj)).float() + (self.poses[ii, 1] - self.poses[jj, 1]) + self.disps[ii, 0, 0] - 1.0
         c = self.coords0[None, None] + off.view(1, -1, 1, 1, 1)
         return c, torch.ones_like(c[..., :1])
 
     def distance(self, ii, jj, beta=0.3, bidirectional=True):
         return self.D[self._ids(ii), self._ids(jj)].clone()
+
+    # ---- used by the update() scenario only
+    ba_log = None
+
+    def ba(self, target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False):
+        """records what FactorGraph hands to the dense BA and applies a deterministic stand-in for its effect"""
+        ii = torch.as_tensor(np.asarray(ii.cpu() if torch.is_tensor(ii) else ii)).long().reshape(-1)
+        jj = torch.as_tensor(np.asarray(jj.cpu() if torch.is_tensor(jj) else jj)).long().reshape(-1)
+        if self.ba_log is None:
+            self.ba_log = []
+        f = lambda t: [list(t.shape), round(float(t.double().sum()), 4), round(float(t.reshape(-1)[0]), 5), bool(t.is_contiguous())]
+        self.ba_log.append({"ii": ii.tolist(), "jj": jj.tolist(), "t0": int(t0), "t1": None if t1 is None else int(t1),
+                            "itrs": int(itrs), "lm": float(lm), "ep": float(ep), "motion_only": bool(motion_only),
+                            "target": f(target), "weight": f(weight), "eta": f(eta)})
+        end = int(max(ii.max(), jj.max())) + 1 if t1 is None else int(t1)
+        self.disps[torch.unique(ii)] *= 1.01
+        self.poses[int(t0):end, 1] += 0.125
+
+    def upsample(self, ix, mask):
+        pass
 
 
 def snapshot(graph, tag):
@@ -141,4 +161,62 @@ def run_scenario(make_graph, seed, n_frames=30, stereo=False, slope=4.0, max_fac
         else:
             for _ in range(2):
                 fake_update(graph, rng)
+    return trace
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# update() / update_lowmem(): the operator and the BA are replaced by deterministic stand-ins with the REAL call
+# conventions (UpdateModule.forward's, networks/droid_net.py:118-150; video.ba's), so that the trace pins everything
+# FactorGraph itself does around them: motion features, state write-back, damping scatter by source frame, inactive
+# edges in the BA window, argument order / shapes / contiguity of the BA call, age.
+def fake_update_net(net, inp, corr, flow=None, ii=None, jj=None):
+    """net [1,E,C,h,w]; flow = motion features [1,E,4,h,w]; -> net', delta [1,E,h,w,2], weight [1,E,h,w,2],
+    eta [1,K,h,w], upmask [1,K,576,h,w] (K = number of distinct source frames, in sorted order)"""
+    b, E, C, h, w = net.shape
+    flow = flow.float()
+    net2 = 0.9 * net.float() + 0.1 * torch.tanh(0.01 * flow[:, :, 0:1]) + 0.001 * corr.float().mean(dim=2, keepdim=True)
+    delta = (0.5 * torch.tanh(0.05 * flow[:, :, 2:4]) + 0.01).permute(0, 1, 3, 4, 2).contiguous()
+    weight = torch.sigmoid(0.02 * flow[:, :, 0:2]).permute(0, 1, 3, 4, 2).contiguous()
+    if ii is None:
+        return net2, delta, weight
+    ii = torch.as_tensor(ii).long().cpu()
+    ux, inv = torch.unique(ii, return_inverse=True)
+    K = len(ux)
+    s = torch.zeros(K, h, w).index_add_(0, inv, net2[0, :, 0])
+    cnt = torch.zeros(K).index_add_(0, inv, torch.ones(E))
+    eta = (0.01 * (s / cnt.view(-1, 1, 1)).abs() + 0.001 * (ux.float().view(-1, 1, 1) + 1))[None]
+    return net2, delta, weight, eta, torch.zeros(1, K, 576, h, w)
+
+
+def snapshot_update(graph, video, tag):
+    d = snapshot(graph, tag)
+    d["damping_sum"] = round(float(graph.damping.double().sum()), 6)
+    d["damping00"] = [round(float(v), 6) for v in graph.damping[:, 0, 0].tolist()]
+    d["flow_sum"] = round(float(graph.gru_estimated_flow.double().sum()), 3)
+    d["weight_sum"] = round(float(graph.gru_estimated_flow_weight.double().sum()), 4)
+    d["hidden_sum"] = round(float(graph.gru_hidden_states.double().sum()), 4)
+    d["ba_calls"] = list(video.ba_log or [])
+    d["dirty"] = [int(v) for v in video.dirty.tolist()]
+    video.ba_log = []
+    return d
+
+
+def run_update_scenario(make_graph, seed, n_kf=9, stereo=False):
+    """make_graph(video, max_factors, update_net) -> FactorGraph"""
+    video = FakeVideo(n_kf + 3, seed, stereo)
+    video.counter.value = n_kf
+    graph = make_graph(video, 48, fake_update_net)
+    trace = []
+    graph.add_neighborhood_factors(0, n_kf, r=3)
+    for k in range(3):
+        graph.update(1, use_inactive=True)                       # DroidFrontend.__initialize: t0 = 1
+        trace.append(snapshot_update(graph, video, f"init.update{k}"))
+    graph.rm_factors(graph.ii < 3, store=True)
+    for k in range(2):
+        graph.update(None, None, use_inactive=True)              # DroidFrontend.__update: t0 from the edges
+        trace.append(snapshot_update(graph, video, f"steady.update{k}"))
+    graph.update(None, None, itrs=3, use_inactive=False, EP=1e-3, motion_only=True)
+    trace.append(snapshot_update(graph, video, "steady.update_active_only"))
+    graph.update_lowmem(steps=2)                                 # global BA path (alt-corr, chunks of 8 source frames)
+    trace.append(snapshot_update(graph, video, "lowmem"))
     return trace

@@ -50,15 +50,27 @@ def main():
     unstable_argsort = torch.argsort
     torch.argsort = lambda x, *a, **k: unstable_argsort(x, *a, **{**k, "stable": True})
     for sc in SCENARIOS:
-        make = lambda video, mf: FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=mf)
+        make = lambda video, mf, net=None: FactorGraph(video, net, device="cpu", corr_impl="volume", max_factors=mf)
         trace = run_scenario(make, **sc)
         out.append({"scenario": sc, "trace": trace})
         last = trace[-1]
         print(sc, "snapshots", len(trace), "max edges", max(len(t["ii"]) for t in trace), "final edges", len(last["ii"]), "inactive", len(last["ii_inac"]), "bad", len(last["ii_bad"]))
     torch.argsort = unstable_argsort
+    # update() / update_lowmem() with stand-ins for the operator, the BA and the two correlation kernels (zeros of
+    # the real shapes: src/droid.cpp:280-288 corr_index_forward -> [n,7,7,h,w]; :303-313 altcorr_forward -> [b,n,49,h,w])
+    import droid_backends as dbk
+    dbk.corr_index_forward = lambda volume, coords, radius: (torch.zeros(volume.shape[0], 2 * radius + 1, 2 * radius + 1, *coords.shape[-2:]),)
+    dbk.altcorr_forward = lambda f1, f2, coords, radius: (torch.zeros(coords.shape[0], coords.shape[1], (2 * radius + 1) ** 2, *coords.shape[2:4]),)
+    from factor_graph_scenario import run_update_scenario
+    upd = []
+    for sc in [dict(seed=11, n_kf=9, stereo=False), dict(seed=12, n_kf=12, stereo=False), dict(seed=13, n_kf=10, stereo=True)]:
+        make = lambda video, mf, net=None: FactorGraph(video, net, device="cpu", corr_impl="volume", max_factors=mf)
+        trace = run_update_scenario(make, **sc)
+        upd.append({"scenario": sc, "trace": trace})
+        print("update scenario", sc, "snapshots", len(trace), "BA calls", sum(len(t["ba_calls"]) for t in trace))
     path = os.path.join(HERE, "ref_factor_graph_traces.json")
     with open(path, "w") as f:
-        json.dump({"torch": torch.__version__, "scenarios": out}, f, separators=(",", ":"))
+        json.dump({"torch": torch.__version__, "scenarios": out, "update_scenarios": upd}, f, separators=(",", ":"))
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

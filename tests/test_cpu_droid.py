@@ -19,7 +19,8 @@ import factor_graph_scenario as scn   # noqa: E402
 from nerf_slam_b200 import droid      # noqa: E402
 
 with open(os.path.join(HERE, "golden", "ref_factor_graph_traces.json")) as f:
-    GOLD = json.load(f)["scenarios"]
+    _G = json.load(f)
+GOLD, GOLD_UPDATE = _G["scenarios"], _G["update_scenarios"]
 
 
 class FakePool:
@@ -41,6 +42,11 @@ class FakePool:
             del self.frames[int(s)]
         self.free.extend(int(s) for s in slots)
 
+    def lookup(self, slots, coords, nhwc=False, out=None):
+        """stand-in for the fused 4-level lookup (zeros of the real shape, like the reference-side recording)"""
+        assert not nhwc and coords.shape[0] == len(slots) and coords.shape[1] == 2
+        return torch.zeros(coords.shape[0], 196, *coords.shape[-2:])
+
     def build(self, f, fi, fj, slots):
         assert f.dim() == 4 and f.is_contiguous()                  # [frames,h,w,C] channels-last
         for a, b, s in zip(fi, fj, slots):
@@ -54,8 +60,46 @@ def fake_pool(monkeypatch):
     monkeypatch.setattr(droid, "_make_pool", lambda cap, ht, wd, dev: FakePool(cap, ht, wd, dev))
 
 
-def _make(video, max_factors=48):
-    return droid.FactorGraph(video, None, device="cpu", corr_impl="volume", max_factors=max_factors)
+def _make(video, max_factors=48, update_net=None):
+    return droid.FactorGraph(video, update_net, device="cpu", corr_impl="volume", max_factors=max_factors)
+
+
+class FakeAltCorr:
+    """AltCorrBlock's call surface with zeros of the real shape (networks/modules/corr.py:92-140)"""
+
+    def __init__(self, fmaps, num_levels=4, radius=3):
+        assert fmaps.dim() == 5 and fmaps.shape[0] == 1
+
+    def __call__(self, coords, ii, jj):
+        b, n, h, w, _ = coords.shape
+        assert len(ii) == len(jj) == n
+        return torch.zeros(b, n, 196, h, w)
+
+
+@pytest.mark.parametrize("k", range(len(GOLD_UPDATE)))
+def test_update_and_update_lowmem_replay_reference_trace(k, monkeypatch):
+    """FactorGraph.update / update_lowmem around stand-ins for the operator and the BA: state write-back, damping
+    scatter, inactive edges in the BA window, t0 / t1, the BA call's arguments — as recorded from the reference's own
+    update() and update_lowmem() (networks/factor_graph.py:202-303)"""
+    monkeypatch.setattr(droid, "AltCorrBlock", FakeAltCorr)
+    sc, ref = GOLD_UPDATE[k]["scenario"], GOLD_UPDATE[k]["trace"]
+    got = scn.run_update_scenario(_make, **sc)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert g["tag"] == r["tag"]
+        for key in ("ii", "jj", "age", "ii_inac", "jj_inac", "n_hidden", "dirty"):
+            assert g[key] == r[key], (g["tag"], key)
+        for key in ("flow00", "weight00", "target_inac00", "hidden00", "damping00"):
+            assert np.allclose(g[key], r[key], rtol=1e-5, atol=2e-5), (g["tag"], key)
+        for key in ("damping_sum", "flow_sum", "weight_sum", "hidden_sum"):
+            assert np.isclose(g[key], r[key], rtol=1e-5, atol=1e-3), (g["tag"], key, g[key], r[key])
+        assert len(g["ba_calls"]) == len(r["ba_calls"]), g["tag"]
+        for a, b in zip(g["ba_calls"], r["ba_calls"]):
+            for key in ("ii", "jj", "t0", "t1", "itrs", "lm", "ep", "motion_only"):
+                assert a[key] == b[key], (g["tag"], key, a[key], b[key])
+            for key in ("target", "weight", "eta"):
+                assert a[key][0] == b[key][0] and a[key][3] and b[key][3], (g["tag"], key)       # shape, contiguous
+                assert np.isclose(a[key][1], b[key][1], rtol=1e-5, atol=1e-2) and np.isclose(a[key][2], b[key][2], rtol=1e-5, atol=1e-4)
 
 
 @pytest.mark.parametrize("k", range(len(GOLD)))
