@@ -675,28 +675,32 @@ class MotionFilter:
         img_normalized = img_normalized.sub_(self.MEAN).div_(self.STDV)
         feature_map = self._feature_encoder(img_normalized)
         if k == 0:
-            self.add_frame_to_video(timestamp, image, img_normalized, feature_map, depth, intrinsics)
+            self.add_frame_to_video(timestamp, image, img_normalized, feature_map, depth, intrinsics, first=True)
             return True
         ht, wd = image.shape[-2] // 8, image.shape[-1] // 8
         coords0 = coords_grid(ht, wd, self.device)[None, None]
         corr = CorrBlock(self.feature_maps[None, [0]], feature_map[None, [0]])(coords0)
         _, delta, weight = self.update_net(self.context_maps[None], self.gru_input_maps[None], corr)
         if delta.norm(dim=-1).mean().item() > self.min_flow_thresh:
-            self.add_frame_to_video(timestamp, image, img_normalized, feature_map, depth, intrinsics)
+            self.add_frame_to_video(timestamp, image, img_normalized, feature_map, depth, intrinsics)      # pose/disp: keep
             self.skipped_frames = 0
             return True
         self.skipped_frames += 1
         return False
 
-    def add_frame_to_video(self, timestamp, image, img_normalized, feature_map, depth_img=None, intrinsics=None):
-        """:76-85.  The reference appends `context_maps[0,0]` / `gru_input_maps[0,0]` — after its own `.squeeze(0)`
-        that is ONE channel plane [h,w], which `video.nets[k] = ...` would broadcast over all 128 channels; the
-        full [128,h,w] maps of camera 0 are stored here (what the live path does, visual_frontend.py:300-330)."""
+    def add_frame_to_video(self, timestamp, image, img_normalized, feature_map, depth_img=None, intrinsics=None, first=False):
+        """:76-85, with two defects of the (never executed) reference method not reproduced:
+        * it appends `context_maps[0,0]` / `gru_input_maps[0,0]` — after its own `.squeeze(0)` that is ONE channel
+          plane [h,w], which `video.nets[k] = ...` would broadcast over all 128 channels; the full [128,h,w] maps of
+          camera 0 are stored here (what the live path does, visual_frontend.py:300-330);
+        * it appends the identity pose and disparity 1.0 for EVERY kept frame, which would overwrite the initial guess
+          DroidFrontend writes into the next slot (`video.poses[t1] = video.poses[t1-1]`, droid_frontend.py:72-73); here
+          only the first frame sets them, later frames pass None (keep what the front end prepared)."""
         context_maps, gru_input_maps = self._context_encoder(img_normalized[:, [0]])
         self.context_maps, self.gru_input_maps, self.feature_maps = context_maps, gru_input_maps, feature_map
-        identity_pose = torch.tensor([0, 0, 0, 0, 0, 0, 1.0])
+        identity_pose = torch.tensor([0, 0, 0, 0, 0, 0, 1.0]) if first else None
         intr = None if intrinsics is None else torch.as_tensor(intrinsics, dtype=torch.float32) / 8.0
-        self.video.append(timestamp, image[0], identity_pose, 1.0, depth_img, intr,
+        self.video.append(timestamp, image[0], identity_pose, 1.0 if first else None, depth_img, intr,
                           feature_map, context_maps[0], gru_input_maps[0])
 
 

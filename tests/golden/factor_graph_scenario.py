@@ -28,11 +28,12 @@ class FakeVideo:
         self.ready = types.SimpleNamespace(value=0)
         self.images = torch.zeros(n, 3, 2, 2)
         self.tstamp = torch.arange(n).float()
+        self.device = "cpu"
         self.poses = torch.zeros(n, 7)
-        self.poses[:, 0] = torch.arange(n).float()          # slot -> frame identity (moves with rm_keyframe)
         self.disps = torch.ones(n, HT8, WD8)
         self.disps_sens = torch.zeros(n, HT8, WD8)
         self.intrinsics = torch.ones(n, 4)
+        self.intrinsics[:, 0] = torch.arange(n).float()     # slot -> frame identity (moves with rm_keyframe)
         self.dirty = torch.zeros(n, dtype=torch.bool)
         rig = 2 if stereo else 1
         self.fmaps = torch.randn(n, rig, CH, HT8, WD8, generator=g)
@@ -53,7 +54,7 @@ class FakeVideo:
         return contextlib.nullcontext()
 
     def _ids(self, ix):
-        return self.poses[torch.as_tensor(ix).long().reshape(-1), 0].long()
+        return self.intrinsics[torch.as_tensor(ix).long().reshape(-1), 0].long()
 
     def reproject(self, ii, jj):
         """coords that encode which frames the edge connects: the trace checks that every per-edge tensor
@@ -219,4 +220,36 @@ def run_update_scenario(make_graph, seed, n_kf=9, stereo=False):
     trace.append(snapshot_update(graph, video, "steady.update_active_only"))
     graph.update_lowmem(steps=2)                                 # global BA path (alt-corr, chunks of 8 source frames)
     trace.append(snapshot_update(graph, video, "lowmem"))
+    return trace
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DroidFrontend (networks/droid_frontend.py:9-121): the keyframe loop on top of FactorGraph, with a stand-in for the
+# motion filter (every step delivers one new frame with a fresh identity), the operator and the BA.
+def frontend_args(keyframe_thresh=4.0):
+    return types.SimpleNamespace(warmup=8, beta=0.3, frontend_nms=1, keyframe_thresh=keyframe_thresh, frontend_window=25,
+                                 frontend_thresh=16.0, frontend_radius=2)
+
+
+def run_frontend_scenario(make_frontend, seed, n_steps=20, slope=1.0, keyframe_thresh=4.0):
+    """make_frontend(droid_net, video, args) -> DroidFrontend; droid_net.update_net = fake_update_net"""
+    video = FakeVideo(n_steps + 12, seed, False, slope)
+    net = types.SimpleNamespace(update_net=fake_update_net)
+    front = make_frontend(net, video, frontend_args(keyframe_thresh))
+    next_id = 0
+    trace = []
+    for step in range(n_steps):
+        slot = video.counter.value                               # MotionFilter.track -> video.append
+        video.intrinsics[slot, 0] = float(next_id)
+        video.tstamp[slot] = float(next_id)
+        next_id += 1
+        video.counter.value += 1
+        front()
+        d = snapshot_update(front.graph, video, f"step{step}") if front.is_initialized else {"tag": f"step{step}"}
+        d.update({"t1": int(front.t1), "counter": int(video.counter.value), "is_initialized": bool(front.is_initialized),
+                  "count": int(front.count), "ready": int(video.ready.value),
+                  "ids": [int(v) for v in video.intrinsics[:, 0].tolist()],
+                  "poses1": [round(float(v), 5) for v in video.poses[:, 1].tolist()],
+                  "disps00": [round(float(v), 6) for v in video.disps[:, 0, 0].tolist()]})
+        trace.append(d)
     return trace

@@ -1,7 +1,7 @@
 """Record golden edge-set traces from the REFERENCE's own `FactorGraph` (networks/factor_graph.py), imported
 from /root/reference and run on CPU — build container only (the reference tree does not travel).
 
-  python tests/golden/make_golden_factor_graph.py        ->  tests/golden/ref_factor_graph_traces.json
+  python tests/golden/make_golden_factor_graph.py        ->  tests/golden/ref_factor_graph_traces.json.gz
 
 Third-party imports of the reference that cannot be installed (lietorch, matplotlib, droid_backends,
 icecream) are stubbed as far as import resolution needs; none of them is executed by the graph-management
@@ -68,9 +68,28 @@ def main():
         trace = run_update_scenario(make, **sc)
         upd.append({"scenario": sc, "trace": trace})
         print("update scenario", sc, "snapshots", len(trace), "BA calls", sum(len(t["ba_calls"]) for t in trace))
-    path = os.path.join(HERE, "ref_factor_graph_traces.json")
-    with open(path, "w") as f:
-        json.dump({"torch": torch.__version__, "scenarios": out, "update_scenarios": upd}, f, separators=(",", ":"))
+    # DroidFrontend (networks/droid_frontend.py) on the same stand-ins; its FactorGraph is created on the CPU
+    # (the class hard-codes the default device "cuda:0") and lietorch's SE3 — used for one unused local — is a no-op
+    import lietorch
+    lietorch.SE3 = lambda data: data
+    import networks.droid_frontend as rdf
+    rdf.SE3 = lietorch.SE3
+    rdf.FactorGraph = lambda video, net, max_factors=-1: FactorGraph(video, net, device="cpu", max_factors=max_factors)
+    from factor_graph_scenario import run_frontend_scenario
+    torch.argsort = lambda x, *a, **k: unstable_argsort(x, *a, **{**k, "stable": True})
+    fr = []
+    for sc in [dict(seed=21, n_steps=22, slope=1.0), dict(seed=22, n_steps=26, slope=0.5, keyframe_thresh=8.0),
+               dict(seed=23, n_steps=24, slope=2.0, keyframe_thresh=10.0)]:
+        trace = run_frontend_scenario(lambda net, video, args: rdf.DroidFrontend(net, video, args), **sc)
+        fr.append({"scenario": sc, "trace": trace})
+        print("frontend scenario", sc, "final t1", trace[-1]["t1"], "counter", trace[-1]["counter"],
+              "dropped keyframes", sum(1 for a, b in zip(trace, trace[1:]) if b["counter"] == a["counter"]))
+    torch.argsort = unstable_argsort
+    path = os.path.join(HERE, "ref_factor_graph_traces.json.gz")
+    import gzip
+    with gzip.open(path, "wt") as f:
+        json.dump({"torch": torch.__version__, "scenarios": out, "update_scenarios": upd, "frontend_scenarios": fr}, f,
+                  separators=(",", ":"))
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

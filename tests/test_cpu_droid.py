@@ -1,6 +1,6 @@
 """DROID-style plugin surface (nerf_slam_b200/droid.py), host side: the factor-graph life cycle must reproduce,
 snapshot for snapshot, the traces recorded from the REFERENCE's own `FactorGraph`
-(tests/golden/ref_factor_graph_traces.json, made by tests/golden/make_golden_factor_graph.py from
+(tests/golden/ref_factor_graph_traces.json.gz, made by tests/golden/make_golden_factor_graph.py from
 /root/reference/networks/factor_graph.py on CPU).  Edge sets, ages, inactive/bad lists: bit-exact; the per-edge
 tensors (flow, confidence, hidden state, stored inactive targets) must follow their edges."""
 import json
@@ -18,9 +18,11 @@ import factor_graph_scenario as scn   # noqa: E402
 
 from nerf_slam_b200 import droid      # noqa: E402
 
-with open(os.path.join(HERE, "golden", "ref_factor_graph_traces.json")) as f:
+import gzip   # noqa: E402
+
+with gzip.open(os.path.join(HERE, "golden", "ref_factor_graph_traces.json.gz"), "rt") as f:
     _G = json.load(f)
-GOLD, GOLD_UPDATE = _G["scenarios"], _G["update_scenarios"]
+GOLD, GOLD_UPDATE, GOLD_FRONTEND = _G["scenarios"], _G["update_scenarios"], _G["frontend_scenarios"]
 
 
 class FakePool:
@@ -217,3 +219,40 @@ def test_depth_video_and_frontend_surface():
              f, f[0] * 2, f[0] * 3)
     assert v.counter.value == 1 and torch.equal(v.fmaps[0], f) and torch.equal(v._nets[0], (f[0] * 2).permute(1, 2, 0))
     assert torch.allclose(v.disps_sens[0], torch.full((8, 12), 0.5))
+
+
+def _cmp_graph_snapshot(g, r, where):
+    for key in ("ii", "jj", "age", "ii_inac", "jj_inac", "ii_bad", "jj_bad", "n_hidden", "dirty"):
+        assert g[key] == r[key], (where, key)
+    for key in ("flow00", "weight00", "target_inac00", "hidden00", "damping00"):
+        assert np.allclose(g[key], r[key], rtol=1e-5, atol=2e-5), (where, key)
+    assert len(g["ba_calls"]) == len(r["ba_calls"]), where
+    for a, b in zip(g["ba_calls"], r["ba_calls"]):
+        for key in ("ii", "jj", "t0", "t1", "itrs", "lm", "ep", "motion_only"):
+            assert a[key] == b[key], (where, key, a[key], b[key])
+        for key in ("target", "weight", "eta"):
+            assert a[key][0] == b[key][0], (where, key)
+            assert np.isclose(a[key][1], b[key][1], rtol=1e-5, atol=1e-2) and np.isclose(a[key][2], b[key][2], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("k", range(len(GOLD_FRONTEND)))
+def test_droid_frontend_replays_reference_trace(k):
+    """DroidFrontend.__call__ (initialisation at `warmup` keyframes, then per keyframe: retire old edges, proximity
+    factors, 4 updates, keyframe decision on the flow distance, rm_keyframe or 2 more updates, initial guess of the next
+    frame) against the trace of the reference's own class (networks/droid_frontend.py:35-121)"""
+    sc, ref = GOLD_FRONTEND[k]["scenario"], GOLD_FRONTEND[k]["trace"]
+    got = scn.run_frontend_scenario(lambda net, video, args: droid.DroidFrontend(net, video, args), **sc)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        where = (sc["seed"], g["tag"])
+        for key in ("tag", "t1", "counter", "is_initialized", "count", "ready", "ids"):
+            assert g[key] == r[key], (where, key, g[key], r[key])
+        for key in ("poses1", "disps00"):
+            assert np.allclose(g[key], r[key], rtol=1e-5, atol=1e-5), (where, key)
+        if g["is_initialized"]:
+            _cmp_graph_snapshot(g, r, where)
+
+
+def test_frontend_traces_contain_dropped_keyframes():
+    drops = sum(1 for sc in GOLD_FRONTEND for a, b in zip(sc["trace"], sc["trace"][1:]) if b["counter"] == a["counter"])
+    assert drops >= 5
