@@ -256,3 +256,110 @@ def test_droid_frontend_replays_reference_trace(k):
 def test_frontend_traces_contain_dropped_keyframes():
     drops = sum(1 for sc in GOLD_FRONTEND for a, b in zip(sc["trace"], sc["trace"][1:]) if b["counter"] == a["counter"])
     assert drops >= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The LIVE path's graph management (RaftVisualFrontend.add_factors / rm_factors / rm_keyframe /
+# add_neighborhood_factors / add_proximity_factors, frontend.py) replayed against the same reference traces: the
+# class is instantiated without its CUDA parts (buffers on the CPU, uploads redirected, kernels replaced by the
+# scenario's stand-ins) and driven through an adapter with FactorGraph's method names.
+def _cpu_frontend(video, max_factors, monkeypatch):
+    from nerf_slam_b200 import _lib, frontend as fr
+    monkeypatch.setattr(_lib, "h2d", lambda a, device, dtype=None: (torch.from_numpy(np.ascontiguousarray(a)) if dtype is None
+                                                                    else torch.from_numpy(np.ascontiguousarray(a)).to(dtype)))
+    ids = lambda ix: video.intrinsics[torch.as_tensor(np.asarray(ix)).long().reshape(-1), 0].long()
+
+    class CpuFrontend(fr.RaftVisualFrontend):
+        def __init__(self):                                       # no networks, no CUDA
+            self.device, self.stereo, self.cameras = "cpu", video.stereo, video.fmaps.shape[1]
+            self.max_factors, self.corr_impl = max_factors, "volume"
+            self.buffer, self.ht, self.wd = video.poses.shape[0], scn.HT8, scn.WD8
+            self.timers = fr._Timers()
+            B, ht, wd, C = self.buffer, self.ht, self.wd, scn.CH
+            z = lambda *s: torch.zeros(*s)
+            self.gt_poses, self.gt_depths, self.cam0_images = z(B, 4, 4), z(B, 1, 2, 2), z(B, 3, 2, 2)
+            self.cam0_timestamps, self.cam0_T_world, self.world_T_body = z(B), z(B, 7), z(B, 7)
+            self.world_T_body_cov, self.cam0_idepths = z(B, 6, 6), torch.ones(B, ht, wd)
+            self.cam0_idepths_cov, self.cam0_depths_cov, self.cam0_idepths_sensed = z(B, ht, wd), z(B, ht, wd), z(B, ht, wd)
+            self.cam0_intrinsics = video.intrinsics              # shared: column 0 = frame identity
+            self.features_imgs = torch.zeros(B, self.cameras, ht, wd, 128)      # the live code fixes 128 feature channels
+            self.features_imgs[..., :C] = video.fmaps.permute(0, 1, 3, 4, 2)
+            self.contexts_imgs = video.nets.permute(0, 2, 3, 1)[:, None].repeat(1, self.cameras, 1, 1, 1).contiguous()
+            self.cst_contexts_imgs = video.inps.permute(0, 2, 3, 1)[:, None].repeat(1, self.cameras, 1, 1, 1).contiguous()
+            self.corr_pool = FakePool(4 * max(max_factors, 32), ht, wd, "cpu")
+            self.kf_idx = 0
+            self._reset_graph()
+
+        def distance(self, ii, jj, beta=0.3, bidirectional=True):
+            return video.D[ids(ii), ids(jj)].clone()
+
+        def reproject(self, ii, jj):
+            off = (ids(ii) * 100 + ids(jj)).float()
+            return video.coords0[None] + off.view(-1, 1, 1, 1), None
+
+    fe = CpuFrontend()
+
+    class AsGraph:
+        """FactorGraph's names on top of the front end's methods (index conventions: kf1 inclusive, kf_idx = t - 1)"""
+        ii = property(lambda s: torch.from_numpy(fe.ii_h))
+        jj = property(lambda s: torch.from_numpy(fe.jj_h))
+        ii_inac = property(lambda s: torch.from_numpy(fe.ii_inactive_h))
+        jj_inac = property(lambda s: torch.from_numpy(fe.jj_inactive_h))
+        ii_bad = property(lambda s: torch.from_numpy(fe.ii_bad_h))
+        jj_bad = property(lambda s: torch.from_numpy(fe.jj_bad_h))
+        age = property(lambda s: torch.from_numpy(fe.age_h), lambda s, v: None)          # += works in place
+        gru_estimated_flow = property(lambda s: fe.gru_estimated_flow[None])
+        target_inac = property(lambda s: fe.gru_estimated_flow_inactive[None])
+        gru_hidden_states = property(lambda s: None if fe.gru_hidden_states is None else fe.gru_hidden_states.permute(0, 3, 1, 2)[None])
+        correlation_volumes = property(lambda s: None if fe.gru_hidden_states is None else fe.corr_pool)
+
+        def _get_w(self):
+            return fe.gru_estimated_flow_weight[None]
+
+        def _set_w(self, v):
+            fe.gru_estimated_flow_weight = v[0]
+        gru_estimated_flow_weight = property(_get_w, _set_w)
+
+        def add_neighborhood_factors(self, t0, t1, r=3):
+            fe.add_neighborhood_factors(t0, t1 - 1, radius=r)
+
+        def add_proximity_factors(self, t0=0, t1=0, rad=2, nms=2, beta=0.25, thresh=16.0, remove=False):
+            fe.kf_idx = video.counter.value - 1
+            fe.add_proximity_factors(kf0=t0, kf1=t1, rad=rad, nms=nms, beta=beta, thresh=thresh, remove=remove)
+
+        def rm_factors(self, mask, store=False):
+            fe.rm_factors(mask.numpy() if torch.is_tensor(mask) else mask, store=store)
+
+        def rm_keyframe(self, ix):
+            fe.rm_keyframe(ix)
+
+        def filter_edges(self):
+            """networks/factor_graph.py:70-77 on the front end's state (the live class has no such method; the
+            scenario calls it, and the `bad` list it fills feeds the proximity suppression)"""
+            conf = fe.gru_estimated_flow_weight.mean(dim=[1, 2, 3]).numpy()
+            mask = (np.abs(fe.ii_h - fe.jj_h) > 2) & (conf < 0.001)
+            fe.ii_bad_h = np.concatenate([fe.ii_bad_h, fe.ii_h[mask]]); fe.jj_bad_h = np.concatenate([fe.jj_bad_h, fe.jj_h[mask]])
+            fe.rm_factors(mask, store=False)
+
+    return AsGraph(), fe
+
+
+@pytest.mark.parametrize("k", range(len(GOLD)))
+def test_live_frontend_graph_management_replays_reference_trace(k, monkeypatch):
+    sc, ref = GOLD[k]["scenario"], GOLD[k]["trace"]
+    holder = {}
+
+    def make(video, max_factors, update_net=None):
+        g, fe = _cpu_frontend(video, max_factors, monkeypatch)
+        holder["fe"] = fe
+        return g
+    got = scn.run_scenario(make, **sc)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert g["tag"] == r["tag"]
+        for key in ("ii", "jj", "age", "ii_inac", "jj_inac", "ii_bad", "jj_bad", "n_hidden"):
+            assert g[key] == r[key], f"{sc} {g['tag']} {key}"
+        for key in ("flow00", "weight00", "target_inac00", "hidden00"):
+            assert np.allclose(g[key], r[key], rtol=0, atol=2e-5), f"{sc} {g['tag']} {key}"
+    fe = holder["fe"]
+    assert fe.corr_pool.capacity - len(fe.corr_pool.free) == len(fe.ii_h) == len(set(fe.slots_h.tolist()))
