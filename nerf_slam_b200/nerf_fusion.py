@@ -59,7 +59,7 @@ class NerfFusion:
         if not packet:
             return True
         slam = packet[1] if isinstance(packet, (list, tuple)) else packet
-        if slam is None or slam.get("is_last_frame", False) and "cam0_poses" not in slam:
+        if slam is None or slam.get("is_last_frame", False):      # the last packet is not ingested (:154-155): just fit
             return True
         viz_idx = slam["viz_idx"]
         images = slam["cam0_images"]

@@ -226,3 +226,48 @@ def pcg(v):
 def rnd01(a, b, c):
     """uniform [0,1) of ngp_common.cuh::rnd01(a, b, c)"""
     return np.float32(np.float32(pcg(pcg(pcg(a) ^ (b & 0xFFFFFFFF)) ^ (c & 0xFFFFFFFF)) >> 8) * np.float32(1.0 / 16777216.0))
+
+
+# ------------------------------------------------------------------------------------------ B1 / B2
+def srgb_to_linear(x):
+    """utils/utils.py:136-139 (fp32 torch)"""
+    return torch.where(x > 0.04045, torch.pow((x + 0.055) / 1.055, 2.4), x / 12.92)
+
+
+def pose_tq_to_matrix(tq):
+    """(t, q_xyzw) -> 4x4, fp64 (lietorch SE3.matrix(); formulas as in src/droid_kernels.cu:66-120)"""
+    tq = np.asarray(tq, np.float64)
+    out = np.zeros((len(tq), 4, 4))
+    for k, v in enumerate(tq):
+        x, y, z, w = v[3:]
+        out[k, :3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        out[k, :3, 3] = v[:3]
+        out[k, 3, 3] = 1.0
+    return out
+
+
+def process_slam_tuples(slam, mask_type="ours"):
+    """What NerfFusion.process_slam + send_data hand to the trainer (fusion/nerf_fusion.py:140-289) for one SLAM packet:
+    -> dict(ids, poses [n,3,4] world_T_cam (scale 1, offset 0, :167-170), images [n,H,W,4] fp32 linear colour
+    premultiplied by alpha = 1 (:203-215), depths [n,H,W,1] = 1/idepth_up, depths_cov [n,H,W,1], scales (1, 1));
+    mask types (:173-183): raw -> unit covariance; ours_w_thresh -> idepth = -1 where sqrt(cov) > median(cov) [sic: the
+    quantile is taken of the covariance, not of its square root]; no_depth -> idepth = -1 everywhere."""
+    idepths = slam["cam0_idepths_up"].clone().float()
+    cov = slam["cam0_depths_cov_up"].clone().float()
+    if mask_type == "raw":
+        cov[...] = 1.0
+    elif mask_type == "ours_w_thresh":
+        idepths[cov.sqrt() > cov.quantile(0.50)] = -1.0
+    elif mask_type == "no_depth":
+        idepths[...] = -1.0
+    elif mask_type != "ours":
+        raise NotImplementedError(mask_type)
+    img = slam["cam0_images"].permute(0, 2, 3, 1).float() / 255.0
+    rgb = srgb_to_linear(img)                      # alpha = 255/255 = 1: premultiplication leaves the colour unchanged
+    images = torch.cat([rgb, torch.ones_like(rgb[..., :1])], -1)
+    w2c = pose_tq_to_matrix(slam["cam0_poses"].cpu().numpy())
+    c2w = np.linalg.inv(w2c.astype(np.float32))    # the reference inverts the fp32 matrices (numpy)
+    return {"ids": [int(v) for v in slam["viz_idx"].tolist()], "poses": c2w[:, :3, :4], "images": images.numpy(),
+            "depths": (1.0 / idepths[..., None]).numpy(), "depths_cov": cov[..., None].numpy(), "scales": (1.0, 1.0)}

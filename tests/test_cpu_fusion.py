@@ -1,0 +1,65 @@
+"""B1 / B2: SLAM packet -> training tuples.  Golden = what the REFERENCE's own NerfFusion.process_slam +
+send_data hand to `update_training_images` (tests/golden/ref_process_slam.npz, recorded by
+tests/golden/make_golden_process_slam.py).  Checked here on the CPU: the oracle restatement, and the host half of the
+product's process_slam (pose conversion, mask types, slot ids, intrinsics) with the trainer replaced by a recorder; the
+device half (sRGB->linear, 1/idepth in one kernel) is compared with the same golden in tests/test_gpu_ngp.py."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import process_slam_scenario as sc   # noqa: E402
+
+from oracle import ngp as ongp   # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "ref_process_slam.npz"))
+
+
+@pytest.mark.parametrize("mt", sc.MASK_TYPES)
+def test_oracle_process_slam_matches_reference(mt):
+    got = ongp.process_slam_tuples(sc.make_packet(), mt)
+    assert got["ids"] == GOLD[f"{mt}.ids"].tolist()
+    assert np.allclose(got["poses"], GOLD[f"{mt}.poses"], rtol=0, atol=2e-6)
+    assert np.array_equal(got["images"], GOLD[f"{mt}.images"])            # same fp32 torch ops -> identical
+    assert np.array_equal(got["depths"], GOLD[f"{mt}.depths"])
+    assert np.array_equal(got["depths_cov"], GOLD[f"{mt}.covs"])
+    assert tuple(GOLD[f"{mt}.scales"]) == got["scales"]
+    if mt in ("ours_w_thresh", "no_depth"):
+        assert (got["depths"] == -1.0).any()
+
+
+@pytest.mark.parametrize("mt", sc.MASK_TYPES)
+def test_product_process_slam_host_half(mt):
+    from nerf_slam_b200.nerf_fusion import NerfFusion
+    calls = []
+    nf = object.__new__(NerfFusion)
+    nf.mask_type, nf.ref_frames = mt, {}
+    training = types.SimpleNamespace(update_training_images_device=lambda *a: calls.append(a))
+    nf.ngp = types.SimpleNamespace(device="cpu", nerf=types.SimpleNamespace(training=training))
+    assert nf.process_slam([None, sc.make_packet()]) is False and len(calls) == 1
+    ids, c2w, images, idepths, covs, focal, pp = calls[0]
+    assert [int(i) for i in ids] == GOLD[f"{mt}.ids"].tolist()
+    assert np.allclose(np.asarray(c2w), GOLD[f"{mt}.poses"], rtol=0, atol=2e-6)
+    assert images.dtype == torch.uint8 and torch.equal(images, sc.make_packet()["cam0_images"])
+    # what the ingest kernel computes from these operands is the golden's depth / covariance
+    assert np.allclose((1.0 / idepths).numpy()[..., None], GOLD[f"{mt}.depths"], rtol=1e-6, atol=0)
+    assert np.array_equal(covs.numpy()[..., None], GOLD[f"{mt}.covs"])
+    assert np.allclose(focal, GOLD[f"{mt}.fl"]) and np.allclose(pp, GOLD[f"{mt}.pp"])
+    # the packet itself is left untouched (the reference mutates its input tensors in place)
+    assert sorted(nf.ref_frames) == GOLD[f"{mt}.ids"].tolist()
+
+
+def test_last_frame_packet_is_not_ingested():
+    from nerf_slam_b200.nerf_fusion import NerfFusion
+    assert bool(GOLD["last_frame_skipped"][0])
+    nf = object.__new__(NerfFusion)
+    nf.mask_type, nf.ref_frames = "ours", {}
+    nf.ngp = types.SimpleNamespace(device="cpu", nerf=types.SimpleNamespace(training=types.SimpleNamespace(
+        update_training_images_device=lambda *a: (_ for _ in ()).throw(AssertionError("ingested")))))
+    last = sc.make_packet(); last["is_last_frame"] = True
+    assert nf.process_slam([None, last]) is True and nf.process_slam(None) is True and nf.process_slam([None, None]) is True

@@ -251,3 +251,38 @@ def test_sample_rays_matches_the_march_oracle():
             assert np.allclose(coords[base + k, 0:3], pos, atol=2e-6)
         checked += 1
     assert checked > 0
+
+
+@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS") != "1", reason="pending first hardware run (NSLAM_PENDING_TESTS=1)")
+@pytest.mark.parametrize("mask_type", ["ours", "raw", "ours_w_thresh", "no_depth"])
+def test_process_slam_ingest_matches_reference_golden(mask_type):
+    """B1/B2 end to end on the device: NerfFusion.process_slam (mask types, pose conversion on the host; sRGB->linear,
+    alpha, 1/idepth in `ingest_image_kernel`) must leave in the trainer's slots what the REFERENCE's process_slam +
+    send_data handed to pyngp (tests/golden/ref_process_slam.npz).  Images are stored in fp16 (2^-11 relative)."""
+    import sys
+    import types
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import process_slam_scenario as sc
+    from nerf_slam_b200.nerf_fusion import NerfFusion
+    gold = np.load(os.path.join(here, "golden", "ref_process_slam.npz"))
+    tb = _testbed()
+    nf = object.__new__(NerfFusion)
+    nf.mask_type, nf.ref_frames, nf.ngp = mask_type, {}, tb
+    slam = sc.make_packet()
+    for k in ("cam0_poses", "cam0_images", "cam0_idepths_up", "cam0_depths_cov_up", "gt_depths", "viz_idx"):
+        slam[k] = slam[k].to(DEV)
+    assert nf.process_slam([None, slam]) is False
+    torch.cuda.synchronize()
+    ids = gold[f"{mask_type}.ids"].tolist()
+    assert tb.active_set == ids and tb.nerf.training.n_images_for_training == len(ids)
+    for k, fid in enumerate(ids):
+        img = tb.rgba[fid].float().cpu().numpy()
+        ref = gold[f"{mask_type}.images"][k]
+        assert np.abs(img - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max()) and np.all(img[..., 3] == 1.0)
+        assert np.allclose(tb.depth[fid].cpu().numpy()[..., None], gold[f"{mask_type}.depths"][k], rtol=2e-6, atol=0)
+        assert np.array_equal(tb.depth_cov[fid].cpu().numpy()[..., None], gold[f"{mask_type}.covs"][k])
+        cam = tb.cams_h[fid]
+        assert np.allclose(cam[:12].reshape(3, 4), gold[f"{mask_type}.poses"][k], atol=2e-6)
+        assert np.allclose(cam[12:14], gold[f"{mask_type}.fl"]) and np.allclose(cam[14:16], gold[f"{mask_type}.pp"])
+        assert cam[16:18].view(np.int32).tolist() == gold[f"{mask_type}.res"].tolist()
