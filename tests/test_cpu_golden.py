@@ -67,3 +67,24 @@ def test_network_mirror_update_module_vs_reference_python():
         o = um(T(d["net"]), T(d["inp"]), T(d["corr"]), T(d["flow"]), T(d["ii"]), T(d["jj"]))
     for got, key, tol in zip(o, ("out_net", "delta", "weight", "eta", "upmask"), (2e-4, 5e-4, 2e-4, 1e-5, 5e-4)):
         assert np.allclose(got.numpy(), d[key], atol=tol), (key, np.abs(got.numpy() - d[key]).max())
+
+
+def test_reproject_oracle_matches_reference_projective_transform():
+    """A6: oracle/geom.py::reproject vs the REFERENCE's own pops.projective_transform (recorded by
+    tests/golden/make_golden_reproject.py; fp32 torch there, fp64 here -> 2e-3 px on coordinates up to ~1e3 px).
+    Covers the stereo edge (i == j), points closer than MIN_DEPTH (Z := 1 rule) and the validity mask."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_reproject.npz"))
+    from oracle import geom as ogeom
+    assert float(g["min_depth"][0]) == ogeom.MIN_DEPTH_PY
+    c, v = ogeom.reproject(g["poses"], g["disps"], g["intr"], g["ii"], g["jj"])
+    ref_c, ref_v = g["coords"], g["valid"]
+    assert c.shape == ref_c.shape and v.shape == ref_v.shape
+    # the mask may differ only where a depth sits on the threshold within fp32 rounding
+    Z_edge = np.abs(v - ref_v).sum()
+    assert Z_edge <= 2, Z_edge
+    assert 0.05 < ref_v.mean() < 0.999                                 # both valid and invalid points are present
+    ok = (v[..., 0] == ref_v[..., 0])
+    err = np.abs(c - ref_c)[ok]
+    scale = np.maximum(1.0, np.abs(ref_c)[ok])
+    assert float((err / scale).max()) < 2e-4, float((err / scale).max())
