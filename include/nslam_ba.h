@@ -110,6 +110,13 @@ int nslam_ba_depth(const nslam_ba_graph* g, const nslam_ba_buffers* b, const flo
 int nslam_ba_cov(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float* Linv,
                  float* Mscratch /* [6P,6P] */, float* z_cov, float* depth_cov, void* stream);
 
+/* A14, reference-exact: as nslam_ba_cov, but reproducing what the reference's covariance block really computes for
+ * the depth maps of OPTIMISED frames — its assignment `Ej[range(P), kf0-min:kf1-min] = Ei[range(P)]`
+ * (visual_frontend.py:1214) broadcasts Ei[q] into every pose row of column q (see csrc/ba_cov_ref.cu).
+ *   Mscratch: [6P*6P + 36] floats. */
+int nslam_ba_cov_reference(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float* Linv,
+                           float* Mscratch /* [6P,6P] + 36 */, float* z_cov, float* depth_cov, void* stream);
+
 /* block-diagonal 6x6 blocks of (L L^T)^-1 = Linv^T Linv: sigma_g [P,6,6] */
 int nslam_ba_pose_cov(const float* Linv, int P, float* sigma_g, void* stream);
 

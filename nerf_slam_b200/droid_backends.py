@@ -18,6 +18,7 @@ from . import _lib
 from .ba_graph import get_graph
 
 _DT = {torch.float16: 0, torch.float32: 1}
+_COV_REFERENCE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "0") == "1"
 
 
 def _chk(*ts):
@@ -338,18 +339,24 @@ class BAProblem:
         _lib.check(lib.nslam_ba_depth(ctypes.byref(self.g), ctypes.byref(self.b), _lib.ptr(dx),
                                       float(clamp_min), _lib.stream_ptr()), "ba_depth")
 
-    def covariances(self, linv):
+    def covariances(self, linv, reference=None):
+        """A14.  reference=True: reproduce the reference's covariance block exactly, including its broadcast of Ei over
+        the pose rows of optimised frames (csrc/ba_cov_ref.cu; default from NSLAM_COV_REFERENCE=1); False: the
+        intended formula (csrc/ba.cu)."""
         lib = _lib.load()
         gh = self.gh
         dev = self.H.device
         n = 6 * gh.P
-        M = torch.empty(n, n, dtype=torch.float32, device=dev)
+        if reference is None:
+            reference = _COV_REFERENCE
+        M = torch.empty(n * n + 36, dtype=torch.float32, device=dev)
         z_cov = torch.empty(gh.K, self.hw, dtype=torch.float32, device=dev)
         d_cov = torch.empty(gh.K, self.hw, dtype=torch.float32, device=dev)
         sg = torch.empty(gh.P, 6, 6, dtype=torch.float32, device=dev)
-        _lib.check(lib.nslam_ba_cov(ctypes.byref(self.g), ctypes.byref(self.b), _lib.ptr(linv),
-                                    _lib.ptr(M), _lib.ptr(z_cov), _lib.ptr(d_cov),
-                                    _lib.stream_ptr()), "ba_cov")
+        fn = lib.nslam_ba_cov_reference if reference else lib.nslam_ba_cov
+        _lib.check(fn(ctypes.byref(self.g), ctypes.byref(self.b), _lib.ptr(linv),
+                      _lib.ptr(M), _lib.ptr(z_cov), _lib.ptr(d_cov),
+                      _lib.stream_ptr()), "ba_cov")
         _lib.check(lib.nslam_ba_pose_cov(_lib.ptr(linv), gh.P, _lib.ptr(sg), _lib.stream_ptr()),
                    "ba_pose_cov")
         return sg, z_cov.view(gh.K, self.ht, self.wd), d_cov.view(gh.K, self.ht, self.wd)

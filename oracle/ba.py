@@ -187,8 +187,42 @@ def gtsam_retract(world_T_body, cam_T_body, dx, kf0):
     return wTb, np.concatenate([tc, qc], -1)
 
 
+def covariances_reference(L, E, Q, ii, jj, kf0, kf1, disps):
+    """What the reference's covariance block REALLY computes (visual_frontend.py:1171-1230, pinned by
+    tests/golden/ref_covariances.npz): as `covariances` below, except that its assignment
+    `Ej[range(P), kf0-min:kf1-min, :, :] = Ei[range(P), :, :]` (:1214) broadcasts over the pose dimension — for a depth
+    map of an OPTIMISED frame q, every pose row p holds Ei[q] and the Ejz blocks of that column are overwritten; depth maps
+    of fixed frames keep their Ejz blocks.  Depth maps = unique(ii) (:1201), assumed contiguous from min(ii, jj)."""
+    ii = np.asarray(ii); jj = np.asarray(jj)
+    P = kf1 - kf0
+    n = 6 * P
+    Linv = np.linalg.solve(L, np.eye(n))
+    sig = Linv.T @ Linv
+    sigma_g = np.stack([sig[6 * i:6 * i + 6, 6 * i:6 * i + 6] for i in range(P)])
+    kx = np.unique(ii)
+    K = len(kx)
+    hw = Q.shape[1]
+    z_cov = np.zeros((K, hw))
+    for k in range(K):
+        x = np.zeros((n, hw))
+        if kf0 <= kx[k] < kf1:
+            for p in range(P):
+                x[6 * p:6 * p + 6] = E[kx[k] - kf0]
+        else:
+            for m in range(len(ii)):
+                if ii[m] == kx[k] and kf0 <= jj[m] < kf1:
+                    p = jj[m] - kf0
+                    x[6 * p:6 * p + 6] = E[P + m]
+        F = (Q[k][:, None] * x.T) @ Linv
+        z_cov[k] = Q[k] + (F ** 2).sum(-1)
+    d = disps[kx].reshape(K, hw).astype(np.float64)
+    return sigma_g, z_cov, z_cov / d ** 4
+
+
 def covariances(L, E, Q, ii, jj, kf0, kf1, disps):
-    """visual_frontend.py:1171-1230. returns sigma_g [P,6,6], z_cov [K,HW], depth_cov [K,HW]"""
+    """The INTENDED formula of visual_frontend.py:1171-1230 (Ei on the diagonal, Ejz off the diagonal) — what
+    csrc/ba.cu::nslam_ba_cov computes; it equals the reference's output for the depth maps of fixed frames only, see
+    covariances_reference.  returns sigma_g [P,6,6], z_cov [K,HW], depth_cov [K,HW]"""
     ii = np.asarray(ii); jj = np.asarray(jj)
     P = kf1 - kf0
     n = 6 * P

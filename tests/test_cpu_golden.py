@@ -88,3 +88,31 @@ def test_reproject_oracle_matches_reference_projective_transform():
     err = np.abs(c - ref_c)[ok]
     scale = np.maximum(1.0, np.abs(ref_c)[ok])
     assert float((err / scale).max()) < 2e-4, float((err / scale).max())
+
+
+def test_covariance_oracle_matches_reference_block():
+    """A14: oracle/ba.py::covariances_reference vs the REFERENCE's own covariance extraction (the `if compute_covariances:`
+    block of RaftVisualFrontend.ba, executed verbatim by tests/golden/make_golden_covariances.py on a seeded window with
+    fixed frames, K = 6 depth maps > P = 4 poses).  fp32 torch there (Cholesky + triangular solve), fp64 here.
+    The block broadcasts Ei over the pose rows of optimised frames (:1214): `covariances` (the intended formula, what
+    nslam_ba_cov computes) agrees with it on the fixed frames' depth maps only — asserted here so that the deviation
+    stays visible."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_covariances.npz"))
+    from oracle import ba as oba
+    kf0, kf1 = [int(v) for v in g["kf"]]
+    L = np.linalg.cholesky(g["H"])
+    args = (L, g["E"].astype(np.float64), g["Q"].astype(np.float64), g["ii"], g["jj"], kf0, kf1, g["disps"])
+    sigma_g, z_cov, d_cov = oba.covariances_reference(*args)
+    K = len(g["kx"])
+    ht, wd = g["disps"].shape[1:]
+    assert sigma_g.shape == g["sigma_g"].shape and z_cov.shape == (K, ht * wd)
+    assert np.allclose(sigma_g, g["sigma_g"], rtol=2e-3, atol=1e-5)
+    assert np.allclose(z_cov.reshape(K, ht, wd), g["z_cov"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(d_cov.reshape(K, ht, wd), g["depth_cov"], rtol=1e-4, atol=1e-6)
+    assert (g["z_cov"] > g["Q"].reshape(K, ht, wd) - 1e-6).all()       # Sigma_z = Q + positive term
+    _, z_int, _ = oba.covariances(*args)
+    fixed = g["kx"] < kf0
+    assert fixed.any() and (~fixed).any()
+    assert np.allclose(z_int.reshape(K, ht, wd)[fixed], g["z_cov"][fixed], rtol=1e-4, atol=1e-6)
+    assert not np.allclose(z_int.reshape(K, ht, wd)[~fixed], g["z_cov"][~fixed], rtol=1e-2)

@@ -274,6 +274,31 @@ def test_ba_full_iteration(db):
     assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9)
 
 
+@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS") != "1", reason="pending first hardware run (NSLAM_PENDING_TESTS=1)")
+def test_ba_covariances_reference_exact(db):
+    """A14, csrc/ba_cov_ref.cu: the reference's covariance block as it really behaves (Ei broadcast over the pose rows of
+    optimised frames, visual_frontend.py:1214) vs oracle.covariances_reference, which is pinned on the CPU against the
+    reference's own code (tests/golden/ref_covariances.npz); and on the golden's own inputs."""
+    p = _ba_problem(66, nframes=7)
+    disps = T(p["disps"])
+    prob = db.BAProblem(T(p["poses"]), disps, T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]),
+                        T(p["weight"]), T(p["eta"]), p["ii"], p["jj"], p["kf0"], p["kf1"])
+    prob.linearize()
+    dx, linv, status = prob.solve(prior_idx=0, prior_err=torch.zeros(6, device=DEV), prior_info=1e8, want_linv=True)
+    assert int(status.item()) == 0
+    Hg = prob.H.double().cpu().numpy(); vg = prob.v.double().cpu().numpy().reshape(-1)
+    _, L = oba.dense_solve(Hg, vg, 0, np.zeros(6), 1e8)
+    sg, zc, dc = prob.covariances(linv, reference=True)
+    rsg, rzc, rdc = oba.covariances_reference(L, prob.E.double().cpu().numpy(), prob.Q.double().cpu().numpy(),
+                                              p["ii"], p["jj"], p["kf0"], p["kf1"], disps.cpu().numpy())
+    assert prob.gh.K == rzc.shape[0]                      # every frame of the window has outgoing edges in this problem
+    assert np.allclose(sg.cpu().numpy(), rsg, rtol=2e-3, atol=1e-9)
+    assert np.allclose(zc.cpu().numpy().reshape(rzc.shape), rzc, rtol=2e-3, atol=1e-9)
+    assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9)
+    _, zi, _ = prob.covariances(linv, reference=False)
+    assert not np.allclose(zi.cpu().numpy().reshape(rzc.shape), rzc, rtol=1e-2)          # the two formulas do differ
+
+
 def test_solve_depth_and_poses_api(db):
     p = _ba_problem(67)
     H, v, Q, E, w = db.reduced_camera_matrix(

@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 NSLAM_PENDING_TESTS=1 timeout 600 python -m pytest -q -m gpu \
   "tests/test_gpu_ngp.py::test_sample_rays_matches_the_march_oracle" \
   "tests/test_gpu_ngp.py::test_process_slam_ingest_matches_reference_golden" \
+  "tests/test_gpu_parity.py::test_ba_covariances_reference_exact" \
   "tests/test_gpu_parity.py::test_droid_backends_ba_all_in_one_loop" > gpurun_out/pending_tests.log 2>&1
 echo "pending tests exit $?" > gpurun_out/summary.txt
 NSLAM_PENDING_TESTS=1 timeout 900 python -m pytest -q -m gpu tests/test_gpu_droid.py > gpurun_out/pending_droid.log 2>&1
