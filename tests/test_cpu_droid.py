@@ -363,3 +363,104 @@ def test_live_frontend_graph_management_replays_reference_trace(k, monkeypatch):
             assert np.allclose(g[key], r[key], rtol=0, atol=2e-5), f"{sc} {g['tag']} {key}"
     fe = holder["fe"]
     assert fe.corr_pool.capacity - len(fe.corr_pool.free) == len(fe.ii_h) == len(set(fe.slots_h.tolist()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The live keyframe loop (RaftVisualFrontend._initialize / _update / rm_keyframe + graph management) against traces
+# recorded by executing the REFERENCE's own methods verbatim (tests/golden/make_golden_live_frontend.py).
+import live_frontend_scenario as lsc   # noqa: E402
+
+with gzip.open(os.path.join(HERE, "golden", "ref_live_frontend_traces.json.gz"), "rt") as f:
+    GOLD_LIVE = json.load(f)
+
+
+def _live_accessor(case, monkeypatch):
+    from nerf_slam_b200 import _lib, frontend as fr
+    monkeypatch.setattr(_lib, "h2d", lambda a, device, dtype=None: (torch.from_numpy(np.ascontiguousarray(a)) if dtype is None
+                                                                    else torch.from_numpy(np.ascontiguousarray(a)).to(dtype)))
+    D, feats, ctx = lsc.bank(case["seed"], case["n_steps"] + 4, case["slope"])
+    buffer = case["n_steps"] + 6
+    c0 = lsc.coords0()
+
+    class CpuFrontend(fr.RaftVisualFrontend):
+        def __init__(self):
+            self.device, self.stereo, self.cameras, self.corr_impl = "cpu", False, 1, "volume"
+            for k, v in lsc.PARAMS.items():
+                setattr(self, k, v)
+            self.keyframe_thresh = case.get("keyframe_thresh", 4.0)
+            self.buffer, self.ht, self.wd, self.kf_idx, self.is_initialized = buffer, lsc.HT8, lsc.WD8, 0, False
+            self.timers = fr._Timers()
+            B, h, w, C = buffer, lsc.HT8, lsc.WD8, lsc.CH
+            z = torch.zeros
+            self.gt_poses, self.gt_depths, self.cam0_images = z(B, 4, 4), z(B, 1, 2, 2), z(B, 3, 2, 2)
+            self.cam0_timestamps, self.cam0_T_world, self.world_T_body = z(B), z(B, 7), z(B, 7)
+            self.world_T_body_cov, self.cam0_idepths = z(B, 6, 6), torch.ones(B, h, w)
+            self.cam0_idepths_cov, self.cam0_depths_cov, self.cam0_idepths_sensed = torch.ones(B, h, w), torch.ones(B, h, w), z(B, h, w)
+            self.cam0_intrinsics = z(B, 4)
+            self.features_imgs = z(B, 1, h, w, 128)
+            self.contexts_imgs, self.cst_contexts_imgs = z(B, 1, h, w, C), z(B, 1, h, w, C)
+            self.corr_pool = FakePool(4 * self.max_factors, h, w, "cpu")
+            self.viz_idx = np.zeros(B, dtype=bool)
+            self.stats = {"updates": 0}
+            self._reset_graph()
+
+        def _ids(self, ix):
+            return self.cam0_intrinsics[torch.as_tensor(np.asarray(ix)).long().reshape(-1), 0].long()
+
+        def distance(self, ii, jj, beta=0.3, bidirectional=True):
+            return D[self._ids(ii), self._ids(jj)].clone()
+
+        def reproject(self, ii, jj):
+            off = (self._ids(ii) * 100 + self._ids(jj)).float()
+            return c0[None] + off.view(-1, 1, 1, 1), None
+
+        def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
+            self.age_h += 1
+            self.cam0_idepths[:self.kf_idx + 1] *= 1.001
+
+    fe = CpuFrontend()
+
+    class Acc:
+        kf_idx = property(lambda s: fe.kf_idx, lambda s, v: setattr(fe, "kf_idx", v))
+        is_initialized = property(lambda s: fe.is_initialized)
+
+        def put_frame(self, slot, fid):
+            fe.cam0_intrinsics[slot, 0] = float(fid)
+            fe.features_imgs[slot, 0, ..., :lsc.CH] = feats[fid].permute(1, 2, 0)
+            fe.contexts_imgs[slot, 0] = ctx[fid].permute(1, 2, 0); fe.cst_contexts_imgs[slot, 0] = -ctx[fid].permute(1, 2, 0)
+
+        def initialize(self):
+            fe._initialize()
+
+        def update(self):
+            return fe._update()
+
+        def rm_keyframe(self, k):
+            fe.rm_keyframe(k)
+
+        def snapshot(self):
+            hid = fe.gru_hidden_states
+            return {"kf_idx": int(fe.kf_idx), "is_initialized": bool(fe.is_initialized),
+                    "ii": fe.ii_h.tolist(), "jj": fe.jj_h.tolist(), "age": fe.age_h.tolist(),
+                    "ii_inac": fe.ii_inactive_h.tolist(), "jj_inac": fe.jj_inactive_h.tolist(),
+                    "ids": [int(v) for v in fe.cam0_intrinsics[:, 0].tolist()], "viz": [int(v) for v in fe.viz_idx.tolist()],
+                    "idepth00": [round(float(v), 6) for v in fe.cam0_idepths[:, 0, 0].tolist()],
+                    "flow00": [float(v) for v in fe.gru_estimated_flow[:, 0, 0, 0].tolist()],
+                    "flow_inac00": [float(v) for v in fe.gru_estimated_flow_inactive[:, 0, 0, 0].tolist()],
+                    "hidden00": [] if hid is None else [round(float(v), 5) for v in hid[:, 0, 0, 0].tolist()],
+                    "n_volumes": fe.corr_pool.capacity - len(fe.corr_pool.free)}
+    return Acc()
+
+
+@pytest.mark.parametrize("k", range(len(GOLD_LIVE)))
+def test_live_keyframe_loop_replays_the_reference_methods(k, monkeypatch):
+    case, ref = GOLD_LIVE[k]["case"], GOLD_LIVE[k]["trace"]
+    got = lsc.run(_live_accessor(case, monkeypatch), **case)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        where = (case["seed"], g["step"])
+        for key in ("step", "accepted", "kf_idx", "is_initialized", "ii", "jj", "age", "ii_inac", "jj_inac", "ids", "viz", "n_volumes"):
+            assert g[key] == r[key], (where, key)
+        for key in ("idepth00", "flow00", "flow_inac00", "hidden00"):
+            assert np.allclose(g[key], r[key], rtol=1e-6, atol=2e-5), (where, key)
+    assert sum(not r["accepted"] for r in ref) > 0 or case["slope"] >= 2.0
