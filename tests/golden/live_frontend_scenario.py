@@ -10,7 +10,7 @@ import torch
 
 HT8, WD8, CH = 16, 16, 4
 PARAMS = dict(max_factors=48, max_age=25, frontend_window=25, frontend_radius=2, frontend_nms=1, frontend_thresh=16.0,
-              beta=0.3, iters1=4, iters2=2, keyframe_warmup=8)
+              beta=0.3, iters1=4, iters2=2, keyframe_warmup=8, backend_thresh=22.0, backend_radius=2, backend_nms=3)
 
 
 def bank(seed, n_ids, slope):
@@ -33,7 +33,8 @@ def coords0():
 def run(acc, seed, n_steps, slope=1.0, keyframe_thresh=4.0):
     """acc: accessor object with
          .put_frame(slot, frame_id)   store features / contexts / identity of the arriving frame in keyframe slot `slot`
-         .kf_idx (get/set), .is_initialized, .initialize(), .update() -> bool, .rm_keyframe(k), .snapshot() -> dict"""
+         .kf_idx (get/set), .is_initialized, .initialize(), .update() -> bool, .rm_keyframe(k), .snapshot() -> dict,
+         .backend(steps) -> [(ii, jj, steps) seen by update_lowmem]"""
     trace = []
     next_id = 0
     acc.put_frame(0, next_id); next_id += 1          # first frame: always a keyframe (forward(), :262-289)
@@ -53,5 +54,12 @@ def run(acc, seed, n_steps, slope=1.0, keyframe_thresh=4.0):
             acc.kf_idx = k + 1
         d = acc.snapshot()
         d.update({"step": step, "accepted": accepted})
+        trace.append(d)
+    # global BA at the end of the stream (terminate(), visual_frontend.py:1308-1335): backend(7), backend(12);
+    # update_lowmem is a stand-in that records the edge set it is given
+    for steps in (7, 12):
+        log = acc.backend(steps)
+        d = acc.snapshot()
+        d.update({"step": f"backend{steps}", "accepted": True, "lowmem": log})
         trace.append(d)
     return trace

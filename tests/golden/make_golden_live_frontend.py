@@ -4,7 +4,8 @@
 
 slam/visual_frontends/visual_frontend.py cannot be imported (gtsam, lietorch, droid_backends, ...).  Its class body is
 parsed with `ast` instead, and the methods that make up the keyframe logic — rm_keyframe, __update, __initialize,
-add_neighborhood_factors, add_proximity_factors, add_factors, rm_factors, __filter_repeated_edges — are compiled from the
+add_neighborhood_factors, add_proximity_factors, add_factors, rm_factors, __filter_repeated_edges, backend,
+clear_edges, normalize — are compiled from the
 reference's source text into a class of the same name (so that private names mangle identically).  Nothing of it is
 copied into this repository.  Stand-ins, as in live_frontend_scenario.py: update(), distance(), reproject(); CorrBlock
 is the reference's own class.  Unstable `torch.argsort` calls are pinned to index order for ties (see
@@ -23,7 +24,7 @@ import torch
 REF = os.environ.get("NSLAM_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 METHODS = ["rm_keyframe", "__update", "__initialize", "add_neighborhood_factors", "add_proximity_factors", "add_factors",
-           "rm_factors", "__filter_repeated_edges"]
+           "rm_factors", "__filter_repeated_edges", "backend", "clear_edges", "normalize"]
 
 
 def reference_class():
@@ -71,6 +72,7 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
             self.gru_estimated_flow, self.gru_estimated_flow_weight = e(), e()
             self.gru_estimated_flow_inactive, self.gru_estimated_flow_weight_inactive = e(), e()
             self.coords0 = sc.coords0()
+            self.ht, self.wd, self.lowmem_log = h, w, []
 
         def _ids(self, ix):
             return self.cam0_intrinsics[torch.as_tensor(ix).long().reshape(-1), 0].long()
@@ -88,14 +90,23 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
             self.cam0_idepths[:self.kf_idx + 1] *= 1.001
             return None, None
 
+        def update_lowmem(self, itrs=2, EP=1e-7, steps=8):
+            self.lowmem_log.append([[int(v) for v in self.ii.tolist()], [int(v) for v in self.jj.tolist()], int(steps)])
+
     fe = Shim()
 
     class Acc:
         kf_idx = property(lambda s: fe.kf_idx, lambda s, v: setattr(fe, "kf_idx", v))
         is_initialized = property(lambda s: fe.is_initialized)
 
+        def backend(self, steps):
+            fe.lowmem_log = []
+            fe.backend(steps)
+            return fe.lowmem_log
+
         def put_frame(self, slot, fid):
             fe.cam0_intrinsics[slot, 0] = float(fid)
+            fe.cam0_T_world[slot, 0] = 0.1 * fid
             fe.features_imgs[slot, 0] = feats[fid]; fe.contexts_imgs[slot, 0] = ctx[fid]; fe.cst_contexts_imgs[slot, 0] = -ctx[fid]
 
         def initialize(self):
@@ -114,6 +125,7 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
                     "ii": tl(fe.ii), "jj": tl(fe.jj), "age": tl(fe.age), "ii_inac": tl(fe.ii_inactive), "jj_inac": tl(fe.jj_inactive),
                     "ids": tl(fe.cam0_intrinsics[:, 0]), "viz": tl(fe.viz_idx),
                     "idepth00": [round(float(v), 6) for v in fe.cam0_idepths[:, 0, 0].tolist()],
+                    "tx": [round(float(v), 6) for v in fe.cam0_T_world[:, 0].tolist()], "max_factors": int(fe.max_factors),
                     "flow00": [float(v) for v in fe.gru_estimated_flow[0, :, 0, 0, 0].tolist()],
                     "flow_inac00": [float(v) for v in fe.gru_estimated_flow_inactive[0, :, 0, 0, 0].tolist()],
                     "hidden00": [] if hid is None else [round(float(v), 5) for v in hid[0, :, 0, 0, 0].tolist()],

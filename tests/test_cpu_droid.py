@@ -402,6 +402,7 @@ def _live_accessor(case, monkeypatch):
             self.corr_pool = FakePool(4 * self.max_factors, h, w, "cpu")
             self.viz_idx = np.zeros(B, dtype=bool)
             self.stats = {"updates": 0}
+            self.lowmem_log = []
             self._reset_graph()
 
         def _ids(self, ix):
@@ -418,14 +419,23 @@ def _live_accessor(case, monkeypatch):
             self.age_h += 1
             self.cam0_idepths[:self.kf_idx + 1] *= 1.001
 
+        def update_lowmem(self, itrs=2, EP=1e-7, steps=8):
+            self.lowmem_log.append([self.ii_h.tolist(), self.jj_h.tolist(), int(steps)])
+
     fe = CpuFrontend()
 
     class Acc:
         kf_idx = property(lambda s: fe.kf_idx, lambda s, v: setattr(fe, "kf_idx", v))
         is_initialized = property(lambda s: fe.is_initialized)
 
+        def backend(self, steps):
+            fe.lowmem_log = []
+            fe.backend(steps)
+            return fe.lowmem_log
+
         def put_frame(self, slot, fid):
             fe.cam0_intrinsics[slot, 0] = float(fid)
+            fe.cam0_T_world[slot, 0] = 0.1 * fid
             fe.features_imgs[slot, 0, ..., :lsc.CH] = feats[fid].permute(1, 2, 0)
             fe.contexts_imgs[slot, 0] = ctx[fid].permute(1, 2, 0); fe.cst_contexts_imgs[slot, 0] = -ctx[fid].permute(1, 2, 0)
 
@@ -445,6 +455,7 @@ def _live_accessor(case, monkeypatch):
                     "ii_inac": fe.ii_inactive_h.tolist(), "jj_inac": fe.jj_inactive_h.tolist(),
                     "ids": [int(v) for v in fe.cam0_intrinsics[:, 0].tolist()], "viz": [int(v) for v in fe.viz_idx.tolist()],
                     "idepth00": [round(float(v), 6) for v in fe.cam0_idepths[:, 0, 0].tolist()],
+                    "tx": [round(float(v), 6) for v in fe.cam0_T_world[:, 0].tolist()], "max_factors": int(fe.max_factors),
                     "flow00": [float(v) for v in fe.gru_estimated_flow[:, 0, 0, 0].tolist()],
                     "flow_inac00": [float(v) for v in fe.gru_estimated_flow_inactive[:, 0, 0, 0].tolist()],
                     "hidden00": [] if hid is None else [round(float(v), 5) for v in hid[:, 0, 0, 0].tolist()],
@@ -459,8 +470,10 @@ def test_live_keyframe_loop_replays_the_reference_methods(k, monkeypatch):
     assert len(got) == len(ref)
     for g, r in zip(got, ref):
         where = (case["seed"], g["step"])
-        for key in ("step", "accepted", "kf_idx", "is_initialized", "ii", "jj", "age", "ii_inac", "jj_inac", "ids", "viz", "n_volumes"):
+        for key in ("step", "accepted", "kf_idx", "is_initialized", "ii", "jj", "age", "ii_inac", "jj_inac", "ids", "viz", "n_volumes",
+                    "max_factors"):
             assert g[key] == r[key], (where, key)
-        for key in ("idepth00", "flow00", "flow_inac00", "hidden00"):
-            assert np.allclose(g[key], r[key], rtol=1e-6, atol=2e-5), (where, key)
+        assert g.get("lowmem") == r.get("lowmem"), where               # the edge set handed to the global BA
+        for key in ("idepth00", "tx", "flow00", "flow_inac00", "hidden00"):
+            assert np.allclose(g[key], r[key], rtol=1e-5, atol=2e-5), (where, key)
     assert sum(not r["accepted"] for r in ref) > 0 or case["slope"] >= 2.0
