@@ -63,3 +63,31 @@ def run(acc, seed, n_steps, slope=1.0, keyframe_thresh=4.0):
         d.update({"step": f"backend{steps}", "accepted": True, "lowmem": log})
         trace.append(d)
     return trace
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# update() of the live class (visual_frontend.py:371-470) around stand-ins for the operator and the BA: what it writes
+# back (flow, confidence, hidden state, damping by source frame, age, viz flags) and what it hands to the dense BA
+# (active + inactive edges inside the window, kf0, planar targets / weights, 0.2 * damping + EP).
+def run_update(acc, seed, n_kf=10, n_updates=3):
+    """acc: .put_frame(slot, id), .kf_idx, .add_neighborhood(kf0, kf1, radius), .retire(first_frames),
+            .live_update(use_inactive) -> None, .snapshot_update() -> dict (incl. the BA calls since the last snapshot)"""
+    for k in range(n_kf):
+        acc.put_frame(k, k)
+    acc.kf_idx = n_kf - 1
+    acc.add_neighborhood(0, n_kf - 1, 3)
+    trace = []
+    for k in range(2):
+        acc.live_update(True)
+        trace.append(acc.snapshot_update())
+    acc.retire(4)                                     # edges leaving frames 0..3 become inactive (stored targets)
+    for k in range(n_updates):
+        acc.live_update(True)
+        trace.append(acc.snapshot_update())
+    acc.live_update(False)
+    trace.append(acc.snapshot_update())
+    return trace
+
+
+def digest(t):
+    return [list(t.shape), round(float(t.double().sum()), 3), round(float(t.reshape(-1)[0]), 5)]

@@ -24,7 +24,7 @@ import torch
 REF = os.environ.get("NSLAM_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 METHODS = ["rm_keyframe", "__update", "__initialize", "add_neighborhood_factors", "add_proximity_factors", "add_factors",
-           "rm_factors", "__filter_repeated_edges", "backend", "clear_edges", "normalize"]
+           "rm_factors", "__filter_repeated_edges", "backend", "clear_edges", "normalize", "update"]
 
 
 def reference_class():
@@ -40,7 +40,11 @@ def reference_class():
         sys.modules.setdefault(name, m)
     sys.path.insert(0, REF)
     from networks.modules.corr import CorrBlock
-    ns = {"torch": torch, "np": np, "ic": lambda *a, **k: None, "CorrBlock": CorrBlock}
+    import droid_backends as dbk                      # the lookup kernel: zeros of its real shape (src/droid.cpp:280-288)
+    dbk.corr_index_forward = lambda volume, coords, radius: (torch.zeros(volume.shape[0], 2 * radius + 1, 2 * radius + 1, *coords.shape[-2:]),)
+    sys.modules.setdefault("icecream", types.ModuleType("icecream")).ic = lambda *a, **k: None
+    from utils.flow_viz import cvx_upsample             # the reference's own (pure torch)
+    ns = {"torch": torch, "np": np, "ic": lambda *a, **k: None, "CorrBlock": CorrBlock, "cvx_upsample": cvx_upsample}
     exec(compile(new, "visual_frontend.py (reference, selected methods)", "exec"), ns)
     return ns["RaftVisualFrontend"]
 
@@ -72,7 +76,14 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
             self.gru_estimated_flow, self.gru_estimated_flow_weight = e(), e()
             self.gru_estimated_flow_inactive, self.gru_estimated_flow_weight_inactive = e(), e()
             self.coords0 = sc.coords0()
-            self.ht, self.wd, self.lowmem_log = h, w, []
+            self.ht, self.wd, self.lowmem_log, self.ba_log = h, w, [], []
+            self.damping = 1e-6 * torch.ones_like(self.cam0_idepths)
+            self.cam0_T_body = torch.tensor([0, 0, 0, 0, 0, 0, 1.0])
+            self.compute_covariances, self.viz = False, False
+            self.cam0_idepths_up, self.cam0_depths_cov_up = z(B, 8 * h, 8 * w), z(B, 8 * h, 8 * w)
+            sys.path.insert(0, HERE)
+            import factor_graph_scenario as fgs
+            self.update_net = fgs.fake_update_net
 
         def _ids(self, ix):
             return self.cam0_intrinsics[torch.as_tensor(ix).long().reshape(-1), 0].long()
@@ -81,13 +92,24 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
             return D[self._ids(ii), self._ids(jj)].clone()
 
         def reproject(self, ii, jj, cam_T_body=None, jacobian=False):
-            off = (self._ids(ii) * 100 + self._ids(jj)).float()
+            off = (self._ids(ii) * 100 + self._ids(jj)).float() + 10.0 * (self.cam0_idepths[ii, 0, 0] - 1.0)
             c = self.coords0[None, None] + off.view(1, -1, 1, 1, 1)
             return c, torch.ones_like(c[..., :1]), (None, None, None)
+
+        real_update = Ref.update                         # the reference's own update() (used by the update scenario)
 
         def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
             self.age += 1
             self.cam0_idepths[:self.kf_idx + 1] *= 1.001
+            return None, None
+
+        def ba(self, flow, weight, damping, ii, jj, kf0=0, kf1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False,
+               compute_covariances=True):
+            self.ba_log.append({"ii": [int(v) for v in ii.tolist()], "jj": [int(v) for v in jj.tolist()], "kf0": int(kf0),
+                                "kf1": None if kf1 is None else int(kf1), "itrs": int(itrs), "motion_only": bool(motion_only),
+                                "target": sc.digest(flow), "weight": sc.digest(weight), "damping": sc.digest(damping),
+                                "contig": bool(flow.is_contiguous() and weight.is_contiguous() and damping.is_contiguous())})
+            self.cam0_idepths[torch.unique(ii)] *= 1.01
             return None, None
 
         def update_lowmem(self, itrs=2, EP=1e-7, steps=8):
@@ -103,6 +125,25 @@ def make_shim(Ref, sc, D, feats, ctx, buffer, keyframe_thresh=4.0):
             fe.lowmem_log = []
             fe.backend(steps)
             return fe.lowmem_log
+
+        # ---- update scenario
+        def add_neighborhood(self, kf0, kf1, radius):
+            fe.add_neighborhood_factors(kf0, kf1, radius)
+
+        def retire(self, first):
+            fe.rm_factors(fe.ii < first, store=True)
+
+        def live_update(self, use_inactive):
+            Shim.real_update(fe, kf0=None, kf1=None, itrs=2, use_inactive=use_inactive)
+
+        def snapshot_update(self):
+            d = {"ii": [int(v) for v in fe.ii.tolist()], "age": [int(v) for v in fe.age.tolist()],
+                 "viz": [int(v) for v in fe.viz_idx.tolist()],
+                 "flow": sc.digest(fe.gru_estimated_flow), "weight": sc.digest(fe.gru_estimated_flow_weight),
+                 "hidden": sc.digest(fe.gru_hidden_states), "damping00": [round(float(v), 7) for v in fe.damping[:, 0, 0].tolist()],
+                 "idepth00": [round(float(v), 6) for v in fe.cam0_idepths[:, 0, 0].tolist()], "ba": fe.ba_log}
+            fe.ba_log = []
+            return d
 
         def put_frame(self, slot, fid):
             fe.cam0_intrinsics[slot, 0] = float(fid)
@@ -149,10 +190,17 @@ def main():
         out.append({"case": case, "trace": trace})
         print(case, "keyframes", trace[-1]["kf_idx"], "rejected", sum(not t["accepted"] for t in trace),
               "max edges", max(len(t["ii"]) for t in trace), "inactive", len(trace[-1]["ii_inac"]))
+    upd = []
+    for case in [dict(seed=41, n_kf=10), dict(seed=42, n_kf=13)]:
+        D, feats, ctx = sc.bank(case["seed"], case["n_kf"] + 4, 1.0)
+        acc = make_shim(Ref, sc, D, feats, ctx, buffer=case["n_kf"] + 4)
+        trace = sc.run_update(acc, **case)
+        upd.append({"case": case, "trace": trace})
+        print("update()", case, "snapshots", len(trace), "BA edges", [len(t["ba"][0]["ii"]) for t in trace])
     torch.argsort = unstable
     path = os.path.join(HERE, "ref_live_frontend_traces.json.gz")
     with gzip.open(path, "wt") as f:
-        json.dump(out, f, separators=(",", ":"))
+        json.dump({"loops": out, "updates": upd}, f, separators=(",", ":"))
     print("wrote", path, os.path.getsize(path))
 
 

@@ -46,7 +46,11 @@ class FakePool:
 
     def lookup(self, slots, coords, nhwc=False, out=None):
         """stand-in for the fused 4-level lookup (zeros of the real shape, like the reference-side recording)"""
-        assert not nhwc and coords.shape[0] == len(slots) and coords.shape[1] == 2
+        assert coords.shape[0] == len(slots)
+        if nhwc:
+            assert coords.shape[-1] == 2
+            return torch.zeros(*coords.shape[:3], 200)
+        assert coords.shape[1] == 2
         return torch.zeros(coords.shape[0], 196, *coords.shape[-2:])
 
     def build(self, f, fi, fj, slots):
@@ -371,15 +375,16 @@ def test_live_frontend_graph_management_replays_reference_trace(k, monkeypatch):
 import live_frontend_scenario as lsc   # noqa: E402
 
 with gzip.open(os.path.join(HERE, "golden", "ref_live_frontend_traces.json.gz"), "rt") as f:
-    GOLD_LIVE = json.load(f)
+    _GL = json.load(f)
+GOLD_LIVE, GOLD_LIVE_UPDATE = _GL["loops"], _GL["updates"]
 
 
-def _live_accessor(case, monkeypatch):
+def _live_accessor(case, monkeypatch, bank_n=None, buffer=None):
     from nerf_slam_b200 import _lib, frontend as fr
     monkeypatch.setattr(_lib, "h2d", lambda a, device, dtype=None: (torch.from_numpy(np.ascontiguousarray(a)) if dtype is None
                                                                     else torch.from_numpy(np.ascontiguousarray(a)).to(dtype)))
-    D, feats, ctx = lsc.bank(case["seed"], case["n_steps"] + 4, case["slope"])
-    buffer = case["n_steps"] + 6
+    D, feats, ctx = lsc.bank(case["seed"], bank_n or case["n_steps"] + 4, case["slope"])
+    buffer = buffer or case["n_steps"] + 6
     c0 = lsc.coords0()
 
     class CpuFrontend(fr.RaftVisualFrontend):
@@ -460,7 +465,9 @@ def _live_accessor(case, monkeypatch):
                     "flow_inac00": [float(v) for v in fe.gru_estimated_flow_inactive[:, 0, 0, 0].tolist()],
                     "hidden00": [] if hid is None else [round(float(v), 5) for v in hid[:, 0, 0, 0].tolist()],
                     "n_volumes": fe.corr_pool.capacity - len(fe.corr_pool.free)}
-    return Acc()
+    a = Acc()
+    a.fe = fe
+    return a
 
 
 @pytest.mark.parametrize("k", range(len(GOLD_LIVE)))
@@ -477,3 +484,94 @@ def test_live_keyframe_loop_replays_the_reference_methods(k, monkeypatch):
         for key in ("idepth00", "tx", "flow00", "flow_inac00", "hidden00"):
             assert np.allclose(g[key], r[key], rtol=1e-5, atol=2e-5), (where, key)
     assert sum(not r["accepted"] for r in ref) > 0 or case["slope"] >= 2.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# update() of the live class: bookkeeping around the operator / BA, and what reaches the BA (edge selection incl. the
+# stored inactive edges of the window, kf0, operands) vs the reference's own update() executed verbatim.
+@pytest.mark.parametrize("k", range(len(GOLD_LIVE_UPDATE)))
+def test_live_update_replays_the_reference_method(k, monkeypatch):
+    import contextlib
+    import types
+    from nerf_slam_b200 import _lib, frontend as fr
+    case, ref = GOLD_LIVE_UPDATE[k]["case"], GOLD_LIVE_UPDATE[k]["trace"]
+    acc = _live_accessor(dict(seed=case["seed"], n_steps=0, slope=1.0), monkeypatch, bank_n=case["n_kf"] + 4, buffer=case["n_kf"] + 4)
+    fe = acc.fe
+    ba_log = []
+
+    class RecorderBA:                                   # stands where droid_backends.BAProblem is
+        def __init__(self, poses, disps, intr, ext, sens, targets, weights, eta, ii, jj, kf0, kf1):
+            self.a = (targets, weights, eta, np.asarray(ii), np.asarray(jj), kf0, kf1)
+            kx = np.unique(np.concatenate([np.arange(kf0, kf1), np.asarray(ii)]))
+            self.gh = types.SimpleNamespace(tables={"kx": kx.astype(np.int32)}, K=len(kx), P=kf1 - kf0)
+
+        def gauss_newton(self, iters, *a, **kw):
+            t, w, eta, ii, jj, kf0, kf1 = self.a
+            ba_log.append({"ii": ii.tolist(), "jj": jj.tolist(), "kf0": int(kf0), "kf1": None, "itrs": int(iters), "motion_only": False,
+                           "target": lsc.digest(t), "weight": lsc.digest(w), "damping": lsc.digest(eta),
+                           "contig": bool(t.is_contiguous() and w.is_contiguous() and eta.is_contiguous())})
+            fe.cam0_idepths[torch.as_tensor(np.unique(ii))] *= 1.01
+            return None, None, None
+
+    def fake_reproject(poses, disps, intr, ii, jj, want_valid=True, out=None):
+        off = (fe._ids(ii) * 100 + fe._ids(jj)).float() + 10.0 * (fe.cam0_idepths[ii, 0, 0] - 1.0)
+        return lsc.coords0()[None] + off.view(-1, 1, 1, 1), None
+
+    def fake_operator(net, inp, corr_nhwc, coords1, target, ii_host=None):
+        c0 = lsc.coords0()
+        motion = torch.cat([coords1 - c0, target - coords1], dim=-1).permute(0, 3, 1, 2).clamp(-64.0, 64.0)
+        out = scn.fake_update_net(net.permute(0, 3, 1, 2)[None], None, torch.zeros(1, net.shape[0], 196, *net.shape[1:3]), motion[None],
+                                  torch.as_tensor(ii_host), None)
+        return (out[0][0].permute(0, 2, 3, 1).contiguous(), out[1][0], out[2][0], out[3][0], out[4][0].permute(0, 2, 3, 1))
+
+    monkeypatch.setattr(fr.db, "BAProblem", RecorderBA)
+    monkeypatch.setattr(fr.db, "reproject", fake_reproject)
+    monkeypatch.setattr(fr.db, "cvx_upsample2", lambda *a, **kw: None)
+    monkeypatch.setattr(_lib, "fixed_stream", contextlib.nullcontext)
+    fe._run_update_net = fake_operator
+    fe.reproject = lambda ii, jj: (fake_reproject(None, None, None, torch.as_tensor(np.asarray(ii)), torch.as_tensor(np.asarray(jj)))[0], None)
+    fe.update = types.MethodType(fr.RaftVisualFrontend.update, fe)       # the real method instead of the loop's stand-in
+    fe.update_tc, fe.use_op_step, fe.use_update_graphs, fe.compute_covariances, fe._static = None, False, False, False, None
+    B = fe.buffer
+    fe.kf_idx_to_f_idx = {i: i for i in range(B)}
+    fe.intr0, fe.cam0_T_body = fe.cam0_intrinsics[0], torch.tensor([0, 0, 0, 0, 0, 0, 1.0])
+    fe.prior_pose, fe.prior_info = torch.zeros(7), 1e8
+    fe.cam0_idepths_up, fe.cam0_depths_cov_up = torch.zeros(B, 8 * lsc.HT8, 8 * lsc.WD8), torch.zeros(B, 8 * lsc.HT8, 8 * lsc.WD8)
+    fe.coords0 = lsc.coords0()
+
+    class UAcc:
+        kf_idx = property(lambda s: fe.kf_idx, lambda s, v: setattr(fe, "kf_idx", v))
+        put_frame = staticmethod(acc.put_frame)
+
+        def add_neighborhood(self, kf0, kf1, radius):
+            fe.add_neighborhood_factors(kf0, kf1, radius)
+
+        def retire(self, first):
+            fe.rm_factors(fe.ii_h < first, store=True)
+
+        def live_update(self, use_inactive):
+            fe.update(kf0=None, kf1=None, itrs=2, use_inactive=use_inactive)
+
+        def snapshot_update(self):
+            d = {"ii": fe.ii_h.tolist(), "age": fe.age_h.tolist(), "viz": [int(v) for v in fe.viz_idx.tolist()],
+                 "flow": lsc.digest(fe.gru_estimated_flow), "weight": lsc.digest(fe.gru_estimated_flow_weight),
+                 "hidden": lsc.digest(fe.gru_hidden_states), "damping00": [round(float(v), 7) for v in fe.damping[:, 0, 0].tolist()],
+                 "idepth00": [round(float(v), 6) for v in fe.cam0_idepths[:, 0, 0].tolist()], "ba": list(ba_log)}
+            ba_log.clear()
+            return d
+    got = lsc.run_update(UAcc(), **case)
+    assert len(got) == len(ref)
+    for n, (g, r) in enumerate(zip(got, ref)):
+        for key in ("ii", "age", "viz"):
+            assert g[key] == r[key], (n, key)
+        for key in ("flow", "weight", "hidden"):
+            assert int(np.prod(g[key][0])) == int(np.prod(r[key][0])), (n, key)   # same element counts (layouts differ: NHWC vs [1,E,C,h,w])
+            assert np.isclose(g[key][1], r[key][1], rtol=1e-5, atol=5e-2), (n, key, g[key], r[key])
+        assert np.allclose(g["damping00"], r["damping00"], rtol=1e-4, atol=1e-7) and np.allclose(g["idepth00"], r["idepth00"], rtol=1e-5)
+        assert len(g["ba"]) == len(r["ba"]) == 1
+        a, b = g["ba"][0], r["ba"][0]
+        for key in ("ii", "jj", "kf0", "itrs"):
+            assert a[key] == b[key], (n, key, a[key], b[key])
+        for key in ("target", "weight", "damping"):
+            assert a[key][0] == b[key][0] and a["contig"] and b["contig"], (n, key, a[key], b[key])
+            assert np.isclose(a[key][1], b[key][1], rtol=1e-5, atol=5e-2) and np.isclose(a[key][2], b[key][2], rtol=1e-5, atol=1e-4), (n, key)
