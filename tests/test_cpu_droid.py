@@ -417,7 +417,8 @@ def _live_accessor(case, monkeypatch, bank_n=None, buffer=None):
             return D[self._ids(ii), self._ids(jj)].clone()
 
         def reproject(self, ii, jj):
-            off = (self._ids(ii) * 100 + self._ids(jj)).float()
+            ii_t = torch.as_tensor(np.asarray(ii)).long().reshape(-1)
+            off = (self._ids(ii) * 100 + self._ids(jj)).float() + 10.0 * (self.cam0_idepths[ii_t, 0, 0] - 1.0)
             return c0[None] + off.view(-1, 1, 1, 1), None
 
         def update(self, kf0=None, kf1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
