@@ -30,6 +30,18 @@ def mse2psnr(x):
     return -10. * np.log(x) / np.log(10.)
 
 
+def compute_error(img, ref):
+    """utils/utils.py:176-188: mean squared error over ALL channels of the image (RGBA: the alpha channel counts),
+    estimate clamped at 0, non-finite values of the estimate and of the error map count as 0"""
+    img = np.array(img, dtype=np.float32, copy=True)
+    img[~np.isfinite(img)] = 0
+    err = (np.maximum(img, 0.) - ref) ** 2
+    err[~np.isfinite(err)] = 0
+    if err.ndim == 3:
+        err = err.mean(axis=2)
+    return float(err.mean())
+
+
 class NerfFusion:
     def __init__(self, name, args, device):
         self.name, self.args, self.device = name, args, device
@@ -151,7 +163,7 @@ class NerfFusion:
             ref = tb.rgba[fid].float().cpu().numpy()
             tb.render_mode = ngp.Shade
             est = tb.render(ref.shape[1], ref.shape[0], 1, True)
-            mse = float(np.mean((np.maximum(est[..., :3], 0) - ref[..., :3]) ** 2))
+            mse = compute_error(est, ref)                       # over RGBA, like the reference (:424)
             tot_psnr += mse2psnr(max(mse, 1e-12))
             if fid in self.ref_frames:
                 k, slam = self.ref_frames[fid]

@@ -63,3 +63,18 @@ def test_last_frame_packet_is_not_ingested():
         update_training_images_device=lambda *a: (_ for _ in ()).throw(AssertionError("ingested")))))
     last = sc.make_packet(); last["is_last_frame"] = True
     assert nf.process_slam([None, last]) is True and nf.process_slam(None) is True and nf.process_slam([None, None]) is True
+
+
+def test_eval_metric_matches_reference_compute_error():
+    """B4 metric (fusion/nerf_fusion.py:424-425, utils/utils.py:168-188): MSE over all four channels with the estimate
+    clamped at 0 and non-finite values zeroed; value recorded from the reference's own compute_error / mse2psnr on these
+    seeded arrays (generator: the snippet in this docstring, run against /root/reference/utils/utils.py):
+        rng = default_rng(3); est = U(-0.2, 1.2, (12,16,4)) f32; ref = U(0, 1, (12,16,4)) f32;
+        est[0,0,0] = nan; est[1,2,3] = inf; est[3,3,1] = -inf  ->  0.2410338968038559, 6.17921878931163 dB"""
+    from nerf_slam_b200.nerf_fusion import compute_error, mse2psnr
+    rng = np.random.default_rng(3)
+    est = rng.uniform(-0.2, 1.2, (12, 16, 4)).astype(np.float32); ref = rng.uniform(0, 1, (12, 16, 4)).astype(np.float32)
+    est[0, 0, 0] = np.nan; est[1, 2, 3] = np.inf; est[3, 3, 1] = -np.inf
+    e = compute_error(est, ref)
+    assert abs(e - 0.2410338968038559) < 1e-7 and abs(mse2psnr(e) - 6.17921878931163) < 1e-5
+    assert np.isnan(est[0, 0, 0])                                     # the caller's array is left untouched
