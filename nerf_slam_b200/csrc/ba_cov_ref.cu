@@ -1,5 +1,6 @@
-// A14, reference-exact variant of the inverse-depth covariance (opt-in: NSLAM_COV_REFERENCE=1; written after the
-// round's GPU budget was spent, validated by a gated test — csrc/ba.cu's nslam_ba_cov stays the default until then).
+// A14, reference-exact variant of the inverse-depth covariance in ONE kernel (opt-in: NSLAM_COV_REFERENCE=kernel; written
+// after the round's GPU budget was spent, validated by a gated test — until then the default obtains the same values
+// from csrc/ba.cu's nslam_ba_cov plus a torch fix-up, droid_backends.cov_reference_fixup).
 //
 // The reference builds, per optimised pose p and depth map k, the 6 x HW block E[p][k] that enters
 //   Sigma_z = Q + sum_cols((Q * E^T) L^-1)^2                        (visual_frontend.py:1196-1230).

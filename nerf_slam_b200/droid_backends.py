@@ -18,7 +18,29 @@ from . import _lib
 from .ba_graph import get_graph
 
 _DT = {torch.float16: 0, torch.float32: 1}
-_COV_REFERENCE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "0") == "1"
+# A14 covariance semantics: "1" (default) = what the reference's block really computes, obtained from
+# the validated kernel (nslam_ba_cov) plus a fix-up of the depth maps of optimised frames in a handful of torch ops;
+# "kernel" = the same in one CUDA kernel (csrc/ba_cov_ref.cu, pending its first hardware run); "0" = the intended formula.
+_COV_MODE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "1")
+
+
+def cov_reference_fixup(M, E, Q, disps_flat, z_cov, d_cov, win_k, win_q, win_f, P):
+    """In place: rows `win_k` of z_cov / d_cov [K,HW] (depth maps whose frame win_f is optimised, pose index win_q) are
+    replaced by the reference's value.  Its assignment `Ej[range(P), kf0-min:kf1-min] = Ei[range(P)]`
+    (visual_frontend.py:1214) broadcasts Ei[q] into EVERY pose row, so for these maps
+        x^T (L^-1 L^-T) x = Ei[q]^T (sum_{p,p'} M[p][p']) Ei[q]        with M = L^-1 L^-T  [6P,6P].
+    M: flat [>= 36 P^2]; E [P+E,6,HW]; Q [K,HW]; disps_flat [N,HW]; index tensors int64 on the same device."""
+    if win_k.numel() == 0:
+        return
+    n = 6 * P
+    Msum = M[:n * n].view(P, 6, P, 6).sum(dim=(0, 2))
+    Ei = E.index_select(0, win_q)
+    acc = (Ei * torch.matmul(Msum, Ei)).sum(dim=1)              # e^T Msum e per pixel: [W,HW]
+    q = Q.index_select(0, win_k)
+    z = q + q * q * acc
+    z_cov.index_copy_(0, win_k, z)
+    d2 = disps_flat.index_select(0, win_f) ** 2
+    d_cov.index_copy_(0, win_k, z / (d2 * d2))
 
 
 def _chk(*ts):
@@ -340,23 +362,30 @@ class BAProblem:
                                       float(clamp_min), _lib.stream_ptr()), "ba_depth")
 
     def covariances(self, linv, reference=None):
-        """A14.  reference=True: reproduce the reference's covariance block exactly, including its broadcast of Ei over
-        the pose rows of optimised frames (csrc/ba_cov_ref.cu; default from NSLAM_COV_REFERENCE=1); False: the
-        intended formula (csrc/ba.cu)."""
+        """A14 -> (sigma_g [P,6,6], z_cov [K,ht,wd], depth_cov [K,ht,wd]).
+        reference: None = NSLAM_COV_REFERENCE (default "1"); True / "1" = the reference's block as it really behaves
+        (its broadcast of Ei over the pose rows of optimised frames, visual_frontend.py:1214) = validated kernel + torch
+        fix-up; "kernel" = the same in one CUDA kernel (csrc/ba_cov_ref.cu); False / "0" = the intended formula."""
         lib = _lib.load()
         gh = self.gh
         dev = self.H.device
         n = 6 * gh.P
-        if reference is None:
-            reference = _COV_REFERENCE
+        mode = _COV_MODE if reference is None else ({True: "1", False: "0"}.get(reference, reference))
         M = torch.empty(n * n + 36, dtype=torch.float32, device=dev)
         z_cov = torch.empty(gh.K, self.hw, dtype=torch.float32, device=dev)
         d_cov = torch.empty(gh.K, self.hw, dtype=torch.float32, device=dev)
         sg = torch.empty(gh.P, 6, 6, dtype=torch.float32, device=dev)
-        fn = lib.nslam_ba_cov_reference if reference else lib.nslam_ba_cov
+        fn = lib.nslam_ba_cov_reference if mode == "kernel" else lib.nslam_ba_cov
         _lib.check(fn(ctypes.byref(self.g), ctypes.byref(self.b), _lib.ptr(linv),
                       _lib.ptr(M), _lib.ptr(z_cov), _lib.ptr(d_cov),
                       _lib.stream_ptr()), "ba_cov")
+        if mode == "1":
+            if getattr(self, "_win", None) is None:
+                kx = gh.tables["kx"].astype(np.int64)
+                k = np.nonzero((kx >= gh.kf0) & (kx < gh.kf0 + gh.P))[0]
+                self._win = (_lib.h2d(k, dev), _lib.h2d(kx[k] - gh.kf0, dev), _lib.h2d(kx[k], dev))
+            disps = self._keep[1]
+            cov_reference_fixup(M, self.E, self.Q, disps.reshape(disps.shape[0], -1), z_cov, d_cov, *self._win, gh.P)
         _lib.check(lib.nslam_ba_pose_cov(_lib.ptr(linv), gh.P, _lib.ptr(sg), _lib.stream_ptr()),
                    "ba_pose_cov")
         return sg, z_cov.view(gh.K, self.ht, self.wd), d_cov.view(gh.K, self.ht, self.wd)

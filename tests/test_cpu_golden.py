@@ -116,3 +116,40 @@ def test_covariance_oracle_matches_reference_block():
     assert fixed.any() and (~fixed).any()
     assert np.allclose(z_int.reshape(K, ht, wd)[fixed], g["z_cov"][fixed], rtol=1e-4, atol=1e-6)
     assert not np.allclose(z_int.reshape(K, ht, wd)[~fixed], g["z_cov"][~fixed], rtol=1e-2)
+
+
+def test_covariance_fixup_turns_the_kernel_output_into_the_reference_output():
+    """droid_backends.cov_reference_fixup (the default A14 path = validated kernel + this fix-up) on the golden's inputs:
+    starting from the intended-formula values (what nslam_ba_cov returns) it must produce what the reference's block
+    produced, for every depth map; also run at the benchmark's shapes (P = 12, K = 14, HW = 4800) for shape safety."""
+    import os
+    import torch
+    from nerf_slam_b200.droid_backends import cov_reference_fixup
+    from oracle import ba as oba
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_covariances.npz"))
+    kf0, kf1 = [int(v) for v in g["kf"]]
+    P = kf1 - kf0
+    L = np.linalg.cholesky(g["H"])
+    Linv = np.linalg.inv(L)
+    _, z_int, d_int = oba.covariances(L, g["E"].astype(np.float64), g["Q"].astype(np.float64), g["ii"], g["jj"], kf0, kf1, g["disps"])
+    kx = g["kx"]
+    K, hw = len(kx), g["Q"].shape[1]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float()
+    M = torch.cat([T(Linv @ Linv.T).reshape(-1), torch.zeros(36)])
+    z, d = T(z_int), T(d_int)
+    k = np.nonzero((kx >= kf0) & (kx < kf1))[0]
+    cov_reference_fixup(M, T(g["E"]), T(g["Q"]), T(g["disps"]).view(g["disps"].shape[0], -1), z, d,
+                        torch.from_numpy(k), torch.from_numpy(kx[k] - kf0), torch.from_numpy(kx[k]), P)
+    ht, wd = g["disps"].shape[1:]
+    assert np.allclose(z.numpy().reshape(K, ht, wd), g["z_cov"], rtol=2e-4, atol=1e-6)
+    assert np.allclose(d.numpy().reshape(K, ht, wd), g["depth_cov"], rtol=2e-4, atol=1e-6)
+    # benchmark-like shapes, window not starting at the first depth map, no fixed-frame maps at the end
+    P, K, hw, N = 12, 14, 4800, 40
+    gen = torch.Generator().manual_seed(0)
+    M = torch.randn(36 * P * P + 36, generator=gen); E = torch.randn(P + 60, 6, hw, generator=gen)
+    Q = torch.rand(K, hw, generator=gen); disps = torch.rand(N, hw, generator=gen) + 0.5
+    z = torch.zeros(K, hw); d = torch.zeros(K, hw)
+    wk = torch.arange(2, 14); wq = torch.arange(0, 12); wf = torch.arange(20, 32)
+    cov_reference_fixup(M, E, Q, disps, z, d, wk, wq, wf, P)
+    assert torch.isfinite(z).all() and (z[:2] == 0).all() and (z[2:] != 0).any() and torch.isfinite(d).all()
+    cov_reference_fixup(M, E, Q, disps, z, d, torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), P)

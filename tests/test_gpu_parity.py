@@ -266,7 +266,7 @@ def test_ba_full_iteration(db):
     prob.depth_update(dx, clamp_min=1e-3)
     assert np.allclose(disps.cpu().numpy(), np.maximum(rd, 1e-3), rtol=1e-4, atol=1e-5)
     # covariances
-    sg, zc, dc = prob.covariances(linv)
+    sg, zc, dc = prob.covariances(linv, reference=False)             # the kernel alone = the intended formula
     rsg, rzc, rdc = oba.covariances(L, prob.E.double().cpu().numpy(), prob.Q.double().cpu().numpy(),
                                     p["ii"], p["jj"], p["kf0"], p["kf1"], disps.cpu().numpy())
     assert np.allclose(sg.cpu().numpy(), rsg, rtol=2e-3, atol=1e-9)
@@ -288,13 +288,14 @@ def test_ba_covariances_reference_exact(db):
     assert int(status.item()) == 0
     Hg = prob.H.double().cpu().numpy(); vg = prob.v.double().cpu().numpy().reshape(-1)
     _, L = oba.dense_solve(Hg, vg, 0, np.zeros(6), 1e8)
-    sg, zc, dc = prob.covariances(linv, reference=True)
     rsg, rzc, rdc = oba.covariances_reference(L, prob.E.double().cpu().numpy(), prob.Q.double().cpu().numpy(),
                                               p["ii"], p["jj"], p["kf0"], p["kf1"], disps.cpu().numpy())
     assert prob.gh.K == rzc.shape[0]                      # every frame of the window has outgoing edges in this problem
-    assert np.allclose(sg.cpu().numpy(), rsg, rtol=2e-3, atol=1e-9)
-    assert np.allclose(zc.cpu().numpy().reshape(rzc.shape), rzc, rtol=2e-3, atol=1e-9)
-    assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9)
+    for mode in ("1", "kernel"):                          # kernel + torch fix-up (the default) / one CUDA kernel
+        sg, zc, dc = prob.covariances(linv, reference=mode)
+        assert np.allclose(sg.cpu().numpy(), rsg, rtol=2e-3, atol=1e-9), mode
+        assert np.allclose(zc.cpu().numpy().reshape(rzc.shape), rzc, rtol=2e-3, atol=1e-9), mode
+        assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9), mode
     _, zi, _ = prob.covariances(linv, reference=False)
     assert not np.allclose(zi.cpu().numpy().reshape(rzc.shape), rzc, rtol=1e-2)          # the two formulas do differ
 
