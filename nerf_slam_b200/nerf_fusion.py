@@ -26,6 +26,14 @@ def _pose_tq_to_c2w(tq):
     return out
 
 
+def get_scale_and_offset(aabb):
+    """utils/utils.py:147-160: isotropic scale + offset that map the aabb [[min],[max]] into the unit cube around 0.5"""
+    aabb = np.array(aabb, dtype=np.float64)
+    ext = aabb[1] - aabb[0]
+    scale = 1.0 / max(0.000001, float(np.abs(ext).max()))
+    return scale, (aabb[1] + aabb[0]) * 0.5 * -scale + 0.5
+
+
 def mse2psnr(x):
     return -10. * np.log(x) / np.log(10.)
 
@@ -100,18 +108,31 @@ class NerfFusion:
         return False
 
     def process_data(self, packet):
-        """ground-truth fitting (fusion/nerf_fusion.py:118-138)"""
+        """ground-truth fitting (fusion/nerf_fusion.py:121-138).  `gt_fit_convention`:
+        "reference" (default) = exactly the tuples the reference hands to the trainer — world_T_cam scaled and offset into
+        the unit cube by the calibration's aabb (get_scale_and_offset), colours = u8 / 255 (NOT linearised, NOT
+        premultiplied, unlike process_slam), depth scale = calib.depth_scale * scale;
+        "metric" = poses as they are, linear premultiplied colours (consistent with process_slam's convention)."""
         calib = packet["calibs"][0]
         c2w = np.linalg.inv(np.asarray(packet["poses"], np.float64))
-        imgs = torch.as_tensor(np.asarray(packet["images"])).float() / 255.0
-        rgb = torch.where(imgs[..., :3] > 0.04045, ((imgs[..., :3] + 0.055) / 1.055) ** 2.4, imgs[..., :3] / 12.92)
-        rgba = torch.cat([rgb * imgs[..., 3:4], imgs[..., 3:4]], -1).numpy()
-        dep = np.asarray(packet["depths"], np.float32)
+        dep = np.asarray(packet["depths"]).astype(np.float32)
         intr = calib.camera_model.numpy()
+        if getattr(self, "gt_fit_convention", "reference") == "reference":
+            scale, offset = get_scale_and_offset(calib.aabb)
+            c2w[:, :3, 3] = c2w[:, :3, 3] * scale + offset
+            rgba = np.asarray(packet["images"]).astype(np.float32) / 255.0
+            depth_scale = calib.depth_scale * scale
+        else:
+            imgs = torch.as_tensor(np.asarray(packet["images"])).float() / 255.0
+            rgb = torch.where(imgs[..., :3] > 0.04045, ((imgs[..., :3] + 0.055) / 1.055) ** 2.4, imgs[..., :3] / 12.92)
+            rgba = torch.cat([rgb * imgs[..., 3:4], imgs[..., 3:4]], -1).numpy()
+            depth_scale = calib.depth_scale
         self.ngp.nerf.training.optimize_extrinsics = False
+        k = packet["k"]
+        ids = k.tolist() if hasattr(k, "tolist") else list(k)
         self.ngp.nerf.training.update_training_images(
-            list(np.asarray(packet["k"]).tolist()), list(c2w[:, :3, :4]), list(rgba), list(dep),
-            list(np.ones_like(dep)), calib.resolution.numpy(), intr[2:], intr[:2], calib.depth_scale, 1.0)
+            [int(i) for i in ids], list(c2w[:, :3, :4]), list(rgba), list(dep),
+            list(np.ones_like(dep)), calib.resolution.numpy(), intr[2:], intr[:2], depth_scale, 1.0)
         return False
 
     def send_data(self, batch):

@@ -47,6 +47,7 @@ def main():
         nf = object.__new__(NerfFusion)                     # __init__ needs the real trainer; process_slam does not
         nf.mask_type, nf.device, nf.viz = mt, "cpu", False
         nf.ngp = types.SimpleNamespace(nerf=types.SimpleNamespace(training=training))
+        training.optimize_extrinsics = True
         assert nf.process_slam([None, sc.make_packet()]) is False and len(calls) == 1
         ids, poses, images, depths, covs, res, pp, fl, dscale, cscale = calls[0]
         out[f"{mt}.ids"] = np.asarray(ids); out[f"{mt}.poses"] = np.stack(poses).astype(np.float64)
@@ -57,6 +58,18 @@ def main():
     last = sc.make_packet(); last["is_last_frame"] = True
     nf.mask_type = "ours"
     out["last_frame_skipped"] = np.array([nf.process_slam([None, last]) is True and len(calls) == 1])
+    # process_data (GT fitting, :121-138).  send_data calls `frame_ids.cpu()` on batch["k"]: the data path hands it a
+    # numpy array, for which that fails in the reference as shipped; the recorder receives a tensor copy of "k".
+    calls.clear()
+    pkt = sc.make_data_packet()
+    pkt["k"] = torch.from_numpy(pkt["k"])
+    assert nf.process_data(pkt) is False and len(calls) == 1
+    ids, poses, images, depths, covs, res, pp, fl, dscale, cscale = calls[0]
+    out["data.ids"] = np.asarray(ids); out["data.poses"] = np.stack(poses).astype(np.float64)
+    out["data.images"] = np.stack(images); out["data.depths"] = np.stack(depths); out["data.covs"] = np.stack(covs)
+    out["data.res"] = np.asarray(res); out["data.pp"] = np.asarray(pp); out["data.fl"] = np.asarray(fl)
+    out["data.scales"] = np.array([dscale, cscale], np.float64)
+    print("data", out["data.images"].shape, out["data.images"].dtype, out["data.poses"][0, :, 3], out["data.scales"])
     np.savez_compressed(os.path.join(HERE, "ref_process_slam.npz"), **out)
     print("wrote ref_process_slam.npz", os.path.getsize(os.path.join(HERE, "ref_process_slam.npz")))
 

@@ -34,3 +34,23 @@ def make_packet(seed=5):
             "gt_depths": torch.from_numpy(rng.uniform(1000, 20000, (N, 1, H, W)).astype(np.float32)),
             "calibs": [calib], "is_last_frame": False}
     return slam
+
+
+def make_data_packet(seed=9):
+    """a dataset packet (datasets/nerf_dataset.py:155-162) as the GT-fitting path receives it (--fusion=nerf without --slam)"""
+    rng = np.random.default_rng(seed)
+    n = 2
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w2c = np.zeros((n, 4, 4)); w2c[:, 3, 3] = 1
+    for k in range(n):
+        x, y, z, w = q[k]
+        w2c[k, :3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        w2c[k, :3, 3] = rng.normal(size=3)
+    calib = types.SimpleNamespace(aabb=np.array([[-2.0, -1.0, -2.0], [2.0, 3.0, 2.0]]), depth_scale=1.0 / 6553.5,
+                                  camera_model=_Model(), resolution=_Res())
+    return {"k": np.array([4, 6]), "t_cams": np.array([4, 6]), "poses": w2c,
+            "images": rng.integers(0, 256, (n, H, W, 4)).astype(np.uint8),
+            "depths": rng.integers(0, 40000, (n, H, W, 1)).astype(np.int32),
+            "calibs": np.array([calib, calib]), "is_last_frame": False}

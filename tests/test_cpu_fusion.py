@@ -78,3 +78,24 @@ def test_eval_metric_matches_reference_compute_error():
     e = compute_error(est, ref)
     assert abs(e - 0.2410338968038559) < 1e-7 and abs(mse2psnr(e) - 6.17921878931163) < 1e-5
     assert np.isnan(est[0, 0, 0])                                     # the caller's array is left untouched
+
+
+def test_product_process_data_matches_reference():
+    """GT-fitting path (fusion/nerf_fusion.py:121-138): the tuples handed to update_training_images — poses scaled /
+    offset into the unit cube by the calibration's aabb, colours u8/255 without linearisation, depth scale times the pose
+    scale, unit covariances — equal what the reference's own process_data + send_data produced."""
+    from nerf_slam_b200.nerf_fusion import NerfFusion, get_scale_and_offset
+    calls = []
+    nf = object.__new__(NerfFusion)
+    training = types.SimpleNamespace(update_training_images=lambda *a: calls.append(a), optimize_extrinsics=True)
+    nf.ngp = types.SimpleNamespace(nerf=types.SimpleNamespace(training=training))
+    assert nf.process_data(sc.make_data_packet()) is False and len(calls) == 1 and training.optimize_extrinsics is False
+    ids, poses, images, depths, covs, res, pp, fl, dscale, cscale = calls[0]
+    assert list(ids) == GOLD["data.ids"].tolist()
+    assert np.allclose(np.stack(poses), GOLD["data.poses"], rtol=0, atol=1e-9)
+    assert np.array_equal(np.stack(images), GOLD["data.images"]) and np.stack(images).dtype == np.float32
+    assert np.array_equal(np.stack(depths), GOLD["data.depths"]) and np.array_equal(np.stack(covs), GOLD["data.covs"])
+    assert np.array_equal(res, GOLD["data.res"]) and np.allclose(pp, GOLD["data.pp"]) and np.allclose(fl, GOLD["data.fl"])
+    assert np.allclose([dscale, cscale], GOLD["data.scales"], rtol=1e-12)
+    s, o = get_scale_and_offset([[-2.0, -1.0, -2.0], [2.0, 3.0, 2.0]])
+    assert s == 0.25 and np.allclose(o, [0.5, 0.25, 0.5])

@@ -168,6 +168,7 @@ def test_nerf_fits_synthetic_room(backend):
     nf = NerfFusion("nerf", args, DEV)
     nf.ngp.nerf.training.depth_supervision_lambda = 1.0
     nf.ngp.mlp_backend = backend
+    nf.gt_fit_convention = "metric"           # metric poses + linear colours (the default mirrors the reference's GT tuples)
     pk = [room.packet(k) for k in range(12)]
     packet = {"k": np.arange(12), "poses": np.stack([p["poses"][0] for p in pk]), "images": np.stack([p["images"][0] for p in pk]),
               "depths": np.stack([p["depths"][0] for p in pk]), "calibs": pk[0]["calibs"]}
