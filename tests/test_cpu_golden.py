@@ -153,3 +153,50 @@ def test_covariance_fixup_turns_the_kernel_output_into_the_reference_output():
     cov_reference_fixup(M, E, Q, disps, z, d, wk, wq, wf, P)
     assert torch.isfinite(z).all() and (z[:2] == 0).all() and (z[2:] != 0).any() and torch.isfinite(d).all()
     cov_reference_fixup(M, E, Q, disps, z, d, torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), P)
+
+
+def _corr_wrapper_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_corr_wrappers.npz"))
+
+
+def test_oracle_pyramid_lookup_matches_reference_corrblock_call():
+    """oracle.corr: corr_volume_pyramid + corr_lookup_pyramid (4 levels, coords / 2^l, channel concatenation) vs the
+    REFERENCE's CorrBlock(...)(coords) with the oracle's single-level kernel inside (make_golden_corr_wrappers.py)"""
+    from oracle import corr as ocorr
+    g = _corr_wrapper_golden()
+    f = g["fmaps"][0]
+    pyr = ocorr.corr_volume_pyramid(f[g["ii"]], f[g["jj"]])
+    c = np.ascontiguousarray(g["coords"][0].transpose(0, 3, 1, 2))
+    out = ocorr.corr_lookup_pyramid(pyr, c, 3)
+    assert out.shape == g["volume_lookup"][0].shape
+    # the oracle keeps the volume in fp16 like the reference under autocast; the recording ran in fp32
+    assert np.allclose(out.astype(np.float32), g["volume_lookup"][0], rtol=2e-2, atol=4e-3)
+
+
+def test_product_corr_wrappers_match_reference_wrappers(monkeypatch):
+    """nerf_slam_b200.corr.AltCorrBlock / CorrBlock (the host wrappers: pyramid by pooling, frame indexing, layouts) vs
+    the REFERENCE's wrappers, with the same CPU restatements of the kernels on both sides"""
+    import torch
+    from nerf_slam_b200 import corr as pcorr
+    from oracle import corr as ocorr
+    g = _corr_wrapper_golden()
+    T = torch.from_numpy
+    monkeypatch.setattr(pcorr.db, "altcorr_forward",
+                        lambda f1, f2, coords, r: (T(ocorr.altcorr_forward(f1.numpy(), f2.numpy(), coords.numpy(), r)),))
+    alt = pcorr.AltCorrBlock(T(g["fmaps"]))
+    out = alt(T(g["coords"]), T(g["ii"]), T(g["jj"]))
+    assert tuple(out.shape) == g["altcorr"].shape
+    assert np.allclose(out.numpy(), g["altcorr"], rtol=1e-5, atol=1e-6)
+
+    def build(f_nhwc, ii, jj):                       # [NF,h,w,C] channels-last fp16 -> 4 levels [E,h,w,h>>l,w>>l]
+        f = f_nhwc.float().numpy().transpose(0, 3, 1, 2)
+        return [T(p) for p in ocorr.corr_volume_pyramid(f[ii.numpy()], f[jj.numpy()])]
+    monkeypatch.setattr(pcorr.db, "corr_volume_build", build)
+    monkeypatch.setattr(pcorr.db, "corr_lookup_pyramid", lambda pyr, c, r: T(ocorr.corr_lookup_pyramid([p.numpy() for p in pyr], c.numpy(), r)))
+    f = T(g["fmaps"])
+    blk = pcorr.CorrBlock(f[:, g["ii"]], f[:, g["jj"]])
+    out = blk(T(g["coords"]))
+    assert tuple(out.shape) == g["volume_lookup"].shape
+    ref = g["volume_lookup"]
+    assert np.abs(out.numpy() - ref).max() < 2e-2 * max(1.0, np.abs(ref).max())      # features pass through fp16 in the product wrapper
