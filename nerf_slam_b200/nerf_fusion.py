@@ -68,6 +68,7 @@ class NerfFusion:
         self.ngp.nerf.training.depth_loss_type = ngp.LossType.L2
         self.mask_type = getattr(args, "mask_type", "ours")
         self.ref_frames = {}
+        self.anneal, self.anneal_every_iters, self.annealing_rate = False, 200, 0.95      # :108-110
         self.evaluate = bool(getattr(args, "eval", False))
         self.eval_every_iters = 200
         self.results = []
@@ -163,7 +164,10 @@ class NerfFusion:
             self.fit_volume_once()
 
     def fit_volume_once(self):
+        """:298-307"""
         self.ngp.frame()
+        if self.anneal and self.total_iters % self.anneal_every_iters == 0:
+            self.ngp.nerf.training.depth_supervision_lambda *= self.annealing_rate
         if self.evaluate and self.total_iters % self.eval_every_iters == 0 and self.ngp.rgba is not None:
             self.eval_gt_traj()
         self.total_iters += 1
