@@ -31,29 +31,23 @@ class BAGraphHost:
         kk = np.searchsorted(kx, ii)
 
         order = np.argsort(kk, kind="stable")
-        src_ptr = np.zeros(K + 1, dtype=np.int64)
-        np.add.at(src_ptr, kk + 1, 1)
-        src_ptr = np.cumsum(src_ptr)
+        src_ptr = np.concatenate([[0], np.cumsum(np.bincount(kk, minlength=K))]).astype(np.int64)
 
         # Schur rows per depth map: self row (if the frame is in the window) + edges whose target
-        # pose is in the window (schur_block keeps `j >= kf0 && j <= kf1`, :1368)
-        row_pose, row_erow, row_k = [], [], []
+        # pose is in the window (schur_block keeps `j >= kf0 && j <= kf1`, :1368).
+        # Order inside a depth map: self row first, then its edges in `order` (stable by edge id); built without Python
+        # loops: self rows and (already k-sorted) edge rows are concatenated and stably sorted by k.
         in_win = (kx >= kf0) & (kx < kf1)
-        jw = (jj >= kf0) & (jj < kf1)
-        for k in range(K):
-            if in_win[k]:
-                row_pose.append(int(kx[k] - kf0)); row_erow.append(int(kx[k] - kf0)); row_k.append(k)
-            for e in order[src_ptr[k]:src_ptr[k + 1]]:
-                if jw[e]:
-                    row_pose.append(int(jj[e] - kf0)); row_erow.append(P + int(e)); row_k.append(k)
-        row_pose = np.asarray(row_pose, dtype=np.int64)
-        row_erow = np.asarray(row_erow, dtype=np.int64)
-        row_k = np.asarray(row_k, dtype=np.int64)
+        k_self = np.nonzero(in_win)[0]
+        e_rows = order[(jj[order] >= kf0) & (jj[order] < kf1)]
+        cand_k = np.concatenate([k_self, kk[e_rows]])
+        cand_pose = np.concatenate([kx[k_self] - kf0, jj[e_rows] - kf0])
+        cand_erow = np.concatenate([kx[k_self] - kf0, P + e_rows])
+        o = np.argsort(cand_k, kind="stable")
+        row_k, row_pose, row_erow = cand_k[o], cand_pose[o].astype(np.int64), cand_erow[o].astype(np.int64)
         NR = int(row_pose.shape[0])
-        row_ptr = np.zeros(K + 1, dtype=np.int64)
-        np.add.at(row_ptr, row_k + 1, 1)
-        row_ptr = np.cumsum(row_ptr)
-        R = np.diff(row_ptr)
+        R = np.bincount(row_k, minlength=K).astype(np.int64)
+        row_ptr = np.concatenate([[0], np.cumsum(R)]).astype(np.int64)
         pair_off = np.concatenate([[0], np.cumsum(R * R)])
         NPAIR = int(pair_off[-1])
         RMAX = int(R.max()) if K else 0
@@ -68,32 +62,23 @@ class BAGraphHost:
         oks = [av, av & bv, av & bv, bv]
         hk = [keys[w][oks[w]] for w in range(4)]
         hv = [(w * E + e_idx)[oks[w]] for w in range(4)]
-        # Schur blocks
-        sk, sv = [], []
-        for k in range(K):
-            r0, r1 = int(row_ptr[k]), int(row_ptr[k + 1])
-            if r1 == r0:
-                continue
-            pp = row_pose[r0:r1]
-            Rk = r1 - r0
-            blk = pair_off[k] + np.arange(Rk * Rk)
-            sk.append((pp[:, None] * P + pp[None, :]).reshape(-1))
-            sv.append(-(blk + 1))
+        # Schur blocks: for every depth map all ordered pairs (ra, rb) of its rows, ra-major; block id = running index
+        rep = R[row_k]                                              # pairs that start at each row
+        ia = np.repeat(np.arange(NR, dtype=np.int64), rep)
+        ib = row_ptr[row_k[ia]] + (np.arange(NPAIR, dtype=np.int64) - np.repeat(np.cumsum(rep) - rep, rep))
+        sk = [row_pose[ia] * P + row_pose[ib]] if NPAIR else []
+        sv = [-(np.arange(NPAIR, dtype=np.int64) + 1)] if NPAIR else []
         hkeys = np.concatenate(hk + sk) if (E or sk) else np.zeros(0, np.int64)
         hvals = np.concatenate(hv + sv) if (E or sv) else np.zeros(0, np.int64)
         o = np.argsort(hkeys, kind="stable")
         hc_idx = hvals[o]
-        hc_ptr = np.zeros(P * P + 1, dtype=np.int64)
-        np.add.at(hc_ptr, hkeys + 1, 1)
-        hc_ptr = np.cumsum(hc_ptr)
+        hc_ptr = np.concatenate([[0], np.cumsum(np.bincount(hkeys, minlength=P * P))]).astype(np.int64)
 
         vkeys = np.concatenate([a[av], b[bv], row_pose])
         vvals = np.concatenate([e_idx[av], (E + e_idx)[bv], -(np.arange(NR) + 1)])
         o = np.argsort(vkeys, kind="stable")
         vc_idx = vvals[o]
-        vc_ptr = np.zeros(P + 1, dtype=np.int64)
-        np.add.at(vc_ptr, vkeys + 1, 1)
-        vc_ptr = np.cumsum(vc_ptr)
+        vc_ptr = np.concatenate([[0], np.cumsum(np.bincount(vkeys, minlength=P))]).astype(np.int64)
 
         self.E, self.P, self.K, self.kf0, self.kf1 = E, P, K, int(kf0), int(kf1)
         self.NR, self.NPAIR, self.RMAX = NR, NPAIR, RMAX

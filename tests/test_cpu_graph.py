@@ -34,3 +34,25 @@ def test_proximity_edges_empty_and_single():
     got = proximity_edges(d.copy(), np.array([0]), np.array([0]), np.zeros(0, np.int64), np.zeros(0, np.int64), 0, 0, 1, 2, 2, 16.0, 48, False)
     ref = add_proximity_factors_edges(d, 0, 0, 1, [], [], 2, 2, 16.0, 48, False)
     assert np.array_equal(got, ref)
+
+
+def test_vectorised_ba_graph_tables_equal_the_loop_formulation():
+    """nerf_slam_b200.ba_graph.BAGraphHost (no Python loops: ~0.2 ms per keyframe candidate while the GPU waits) must
+    produce byte-identical int32 tables to the loop formulation on random windows: edges outside the window, fixed
+    frames, duplicate and self (stereo) edges, empty edge lists, single-pose windows."""
+    from nerf_slam_b200.ba_graph import BAGraphHost
+    from tests.ba_graph_loops import BAGraphLoops
+    rng = np.random.default_rng(0)
+    for trial in range(600):
+        P = int(rng.integers(1, 14)); kf0 = int(rng.integers(0, 6)); kf1 = kf0 + P
+        E = int(rng.integers(0, 90))
+        lo = max(0, kf0 - int(rng.integers(0, 5))); hi = kf1 + int(rng.integers(0, 3))
+        ii = rng.integers(lo, hi, E); jj = rng.integers(lo, hi, E)
+        if trial % 7 == 0:
+            jj = ii.copy()
+        a, b = BAGraphLoops(ii, jj, kf0, kf1), BAGraphHost(ii, jj, kf0, kf1)
+        for name in ("E", "P", "K", "kf0", "kf1", "NR", "NPAIR", "RMAX", "NHC", "NVC"):
+            assert getattr(a, name) == getattr(b, name), (trial, name)
+        assert list(a.tables) == list(b.tables)
+        for k in a.tables:
+            assert b.tables[k].dtype == np.int32 and np.array_equal(a.tables[k], b.tables[k]), (trial, k)
