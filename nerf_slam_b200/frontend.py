@@ -509,9 +509,10 @@ class RaftVisualFrontend:
             self.add_factors(es[:, 0], es[:, 1], remove)
 
     def _filter_repeated_edges(self, ii, jj):
-        eset = set(zip(self.ii_h.tolist(), self.jj_h.tolist())) | \
-            set(zip(self.ii_inactive_h.tolist(), self.jj_inactive_h.tolist()))
-        keep = np.array([(int(i), int(j)) not in eset for i, j in zip(ii, jj)], dtype=bool)
+        """visual_frontend.py:896-907: drop candidates that are already active or stored as inactive (duplicates INSIDE
+        the candidate list are kept, as in the reference); membership on (i, j) packed into one integer"""
+        have = np.concatenate([self.ii_h * 65536 + self.jj_h, self.ii_inactive_h * 65536 + self.jj_inactive_h])
+        keep = ~np.isin(ii * 65536 + jj, have)
         return ii[keep], jj[keep]
 
     def add_factors(self, ii, jj, remove=False):
