@@ -421,8 +421,8 @@ class FactorGraph:
     # ---- edge bookkeeping
     def _filter_repeated_edges(self, ii, jj):
         """:43-54 — drop edges that are already active or inactive"""
-        eset = set(zip(self._ii.tolist(), self._jj.tolist())) | set(zip(self._ii_inac.tolist(), self._jj_inac.tolist()))
-        keep = np.array([(int(i), int(j)) not in eset for i, j in zip(ii, jj)], dtype=bool)
+        have = np.concatenate([self._ii * 65536 + self._jj, self._ii_inac * 65536 + self._jj_inac])
+        keep = ~np.isin(ii * 65536 + jj, have)
         return ii[keep], jj[keep]
 
     def print_edges(self):
