@@ -17,6 +17,8 @@ echo "corr rows tests exit $?" >> gpurun_out/summary.txt
 # 3. the CTA-pair convolution kernel (csrc/conv_igemm2.cu, cta_group::2): parity, then the kernel table with it enabled
 NSLAM_CONV_CTA2=1 timeout 600 python -m pytest -q -m gpu tests/test_gpu_conv.py > gpurun_out/conv_pairs_tests.log 2>&1
 echo "conv pairs tests exit $?" >> gpurun_out/summary.txt
+NSLAM_CONV_CTA2=1 timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -q -m gpu tests/test_gpu_conv.py -k "pairs or gru_fused" > gpurun_out/conv_pairs_memcheck.log 2>&1
+echo "conv pairs memcheck exit $?" >> gpurun_out/summary.txt
 NSLAM_CONV_CTA2=1 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_pairs.log 2>&1
 timeout 300 python tools/kernel_table.py > gpurun_out/kernel_table_default.log 2>&1
 # 3b. the reference's command line on this implementation (procedural stream, then the same stream from files)
