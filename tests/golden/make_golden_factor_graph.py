@@ -87,7 +87,7 @@ def main():
     torch.argsort = unstable_argsort
     path = os.path.join(HERE, "ref_factor_graph_traces.json.gz")
     import gzip
-    with gzip.open(path, "wt") as f:
+    with gzip.GzipFile(path, "wb", mtime=0) as gz, __import__("io").TextIOWrapper(gz) as f:   # mtime=0: reproducible bytes
         json.dump({"torch": torch.__version__, "scenarios": out, "update_scenarios": upd, "frontend_scenarios": fr}, f,
                   separators=(",", ":"))
     print("wrote", path, os.path.getsize(path), "bytes")

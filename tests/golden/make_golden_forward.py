@@ -121,7 +121,7 @@ def main():
         print(o["case"], "frames run", len(t), "keyframes", t[-1]["kf_idx"], "stop", t[-1]["stop"],
               "viz packets", sum(1 for x in t if x["viz"] and "viz_idx" in x["viz"]))
     path = os.path.join(HERE, "ref_forward_traces.json.gz")
-    with gzip.open(path, "wt") as f:
+    with gzip.GzipFile(path, "wb", mtime=0) as gz, __import__("io").TextIOWrapper(gz) as f:   # mtime=0: reproducible bytes
         json.dump(out, f, separators=(",", ":"))
     print("wrote", path, os.path.getsize(path))
 

@@ -199,7 +199,7 @@ def main():
         print("update()", case, "snapshots", len(trace), "BA edges", [len(t["ba"][0]["ii"]) for t in trace])
     torch.argsort = unstable
     path = os.path.join(HERE, "ref_live_frontend_traces.json.gz")
-    with gzip.open(path, "wt") as f:
+    with gzip.GzipFile(path, "wb", mtime=0) as gz, __import__("io").TextIOWrapper(gz) as f:   # mtime=0: reproducible bytes
         json.dump({"loops": out, "updates": upd}, f, separators=(",", ":"))
     print("wrote", path, os.path.getsize(path))
 
