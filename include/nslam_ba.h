@@ -76,6 +76,15 @@ typedef struct nslam_ba_buffers {
 /* A7-A11: linearise, accumulate, Schur-complement, assemble dense reduced camera matrix. */
 int nslam_ba_reduced_camera_matrix(const nslam_ba_graph* g, const nslam_ba_buffers* b, void* stream);
 
+/* HOST: edge list -> the tables of nslam_ba_graph, packed into one int32 buffer (each table padded to 4 ints) ready for a
+ * single upload.  Replaces what reduced_camera_matrix_cuda / accum_cuda / schur_block compute on the CPU on every call
+ * (src/droid_kernels.cu:1697-1706, 1065-1115, 1349-1399).  ii, jj: HOST int64 [E]; out: HOST int32 [capacity];
+ * meta: HOST int [36] = {E,P,K,kf0,NR,NPAIR,RMAX,NHC,NVC,total, offsets[13], lengths[13]} in the table order
+ * ii,jj,kx,src_ptr,src_edges,row_ptr,row_pose,row_erow,pair_off,hc_ptr,hc_idx,vc_ptr,vc_idx.
+ * returns 0 ok, 1 capacity too small (meta[9] = ints needed), 2 invalid window. */
+int nslam_ba_graph_build(const long long* ii, const long long* jj, int E, int kf0, int kf1, int* out, int capacity,
+                         int* meta);
+
 /* A12: dense solve (fp64 Cholesky in one CTA).
  *   Hin [n,n] fp32, vin [n] fp32 (n = 6P);  dx [P,6] fp32 out.
  *   prior_pose_idx >= 0: adds the 1e-4-sigma PriorFactorPose3 on that pose (visual_frontend.py:1234-1252)

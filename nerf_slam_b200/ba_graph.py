@@ -15,10 +15,52 @@ import numpy as np
 from . import _lib
 
 
+_TABLES = ("ii", "jj", "kx", "src_ptr", "src_edges", "row_ptr", "row_pose", "row_erow", "pair_off", "hc_ptr", "hc_idx",
+           "vc_ptr", "vc_idx")
+
+
 class BAGraphHost:
-    """numpy tables; see include/nslam_ba.h::nslam_ba_graph for the meaning of each field."""
+    """Tables of one BA window; see include/nslam_ba.h::nslam_ba_graph for the meaning of each field.
+
+    Built by the native host routine `nslam_ba_graph_build` (csrc/ba_graph_host.cu) directly into the packed int32 buffer
+    that is uploaded — the reference does this part in C++ on the CPU too (src/droid_kernels.cu:1065-1115, 1349-1399,
+    1697-1706), on every call.  `BAGraphHost.from_numpy` is the same construction in vectorised numpy, kept as the
+    table-for-table check of the native routine (tests/test_cpu_graph.py)."""
 
     def __init__(self, ii, jj, kf0, kf1):
+        ii = np.ascontiguousarray(np.asarray(ii, dtype=np.int64).reshape(-1))
+        jj = np.ascontiguousarray(np.asarray(jj, dtype=np.int64).reshape(-1))
+        E = int(ii.shape[0])
+        if int(kf1 - kf0) <= 0:
+            raise ValueError("empty BA window")
+        lib = _lib.load(require_cuda=False)
+        meta = np.zeros(36, np.int32)
+        cap = 4096 + 64 * E
+        for _ in range(2):
+            flat = np.empty(cap, np.int32)
+            rc = lib.nslam_ba_graph_build(ii.ctypes.data_as(ctypes.c_void_p), jj.ctypes.data_as(ctypes.c_void_p), E, int(kf0), int(kf1),
+                                          flat.ctypes.data_as(ctypes.c_void_p), cap, meta.ctypes.data_as(ctypes.c_void_p))
+            if rc != 1:
+                break
+            cap = int(meta[9])
+        if rc != 0:
+            raise RuntimeError(f"nslam_ba_graph_build failed ({rc})")
+        self.E, self.P, self.K, self.kf0 = (int(v) for v in meta[:4])
+        self.kf1 = int(kf1)
+        self.NR, self.NPAIR, self.RMAX, self.NHC, self.NVC = (int(v) for v in meta[4:9])
+        self._flat = flat[:int(meta[9])]
+        self._offs = {name: int(meta[10 + t]) for t, name in enumerate(_TABLES)}
+        self.tables = OrderedDict((name, self._flat[self._offs[name]:self._offs[name] + int(meta[23 + t])])
+                                  for t, name in enumerate(_TABLES))
+
+    @classmethod
+    def from_numpy(cls, ii, jj, kf0, kf1):
+        self = cls.__new__(cls)
+        self._flat = None
+        self._init_numpy(ii, jj, kf0, kf1)
+        return self
+
+    def _init_numpy(self, ii, jj, kf0, kf1):
         ii = np.asarray(ii, dtype=np.int64).reshape(-1)
         jj = np.asarray(jj, dtype=np.int64).reshape(-1)
         E = int(ii.shape[0])
@@ -94,6 +136,8 @@ class BAGraphHost:
     # ------------------------------------------------------------------ device side
     def packed(self):
         """one int32 vector + offsets (each table 16-byte aligned)"""
+        if self._flat is not None:
+            return self._flat, self._offs
         offs, chunks, pos = {}, [], 0
         for k, v in self.tables.items():
             offs[k] = pos

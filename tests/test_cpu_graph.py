@@ -36,10 +36,11 @@ def test_proximity_edges_empty_and_single():
     assert np.array_equal(got, ref)
 
 
-def test_vectorised_ba_graph_tables_equal_the_loop_formulation():
-    """nerf_slam_b200.ba_graph.BAGraphHost (no Python loops: ~0.2 ms per keyframe candidate while the GPU waits) must
-    produce byte-identical int32 tables to the loop formulation on random windows: edges outside the window, fixed
-    frames, duplicate and self (stereo) edges, empty edge lists, single-pose windows."""
+def test_native_and_vectorised_ba_graph_tables_equal_the_loop_formulation():
+    """nerf_slam_b200.ba_graph.BAGraphHost — built by the native host routine nslam_ba_graph_build (csrc/ba_graph_host.cu,
+    0.04 ms per keyframe candidate while the GPU waits) — and its vectorised numpy twin `from_numpy` must produce
+    byte-identical int32 tables (and the same packed upload buffer) as the loop formulation on random windows: edges
+    outside the window, fixed frames, duplicate and self (stereo) edges, empty edge lists, single-pose windows."""
     from nerf_slam_b200.ba_graph import BAGraphHost
     from tests.ba_graph_loops import BAGraphLoops
     rng = np.random.default_rng(0)
@@ -50,9 +51,13 @@ def test_vectorised_ba_graph_tables_equal_the_loop_formulation():
         ii = rng.integers(lo, hi, E); jj = rng.integers(lo, hi, E)
         if trial % 7 == 0:
             jj = ii.copy()
-        a, b = BAGraphLoops(ii, jj, kf0, kf1), BAGraphHost(ii, jj, kf0, kf1)
-        for name in ("E", "P", "K", "kf0", "kf1", "NR", "NPAIR", "RMAX", "NHC", "NVC"):
-            assert getattr(a, name) == getattr(b, name), (trial, name)
-        assert list(a.tables) == list(b.tables)
-        for k in a.tables:
-            assert b.tables[k].dtype == np.int32 and np.array_equal(a.tables[k], b.tables[k]), (trial, k)
+        a = BAGraphLoops(ii, jj, kf0, kf1)
+        for b in (BAGraphHost(ii, jj, kf0, kf1), BAGraphHost.from_numpy(ii, jj, kf0, kf1)):
+            for name in ("E", "P", "K", "kf0", "kf1", "NR", "NPAIR", "RMAX", "NHC", "NVC"):
+                assert getattr(a, name) == getattr(b, name), (trial, name)
+            assert list(a.tables) == list(b.tables)
+            for k in a.tables:
+                assert b.tables[k].dtype == np.int32 and np.array_equal(a.tables[k], b.tables[k]), (trial, k)
+        fa, oa = BAGraphHost(ii, jj, kf0, kf1).packed()
+        fb, ob = BAGraphHost.from_numpy(ii, jj, kf0, kf1).packed()
+        assert oa == ob and np.array_equal(fa, fb) and all(o % 4 == 0 for o in oa.values()), trial
