@@ -85,6 +85,13 @@ int nslam_ba_reduced_camera_matrix(const nslam_ba_graph* g, const nslam_ba_buffe
 int nslam_ba_graph_build(const long long* ii, const long long* jj, int E, int kf0, int kf1, int* out, int capacity,
                          int* meta);
 
+/* HOST (A18): order-sensitive choice of new edges from the pairwise flow distances — add_proximity_factors
+ * (visual_frontend.py:712-775).  d: HOST fp32 [(t-kf0)*(t-kf1)], row-major over (i in [kf0,t), j in [kf1,t)), modified in
+ * place; ii1/jj1 [n1]: existing edges (active + bad + inactive); es: HOST int64 [cap][2] out, *n_out edges (may exceed cap:
+ * then 1 is returned and the call is to be repeated with cap >= *n_out). */
+int nslam_proximity_edges(float* d, int kf0, int kf1, int t, const long long* ii1, const long long* jj1, int n1, int rad,
+                          int nms, float thresh, int max_factors, int stereo, long long* es, int cap, int* n_out);
+
 /* A12: dense solve (fp64 Cholesky in one CTA).
  *   Hin [n,n] fp32, vin [n] fp32 (n = 6P);  dx [P,6] fp32 out.
  *   prior_pose_idx >= 0: adds the 1e-4-sigma PriorFactorPose3 on that pose (visual_frontend.py:1234-1252)

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "nslam_pose_prior_error": [_P, _P, _P, _P],
     "nslam_ba_depth": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, c_float, _P],
     "nslam_ba_cov": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, _P, _P, _P],
+    "nslam_proximity_edges": [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_float, c_int, c_int, _P, c_int, _P],
     "nslam_ba_graph_build": [_P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "nslam_ba_cov_reference": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, _P, _P, _P],
     "nslam_ba_pose_cov": [_P, c_int, _P, _P],

@@ -120,3 +120,66 @@ extern "C" int nslam_ba_graph_build(const long long* ii, const long long* jj, in
   o = out + offs[12]; for (int64_t i = 0; i < NVC; i++) o[i] = (int)vval[(size_t)vo[(size_t)i]];
   return 0;
 }
+
+// Host side of add_proximity_factors (visual_frontend.py:712-775 / networks/factor_graph.py:323-387): the order-sensitive
+// choice of new edges from the pairwise flow distances — the reference runs three nested Python loops per existing edge
+// on values it first copies from the GPU.  d: HOST fp32 [(t-kf0)*(t-kf1)] over the meshgrid (i in [kf0,t), j in [kf1,t)),
+// modified in place; ii1/jj1: existing (active + bad + inactive) edges whose neighbourhoods are suppressed first.
+// Writes the chosen directed edges (i, j) pairs to es [cap][2]; returns 0 ok, 1 capacity too small.
+// Same results as nerf_slam_b200/graph.py::proximity_edges_numpy (bit-exact incl. ties, which take index order, and the
+// reference's wrapping of negative flat indices); pinned against the reference's own loops by the recorded traces.
+extern "C" int nslam_proximity_edges(float* d, int kf0, int kf1, int t, const long long* ii1, const long long* jj1, int n1,
+                                     int rad, int nms, float thresh, int max_factors, int stereo, long long* es, int cap,
+                                     int* n_out) {
+  const int64_t W = (int64_t)t - kf1, Hh = (int64_t)t - kf0;
+  const int64_t n = Hh * W;
+  const float INF = __builtin_inff();
+  *n_out = 0;
+  if (Hh < 0 || W < 0) return 2;
+  auto put = [&](int64_t idx) {                 // numpy semantics of d[idx] = inf with a possibly negative index
+    if (idx < 0) idx += n;
+    if (idx >= 0 && idx < n) d[idx] = INF;
+  };
+  for (int64_t a = 0; a < Hh; a++)
+    for (int64_t b = 0; b < W; b++) {
+      const int64_t i = kf0 + a, j = kf1 + b;
+      float& v = d[a * W + b];
+      if (i - rad < j) v = INF;
+      if (v > 100.f) v = INF;
+    }
+  auto suppress = [&](int64_t i, int64_t j) {
+    int64_t r = (i > j ? i - j : j - i) - 2;
+    r = r < 0 ? 0 : (r > nms ? nms : r);
+    for (int64_t di = -r; di <= r; di++)
+      for (int64_t dj = -r; dj <= r; dj++) {
+        if ((di < 0 ? -di : di) + (dj < 0 ? -dj : dj) > r) continue;
+        const int64_t i1 = i + di, j1 = j + dj;
+        if (i1 >= kf0 && i1 < t && j1 >= kf1 && j1 < t) d[(i1 - kf0) * W + (j1 - kf1)] = INF;
+      }
+  };
+  for (int e = 0; e < n1; e++) suppress(ii1[e], jj1[e]);
+  int cnt = 0;
+  bool overflow = false;
+  auto add = [&](int64_t i, int64_t j) {
+    if (cnt < cap) { es[2 * cnt] = i; es[2 * cnt + 1] = j; } else overflow = true;
+    cnt++;
+  };
+  for (int64_t i = kf0; i < t; i++) {
+    if (stereo) { add(i, i); put((i - kf0) * W + (i - kf1)); }
+    for (int64_t j = std::max<int64_t>(i - rad - 1, 0); j < i; j++) { add(i, j); add(j, i); put((i - kf0) * W + (j - kf1)); }
+  }
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t k = 0; k < n; k++) order[(size_t)k] = k;
+  std::vector<float> d0(d, d + n);              // the order is fixed by the values BEFORE the selection loop mutates them
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return d0[(size_t)a] < d0[(size_t)b]; });
+  for (int64_t s = 0; s < n; s++) {
+    const int64_t k = order[(size_t)s];
+    if (d[k] > thresh) continue;
+    if (cnt > max_factors) break;
+    const int64_t i = kf0 + k / W, j = kf1 + k % W;
+    add(i, j); add(j, i);
+    suppress(i, j);
+  }
+  *n_out = cnt;
+  return overflow ? 1 : 0;
+}

@@ -12,6 +12,26 @@ def _diamonds(nms):
 
 
 def proximity_edges(d, ii, jj, ii1, jj1, kf0, kf1, t, rad, nms, thresh, max_factors, stereo):
+    """The selection through the native host routine nslam_proximity_edges (csrc/ba_graph_host.cu); same arguments and
+    results as proximity_edges_numpy below (the check in tests/test_cpu_graph.py)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load(require_cuda=False)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    i1 = np.ascontiguousarray(ii1, dtype=np.int64).reshape(-1); j1 = np.ascontiguousarray(jj1, dtype=np.int64).reshape(-1)
+    n_out = ctypes.c_int(0)
+    # forced edges: <= 2 (rad + 1) + 1 per frame; the selection loop stops once the count exceeds max_factors
+    cap = max(int(t) - int(kf0), 0) * (2 * int(rad) + 3) + max(int(max_factors), 0) + 8
+    es = np.empty((cap, 2), np.int64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.nslam_proximity_edges(P(d), int(kf0), int(kf1), int(t), P(i1), P(j1), int(i1.shape[0]), int(rad), int(nms),
+                                   float(thresh), int(max_factors), int(bool(stereo)), P(es), cap, ctypes.byref(n_out))
+    if rc != 0:
+        raise RuntimeError(f"nslam_proximity_edges failed ({rc}; {n_out.value} edges, capacity {cap})")
+    return es[:n_out.value].copy()
+
+
+def proximity_edges_numpy(d, ii, jj, ii1, jj1, kf0, kf1, t, rad, nms, thresh, max_factors, stereo):
     """d: fp32 distances over the meshgrid (ii, jj) = [kf0,t) x [kf1,t) (row-major), MODIFIED in place;
     ii1/jj1: existing (active + bad + inactive) edges whose neighbourhoods are suppressed first.
     Returns the selected directed edges [n,2] in the reference's order."""

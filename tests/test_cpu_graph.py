@@ -3,7 +3,7 @@ as the loop-for-loop restatement of the reference (oracle/graph.py)"""
 import numpy as np
 import pytest
 
-from nerf_slam_b200.graph import proximity_edges
+from nerf_slam_b200.graph import proximity_edges, proximity_edges_numpy
 from oracle.graph import add_proximity_factors_edges
 
 
@@ -25,8 +25,9 @@ def test_proximity_edges_bit_exact(seed):
     ii1 = rng.integers(0, t, ne); jj1 = rng.integers(0, t, ne)
     ix, jx = np.meshgrid(np.arange(kf0, t), np.arange(kf1, t), indexing="ij")
     ref = add_proximity_factors_edges(d, kf0, kf1, t, ii1, jj1, rad, nms, thresh, max_factors, stereo)
-    got = proximity_edges(d.copy(), ix.reshape(-1), jx.reshape(-1), ii1, jj1, kf0, kf1, t, rad, nms, thresh, max_factors, stereo)
-    assert got.shape == ref.shape and np.array_equal(got, ref)
+    for fn in (proximity_edges, proximity_edges_numpy):           # native host routine (the product), vectorised numpy twin
+        got = fn(d.copy(), ix.reshape(-1), jx.reshape(-1), ii1, jj1, kf0, kf1, t, rad, nms, thresh, max_factors, stereo)
+        assert got.shape == ref.shape and np.array_equal(got, ref), fn.__name__
 
 
 def test_proximity_edges_empty_and_single():
@@ -61,3 +62,30 @@ def test_native_and_vectorised_ba_graph_tables_equal_the_loop_formulation():
         fa, oa = BAGraphHost(ii, jj, kf0, kf1).packed()
         fb, ob = BAGraphHost.from_numpy(ii, jj, kf0, kf1).packed()
         assert oa == ob and np.array_equal(fa, fb) and all(o % 4 == 0 for o in oa.values()), trial
+
+
+def test_native_proximity_selection_equals_numpy_on_many_windows():
+    """nslam_proximity_edges (csrc/ba_graph_host.cu) vs proximity_edges_numpy: ties, > 100 cut-off, all nms radii, stereo,
+    the max_factors break, negative (wrapping) flat indices; windows that the reference's own indexing rejects are skipped"""
+    ok = 0
+    for seed in range(1200):
+        rng = np.random.default_rng(10_000 + seed)
+        t = int(rng.integers(1, 30)); kf0 = int(rng.integers(0, t)); kf1 = int(rng.integers(0, t))
+        if seed % 3 == 0:
+            kf0 = max(t - 5, 0); kf1 = max(t - 25, 0)
+        if seed % 5 == 0:
+            kf0 = kf1 = 0
+        rad = int(rng.integers(1, 4)); nms = int(rng.integers(0, 4)); stereo = bool(rng.integers(0, 2))
+        mf = int(rng.integers(4, 120)); thresh = float(rng.uniform(5, 40))
+        n = (t - kf0) * (t - kf1)
+        d = rng.uniform(0, 60, n).astype(np.float32); d[rng.random(n) < 0.05] = 150.0; d[rng.random(n) < 0.1] = np.float32(7.5)
+        ne = int(rng.integers(0, 40)); ii1 = rng.integers(0, t, ne); jj1 = rng.integers(0, t, ne)
+        ix, jx = np.meshgrid(np.arange(kf0, t), np.arange(kf1, t), indexing="ij")
+        try:
+            a = proximity_edges_numpy(d.copy(), ix.reshape(-1), jx.reshape(-1), ii1, jj1, kf0, kf1, t, rad, nms, thresh, mf, stereo)
+        except IndexError:
+            continue
+        b = proximity_edges(d.copy(), ix.reshape(-1), jx.reshape(-1), ii1, jj1, kf0, kf1, t, rad, nms, thresh, mf, stereo)
+        assert a.shape == b.shape and np.array_equal(a, b), seed
+        ok += 1
+    assert ok > 1000
