@@ -27,6 +27,8 @@ echo "slam_demo synthetic exit $?" >> gpurun_out/summary.txt
 python -c "from nerf_slam_b200 import datasets, synthetic; datasets.write_transforms_dataset(synthetic.SyntheticRoom(640, 480, 60), '/tmp/nslam_ds')" \
   && timeout 300 python examples/slam_demo.py --dataset_dir=/tmp/nslam_ds --dataset_name=nerf --buffer=60 --slam --fusion=nerf --eval > gpurun_out/demo_files.log 2>&1
 echo "slam_demo files exit $?" >> gpurun_out/summary.txt
+# 3c. host-side timers after the native graph / proximity routines (compare with profiles/r01_host_timers_run21.log)
+NSLAM_TIMERS=1 timeout 300 python tools/host_profile.py > gpurun_out/host_timers.log 2>&1
 # 4. hardware question for the next convolution redesign (one halo box for all nine taps): see tools/probes/
 timeout 200 python tools/probes/run_umma_probe.py > gpurun_out/umma_probe.log 2>&1
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
@@ -36,4 +38,4 @@ echo "suite with rows kernel exit $?" >> gpurun_out/summary.txt
 NSLAM_CORRVOL_ROWS=1 timeout 400 python bench.py > gpurun_out/bench_rows.json 2> gpurun_out/bench_rows.err
 echo "bench with rows kernel exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -n 15 gpurun_out/pending_tests.log; tail -n 25 gpurun_out/pending_droid.log; tail -n 5 gpurun_out/corr_rows_tests.log; tail -n 8 gpurun_out/conv_pairs_tests.log; grep -h "conv_igemm" gpurun_out/kernel_table_pairs.log | head -8; grep -h "conv_igemm" gpurun_out/kernel_table_default.log | head -8
-tail -n 3 gpurun_out/demo_synthetic.log; tail -n 3 gpurun_out/demo_files.log; cat gpurun_out/umma_probe.log | head -40; head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
+head -n 2 gpurun_out/host_timers.log; tail -n 3 gpurun_out/demo_synthetic.log; tail -n 3 gpurun_out/demo_files.log; cat gpurun_out/umma_probe.log | head -40; head -1 gpurun_out/microbench_tiled.jsonl; head -1 gpurun_out/microbench_rows.jsonl; tail -n 3 gpurun_out/suite_with_rows.log; cut -c1-300 gpurun_out/bench_rows.json
