@@ -25,7 +25,7 @@ pr.disable()
 dt = time.perf_counter() - t0
 print("host section timers (ms total, calls):", fe.timers.report())
 print(f"64 frames in {dt * 1e3:.1f} ms -> {dt / 64 * 1e3:.2f} ms/frame, kf now {fe.kf_idx}, updates {fe.stats['updates']}")
-for key in ("cumulative", "tottime"):
+for key in (("cumulative", "tottime") if os.environ.get("NSLAM_CPROFILE", "1") == "1" else ()):
     s = io.StringIO()
     pstats.Stats(pr, stream=s).sort_stats(key).print_stats(45)
     print(s.getvalue()[:9000])

@@ -28,7 +28,7 @@ python -c "from nerf_slam_b200 import datasets, synthetic; datasets.write_transf
   && timeout 300 python examples/slam_demo.py --dataset_dir=/tmp/nslam_ds --dataset_name=nerf --buffer=60 --slam --fusion=nerf --eval > gpurun_out/demo_files.log 2>&1
 echo "slam_demo files exit $?" >> gpurun_out/summary.txt
 # 3c. host-side timers after the native graph / proximity routines (compare with profiles/r01_host_timers_run21.log)
-NSLAM_TIMERS=1 timeout 300 python tools/host_profile.py > gpurun_out/host_timers.log 2>&1
+NSLAM_TIMERS=1 NSLAM_CPROFILE=0 timeout 300 python tools/host_profile.py > gpurun_out/host_timers.log 2>&1
 # 4. hardware question for the next convolution redesign (one halo box for all nine taps): see tools/probes/
 timeout 200 python tools/probes/run_umma_probe.py > gpurun_out/umma_probe.log 2>&1
 NSLAM_E=16 timeout 200 python tools/microbench.py 2> /dev/null | head -3 > gpurun_out/microbench_tiled.jsonl
