@@ -197,21 +197,19 @@ class SlamNerfJob:
 
     def _send(self, viz):
         torch = self.torch
-        from nerf_slam_b200.nerf_fusion import _pose_tq_to_c2w
         if viz is None or "cam0_poses" not in viz:
             z = torch.zeros(0, dtype=torch.long, device=self.dev)
             self.handoff.send(z, None, torch.zeros(0, 3, H_IMG, W_IMG, dtype=torch.uint8, device=self.dev), None, None)
             return
-        c2w = torch.as_tensor(_pose_tq_to_c2w(viz.get("cam0_poses_host", viz["cam0_poses"]))[:, :3, :4], device=self.dev, dtype=torch.float32)
-        self.handoff.send(viz["viz_idx"], c2w, viz["cam0_images"], viz["cam0_idepths_up"], viz["cam0_depths_cov_up"])
+        self.handoff.send(viz["viz_idx"], viz["cam0_poses"], viz["cam0_images"], viz["cam0_idepths_up"], viz["cam0_depths_cov_up"])
 
     def _recv(self):
         n, last, data = self.handoff.recv()
         if n:
-            idx, c2w, img, idep, cov = data
+            idx, tq, img, idep, cov = data
             intr = self.room.calib.camera_model.numpy()
-            self.nf.ngp.nerf.training.update_training_images_device(idx.tolist(), c2w.double().cpu().numpy(), img, idep, cov,
-                                                                    intr[:2], intr[2:])
+            self.nf.ngp.nerf.training.update_training_images_device(idx.tolist(), None, img, idep, cov, intr[:2], intr[2:],
+                                                                    cam_T_world=tq)
 
     def drain_results(self):
         """all asynchronous result read-backs of the e2e arm have landed on the host"""

@@ -144,6 +144,27 @@ int nslam_ba_gn_iterations(const nslam_ba_graph* g, const nslam_ba_buffers* b, i
                            double* work, float* dx, float* Linv, float* prior_err, int* status,
                            float clamp_min, void* stream);
 
+/* A14 as the live path uses it: covariances written in place into the keyframe arenas (idepths_cov, depths_cov
+ * [buffer,HW]: rows kx[k]; pose_cov [buffer,6,6]: rows kf0..kf0+P-1; visual_frontend.py:1192-1194,1228-1230).
+ * mode 1 = reference-exact (as nslam_ba_cov_reference), 0 = intended formula.  guard: DEVICE int or NULL; non-zero
+ * (failed factorisation) -> nothing is written.  Mscratch: [6P*6P + 36] floats. */
+int nslam_ba_cov_arena(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float* Linv, float* Mscratch,
+                       int mode, const int* guard, float* idepths_cov, float* depths_cov, float* pose_cov,
+                       void* stream);
+
+/* The live front end's BA step in one host call (RaftVisualFrontend.ba, visual_frontend.py:1071-1232):
+ * nslam_ba_gn_iterations + nslam_ba_cov_arena (cov_mode < 0: no covariances).  status: DEVICE int[2] —
+ * [0] = 1 when the LAST factorisation failed, [1] += 1 per failed factorisation (cumulative counter owned by the
+ * caller).  A failed iteration leaves poses / depths / covariances untouched (the reference's gtsam solve raises).
+ * lm, ep: Levenberg damping diag += ep + lm*diag of the pose system (0, 0 on the live path). */
+int nslam_ba_frontend_update(const nslam_ba_graph* g, const nslam_ba_buffers* b, int iters,
+                             float* world_T_body, float* cam_T_world, const float* cam_T_body,
+                             int prior_pose_idx, const float* prior_pose, float prior_info,
+                             float lm, float ep,
+                             double* work, float* dx, float* Linv, float* prior_err, int* status,
+                             float clamp_min, int cov_mode, float* Mscratch, float* idepths_cov,
+                             float* depths_cov, float* pose_cov, void* stream);
+
 /* pixels per CTA tile of the BA kernels: nslam_ba_buffers.T = ceil(ht*wd / tile) */
 int nslam_ba_tile_pixels(void);
 

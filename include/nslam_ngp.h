@@ -73,6 +73,12 @@ int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, co
                           float bg_b, float* out_rgbd, void* stream);
 int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream);
+/* process_slam + send_data (fusion/nerf_fusion.py:140-289) for a whole packet in one launch, device to device: images,
+ * depths (1 / idepth), covariances into slots ids[k]; camera records from the packet's cam_T_world poses [n,7] (t, q_xyzw;
+ * world_T_cam 3x4 = inverse, nerf scale 1 / offset 0) or untouched when cam_T_world is NULL.  ids: DEVICE int64 [n]. */
+int nslam_ngp_ingest_batch(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
+                           const long long* ids, int n, int H, int W, void* rgba, float* depth, float* depth_cov,
+                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* stream);
 
 /* tensor-core (tcgen05) variants of the network forward / backward, fused with the hash encoding
  * (csrc/ngp_tc.cu).  `packed` = 61 440-byte buffer of fp16 UMMA-ready weight images (forward images

@@ -87,6 +87,9 @@ _SIGNATURES = {
     "nslam_ba_pose_cov": [_P, c_int, _P, _P],
     "nslam_ba_gn_iterations": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), c_int, _P, _P, _P, c_int, _P,
                                c_float, _P, _P, _P, _P, _P, c_float, _P],
+    "nslam_ba_cov_arena": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P, _P, c_int, _P, _P, _P, _P, _P],
+    "nslam_ba_frontend_update": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), c_int, _P, _P, _P, c_int, _P,
+                                 c_float, c_float, c_float, _P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P],
     # Path B (include/nslam_ngp.h); struct pointers are passed with ctypes.byref
     "nslam_ngp_train_step": [_P, _P, _P, c_int, ctypes.c_uint, c_float, c_float, c_float, c_float, c_int, _P],
     "nslam_ngp_adam": [_P, c_int, c_float, c_float, c_float, c_float, c_float, _P],
@@ -96,6 +99,7 @@ _SIGNATURES = {
     "nslam_ngp_density_sample_tc": [_P, _P, c_int, ctypes.c_uint, c_float, c_int, _P],
     "nslam_ngp_render_tile": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P],
     "nslam_ngp_ingest_image": [_P, _P, _P, c_int, c_int, _P, _P, _P, _P],
+    "nslam_ngp_ingest_batch": [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P],
     "nslam_ngp_pack_mlp": [_P, _P, _P],
     "nslam_ngp_forward_tc": [_P, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P],
     "nslam_ngp_backward_tc": [_P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int, _P],

@@ -19,6 +19,7 @@
 //    (deterministic order, fp64 accumulation like the reference's Eigen path), factorised by a
 //    single-CTA fp64 Cholesky (n <= 168 in shared memory) and the SE3/inverse-depth updates
 //    follow on the same stream.
+#include <atomic>
 #include "common.cuh"
 #include "../../include/nslam_ba.h"
 
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256)
 ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, int n,
                 int prior_idx, const float* __restrict__ prior_err, float prior_info, float lm,
                 float ep, double* __restrict__ work, float* __restrict__ dx,
-                float* __restrict__ Linv, int* __restrict__ status) {
+                float* __restrict__ Linv, int* __restrict__ status, int* __restrict__ fail_count) {
   extern __shared__ double sA[];
   double* A = SMEM ? sA : work;
   double* y = work + (size_t)n * n;  // rhs / solution
@@ -461,6 +462,7 @@ ba_solve_kernel(const float* __restrict__ Hin, const float* __restrict__ vin, in
     for (int id = tid; id < n; id += nt) dx[id] = 0.f;
     if (Linv) for (int id = tid; id < n * n; id += nt) Linv[id] = 0.f;
     if (tid == 0 && status) *status = 1;
+    if (tid == 0 && fail_count) *fail_count += 1;     // single CTA, stream-ordered: no atomic needed
     return;
   }
   // L is now in the lower triangle of A (diagonal included); diag[] holds 1 / L[i][i].
@@ -576,9 +578,10 @@ __device__ inline void d_pose3_expmap(const double* xi, double* dt, double* dq) 
 
 __global__ void ba_retract_kernel(float* __restrict__ wTb, float* __restrict__ cTw,
                                   const float* __restrict__ cTb, const float* __restrict__ dx,
-                                  int kf0, int P) {
+                                  int kf0, int P, const int* __restrict__ guard) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
+  if (guard && *guard) return;      // the solve of this iteration failed: leave the state untouched
   float* T = wTb + (size_t)(kf0 + i) * 7;
   double t[3] = {T[0], T[1], T[2]}, q[4] = {T[3], T[4], T[5], T[6]};
   double xi[6];
@@ -660,7 +663,8 @@ __global__ void pose_prior_error_kernel(const float* __restrict__ x, const float
 // A13: depth back-substitution, grid (T, K)
 __global__ void __launch_bounds__(TILE)
 ba_depth_kernel(nslam_ba_graph g, nslam_ba_buffers b, const float* __restrict__ dx,
-                float clamp_min) {
+                float clamp_min, const int* __restrict__ guard) {
+  if (guard && *guard) return;      // failed solve: no depth step either (the live path's gtsam solve would raise)
   const int k = blockIdx.y;
   const int hw = b.ht * b.wd;
   const int p = blockIdx.x * TILE + threadIdx.x;
@@ -754,6 +758,23 @@ __global__ void ba_pose_cov_kernel(const float* __restrict__ Linv, int P, float*
 
 }  // namespace nslam
 
+namespace nslam {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was configured per device
+// (a process may drive several GPUs, or reset one) instead of once per process
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kernel, size_t smem, std::atomic<size_t>* cache /* [NSLAM_MAX_DEVICES] */) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= NSLAM_MAX_DEVICES) dev = NSLAM_MAX_DEVICES - 1, cache[dev] = 0;   // overflow slot: always set
+  if (smem <= cache[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) cache[dev].store(smem, std::memory_order_release);
+  return e;
+}
+}  // namespace nslam
+
 extern "C" {
 
 int nslam_ba_reduced_camera_matrix(const nslam_ba_graph* g, const nslam_ba_buffers* b,
@@ -774,12 +795,10 @@ int nslam_ba_reduced_camera_matrix(const nslam_ba_graph* g, const nslam_ba_buffe
   }
   const size_t smem = ((size_t)6 * g->RMAX * (TILE + 1) + 2 * TILE) * sizeof(float);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ba_schur_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<size_t> configured[NSLAM_MAX_DEVICES];
+  {
+    cudaError_t e = ensure_dyn_smem(ba_schur_kernel, smem, configured);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   ba_schur_kernel<<<grid, TILE, smem, st>>>(*g, *b);
   NSLAM_CHECK_LAUNCH();
@@ -793,29 +812,31 @@ int nslam_ba_reduced_camera_matrix(const nslam_ba_graph* g, const nslam_ba_buffe
   return 0;
 }
 
-int nslam_ba_solve(const float* Hin, const float* vin, int P, int prior_pose_idx,
-                   const float* prior_err, float prior_info, float lm, float ep, double* work,
-                   float* dx, float* Linv, int* status, void* stream) {
+static int launch_solve(const float* Hin, const float* vin, int P, int prior_pose_idx,
+                        const float* prior_err, float prior_info, float lm, float ep, double* work,
+                        float* dx, float* Linv, int* status, int* fail_count, cudaStream_t st) {
   using namespace nslam;
   const int n = 6 * P;
   const size_t smem = (size_t)n * n * sizeof(double);
-  cudaStream_t st = (cudaStream_t)stream;
   if (smem <= 200 * 1024) {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      configured = 200 * 1024;
-    }
+    static std::atomic<size_t> configured[NSLAM_MAX_DEVICES];
+    cudaError_t e = ensure_dyn_smem(ba_solve_kernel<true>, smem > 48 * 1024 ? (size_t)200 * 1024 : smem, configured);
+    if (e != cudaSuccess) return (int)e;
     ba_solve_kernel<true><<<1, 256, smem, st>>>(Hin, vin, n, prior_pose_idx, prior_err, prior_info,
-                                                lm, ep, work, dx, Linv, status);
+                                                lm, ep, work, dx, Linv, status, fail_count);
   } else {
     ba_solve_kernel<false><<<1, 256, 0, st>>>(Hin, vin, n, prior_pose_idx, prior_err, prior_info,
-                                              lm, ep, work, dx, Linv, status);
+                                              lm, ep, work, dx, Linv, status, fail_count);
   }
   NSLAM_CHECK_LAUNCH();
   return 0;
+}
+
+int nslam_ba_solve(const float* Hin, const float* vin, int P, int prior_pose_idx,
+                   const float* prior_err, float prior_info, float lm, float ep, double* work,
+                   float* dx, float* Linv, int* status, void* stream) {
+  return launch_solve(Hin, vin, P, prior_pose_idx, prior_err, prior_info, lm, ep, work, dx, Linv, status, nullptr,
+                      (cudaStream_t)stream);
 }
 
 /* pixels per CTA tile of the BA kernels: callers size `part`/`spart` with T = ceil(ht*wd / tile) */
@@ -825,7 +846,7 @@ int nslam_ba_retract(float* world_T_body, float* cam_T_world, const float* cam_T
                      const float* dx, int kf0, int P, void* stream) {
   if (P <= 0) return 0;
   nslam::ba_retract_kernel<<<(P + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
-      world_T_body, cam_T_world, cam_T_body, dx, kf0, P);
+      world_T_body, cam_T_world, cam_T_body, dx, kf0, P, nullptr);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }
@@ -846,7 +867,7 @@ int nslam_pose_prior_error(const float* world_T_body_k, const float* prior_pose,
 int nslam_ba_depth(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float* dx,
                    float clamp_min, void* stream) {
   dim3 grid(b->T, g->K);
-  nslam::ba_depth_kernel<<<grid, nslam::TILE, 0, (cudaStream_t)stream>>>(*g, *b, dx, clamp_min);
+  nslam::ba_depth_kernel<<<grid, nslam::TILE, 0, (cudaStream_t)stream>>>(*g, *b, dx, clamp_min, nullptr);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }
@@ -860,12 +881,10 @@ int nslam_ba_cov(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float
   NSLAM_CHECK_LAUNCH();
   const size_t smem = (size_t)g->RMAX * g->RMAX * 36 * sizeof(float);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ba_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+  static std::atomic<size_t> configured[NSLAM_MAX_DEVICES];
+  {
+    cudaError_t e = ensure_dyn_smem(ba_cov_kernel, smem, configured);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   dim3 grid(b->T, g->K);
   ba_cov_kernel<<<grid, TILE, smem, st>>>(*g, *b, Mscratch, z_cov, depth_cov);
@@ -903,6 +922,43 @@ int nslam_ba_gn_iterations(const nslam_ba_graph* g, const nslam_ba_buffers* b, i
     r = nslam_ba_depth(g, b, dx, clamp_min, stream);
     if (r) return r;
   }
+  return 0;
+}
+
+/* The live front end's whole BA step in ONE host call (visual_frontend.py:1097-1230): `iters` Gauss-Newton iterations
+ * as nslam_ba_gn_iterations, then the covariance block written straight into the keyframe arenas.  A failed
+ * factorisation (status[0] = 1, status[1] += 1) leaves poses, depths and covariances of that iteration untouched —
+ * the reference's gtsam solve raises there; its CUDA twin zeroes dx but still applies dz = Q w.
+ * lm, ep: Levenberg damping of the pose system, diag += ep + lm*diag (0, 0 on the live path; DROID's FactorGraph
+ * passes 1e-4 / 0.1, networks/factor_graph.py:251-253). */
+int nslam_ba_frontend_update(const nslam_ba_graph* g, const nslam_ba_buffers* b, int iters,
+                             float* world_T_body, float* cam_T_world, const float* cam_T_body,
+                             int prior_pose_idx, const float* prior_pose, float prior_info,
+                             float lm, float ep,
+                             double* work, float* dx, float* Linv, float* prior_err, int* status,
+                             float clamp_min, int cov_mode, float* Mscratch, float* idepths_cov,
+                             float* depths_cov, float* pose_cov, void* stream) {
+  using namespace nslam;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool want_cov = cov_mode >= 0;
+  for (int it = 0; it < iters; it++) {
+    int r = nslam_ba_reduced_camera_matrix(g, b, stream);
+    if (r) return r;
+    if (prior_pose_idx >= 0) {
+      r = nslam_pose_prior_error(world_T_body + (size_t)(g->kf0 + prior_pose_idx) * 7, prior_pose, prior_err, stream);
+      if (r) return r;
+    }
+    r = launch_solve(b->H, b->v, g->P, prior_pose_idx, prior_err, prior_pose_idx >= 0 ? prior_info : 0.f, lm, ep,
+                     work, dx, (want_cov && it == iters - 1) ? Linv : nullptr, status, status + 1, st);
+    if (r) return r;
+    ba_retract_kernel<<<(g->P + 63) / 64, 64, 0, st>>>(world_T_body, cam_T_world, cam_T_body, dx, g->kf0, g->P, status);
+    NSLAM_CHECK_LAUNCH();
+    dim3 grid(b->T, g->K);
+    ba_depth_kernel<<<grid, TILE, 0, st>>>(*g, *b, dx, clamp_min, status);
+    NSLAM_CHECK_LAUNCH();
+  }
+  if (want_cov && iters > 0)
+    return nslam_ba_cov_arena(g, b, Linv, Mscratch, cov_mode, status, idepths_cov, depths_cov, pose_cov, stream);
   return 0;
 }
 

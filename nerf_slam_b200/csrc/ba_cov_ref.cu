@@ -39,10 +39,15 @@ __global__ void cov_ref_msum_kernel(const float* __restrict__ M, int P, float* _
   Msum[threadIdx.x] = s;
 }
 
-// grid (ceil(HW / COV_TILE), K)
+// grid (ceil(HW / COV_TILE), K).  ARENA: output row of depth map k is its FRAME id kx[k] (the front end's [buffer,HW]
+// arenas) instead of k; `guard` (device int, may be NULL): non-zero = the solve failed, write nothing.
+// reference_quirk = false: the intended formula for every map (what nslam_ba_cov computes).
+template <bool ARENA>
 __global__ void __launch_bounds__(COV_TILE)
 ba_cov_ref_kernel(nslam_ba_graph g, nslam_ba_buffers b, const float* __restrict__ M, const float* __restrict__ Msum,
-                  float* __restrict__ z_cov, float* __restrict__ depth_cov) {
+                  float* __restrict__ z_cov, float* __restrict__ depth_cov, bool reference_quirk,
+                  const int* __restrict__ guard) {
+  if (guard && *guard) return;
   const int k = blockIdx.y;
   const int hw = b.ht * b.wd;
   const int n = 6 * g.P;
@@ -50,8 +55,9 @@ ba_cov_ref_kernel(nslam_ba_graph g, nslam_ba_buffers b, const float* __restrict_
   if (p >= hw) return;
   const float q = b.Q[(size_t)k * hw + p];
   const int win = g.kx[k] - g.kf0;
+  const size_t orow = ARENA ? (size_t)g.kx[k] : (size_t)k;
   float acc = 0.f;
-  if (win >= 0 && win < g.P) {
+  if (reference_quirk && win >= 0 && win < g.P) {
     // optimised frame: every pose row holds Ei[win] (E rows 0..P-1 are Ei)
     float e[6];
 #pragma unroll
@@ -87,12 +93,24 @@ ba_cov_ref_kernel(nslam_ba_graph g, nslam_ba_buffers b, const float* __restrict_
     }
   }
   const float zc = q + q * q * acc;
-  z_cov[(size_t)k * hw + p] = zc;
+  z_cov[orow * hw + p] = zc;
   if (depth_cov) {
     const float d = b.disps[(size_t)g.kx[k] * hw + p];
     const float d2 = d * d;
-    depth_cov[(size_t)k * hw + p] = zc / (d2 * d2);
+    depth_cov[orow * hw + p] = zc / (d2 * d2);
   }
+}
+
+// block-diagonal 6x6 blocks of (L L^T)^-1 = Linv^T Linv, written to rows kf0 + i of the [buffer,6,6] pose-covariance arena
+__global__ void pose_cov_arena_kernel(const float* __restrict__ Linv, int P, int kf0, float* __restrict__ sg,
+                                      const int* __restrict__ guard) {
+  if (guard && *guard) return;
+  const int i = blockIdx.x;
+  const int r = threadIdx.x / 6, c = threadIdx.x % 6;
+  const int n = 6 * P;
+  float s = 0.f;
+  for (int k = 0; k < n; k++) s += Linv[(size_t)k * n + i * 6 + r] * Linv[(size_t)k * n + i * 6 + c];
+  sg[(size_t)(kf0 + i) * 36 + threadIdx.x] = s;
 }
 
 }  // namespace nslam
@@ -110,7 +128,36 @@ extern "C" int nslam_ba_cov_reference(const nslam_ba_graph* g, const nslam_ba_bu
   NSLAM_CHECK_LAUNCH();
   const int hw = b->ht * b->wd;
   dim3 grid((hw + COV_TILE - 1) / COV_TILE, g->K);
-  ba_cov_ref_kernel<<<grid, COV_TILE, 0, st>>>(*g, *b, Mscratch, Msum, z_cov, depth_cov);
+  ba_cov_ref_kernel<false><<<grid, COV_TILE, 0, st>>>(*g, *b, Mscratch, Msum, z_cov, depth_cov, true, nullptr);
   NSLAM_CHECK_LAUNCH();
+  return 0;
+}
+
+/* The live path's covariance block (visual_frontend.py:1164-1230) in three launches, results written in place into
+ * the keyframe arenas: idepths_cov / depths_cov [buffer,HW] rows kx[k], pose_cov [buffer,6,6] rows kf0..kf0+P-1.
+ * mode 1 = the reference's real behaviour (Ei broadcast, see the head of this file), 0 = the intended formula.
+ * guard: device int, non-zero = the factorisation failed -> nothing is written. */
+extern "C" int nslam_ba_cov_arena(const nslam_ba_graph* g, const nslam_ba_buffers* b, const float* Linv, float* Mscratch,
+                                  int mode, const int* guard, float* idepths_cov, float* depths_cov, float* pose_cov,
+                                  void* stream) {
+  using namespace nslam;
+  const int n = 6 * g->P;
+  if (n <= 0) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  cov_ref_M_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(Linv, n, Mscratch);
+  NSLAM_CHECK_LAUNCH();
+  float* Msum = Mscratch + (size_t)n * n;
+  if (mode == 1) {
+    cov_ref_msum_kernel<<<1, 36, 0, st>>>(Mscratch, g->P, Msum);
+    NSLAM_CHECK_LAUNCH();
+  }
+  const int hw = b->ht * b->wd;
+  dim3 grid((hw + COV_TILE - 1) / COV_TILE, g->K);
+  ba_cov_ref_kernel<true><<<grid, COV_TILE, 0, st>>>(*g, *b, Mscratch, Msum, idepths_cov, depths_cov, mode == 1, guard);
+  NSLAM_CHECK_LAUNCH();
+  if (pose_cov) {
+    pose_cov_arena_kernel<<<g->P, 36, 0, st>>>(Linv, g->P, g->kf0, pose_cov, guard);
+    NSLAM_CHECK_LAUNCH();
+  }
   return 0;
 }

@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #define NSLAM_MIN_DEPTH 0.25f   // src/droid_kernels.cu:26
+#define NSLAM_MAX_DEVICES 64    // per-device caches of kernel attributes (last slot = overflow: always re-set)
 
 #define NSLAM_CHECK_LAUNCH()                         \
   do {                                               \

@@ -746,6 +746,49 @@ __global__ void ingest_image_kernel(const uint8_t* __restrict__ rgb_chw, const f
   depth_cov[i] = dcov[i];
 }
 
+// the whole SLAM packet in ONE launch (grid: pixel blocks x keyframes): images / depths / covariances into their
+// slots `ids[k]`, and the camera record of each slot from the packet's cam_T_world pose [t, q_xyzw]:
+// world_T_cam = inverse, 3x4 row-major (fusion/nerf_fusion.py:163-170: scale 1, offset 0), computed in fp64 like the
+// host formulation it replaces.  No host copy of the poses is needed any more (that copy was a device sync per tick).
+__global__ void ingest_batch_kernel(const uint8_t* __restrict__ rgb_chw, const float* __restrict__ idepth,
+                                    const float* __restrict__ dcov, const long long* __restrict__ ids, int H, int W,
+                                    __half* __restrict__ rgba, float* __restrict__ depth, float* __restrict__ depth_cov,
+                                    const float* __restrict__ cam_T_world, float fx, float fy, float cx, float cy,
+                                    Camera* __restrict__ cams) {
+  const int k = blockIdx.y;
+  const size_t hw = (size_t)H * W;
+  const size_t slot = (size_t)ids[k];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cams && blockIdx.x == 0 && threadIdx.x == 0) {
+    const float* p = cam_T_world + (size_t)k * 7;
+    const double t[3] = {p[0], p[1], p[2]};
+    const double x = p[3], y = p[4], z = p[5], w = p[6];
+    // R (cam <- world); world_T_cam = [R^T | -R^T t]
+    const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                            {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                            {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+    Camera c;
+    for (int r = 0; r < 3; r++) {
+      for (int cc = 0; cc < 3; cc++) c.c2w[r * 4 + cc] = (float)R[cc][r];
+      c.c2w[r * 4 + 3] = (float)(-(R[0][r] * t[0] + R[1][r] * t[1] + R[2][r] * t[2]));
+    }
+    c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.w = W; c.h = H;
+    cams[slot] = c;
+  }
+  if (i >= H * W) return;
+  const uint8_t* src = rgb_chw + (size_t)k * 3 * hw;
+  float c[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float s = src[(size_t)ch * hw + i] * (1.f / 255.f);
+    c[ch] = s > 0.04045f ? powf((s + 0.055f) / 1.055f, 2.4f) : s / 12.92f;
+  }
+  __half* o = rgba + (slot * hw + i) * 4;
+  o[0] = __float2half_rn(c[0]); o[1] = __float2half_rn(c[1]); o[2] = __float2half_rn(c[2]); o[3] = __float2half_rn(1.f);
+  depth[slot * hw + i] = 1.0f / idepth[(size_t)k * hw + i];
+  depth_cov[slot * hw + i] = dcov[(size_t)k * hw + i];
+}
+
 }  // namespace ngp
 
 // ============================================================================================
@@ -958,6 +1001,21 @@ int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up,
                            int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream) {
   ngp::ingest_image_kernel<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       rgb_chw, idepth_up, depth_cov_up, H, W, (__half*)rgba_slot, depth_slot, cov_slot);
+  NGP_CHECK_LAUNCH();
+  return 0;
+}
+
+/* B1/B2 in one launch: n keyframes of a SLAM packet (images u8 [n,3,H,W], idepth_up / depth_cov_up [n,H,W], slot ids
+ * [n] int64, cam_T_world [n,7] or NULL) into the trainer's slot arrays (rgba [N,H,W,4] fp16, depth / depth_cov [N,H,W])
+ * and camera records cams [N] (when cam_T_world is given).  All pointers DEVICE. */
+int nslam_ngp_ingest_batch(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
+                           const long long* ids, int n, int H, int W, void* rgba, float* depth, float* depth_cov,
+                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* stream) {
+  if (n <= 0) return 0;
+  dim3 grid((H * W + 255) / 256, n);
+  ngp::ingest_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      rgb_chw, idepth_up, depth_cov_up, ids, H, W, (__half*)rgba, depth, depth_cov, cam_T_world, fx, fy, cx, cy,
+      (ngp::Camera*)cams);
   NGP_CHECK_LAUNCH();
   return 0;
 }

@@ -8,8 +8,9 @@ The keyframe hand-off replaces the reference's `.to("cpu")` + torch.multiprocess
 (slam/visual_frontends/visual_frontend.py:1355-1360, "super slow"): dirty keyframes are packed into
 ONE device buffer and broadcast rank 0 -> trainers with NCCL over NVLink (device to device, no host
 staging); a 4-int header (n_keyframes, H, W, is_last) precedes the payload.
-Packet layout per keyframe: idx(int32 as 4 bytes) | pose c2w 3x4 fp32 (48 B) | image u8 3xHxW |
-idepth_up fp32 HxW | depth_cov_up fp32 HxW.
+Packet layout per keyframe: idx(int32 as 4 bytes) | pose cam_T_world [t, q_xyzw] fp32 (28 B) + 20 B reserved | image u8
+3xHxW | idepth_up fp32 HxW | depth_cov_up fp32 HxW.  The pose travels as the front end stores it; the receiving trainer's
+ingest kernel turns it into its world_T_cam record (no host copy on either side).
 """
 import numpy as np
 import torch
@@ -20,7 +21,7 @@ def kf_bytes(H, W):
     return 4 + 48 + 3 * H * W + 4 * H * W + 4 * H * W
 
 
-def pack_keyframes(idx, c2w34, images_u8, idepths_up, depths_cov_up, out=None):
+def pack_keyframes(idx, poses_tq, images_u8, idepths_up, depths_cov_up, out=None):
     """tensors on one device -> uint8 buffer [n * kf_bytes]"""
     n, _, H, W = images_u8.shape
     kb = kf_bytes(H, W)
@@ -29,7 +30,7 @@ def pack_keyframes(idx, c2w34, images_u8, idepths_up, depths_cov_up, out=None):
         out = torch.empty(n * kb, dtype=torch.uint8, device=dev)
     v = out[:n * kb].view(n, kb)
     v[:, 0:4] = idx.to(torch.int32).contiguous().view(torch.uint8).view(n, 4)
-    v[:, 4:52] = c2w34.to(torch.float32).contiguous().view(n, 12).view(torch.uint8).view(n, 48)
+    v[:, 4:32] = poses_tq.to(torch.float32).contiguous().view(n, 7).view(torch.uint8).view(n, 28)
     o = 52
     v[:, o:o + 3 * H * W] = images_u8.reshape(n, -1); o += 3 * H * W
     v[:, o:o + 4 * H * W] = idepths_up.to(torch.float32).contiguous().view(n, H * W).view(torch.uint8).view(n, -1); o += 4 * H * W
@@ -41,7 +42,7 @@ def unpack_keyframes(buf, n, H, W):
     kb = kf_bytes(H, W)
     v = buf[:n * kb].view(n, kb)
     idx = v[:, 0:4].contiguous().view(torch.int32).view(n)
-    c2w = v[:, 4:52].contiguous().view(torch.float32).view(n, 3, 4)
+    c2w = v[:, 4:32].contiguous().view(torch.float32).view(n, 7)           # cam_T_world [t, q_xyzw]
     o = 52
     img = v[:, o:o + 3 * H * W].reshape(n, 3, H, W); o += 3 * H * W
     idep = v[:, o:o + 4 * H * W].contiguous().view(torch.float32).view(n, H, W); o += 4 * H * W
@@ -59,13 +60,13 @@ class Handoff:
         self.max_kf = max_kf
         self.bytes_sent = 0
 
-    def send(self, idx, c2w34, images_u8, idepths_up, depths_cov_up, is_last=False):
+    def send(self, idx, poses_tq, images_u8, idepths_up, depths_cov_up, is_last=False):
         n = int(idx.shape[0])
         assert n <= self.max_kf
         self.hdr.copy_(torch.tensor([n, self.H, self.W, int(is_last)], dtype=torch.int32))
         dist.broadcast(self.hdr, src=0, group=self.group)
         if n:
-            pack_keyframes(idx, c2w34, images_u8, idepths_up, depths_cov_up, self.buf)
+            pack_keyframes(idx, poses_tq, images_u8, idepths_up, depths_cov_up, self.buf)
             dist.broadcast(self.buf[:n * kf_bytes(self.H, self.W)], src=0, group=self.group)
             self.bytes_sent += n * kf_bytes(self.H, self.W)
 

@@ -35,6 +35,16 @@ from .graph import proximity_edges
 
 
 # ----------------------------------------------------------------------------------------------- helpers
+def _se3_inverse(tq):
+    """[N,7] (t, q xyzw) -> inverse transforms, same layout"""
+    t, q = tq[:, :3], tq[:, 3:]
+    qi = torch.cat([-q[:, :3], q[:, 3:]], dim=1)
+    u = qi[:, :3]
+    c = torch.cross(u, t, dim=1)
+    rt = t + 2.0 * (qi[:, 3:] * c + torch.cross(u, c, dim=1))          # R(qi) t
+    return torch.cat([-rt, qi], dim=1).contiguous()
+
+
 def coords_grid(ht, wd, device):
     """networks/geom/projective_ops.py:14-19 -> [ht,wd,2] (x,y)"""
     y, x = torch.meshgrid(torch.arange(ht, device=device).float(), torch.arange(wd, device=device).float(), indexing="ij")
@@ -264,14 +274,32 @@ class DepthVideo:
         return d.reshape(n, n) if return_matrix else d
 
     def ba(self, target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False):
-        """A15: dense bundle adjustment of poses [t0,t1) and the depths of the edges' source frames, in place
-        (droid_backends.ba, src/droid.cpp:133-165; the edge list stays on the host)"""
+        """dense bundle adjustment of poses [t0,t1) and the depths of the edges' source frames, in place — what
+        networks/factor_graph.py:251-253,300-301 call on the `video` object (which the reference does not ship).
+
+        Default (`ba_mode = "consistent"`): the linearisation of this code base (body-frame Jacobians in [omega, t]
+        order, src/droid_kernels.cu:376-403) with the matching retraction (right perturbation of world_T_cam, the one
+        the live path's gtsam step applies) and DROID's Levenberg damping `ep + lm*diag` — one host call, edge list
+        stays on the host.  `ba_mode = "reference"` runs droid_backends.ba (A15: ba_cuda, src/droid_kernels.cu:1441-1568)
+        as it is in the reference: the SAME body-frame Jacobians followed by the ORIGINAL DROID left retraction
+        `exp([tau,phi]) * T` (`pose_retr_kernel`) — the two do not belong together (the reference's own comment on
+        `body_poses`: "SEND IDENTITY, this is not supposed to work otw"), the pose step has the wrong parametrisation and
+        the iteration diverges on real data; ba_cuda has no live caller in the reference.  Parity of that loop is kept
+        at the operator level (tests/test_gpu_parity.py::test_droid_backends_ba_all_in_one_loop)."""
         with self.get_lock():
             ih, jh = _host_index(ii), _host_index(jj)
             if t1 is None:
                 t1 = int(max(ih.max(), jh.max())) + 1
-            db.ba_host_edges(self.poses, self.disps, self.intrinsics[0], self.extrinsics, self.disps_sens,
-                             target.contiguous(), weight.contiguous(), eta, ih, jh, t0, t1, itrs, lm, ep, motion_only)
+            if getattr(self, "ba_mode", "consistent") == "reference" or motion_only:
+                db.ba_host_edges(self.poses, self.disps, self.intrinsics[0], self.extrinsics, self.disps_sens,
+                                 target.contiguous(), weight.contiguous(), eta, ih, jh, t0, t1, itrs, lm, ep, motion_only)
+            else:
+                prob = db.BAProblem(self.poses, self.disps, self.intrinsics[0], self.extrinsics, self.disps_sens,
+                                    target.contiguous(), weight.contiguous(), eta.contiguous(), ih, jh, t0, t1)
+                if getattr(self, "_ba_status", None) is None:
+                    self._ba_status = torch.zeros(2, dtype=torch.int32, device=self.device)
+                wTc = _se3_inverse(self.poses)                     # body == camera (extrinsics = identity)
+                prob.frontend_update(itrs, wTc, self.poses, self.extrinsics, self._ba_status, clamp_min=0.0, lm=lm, ep=ep)
             self.disps.clamp_(min=0.001)
 
     def upsample(self, ix, mask):

@@ -18,10 +18,11 @@ from . import _lib
 from .ba_graph import get_graph
 
 _DT = {torch.float16: 0, torch.float32: 1}
-# A14 covariance semantics: "1" (default) = what the reference's block really computes, obtained from
-# the validated kernel (nslam_ba_cov) plus a fix-up of the depth maps of optimised frames in a handful of torch ops;
-# "kernel" = the same in one CUDA kernel (csrc/ba_cov_ref.cu, pending its first hardware run); "0" = the intended formula.
-_COV_MODE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "1")
+# A14 covariance semantics: "kernel" (default) = what the reference's block really computes, in one CUDA
+# kernel (csrc/ba_cov_ref.cu); "1" = the same values from nslam_ba_cov plus a fix-up of the depth maps of optimised
+# frames in a handful of torch ops (kept as an independent cross-check in the tests); "0" = the intended formula.
+# The live front end does not come through here: it uses nslam_ba_frontend_update (covariances written into the arenas).
+_COV_MODE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "kernel")
 
 
 def cov_reference_fixup(M, E, Q, disps_flat, z_cov, d_cov, win_k, win_q, win_f, P):
@@ -109,10 +110,10 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coor
 
 
 def _corrvol_entry(lib, H, W, C):
-    """the row-pair kernel (csrc/corr_volume_rows.cu) is EXPERIMENTAL: opt-in with NSLAM_CORRVOL_ROWS=1 and only
-    for the shapes it supports; everything else runs the validated tiled kernel"""
+    """the row-pair kernel (csrc/corr_volume_rows.cu; bit-identical output, tests/test_gpu_parity.py) for the shapes it
+    supports, the tiled kernel for everything else"""
     import os
-    if os.environ.get("NSLAM_CORRVOL_ROWS", "0") == "1" and C == 128 and H % 2 == 0 and W in (64, 80):
+    if os.environ.get("NSLAM_CORRVOL_ROWS", "1") == "1" and C == 128 and H % 2 == 0 and W in (64, 80):
         return lib.nslam_corr_volume_build_rows
     return lib.nslam_corr_volume_build
 
@@ -356,6 +357,38 @@ class BAProblem:
         self._work = (work, perr)
         return dx, linv, status
 
+    def frontend_update(self, iters, world_T_body, cam_T_world, cam_T_body, status, prior_idx=-1, prior_pose=None,
+                        prior_info=0.0, clamp_min=1e-3, cov_mode=None, idepths_cov=None, depths_cov=None, pose_cov=None,
+                        lm=0.0, ep=0.0):
+        """The live path's whole BA step (visual_frontend.py:1071-1232) as ONE host call on buffers owned by this
+        problem: `iters` Gauss-Newton iterations, then the covariance block written in place into the keyframe arenas
+        (idepths_cov / depths_cov [buffer,ht,wd], pose_cov [buffer,6,6]).  status: int32[2] device tensor owned by the
+        caller ([0] last factorisation failed, [1] cumulative failures); a failed iteration changes nothing.
+        cov_mode: None = no covariances, 1 = reference-exact, 0 = intended formula."""
+        lib = _lib.load()
+        P = self.gh.P
+        n = 6 * P
+        if getattr(self, "_fu", None) is None:
+            dev = self.H.device
+            self._fu = (torch.empty(2 * n * n + 2 * n, dtype=torch.float64, device=dev),
+                        torch.empty(P, 6, dtype=torch.float32, device=dev),
+                        torch.empty(n, n, dtype=torch.float32, device=dev),
+                        torch.zeros(6, dtype=torch.float32, device=dev),
+                        torch.empty(n * n + 36, dtype=torch.float32, device=dev))
+        work, dx, linv, perr, M = self._fu
+        assert status.dtype == torch.int32 and status.numel() >= 2
+        if cov_mode is not None:
+            for t in (idepths_cov, depths_cov, pose_cov):
+                assert t.is_contiguous() and t.dtype == torch.float32
+        _lib.check(lib.nslam_ba_frontend_update(
+            ctypes.byref(self.g), ctypes.byref(self.b), int(iters), _lib.ptr(world_T_body), _lib.ptr(cam_T_world),
+            _lib.ptr(cam_T_body), int(prior_idx), _lib.ptr(prior_pose), float(prior_info), float(lm), float(ep),
+            _lib.ptr(work), _lib.ptr(dx),
+            _lib.ptr(linv), _lib.ptr(perr), _lib.ptr(status), float(clamp_min), -1 if cov_mode is None else int(cov_mode),
+            _lib.ptr(M), _lib.ptr(idepths_cov), _lib.ptr(depths_cov), _lib.ptr(pose_cov), _lib.stream_ptr()),
+            "ba_frontend_update")
+        return dx, linv
+
     def depth_update(self, dx, clamp_min=0.0):
         lib = _lib.load()
         _lib.check(lib.nslam_ba_depth(ctypes.byref(self.g), ctypes.byref(self.b), _lib.ptr(dx),
@@ -363,9 +396,9 @@ class BAProblem:
 
     def covariances(self, linv, reference=None):
         """A14 -> (sigma_g [P,6,6], z_cov [K,ht,wd], depth_cov [K,ht,wd]).
-        reference: None = NSLAM_COV_REFERENCE (default "1"); True / "1" = the reference's block as it really behaves
-        (its broadcast of Ei over the pose rows of optimised frames, visual_frontend.py:1214) = validated kernel + torch
-        fix-up; "kernel" = the same in one CUDA kernel (csrc/ba_cov_ref.cu); False / "0" = the intended formula."""
+        reference: None = NSLAM_COV_REFERENCE (default "kernel"); "kernel" = the reference's block as it really behaves
+        (its broadcast of Ei over the pose rows of optimised frames, visual_frontend.py:1214) in one CUDA kernel
+        (csrc/ba_cov_ref.cu); True / "1" = the same from nslam_ba_cov + torch fix-up; False / "0" = the intended formula."""
         lib = _lib.load()
         gh = self.gh
         dev = self.H.device

@@ -212,6 +212,9 @@ class RaftVisualFrontend:
         self._mean = torch.tensor([0.485, 0.456, 0.406], device=device)[:, None, None]
         self._std = torch.tensor([0.229, 0.224, 0.225], device=device)[:, None, None]
         self.stats = {"updates": 0, "ba_fail": 0}
+        # A14 semantics: 1 = what the reference's covariance block really computes (default), 0 = the
+        # formula its comments describe
+        self.cov_mode = int(getattr(args, "cov_reference", 1))
         self.use_cuda_graphs = bool(getattr(args, "cuda_graphs", True))
         if self.conv_backend != "tcgen05":
             self.use_cuda_graphs = False       # the library path syncs inside GraphAgg (torch.unique)
@@ -229,6 +232,28 @@ class RaftVisualFrontend:
 
     def stop_condition(self):
         return self.stop
+
+    def ba_failures(self, wait=False):
+        """number of failed BA factorisations so far (stats['ba_fail']).  The counter lives on the device; each call
+        consumes the previous asynchronous read-back (if it has landed, or `wait`) and starts the next one, so the hot
+        loop never synchronises on it."""
+        if not self._ba_status.is_cuda:          # CPU harness of the reference-trace tests
+            self.stats["ba_fail"] = int(self._ba_status[1])
+            return self.stats["ba_fail"]
+        ev = self._ba_status_event
+        if ev is not None and (wait or ev.query()):
+            ev.synchronize()
+            self.stats["ba_fail"] = int(self._ba_status_host[1])
+            ev = None
+        if ev is None:
+            self._ba_status_host.copy_(self._ba_status, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record()
+            if wait:
+                ev.synchronize()
+                self.stats["ba_fail"] = int(self._ba_status_host[1])
+                ev = None
+        self._ba_status_event = ev
+        return self.stats["ba_fail"]
 
     # ------------------------------------------------------------------ buffers
     def initialize_buffers(self, image_size):
@@ -266,6 +291,10 @@ class RaftVisualFrontend:
         self.intr0 = self.cam0_intrinsics[0]      # the kernels only ever see the first keyframe's intrinsics
         self.corr_pool = CorrPool(int(getattr(self.args, "corr_slots", 2 * self.max_factors)), ht, wd, dev)
         self._reset_graph()
+        # BA status: [0] = last factorisation failed, [1] = cumulative failures (read back asynchronously: ba_failures())
+        self._ba_status = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._ba_status_host = torch.zeros(2, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(2, dtype=torch.int32)
+        self._ba_status_event = None
         self.viz_idx = np.zeros(B, dtype=bool)          # host-side dirty flags (a device mask would need a sync to read)
 
     def _reset_graph(self):
@@ -688,7 +717,6 @@ class RaftVisualFrontend:
         st.kf1 = kf1
         st.prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
                                self.cam0_idepths_sensed, st.target, st.weight, st.damp, ii, jj, kf0, kf1)
-        st.kx_prob = _lib.h2d(st.prob.gh.tables["kx"].astype(np.int64), dev)
         st.has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
         if self.update_tc is not None and self.use_op_step:
             # the whole update operator as one host call on fixed buffers (csrc/update_step.cu)
@@ -747,16 +775,15 @@ class RaftVisualFrontend:
             st.weight[st.n_in:].copy_(self.gru_estimated_flow_weight.permute(0, 3, 1, 2))
             torch.mul(self.damping[st.kx_ba], 0.2, out=st.damp)
             st.damp.add_(st.EP)
-        dx, linv, status = st.prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
-                                                prior_idx=0 if st.has_prior else -1,
-                                                prior_pose=self.prior_pose if st.has_prior else None,
-                                                prior_info=self.prior_info if st.has_prior else 0.0,
-                                                want_linv=compute_covariances, clamp_min=1e-3)
-        if compute_covariances:
-            sg, z_cov, d_cov = st.prob.covariances(linv)
-            self.world_T_body_cov[st.kf0:st.kf1] = sg
-            self.cam0_idepths_cov[st.kx_prob] = z_cov
-            self.cam0_depths_cov[st.kx_prob] = d_cov
+        # the whole BA step (2 Gauss-Newton iterations + covariance block) is one host call; results land in place
+        # in the pose / depth / covariance arenas; a failed factorisation changes nothing and bumps _ba_status[1]
+        st.prob.frontend_update(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body, self._ba_status,
+                                prior_idx=0 if st.has_prior else -1,
+                                prior_pose=self.prior_pose if st.has_prior else None,
+                                prior_info=self.prior_info if st.has_prior else 0.0, clamp_min=1e-3,
+                                cov_mode=self.cov_mode if compute_covariances else None,
+                                idepths_cov=self.cam0_idepths_cov, depths_cov=self.cam0_depths_cov,
+                                pose_cov=self.world_T_body_cov)
         # inverse depths and depth covariances of the K source keyframes through one softmax, gathered /
         # scattered by keyframe index inside the kernel
         db.cvx_upsample2(self.cam0_idepths, self.cam0_depths_cov, upmask, self.cam0_idepths_up, self.cam0_depths_cov_up,
@@ -806,17 +833,12 @@ class RaftVisualFrontend:
         prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
                             self.cam0_idepths_sensed, target, weight, damping, ii, jj, kf0, kf1)
         has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
-        dx, linv, status = prob.gauss_newton(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body,
-                                             prior_idx=0 if has_prior else -1,
-                                             prior_pose=self.prior_pose if has_prior else None,
-                                             prior_info=self.prior_info if has_prior else 0.0,
-                                             want_linv=compute_covariances, clamp_min=1e-3)
-        if compute_covariances and linv is not None:
-            sg, z_cov, d_cov = prob.covariances(linv)
-            kx = _lib.h2d(prob.gh.tables["kx"].astype(np.int64), self.device)
-            self.world_T_body_cov[kf0:kf1] = sg
-            self.cam0_idepths_cov[kx] = z_cov
-            self.cam0_depths_cov[kx] = d_cov
+        prob.frontend_update(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body, self._ba_status,
+                             prior_idx=0 if has_prior else -1, prior_pose=self.prior_pose if has_prior else None,
+                             prior_info=self.prior_info if has_prior else 0.0, clamp_min=1e-3,
+                             cov_mode=self.cov_mode if compute_covariances else None,
+                             idepths_cov=self.cam0_idepths_cov, depths_cov=self.cam0_depths_cov,
+                             pose_cov=self.world_T_body_cov)
         self.last_ba = prob
         return None, None
 
@@ -888,6 +910,7 @@ class RaftVisualFrontend:
     def get_viz_out(self, batch):
         """visual_frontend.py:1337-1391.  Tensors stay on the device: the NeRF side receives them
         through NCCL / peer copies (nerf_slam_b200.dist), never through the CPU."""
+        self.ba_failures()                      # asynchronous read-back of the BA failure counter (no sync)
         idx_h = np.nonzero(self.viz_idx)[0]
         if len(idx_h) == 0:
             return {"is_last_frame": True} if batch["is_last_frame"] else None
@@ -901,7 +924,5 @@ class RaftVisualFrontend:
                "cam0_images": sel(self.cam0_images), "cam0_intrinsics": sel(self.cam0_intrinsics),
                "calibs": batch["calibs"], "viz_idx": idx, "viz_idx_host": idx_h.tolist(), "kf_idx": self.kf_idx,
                "kf_idx_to_f_idx": dict(self.kf_idx_to_f_idx), "is_last_frame": batch["is_last_frame"]}
-        # host copy of the (tiny) pose block, read on THIS stream: consumers on other streams then need no sync
-        out["cam0_poses_host"] = out["cam0_poses"].double().cpu().numpy()
         self.viz_idx[:] = False
         return out

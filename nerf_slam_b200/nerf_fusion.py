@@ -67,7 +67,11 @@ class NerfFusion:
         self.ngp.nerf.training.depth_supervision_lambda = 1.0
         self.ngp.nerf.training.depth_loss_type = ngp.LossType.L2
         self.mask_type = getattr(args, "mask_type", "ours")
-        self.ref_frames = {}
+        # ground-truth depth of the ingested keyframes, for eval_gt_traj only: ONE preallocated [buffer,H,W] device
+        # tensor filled per frame id (allocated on first use when args.eval is set) + the depth scale; the SLAM packets
+        # themselves are not retained (they hold full-resolution images / depths of the whole BA window)
+        self.ref_frames = {}            # fid -> depth_scale (membership = "a GT depth is stored for this frame id")
+        self._gt_depths = None
         self.anneal, self.anneal_every_iters, self.annealing_rate = False, 200, 0.95      # :108-110
         self.evaluate = bool(getattr(args, "eval", False))
         self.eval_every_iters = 200
@@ -96,16 +100,34 @@ class NerfFusion:
             idepths_up = -torch.ones_like(idepths_up)
         elif self.mask_type != "ours":
             raise NotImplementedError(f"Unknown mask type: {self.mask_type}")
-        c2w = _pose_tq_to_c2w(slam.get("cam0_poses_host", slam["cam0_poses"]))          # scale 1.0, offset 0 (:167-170)
         ids = slam["viz_idx_host"] if "viz_idx_host" in slam else viz_idx.tolist()
+        poses = slam["cam0_poses"]                                  # cam_T_world [n,7]; scale 1.0, offset 0 (:167-170)
+        on_device = torch.is_tensor(poses) and poses.is_cuda
+        c2w = None if on_device else _pose_tq_to_c2w(poses)[:, :3, :4]
         intr = calib.camera_model.numpy()
         dev = self.ngp.device
+        images, idepths_up, depths_cov_up = images.to(dev), idepths_up.to(dev), depths_cov_up.to(dev)
+        # the packet was allocated on the SLAM stream and is read here by kernels of the (possibly different) current
+        # stream: tell the caching allocator, so that the blocks are not handed back to the producer stream while the
+        # ingest kernels are still pending
+        cur = torch.cuda.current_stream(dev) if images.is_cuda else None
+        if cur is not None:
+            for t in (images, idepths_up, depths_cov_up):
+                t.record_stream(cur)
+        # world_T_cam records are computed on the device from the packet's poses (no host copy, no sync)
         self.ngp.nerf.training.update_training_images_device(
-            ids, c2w[:, :3, :4], images.to(dev), idepths_up.to(dev), depths_cov_up.to(dev),
-            intr[:2], intr[2:])
-        if "gt_depths" in slam:
-            for k, fid in enumerate(ids):
-                self.ref_frames[fid] = (k, slam)           # lazily materialised by eval_gt_traj
+            ids, c2w, images, idepths_up, depths_cov_up, intr[:2], intr[2:],
+            cam_T_world=poses.to(dev) if on_device else None,
+            ids_device=viz_idx.to(dev) if torch.is_tensor(viz_idx) and viz_idx.is_cuda and viz_idx.dtype == torch.int64 else None)
+        if getattr(self, "evaluate", False) and "gt_depths" in slam:
+            gt = slam["gt_depths"].to(dev)
+            if cur is not None:
+                gt.record_stream(cur)
+            if self._gt_depths is None:
+                self._gt_depths = torch.zeros(self.args.buffer, gt.shape[-2], gt.shape[-1], device=dev)
+            self._gt_depths[torch.as_tensor(ids, device=dev, dtype=torch.long)] = gt[:, 0].float()
+            for fid in ids:
+                self.ref_frames[fid] = float(calib.depth_scale)
         return False
 
     def process_data(self, packet):
@@ -191,8 +213,7 @@ class NerfFusion:
             mse = compute_error(est, ref)                       # over RGBA, like the reference (:424)
             tot_psnr += mse2psnr(max(mse, 1e-12))
             if fid in self.ref_frames:
-                k, slam = self.ref_frames[fid]
-                gt = slam["gt_depths"][k, 0].float().cpu().numpy() * slam["calibs"][0].depth_scale
+                gt = self._gt_depths[fid].cpu().numpy() * self.ref_frames[fid]
                 tb.render_mode = ngp.Depth
                 d = tb.render(ref.shape[1], ref.shape[0], 1, True)[..., 0]
                 s = gt.mean() / max(d.mean(), 1e-9)

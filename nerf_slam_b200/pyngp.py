@@ -108,21 +108,36 @@ class _Training:
         tb._activate(frame_ids)
 
     def update_training_images_device(self, frame_ids, c2w, images_u8_chw, idepths_up, depths_cov_up,
-                                      focal_length, principal_point):
-        """device fast path: images uint8 [n,3,H,W] (sRGB), idepths_up/depths_cov_up [n,H,W] CUDA tensors;
-        sRGB->linear, premultiply and 1/idepth are fused in one kernel per image."""
+                                      focal_length, principal_point, cam_T_world=None, ids_device=None):
+        """device fast path: images uint8 [n,3,H,W] (sRGB), idepths_up / depths_cov_up [n,H,W] CUDA tensors; ONE kernel
+        launch for the whole packet (sRGB->linear, premultiply, 1/idepth, slot scatter).
+        Cameras: `cam_T_world` [n,7] (t, q_xyzw) CUDA tensor -> world_T_cam records computed by the same kernel (no host
+        copy of the poses: that copy was a device synchronisation per SLAM tick); else `c2w` [n,3,4] host matrices.
+        frame_ids: host list (the slot ids are known on the host: dirty flags live there); ids_device: the same ids as
+        an int64 CUDA tensor when the caller already has it."""
         tb = self._tb
         lib = _lib.load()
         n, _, H, W = images_u8_chw.shape
         tb._ensure_store(H, W)
-        for k in range(n):
-            fid = int(frame_ids[k])
-            _lib.check(lib.nslam_ngp_ingest_image(_lib.ptr(images_u8_chw[k].contiguous()), _lib.ptr(idepths_up[k].contiguous()),
-                                                  _lib.ptr(depths_cov_up[k].contiguous()), H, W, _lib.ptr(tb.rgba[fid]),
-                                                  _lib.ptr(tb.depth[fid]), _lib.ptr(tb.depth_cov[fid]),
-                                                  _lib.stream_ptr()), "ngp_ingest_image")
-            tb._set_camera(fid, np.asarray(c2w[k], np.float64), focal_length, principal_point, (W, H))
-        tb._activate([int(f) for f in frame_ids])
+        ids = [int(f) for f in frame_ids]
+        if n:
+            ids_d = ids_device if ids_device is not None else _lib.h2d(np.asarray(ids, np.int64), tb.device)
+            fl = np.asarray(focal_length, np.float32).reshape(-1); pp = np.asarray(principal_point, np.float32).reshape(-1)
+            pose = None
+            if cam_T_world is not None:
+                pose = cam_T_world.to(torch.float32).contiguous()
+                assert pose.shape == (n, 7) and pose.is_cuda
+            _lib.check(lib.nslam_ngp_ingest_batch(
+                _lib.ptr(images_u8_chw.contiguous()), _lib.ptr(idepths_up.contiguous()), _lib.ptr(depths_cov_up.contiguous()),
+                _lib.ptr(ids_d), n, H, W, _lib.ptr(tb.rgba), _lib.ptr(tb.depth), _lib.ptr(tb.depth_cov), _lib.ptr(pose),
+                float(fl[0]), float(fl[1]), float(pp[0]), float(pp[1]), _lib.ptr(tb.cams) if pose is not None else None,
+                _lib.stream_ptr()), "ngp_ingest_batch")
+            if pose is not None:
+                tb._cams_host_stale = True
+            else:
+                for k, fid in enumerate(ids):
+                    tb._set_camera(fid, np.asarray(c2w[k], np.float64), focal_length, principal_point, (W, H))
+        tb._activate(ids)
 
 
 class _Nerf:
@@ -206,7 +221,8 @@ class Testbed:
             m.scale[l], m.res[l], m.size[l], m.offset[l], m.dense[l] = sc, res, n, off, dense
         m.n_grid = total
         self.model = m
-        self.cams_h = np.zeros((self.n_images, 18), np.float32)
+        self._cams_h = np.zeros((self.n_images, 18), np.float32)
+        self._cams_host_stale, self._cams_upload = False, []
         self.cams = torch.zeros(self.n_images, 18, **f)
         self.active = torch.zeros(self.n_images, dtype=torch.int32, device=dev)
         self.active_set = []
@@ -237,6 +253,15 @@ class Testbed:
             self.depth_cov = torch.ones(self.n_images, H, W, dtype=torch.float32, device=dev)
         assert (H, W) == (self.H, self.W), "all training images share one resolution"
 
+    @property
+    def cams_h(self):
+        """host mirror of the camera records [n_images,18]; refreshed from the device (one synchronising copy) when the
+        device-side ingest wrote cameras since the last read — evaluation / tests only, never in the training loop"""
+        if self._cams_host_stale:
+            self._cams_h[:] = self.cams.cpu().numpy()
+            self._cams_host_stale = False
+        return self._cams_h
+
     def _set_camera(self, fid, c2w34, focal, pp, resolution):
         row = np.zeros(18, np.float32)
         row[:12] = np.asarray(c2w34, np.float32)[:3, :4].reshape(-1)
@@ -245,12 +270,16 @@ class Testbed:
         # the camera record holds w,h as int32 in the last two slots
         row[16:18] = np.array([int(resolution[0]), int(resolution[1])], np.int32).view(np.float32)
         self.cams_h[fid] = row
+        self._cams_upload.append(int(fid))
 
     def _activate(self, ids):
         for i in ids:
             if int(i) not in self.active_set:
                 self.active_set.append(int(i))
-        self.cams.copy_(torch.from_numpy(self.cams_h).pin_memory(), non_blocking=True)
+        if self._cams_upload:                       # host-set camera rows only (device-written rows are not touched)
+            rows = sorted(set(self._cams_upload))
+            self.cams.index_copy_(0, _lib.h2d(np.asarray(rows, np.int64), self.device), _lib.h2d(self._cams_h[rows], self.device))
+            self._cams_upload = []
         n = len(self.active_set)
         self.active[:n].copy_(torch.as_tensor(self.active_set, dtype=torch.int32).pin_memory(), non_blocking=True)
         self.nerf.training.n_images_for_training = n

@@ -12,7 +12,7 @@ def test_pack_unpack_roundtrip():
     g = torch.Generator().manual_seed(0)
     n, H, W = 3, 8, 12
     idx = torch.tensor([4, 9, 2])
-    c2w = torch.randn(n, 3, 4, generator=g)
+    c2w = torch.randn(n, 7, generator=g)                    # cam_T_world [t, q]
     img = torch.randint(0, 255, (n, 3, H, W), dtype=torch.uint8, generator=g)
     idep = torch.rand(n, H, W, generator=g); cov = torch.rand(n, H, W, generator=g)
     buf = nd.pack_keyframes(idx, c2w, img, idep, cov)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
     H, W = 6, 10
     h = nd.Handoff(torch.device("cpu"), 4, H, W)
     g = torch.Generator().manual_seed(7)
-    ref = (torch.tensor([1, 3]), torch.randn(2, 3, 4, generator=g), torch.randint(0, 255, (2, 3, H, W), dtype=torch.uint8, generator=g),
+    ref = (torch.tensor([1, 3]), torch.randn(2, 7, generator=g), torch.randint(0, 255, (2, 3, H, W), dtype=torch.uint8, generator=g),
            torch.rand(2, H, W, generator=g), torch.rand(2, H, W, generator=g))
     ok = True
     if rank == 0:

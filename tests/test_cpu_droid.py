@@ -506,13 +506,13 @@ def test_live_update_replays_the_reference_method(k, monkeypatch):
             kx = np.unique(np.concatenate([np.arange(kf0, kf1), np.asarray(ii)]))
             self.gh = types.SimpleNamespace(tables={"kx": kx.astype(np.int32)}, K=len(kx), P=kf1 - kf0)
 
-        def gauss_newton(self, iters, *a, **kw):
+        def frontend_update(self, iters, *a, **kw):           # the live path's one-call BA step
             t, w, eta, ii, jj, kf0, kf1 = self.a
             ba_log.append({"ii": ii.tolist(), "jj": jj.tolist(), "kf0": int(kf0), "kf1": None, "itrs": int(iters), "motion_only": False,
                            "target": lsc.digest(t), "weight": lsc.digest(w), "damping": lsc.digest(eta),
                            "contig": bool(t.is_contiguous() and w.is_contiguous() and eta.is_contiguous())})
             fe.cam0_idepths[torch.as_tensor(np.unique(ii))] *= 1.01
-            return None, None, None
+            return None, None
 
     def fake_reproject(poses, disps, intr, ii, jj, want_valid=True, out=None):
         off = (fe._ids(ii) * 100 + fe._ids(jj)).float() + 10.0 * (fe.cam0_idepths[ii, 0, 0] - 1.0)
@@ -537,6 +537,7 @@ def test_live_update_replays_the_reference_method(k, monkeypatch):
     fe.kf_idx_to_f_idx = {i: i for i in range(B)}
     fe.intr0, fe.cam0_T_body = fe.cam0_intrinsics[0], torch.tensor([0, 0, 0, 0, 0, 0, 1.0])
     fe.prior_pose, fe.prior_info = torch.zeros(7), 1e8
+    fe._ba_status, fe.cov_mode = torch.zeros(2, dtype=torch.int32), 1
     fe.cam0_idepths_up, fe.cam0_depths_cov_up = torch.zeros(B, 8 * lsc.HT8, 8 * lsc.WD8), torch.zeros(B, 8 * lsc.HT8, 8 * lsc.WD8)
     fe.coords0 = lsc.coords0()
 

@@ -39,7 +39,8 @@ def test_product_process_slam_host_half(mt):
     calls = []
     nf = object.__new__(NerfFusion)
     nf.mask_type, nf.ref_frames = mt, {}
-    training = types.SimpleNamespace(update_training_images_device=lambda *a: calls.append(a))
+    nf.evaluate, nf._gt_depths, nf.args = True, None, types.SimpleNamespace(buffer=32)
+    training = types.SimpleNamespace(update_training_images_device=lambda *a, **kw: calls.append(a))
     nf.ngp = types.SimpleNamespace(device="cpu", nerf=types.SimpleNamespace(training=training))
     assert nf.process_slam([None, sc.make_packet()]) is False and len(calls) == 1
     ids, c2w, images, idepths, covs, focal, pp = calls[0]
@@ -51,7 +52,11 @@ def test_product_process_slam_host_half(mt):
     assert np.array_equal(covs.numpy()[..., None], GOLD[f"{mt}.covs"])
     assert np.allclose(focal, GOLD[f"{mt}.fl"]) and np.allclose(pp, GOLD[f"{mt}.pp"])
     # the packet itself is left untouched (the reference mutates its input tensors in place)
-    assert sorted(nf.ref_frames) == GOLD[f"{mt}.ids"].tolist()
+    # ... and is not retained: only the GT depth maps of the ingested frame ids are kept (for eval_gt_traj)
+    ids_g = GOLD[f"{mt}.ids"].tolist()
+    assert sorted(nf.ref_frames) == ids_g
+    assert torch.equal(nf._gt_depths[ids_g], sc.make_packet()["gt_depths"][:, 0].float())
+    assert not any(torch.is_tensor(v) or isinstance(v, dict) for v in nf.ref_frames.values())
 
 
 def test_last_frame_packet_is_not_ingested():
@@ -60,7 +65,7 @@ def test_last_frame_packet_is_not_ingested():
     nf = object.__new__(NerfFusion)
     nf.mask_type, nf.ref_frames = "ours", {}
     nf.ngp = types.SimpleNamespace(device="cpu", nerf=types.SimpleNamespace(training=types.SimpleNamespace(
-        update_training_images_device=lambda *a: (_ for _ in ()).throw(AssertionError("ingested")))))
+        update_training_images_device=lambda *a, **kw: (_ for _ in ()).throw(AssertionError("ingested")))))
     last = sc.make_packet(); last["is_last_frame"] = True
     assert nf.process_slam([None, last]) is True and nf.process_slam(None) is True and nf.process_slam([None, None]) is True
 

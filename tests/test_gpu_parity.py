@@ -274,7 +274,6 @@ def test_ba_full_iteration(db):
     assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9)
 
 
-@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS") != "1", reason="pending first hardware run (NSLAM_PENDING_TESTS=1)")
 def test_ba_covariances_reference_exact(db):
     """A14, csrc/ba_cov_ref.cu: the reference's covariance block as it really behaves (Ei broadcast over the pose rows of
     optimised frames, visual_frontend.py:1214) vs oracle.covariances_reference, which is pinned on the CPU against the
@@ -298,6 +297,62 @@ def test_ba_covariances_reference_exact(db):
         assert np.allclose(dc.cpu().numpy().reshape(rdc.shape), rdc, rtol=2e-3, atol=1e-9), mode
     _, zi, _ = prob.covariances(linv, reference=False)
     assert not np.allclose(zi.cpu().numpy().reshape(rzc.shape), rzc, rtol=1e-2)          # the two formulas do differ
+
+
+@pytest.mark.parametrize("cov_mode", [1, 0])
+def test_ba_frontend_update_matches_piecewise_path(db, cov_mode):
+    """nslam_ba_frontend_update (the live path's one-call BA step: 2 Gauss-Newton iterations + covariances written into
+    the keyframe arenas) vs the piecewise entry points each validated above (gauss_newton, covariances)."""
+    p = _ba_problem(68, nframes=7)
+    wTb0 = np.stack([np.concatenate(se3.inv_se3(q[:3].astype(np.float64), q[3:].astype(np.float64))) for q in p["poses"]]).astype(np.float32)
+    N, (ht, wd) = p["disps"].shape[0], p["disps"].shape[1:]
+    prior = T(wTb0[p["kf0"]].copy())
+
+    def fresh():
+        cTw, wTb, disps = T(p["poses"].copy()), T(wTb0.copy()), T(p["disps"].copy())
+        prob = db.BAProblem(cTw, disps, T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]), T(p["weight"]), T(p["eta"]),
+                            p["ii"], p["jj"], p["kf0"], p["kf1"])
+        return prob, cTw, wTb, disps
+    # piecewise
+    prob, cTw, wTb, disps = fresh()
+    dx, linv, status = prob.gauss_newton(2, wTb, cTw, T(p["ext"]), prior_idx=0, prior_pose=prior, prior_info=1e8, want_linv=True)
+    assert int(status.item()) == 0
+    sg, zc, dc = prob.covariances(linv, reference="1" if cov_mode else "0")
+    kx = prob.gh.tables["kx"].astype(np.int64)
+    # one call, arenas
+    prob2, cTw2, wTb2, disps2 = fresh()
+    st = torch.zeros(2, dtype=torch.int32, device=DEV)
+    zarena = torch.full((N, ht, wd), -7.0, device=DEV); darena = torch.full((N, ht, wd), -7.0, device=DEV)
+    parena = torch.full((N, 6, 6), -7.0, device=DEV)
+    dx2, _ = prob2.frontend_update(2, wTb2, cTw2, T(p["ext"]), st, prior_idx=0, prior_pose=prior, prior_info=1e8,
+                                   cov_mode=cov_mode, idepths_cov=zarena, depths_cov=darena, pose_cov=parena)
+    assert st.tolist() == [0, 0]
+    assert torch.equal(dx, dx2) and torch.equal(cTw, cTw2) and torch.equal(wTb, wTb2) and torch.equal(disps, disps2)
+    assert np.allclose(zarena[kx].cpu().numpy(), zc.cpu().numpy(), rtol=2e-5, atol=1e-12)
+    assert np.allclose(darena[kx].cpu().numpy(), dc.cpu().numpy(), rtol=2e-5, atol=1e-12)
+    assert np.allclose(parena[p["kf0"]:p["kf1"]].cpu().numpy(), sg.cpu().numpy(), rtol=1e-6, atol=0)
+    rest = np.setdiff1d(np.arange(N), kx)
+    assert (zarena[rest] == -7.0).all() and (darena[rest] == -7.0).all()          # rows of untouched frames stay
+    outside = np.setdiff1d(np.arange(N), np.arange(p["kf0"], p["kf1"]))
+    assert (parena[outside] == -7.0).all()
+
+
+def test_ba_frontend_update_failed_factorisation_changes_nothing(db):
+    """a singular window (zero confidence weights, no prior, no damping of the poses) must not corrupt the
+    state: poses, depths and covariance arenas stay as they were, status = [1, #failures]."""
+    p = _ba_problem(69, nframes=6)
+    wTb0 = np.stack([np.concatenate(se3.inv_se3(q[:3].astype(np.float64), q[3:].astype(np.float64))) for q in p["poses"]]).astype(np.float32)
+    N, (ht, wd) = p["disps"].shape[0], p["disps"].shape[1:]
+    cTw, wTb, disps = T(p["poses"].copy()), T(wTb0.copy()), T(p["disps"].copy())
+    prob = db.BAProblem(cTw, disps, T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]), T(np.zeros_like(p["weight"])),
+                        T(p["eta"]), p["ii"], p["jj"], p["kf0"], p["kf1"])
+    st = torch.zeros(2, dtype=torch.int32, device=DEV)
+    zarena = torch.full((N, ht, wd), -7.0, device=DEV); darena = zarena.clone(); parena = torch.full((N, 6, 6), -7.0, device=DEV)
+    prob.frontend_update(2, wTb, cTw, T(p["ext"]), st, prior_idx=-1, cov_mode=1, idepths_cov=zarena, depths_cov=darena, pose_cov=parena)
+    assert st.tolist() == [1, 2]
+    assert np.array_equal(cTw.cpu().numpy(), p["poses"]) and np.array_equal(wTb.cpu().numpy(), wTb0)
+    assert np.array_equal(disps.cpu().numpy(), p["disps"])
+    assert (zarena == -7.0).all() and (darena == -7.0).all() and (parena == -7.0).all()
 
 
 def test_solve_depth_and_poses_api(db):
@@ -360,8 +415,6 @@ def test_corr_lookup_nhwc_equals_reference_layout(db):
     assert float(got[..., 196:].abs().max()) == 0.0
 
 
-@pytest.mark.skipif(os.environ.get("NSLAM_CORRVOL_ROWS", "0") != "1",
-                    reason="experimental row-pair correlation kernel: enable with NSLAM_CORRVOL_ROWS=1")
 @pytest.mark.parametrize("H,W,E", [(60, 80, 3), (16, 64, 2), (30, 80, 1)])
 def test_corr_volume_rows_matches_tiled_kernel(H, W, E):
     """csrc/corr_volume_rows.cu (two full target rows per MMA tile) must reproduce csrc/corr_volume.cu bit for
@@ -384,8 +437,6 @@ def test_corr_volume_rows_matches_tiled_kernel(H, W, E):
         assert torch.equal(a[l], b[l]), (l, float((a[l].float() - b[l].float()).abs().max()))
 
 
-@pytest.mark.skipif(os.environ.get("NSLAM_PENDING_TESTS", "0") != "1",
-                    reason="written without GPU access at the end of round 1: enable with NSLAM_PENDING_TESTS=1, validate, then unconditional")
 def test_droid_backends_ba_all_in_one_loop(db):
     """A15: droid_backends.ba (ba_cuda, src/droid_kernels.cu:1441-1568, motion_only=False) = per iteration
     linearise -> (A - S) solve with `ep + lm*diag` damping -> depth back-substitution -> left pose retraction, all

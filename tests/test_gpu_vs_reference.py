@@ -99,6 +99,31 @@ def test_reduced_camera_matrix_vs_reference(db, refdroid, cfg):
     assert torch.allclose(d_got, d_ref, rtol=2e-4, atol=2e-5)
 
 
+def test_ba_all_in_one_loop_vs_reference_kernels(db, refdroid):
+    """A15: droid_backends.ba vs ba_cuda (src/droid_kernels.cu:1441-1568) rebuilt from the reference's OWN kernels in its
+    own order — per iteration: reference linearisation + Schur (projective_transform / accum / EEt6x6 / Ev6x1 kernels),
+    SparseBlock::solve's `diag += ep + lm*diag` Cholesky (:1320-1337, dense fp64 here), reference solve_depth
+    (EvT6x1 + accum + disp_retr kernels), reference solve_poses (pose_retr_kernel).  In-place state after 2 iterations."""
+    p = _ba_problem(75, nframes=7)
+    lm, ep, iters = 1e-4, 0.1, 2
+    ii, jj = T(p["ii"]), T(p["jj"])
+    fixed = (T(p["intr"]), T(p["ext"]), T(p["sens"]), T(p["target"]), T(p["weight"]), T(p["eta"]))
+    poses, disps = T(p["poses"].copy()), T(p["disps"].copy())
+    dx, dz = db.ba(poses, T(p["poses"].copy()), disps, *fixed, ii, jj, p["kf0"], p["kf1"], iters, lm, ep, False)
+    rposes, rdisps = T(p["poses"].copy()), T(p["disps"].copy())
+    for _ in range(iters):
+        rH, rv, rQ, rE, rw, _, _ = refdroid.reduced_camera_matrix(rposes, rposes, rdisps, *fixed, ii, jj, p["kf0"], p["kf1"])
+        A = rH.double().cpu()
+        A = A + torch.diag(ep + lm * torch.diagonal(A))
+        rdx = torch.cholesky_solve(rv.double().cpu(), torch.linalg.cholesky(A)).float().view(-1, 6).to(DEV).contiguous()
+        refdroid.solve_depth(rdx, rdisps, rQ, rE, rw, ii, jj, p["kf0"], p["kf1"])
+        refdroid.solve_poses(rposes, rdx, p["kf0"], p["kf1"])
+    assert torch.allclose(dx, rdx, rtol=2e-3, atol=2e-6)
+    sgn = torch.sign((poses[:, 3:] * rposes[:, 3:]).sum(-1, keepdim=True))
+    assert torch.allclose(poses[:, :3], rposes[:, :3], atol=2e-5) and torch.allclose(poses[:, 3:] * sgn, rposes[:, 3:], atol=2e-5)
+    assert torch.allclose(disps, rdisps, rtol=5e-4, atol=5e-5)
+
+
 def test_misc_geometry_vs_reference(db, refdroid):
     rng = np.random.default_rng(1238)
     poses, disps, intr, ii, jj = make_window(rng, 8, 30, 40)
