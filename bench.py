@@ -90,10 +90,7 @@ class ClockSampler:
 def make_args(buffer):
     w = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
     return types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False, eval=False, mask_type="ours",
-                                 weights=w if os.path.exists(w) else None, corr_slots=112,
-                                 update_graphs=os.environ.get("NSLAM_UPDATE_GRAPHS", "0") == "1",
-                                 encoder_backend=os.environ.get("NSLAM_ENCODER", "tcgen05"),
-                                 op_step=os.environ.get("NSLAM_OP_STEP", "1") == "1")
+                                 weights=w if os.path.exists(w) else None, corr_slots=112)
 
 
 class SlamNerfJob:
@@ -340,15 +337,23 @@ def run_ours(a):
         "clocks": clk,
     }
     st_dev["frames"] = a.steps
-    counts = count_own_launches(job, st_dev)
-    line.update(extra_sections(a, job, pk, counts))
+    shares, counts = kernel_shares(job, st_dev)
+    entries = roofline_entries(job, pk)
+    key, roof = pick_roofline(shares, entries)
+    line["roofline"] = roof
+    line["roofline_others"] = [v for k, v in entries.items() if k != key]
+    line["kernel_shares"] = shares
+    line["gpu_launches"] = counts["total"]
+    line["gpu_launches_detail"] = counts
+    line["cpu_baseline"] = cpu_baseline_sample()
     sys.stdout.flush()
     os.dup2(_saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
 def _time_kernel(torch, fn, dev, iters=8, skip=3):
-    """CUDA-event timing on the launching (current) stream, L2 flushed between launches"""
+    """CUDA-event timing on the launching (current) stream of ONE launch at a time, L2 flushed before each (a write
+    of 256 MB > the 126 MB L2), device idle before and after: the isolated case -> compare with the BURST peaks"""
     flush = torch.empty(64 * 1024 * 1024, device=dev)
     ts = []
     for i in range(iters):
@@ -360,20 +365,87 @@ def _time_kernel(torch, fn, dev, iters=8, skip=3):
     return float(np.mean(ts))
 
 
-def extra_sections(a, job, pk, counts):
-    """roofline of the dominant hand-written kernel (live CUDA-event timing), secondary rooflines,
-    cpu_baseline, launch count"""
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures,
+# keyed by kernel; None where no capture at the live size exists.  See profiles/README.md.
+NCU_TRAFFIC = {
+    "conv_zr": (92820000, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
+    "conv_q": (132800512, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
+    "corr_lookup": (174600000, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
+}
+
+
+def kernel_shares(job, st):
+    """GPU-time share of every kernel in the timed region: CUPTI durations of one update(), one frame front and one NeRF
+    iteration (own and library kernels alike), weighted by how often the timed region ran each.  Also returns the launch
+    counts of OUR kernels (namespaces nslam:: / ngp::) for `gpu_launches`."""
     import torch
-    from nerf_slam_b200 import conv as nconv
-    from nerf_slam_b200 import droid_backends as db
-    out = {}
+    from torch.profiler import profile, ProfilerActivity
     fe = job.fe
-    E = int(fe.ii.shape[0])
-    hw = fe.ht * fe.wd
-    dev = job.dev
-    h16 = dict(dtype=torch.float16, device=dev)
-    # ---- dominant kernel: the ConvGRU z|r gate convolution (3x3, 448 -> 256 channels, fused gating epilogue),
-    # the single largest kernel of update() (profiles/r01_kernel_table_*.log); tensor-pipe bound
+
+    def prof(fn):
+        fn(); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as pr:
+            fn()
+            torch.cuda.synchronize()
+        t, own, n_all = {}, 0, 0
+        for ev in pr.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA and not ev.name.startswith("Mem"):
+                n_all += 1
+                own += ("nslam::" in ev.name or "ngp::" in ev.name)
+                t[ev.name] = t.get(ev.name, 0.0) + ev.device_time_total
+        return t, own, n_all
+    img = job.make_frames(1, True)[0]
+    x = img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3)
+    with torch.cuda.stream(job.slam_stream):
+        up = prof(lambda: fe.update(use_inactive=True))
+        fr = prof(lambda: fe._frame_front(x))
+    ne = ({}, 0, 0)
+    if job.is_nerf:
+        with torch.cuda.stream(job.nerf_stream):
+            ne = prof(job.nf.fit_volume_once)
+    tot = {}
+    for (t, _, _), calls in ((up, st["updates"]), (fr, st["frames"]), (ne, st["nerf_iters"])):
+        for k, v in t.items():
+            tot[k] = tot.get(k, 0.0) + v * calls
+    total_us = sum(tot.values()) or 1.0
+    top = sorted(tot.items(), key=lambda kv: -kv[1])[:8]
+    counts = {"total": int(up[1] * st["updates"] + fr[1] * st["frames"] + ne[1] * st["nerf_iters"]),
+              "own_per_update_call": up[1], "all_per_update_call": up[2], "own_per_frame_front": fr[1],
+              "all_per_frame_front": fr[2], "own_per_nerf_iter": ne[1], "all_per_nerf_iter": ne[2],
+              "note": "own = kernels of libnslam_sm100a.so; the remainder are torch glue (index/copy/normalise) kernels; "
+                      "per-keyframe extras (context encoder, correlation volumes of new edges) are not included in total"}
+    shares = [{"kernel": k[:110], "share": round(v / total_us, 4)} for k, v in top]
+    return shares, counts
+
+
+def roofline_entries(job, pk):
+    """isolated live timings (CUDA events, L2 flushed) of the kernels that carry the path, each against its bound;
+    peaks: the BURST figures of MEASURED_PEAKS.json (a kernel timed alone)"""
+    import ctypes
+    import torch
+    from nerf_slam_b200 import _lib, conv as nconv
+    from nerf_slam_b200 import droid_backends as db
+    fe, dev = job.fe, job.dev
+    E, hw = int(fe.ii.shape[0]), fe.ht * fe.wd
+    tf_peak, hbm_peak = pk["bf16_tflops"], pk["hbm_gbs"]
+    src = pk["_src"] + " (burst figures: each kernel is timed alone, device idle around it)"
+    out = {}
+
+    def tensor_entry(key, name, flops, ms, extra=None):
+        e = {"kernel": name, "bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": tf_peak, "unit": "TFLOP/s",
+             "frac": round(flops / ms / 1e9 / tf_peak, 3), "launch_ms": round(ms, 4), "edges": E,
+             "algorithmic_flops_per_launch": flops, "peak_source": src,
+             "traffic": NCU_TRAFFIC.get(key, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(key, (None, None))[1]}
+        e.update(extra or {})
+        out[key] = e
+
+    def hbm_entry(key, name, nbytes, ms, edges, extra=None):
+        e = {"kernel": name, "bound": "hbm", "achieved": round(nbytes / ms / 1e6, 1), "peak": hbm_peak, "unit": "GB/s",
+             "frac": round(nbytes / ms / 1e6 / hbm_peak, 3), "launch_ms": round(ms, 4), "edges": edges,
+             "algorithmic_bytes_per_launch": nbytes, "peak_source": src,
+             "traffic": NCU_TRAFFIC.get(key, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(key, (None, None))[1]}
+        e.update(extra or {})
+        out[key] = e
     op = fe.update_tc
     net = torch.randn(E, fe.ht, fe.wd, 128, device=dev).half(); inp = torch.randn_like(net); c2 = torch.randn_like(net)
     f2 = torch.randn(E, fe.ht, fe.wd, 64, device=dev).half()
@@ -381,149 +453,194 @@ def extra_sections(a, job, pk, counts):
     wp, b = op.P["zr"]
     ms = _time_kernel(torch, lambda: nconv.conv_tc([net, inp, c2, f2], wp, b, E, fe.ht, fe.wd, 3, 1, 256, mode=1, gctx=gzr, net=net,
                                                    out0=z, out0_channels=128, out1=rnet, num_sms=op.num_sms), dev)
-    flops = 2.0 * E * hw * 9 * 448 * 256
-    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    out["roofline"] = {"kernel": "conv_igemm_kernel<256,1> (A5: ConvGRU z|r gates, 3x3 448->256 + fused sigmoid / r*h epilogue)",
-                       "bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": peak, "unit": "TFLOP/s",
-                       "frac": round(flops / ms / 1e9 / peak, 3),
-                       "traffic": 92820000, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                       "traffic_source": "profiles/r01_ncu_raw_run22.csv, captured at 18 edges (sm__pipe_tensor_cycles_active 68.2 %)",
-                       "peak_source": pk["_src"] + " (dense bf16 cuBLAS, sustained figure: the kernel is timed inside a long step)",
-                       "launch_ms": round(ms, 4), "edges": E, "algorithmic_flops_per_launch": flops}
-    # ---- secondary rooflines (HBM-bound kernels of the path)
-    others = []
+    tensor_entry("conv_zr", "conv_igemm_kernel<256,1> (A5: ConvGRU z|r gates, 3x3 448->256 + fused sigmoid / r*h epilogue)",
+                 2.0 * E * hw * 9 * 448 * 256, ms)
+    wq, bq = op.P["q"]
+    gq = torch.zeros(E, 128, device=dev); hnew = torch.empty_like(net)
+    ms = _time_kernel(torch, lambda: nconv.conv_tc([rnet, inp, c2, f2], wq, bq, E, fe.ht, fe.wd, 3, 1, 128, mode=2, gctx=gq, net=net,
+                                                   zbuf=z, out0=hnew, out0_channels=128, num_sms=op.num_sms), dev)
+    tensor_entry("conv_q", "conv_igemm_kernel<128,2> (A5: ConvGRU candidate state, 3x3 448->128 + fused tanh / state update)",
+                 2.0 * E * hw * 9 * 448 * 128, ms)
+    # the whole update operator (15 convolutions + glue kernels, one C call): FLOP-weighted aggregate of A5
+    st = fe._static
+    if st is not None and st.op_ctx is not None:
+        ms = _time_kernel(torch, lambda: op.step(st.op_ctx), dev)
+        tensor_entry("update_operator", "nslam_update_op_step (A5: all 15 tcgen05 implicit-GEMM convolutions + glue of UpdateModule.forward)",
+                     2.0 * 2283008 * hw * E, ms, {"note": "2*2,283,008 MAC per edge-pixel (SURVEY.md §8a A5); includes the glue kernels' time"})
+    # HBM-bound correlation kernels
     coords1, _ = fe.reproject(fe.ii, fe.jj)
     ms = _time_kernel(torch, lambda: fe.corr_pool.lookup(fe.slots_d, coords1, nhwc=True), dev)
-    alg = E * hw * (4 * 64 * 2 + 8 + nconv.CORR_PAD * 2)
-    others.append({"kernel": "corr_lookup_nhwc_kernel<half,3> (A3, 4 pyramid levels fused)", "bound": "hbm",
-                   "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                   "frac": round(alg / ms / 1e6 / pk["hbm_gbs"], 3), "launch_ms": round(ms, 4), "edges": E})
-    Ev = 4
-    fm = torch.randn(6, fe.ht, fe.wd, 128, device=dev).half()
-    ii32 = torch.tensor([0, 1, 2, 3], dtype=torch.int32, device=dev); jj32 = torch.tensor([1, 2, 3, 4], dtype=torch.int32, device=dev)
-    ms = _time_kernel(torch, lambda: db.corr_volume_build(fm, ii32, jj32), dev)
+    hbm_entry("corr_lookup", "corr_lookup_nhwc_kernel<half,3> (A3, 4 pyramid levels fused)",
+              E * hw * (4 * 64 * 2 + 8 + nconv.CORR_PAD * 2), ms, E)
     lv = sum((fe.ht >> l) * (fe.wd >> l) for l in range(4))
-    alg = Ev * (2 * 128 * hw * 2 + hw * lv * 2)
-    others.append({"kernel": "corr_volume_tc_kernel (A2, volume + 3 pooled levels in one pass)", "bound": "hbm",
-                   "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                   "frac": round(alg / ms / 1e6 / pk["hbm_gbs"], 3), "launch_ms": round(ms, 4), "edges": Ev})
-    out["roofline_others"] = others
-    out["gpu_launches"] = counts["total"]
-    out["gpu_launches_detail"] = counts
-    out["cpu_baseline"] = cpu_port_sample(a, st_updates_per_frame=None)
+    for Ev in (4, 16):
+        fm = torch.randn(Ev + 1, fe.ht, fe.wd, 128, device=dev).half()
+        ii32 = torch.arange(0, Ev, dtype=torch.int32, device=dev); jj32 = ii32 + 1
+        ms = _time_kernel(torch, lambda: db.corr_volume_build(fm, ii32, jj32), dev)
+        hbm_entry(f"corr_volume_E{Ev}", "corr_volume kernel (A2: all-pairs volume + 3 pooled levels in one pass)",
+                  Ev * (2 * 128 * hw * 2 + hw * lv * 2), ms, Ev)
+        del fm
+    # the reference composite the volume kernel replaces: torch.matmul (cuBLAS) + 3x avg_pool2d (corr.py:23-38,63-72)
+    Ev = 16
+    f1 = torch.randn(Ev, 128, hw, device=dev).half(); f2_ = torch.randn(Ev, 128, hw, device=dev).half()
+
+    def ref_volume():
+        c = torch.matmul((f1 / 4.0).transpose(1, 2), f2_ / 4.0).view(Ev * hw, 1, fe.ht, fe.wd)
+        for _ in range(3):
+            c = torch.nn.functional.avg_pool2d(c, 2, stride=2)
+    ms = _time_kernel(torch, ref_volume, dev)
+    out["corr_volume_E16"]["library_composite_ms"] = round(ms, 4)
+    out["corr_volume_E16"]["library_composite"] = "torch.matmul fp16 + 3x avg_pool2d at the same 16 edges (what CorrBlock.__init__ runs)"
+    del f1, f2_
+    # NeRF (B3): the tensor-core MLP backward = largest single kernel of the trainer
+    if job.is_nerf:
+        tb = job.nf.ngp
+        lib = _lib.load()
+        with torch.cuda.stream(job.nerf_stream):
+            tb.train_step(); torch.cuda.synchronize()
+        n = int(tb._bufs["counters"][0].item())
+        bufs = tb._bufs
+        with torch.cuda.stream(job.nerf_stream):
+            def bwd():
+                _lib.check(lib.nslam_ngp_backward_tc(ctypes.byref(tb.model), _lib.ptr(tb.packed), _lib.ptr(bufs["coords"]),
+                                                     _lib.ptr(bufs["counters"]), _lib.ptr(bufs["dout"]), float(tb.loss_scale),
+                                                     _lib.ptr(bufs["enc"]), _lib.ptr(bufs["denc"]), tb.max_samples, tb.num_sms,
+                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "backward_tc")
+            ms = _time_kernel(torch, bwd, dev)
+            ms_step = _time_kernel(torch, tb.train_step, dev)
+        tensor_entry("ngp_backward", "ngp::backward_tc_kernel (+ grid scatter) (B3: MLP backward on tcgen05, recompute + dW + dX)",
+                     3.0 * 2 * 10240 * n, ms, {"samples": n, "num_sms": tb.num_sms, "edges": None,
+                                               "note": "3 x forward MACs (recompute, dW, dX) x samples of one batch"})
+        out["ngp_backward"]["train_step_ms"] = round(ms_step, 4)
     return out
 
 
-def count_own_launches(job, st):
-    """launches of OUR kernels (namespaces nslam:: / ngp::) inside the timed region: kernels per update(),
-    per frame front and per NeRF iteration are counted with the CUPTI profiler on one call each (CUDA-graph
-    replays included), then multiplied by the number of calls the timed region made."""
-    import torch
-    from torch.profiler import profile, ProfilerActivity
-    fe = job.fe
-
-    def own(fn):
-        fn(); torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            fn()
-            torch.cuda.synchronize()
-        n_own = n_all = 0
-        for ev in prof.events():
-            if ev.device_type == torch.autograd.DeviceType.CUDA and not ev.name.startswith("Mem"):
-                n_all += 1
-                if "nslam::" in ev.name or "ngp::" in ev.name:
-                    n_own += 1
-        return n_own, n_all
-    img = job.make_frames(1, True)[0]
-    x = img["images"].to(fe.device)[None].permute(0, 1, 4, 2, 3)
-    with torch.cuda.stream(job.slam_stream):
-        up = own(lambda: fe.update(use_inactive=True))
-        fr = own(lambda: fe._frame_front(x))
-    ne = (0, 0)
-    if job.is_nerf:
-        with torch.cuda.stream(job.nerf_stream):
-            ne = own(job.nf.fit_volume_once)
-    total = up[0] * st["updates"] + fr[0] * st["frames"] + ne[0] * st["nerf_iters"]
-    return {"total": int(total), "own_per_update_call": up[0], "all_per_update_call": up[1], "own_per_frame_front": fr[0],
-            "all_per_frame_front": fr[1], "own_per_nerf_iter": ne[0], "all_per_nerf_iter": ne[1],
-            "note": "own = kernels of libnslam_sm100a.so; the remainder are torch glue (index/copy/normalise) kernels; "
-                    "per-keyframe extras (context encoder, correlation volumes of new edges) are not included in total"}
+def pick_roofline(shares, entries):
+    """the `roofline` object = the entry of the kernel with the LARGEST GPU-time share of the timed region that has an
+    isolated timing; the FLOP-weighted aggregate of the update operator and everything else go to roofline_others"""
+    table = (("conv_igemm_kernel<256, 1", "conv_zr"), ("conv_igemm_kernel<128, 2", "conv_q"), ("backward_tc", "ngp_backward"),
+             ("corr_lookup_nhwc", "corr_lookup"), ("corr_volume", "corr_volume_E4"))
+    for s in shares:
+        for needle, key in table:
+            if needle in s["kernel"] and key in entries:
+                e = dict(entries[key])
+                e["share_of_gpu_time_in_timed_region"] = s["share"]
+                return key, e
+    return "conv_zr", dict(entries["conv_zr"])
 
 
-# ------------------------------------------------------------------------------------------ CPU port
-def cpu_port_sample(a, st_updates_per_frame=None, repeats=1):
-    """reference CPU path, PORT (oracle/): one update() of the hot path on a bounded sample.
-    sample: E=4 edges at 60x80 (640x480/8): all-pairs correlation + 4-level pyramid, 4-level lookup,
-    UpdateModule forward (fp32, torch CPU), reduced camera matrix + dense solve + depth update (1 BA
-    iteration), plus one feature-encoder pass on a 640x480 frame.  Converted to frames/s with the
-    steady-state mix measured on the GPU run: 1 encoder pass per frame + ~1.7 update() calls per
-    frame at ~24 edges."""
-    import torch
-    from oracle import ba as oba, corr as ocorr
-    from nerf_slam_b200.networks import BasicEncoder, UpdateModule
-    from tests.util import make_targets, make_window
-    torch.set_num_threads(os.cpu_count() or 1)
-    rng = np.random.default_rng(1235)
-    E, ht, wd = 4, 60, 80
-    fnet, upd = BasicEncoder(128, "instance"), UpdateModule()
-    img = torch.randn(1, 1, 3, H_IMG, W_IMG)
-    poses, disps, intr, ii, jj = make_window(rng, 3, ht, wd, extra_edges=0)
-    ii, jj = ii[:E], jj[:E]
-    target, weight = make_targets(rng, poses, disps, intr, ii, jj)
-    fm = rng.normal(0, 1, (3, 128, ht, wd)).astype(np.float16)
-    coords = (np.stack(np.meshgrid(np.arange(wd), np.arange(ht)), 0)[None] + rng.uniform(-4, 4, (E, 2, ht, wd))).astype(np.float32)
-    net = torch.randn(1, E, 128, ht, wd); inp = torch.randn(1, E, 128, ht, wd); motion = torch.randn(1, E, 4, ht, wd)
-    eta = np.full((3, ht, wd), 1e-2, np.float32)
-    ext = np.array([0, 0, 0, 0, 0, 0, 1], np.float32)
-    t_enc = t_upd = 0.0
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            fnet(img)
-        t_enc += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        pyr = ocorr.corr_volume_pyramid(fm[ii], fm[jj])
-        corr = ocorr.corr_lookup_pyramid(pyr, coords, 3)
-        with torch.no_grad():
-            upd(net, inp, torch.from_numpy(corr.astype(np.float32))[None], motion, torch.as_tensor(ii), torch.as_tensor(jj))
-        r = oba.reduced_camera_matrix(poses, disps, intr, ext, np.zeros_like(disps), target, weight, eta, ii, jj, 0, 3)
-        dx, _ = oba.dense_solve(r["H"], r["v"], 0, np.zeros(6), 1e8)
-        oba.solve_depth(dx, disps, r["Q"], r["E"], r["w"], ii, jj, 0, 3)
-        t_upd += time.perf_counter() - t0
-    t_enc /= repeats; t_upd /= repeats
-    per_edge_update = t_upd / E
-    frame_s = t_enc + 1.7 * 24 * per_edge_update
-    return {"value": round(1.0 / frame_s, 4), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"1 update() at E={E} edges 60x80 (corr volume+pyramid, lookup, UpdateModule fp32, 1 BA iter) = {t_upd:.2f}s "
-                      f"+ 1 fnet pass = {t_enc:.2f}s; scaled to 1.7 update()/frame x 24 edges (steady-state mix); NeRF not included"}
+def cpu_baseline_sample(max_seconds=40.0):
+    """reference's CPU-only PyTorch path (oracle/cpu_path.py) on this box's host cores: steady-state cycles of the same
+    workload, timed directly (one untimed warm-up cycle first: thread pools, oneDNN primitives)"""
+    from oracle import cpu_path as cp
+    w = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
+    path = cp.CpuPath(w if os.path.exists(w) else None)
+    path.frame_front(); path.candidate_setup(); path.update()          # warm-up (untimed)
+    secs, parts_sum, n = 0.0, None, 0
+    t0 = time.perf_counter()
+    while n == 0 or (time.perf_counter() - t0) + secs / max(n, 1) < max_seconds:
+        t, parts = cp.steady_state_cycle(path)
+        secs += t; n += 1
+        parts_sum = parts if parts_sum is None else {k: parts_sum[k] + v for k, v in parts.items()}
+    per = secs / n
+    return {"value": round(cp.CYCLE["frames"] / per, 4), "unit": "frames/s", "cores": cp.host_threads(), "kind": "port",
+            "sample": cp.sample_description(per, {k: v / n for k, v in parts_sum.items()}, n), "cycles": n}
+
+
+# ------------------------------------------------------------------------------------------ reference arms
+def _ref_line(a, impl, value, steps, extra):
+    line = {"impl": impl, "metric": "SLAM+NeRF frames/sec on 640x480 synthetic stream", "value": round(value, 4),
+            "unit": "frames/s", "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup,
+            "ms_per_step": round(1e3 / max(value, 1e-9), 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "data": "synthetic (procedural box room, seeded)",
+            "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra)
+    return line
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU-only path (oracle port) on this box's host cores"""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    """--impl reference: the reference's CPU-only PyTorch path on this box's host cores (rank 0 only).  A step = one
+    frame of the steady-state cycle of oracle/cpu_path.py; cycles are timed directly until --steps frames or ~150 s."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    vals = []
-    for _ in range(max(a.warmup, 0)):
-        cpu_port_sample(a)
-        break                                   # one warm-up pass is enough for thread pools
+    from oracle import cpu_path as cp
+    w = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
+    path = cp.CpuPath(w if os.path.exists(w) else None)
+    for _ in range(1 if a.warmup > 0 else 0):
+        path.frame_front(); path.candidate_setup(); path.update()
+    secs, parts_sum, n = 0.0, None, 0
     t0 = time.perf_counter()
-    res = None
-    for _ in range(a.steps):
-        res = cpu_port_sample(a)
-        vals.append(res["value"])
-        if time.perf_counter() - t0 > 150:      # bounded: keep the whole arm within minutes
-            break
-    v = float(np.mean(vals))
-    res["value"] = round(v, 4)
-    line = {"impl": "reference", "metric": "SLAM+NeRF frames/sec on 640x480 synthetic stream", "value": round(v, 4),
-            "unit": "frames/s", "n_gpus": a.gpus, "steps": len(vals), "warmup": min(a.warmup, 1),
-            "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic (procedural box room, seeded)",
-            "config": {"workload": "configs[1]: Replica-office0-shaped synthetic 640x480, buffer=100, --slam --fusion=nerf",
-                       "note": "CPU port of the reference path on a bounded sample of this workload, see cpu_baseline.sample"},
-            "cpu_baseline": res, "e2e": {"value": round(v, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    want = max(1, -(-a.steps // cp.CYCLE["frames"]))
+    while n < want and (n == 0 or (time.perf_counter() - t0) + secs / n < 150.0):
+        t, parts = cp.steady_state_cycle(path)
+        secs += t; n += 1
+        parts_sum = parts if parts_sum is None else {k: parts_sum[k] + v for k, v in parts.items()}
+    per = secs / n
+    v = cp.CYCLE["frames"] / per
+    base = {"value": round(v, 4), "unit": "frames/s", "cores": cp.host_threads(), "kind": "port",
+            "sample": cp.sample_description(per, {k: x / n for k, x in parts_sum.items()}, n)}
+    print(json.dumps(_ref_line(a, "reference", v, n * cp.CYCLE["frames"], {
+        "dtype": "f32 (networks, correlation) / f64 (BA)",
+        "config": {"workload": "configs[1]: Replica-office0-shaped synthetic 640x480, buffer=100, --slam --fusion=nerf",
+                   "note": "reference's CPU-only PyTorch path on a bounded sample of this workload (steady-state cycles), see cpu_baseline.sample"},
+        "cpu_baseline": base})), flush=True)
+
+
+def run_reference_cuda(a):
+    """--impl reference-cuda: the reference's OWN CUDA kernels (oracle/_ref, compiled from /root/reference/src) + library
+    PyTorch in the reference's sequencing (oracle/ref_cuda_frontend.py) on the SAME stream, same priming, same timing
+    rules as the product arm; SLAM only (the reference's NeRF is the absent instant-ngp fork).  One GPU."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    sys.stdout.flush()
+    saved = os.dup(1); os.dup2(2, 1)
+    import torch
+    from nerf_slam_b200.synthetic import SyntheticRoom
+    from oracle.ref_cuda_frontend import RefCudaFrontend
+    torch.cuda.set_device(0)
+    torch.set_grad_enabled(False)
+    dev = torch.device("cuda", 0)
+    room = SyntheticRoom(W_IMG, H_IMG, 100000, seed=0, step=STREAM_STEP)
+    n_frames = a.steps + a.warmup + 40
+    fe = RefCudaFrontend(np.linalg.inv(room.packet(0)["poses"][0]), np.eye(4), make_args(100 if n_frames <= 460 else int(24 + 0.2 * n_frames)), dev)
+    k = 0
+
+    def frames(n):
+        nonlocal k
+        out = []
+        for _ in range(n):
+            p = room.packet(k); k += 1
+            p["images"] = torch.from_numpy(p["images"]).to(dev); p["depths"] = [None]; p["is_last_frame"] = False
+            out.append(p)
+        return out
+    primed = 0
+    while not (fe.is_initialized and fe.kf_idx >= 12) and primed < 400:
+        for p in frames(8):
+            fe.forward(p); primed += 1
+    torch.cuda.synchronize()
+    fr = frames(a.warmup + a.steps)
+    for p in fr[:a.warmup]:
+        fe.forward(p)
+    torch.cuda.synchronize()
+    kf0, up0 = fe.kf_idx, fe.stats["updates"]
+    clocks = ClockSampler(0); clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for p in fr[a.warmup:]:
+        fe.forward(p)
+    e1.record(); torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    v = a.steps / (ms / 1e3)
+    sys.stdout.flush(); os.dup2(saved, 1)
+    print(json.dumps(_ref_line(a, "reference-cuda", v, a.steps, {
+        "dtype": "f16 autocast (networks, correlation) / f32 (kernels) / f64 (host solve)",
+        "config": {"workload": "configs[1]: Replica-office0-shaped synthetic 640x480, --slam (NeRF not included: instant-ngp fork absent)",
+                   "implementation": "reference CUDA kernels from oracle/_ref + library PyTorch in the reference's sequencing; gtsam / lietorch "
+                                     "replaced by faster stand-ins (oracle/ref_cuda_frontend.py)",
+                   "primed_frames": primed, "keyframes_in_timed_region": fe.kf_idx - kf0,
+                   "update_calls_in_timed_region": fe.stats["updates"] - up0},
+        "clocks": clk})), flush=True)
 
 
 def main():
@@ -531,11 +648,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=192)
     ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--nerf-iters", type=int, default=2)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-cuda":
+        run_reference_cuda(a)
     else:
         run_ours(a)
 

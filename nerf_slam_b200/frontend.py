@@ -74,6 +74,11 @@ def matrix_to_tq(T):
     return np.array([T[0, 3], T[1, 3], T[2, 3], x, y, z, w])
 
 
+def types_ns(**kw):
+    import types
+    return types.SimpleNamespace(**kw)
+
+
 def coords_grid(ht, wd, device):
     y, x = torch.meshgrid(torch.arange(ht, device=device).float(), torch.arange(wd, device=device).float(),
                           indexing="ij")
@@ -188,22 +193,14 @@ class RaftVisualFrontend:
             self.weights_source = wpath
         for m in (self.feature_net, self.context_net, self.update_net):
             m.to(device=device, dtype=torch.float16)
-        # update operator: hand-written tcgen05 implicit-GEMM convolutions (default) or the cuDNN
-        # library path (args.conv_backend == "cudnn"; kept as the A/B reference for the parity tests)
-        self.conv_backend = getattr(args, "conv_backend", "tcgen05")
-        # the encoders' library convolutions: let cuDNN time its algorithms once per shape (its heuristic picks a
-        # CUDA-core kernel for the 32-channel layers); set args.cudnn_benchmark = False to disable
-        if getattr(args, "cudnn_benchmark", True):
-            torch.backends.cudnn.benchmark = True
+        # encoders and update operator: hand-written tcgen05 implicit-GEMM convolutions.  There is no library / CPU
+        # alternative in the product (the cuDNN formulation of the same networks lives with the reference arm,
+        # oracle/ref_cuda_frontend.py, and in the parity tests).
+        from .conv import EncoderTC, UpdateOperatorTC
         self.timers = _Timers()
-        self.update_tc = None
-        self.feature_tc = self.context_tc = None
-        if self.conv_backend == "tcgen05":
-            from .conv import EncoderTC, UpdateOperatorTC
-            self.update_tc = UpdateOperatorTC(self.update_net, device)
-            if getattr(args, "encoder_backend", "tcgen05") == "tcgen05":
-                self.feature_tc = EncoderTC(self.feature_net, device)
-                self.context_tc = EncoderTC(self.context_net, device)
+        self.update_tc = UpdateOperatorTC(self.update_net, device)
+        self.feature_tc = EncoderTC(self.feature_net, device)
+        self.context_tc = EncoderTC(self.context_net, device)
 
         # prior sigmas (visual_frontend.py:142-153)
         self.g_prior_cov = torch.block_diag(0.01 ** 2 * torch.eye(3), 0.01 ** 2 * torch.eye(3)).to(device)
@@ -216,8 +213,6 @@ class RaftVisualFrontend:
         # formula its comments describe
         self.cov_mode = int(getattr(args, "cov_reference", 1))
         self.use_cuda_graphs = bool(getattr(args, "cuda_graphs", True))
-        if self.conv_backend != "tcgen05":
-            self.use_cuda_graphs = False       # the library path syncs inside GraphAgg (torch.unique)
         self._static = None
         self._img_static = None
         # update(): replaying a captured graph saves host time per call but costs a re-capture (~2 ms of host
@@ -336,16 +331,11 @@ class RaftVisualFrontend:
         self.cam0_intrinsics[idx] = (1.0 / self.dsf) * _lib.h2d(np.asarray(cm), dev, torch.float32)
 
     def _feature_encoder(self, imgs_norm):
-        if self.feature_tc is not None:
-            return self.feature_tc(imgs_norm[0])       # tensor-core path, [cams,128,ht,wd] fp16 (NHWC storage)
-        return self.feature_net(imgs_norm)[0]          # [cams,128,ht,wd] fp16
+        return self.feature_tc(imgs_norm[0])           # [cams,128,ht,wd] fp16 (NHWC storage)
 
     def _context_encoder(self, imgs_norm):
         """-> (tanh(context), relu(gru input)), both channels-last [cams,ht,wd,128]"""
-        if self.context_tc is not None:
-            c = self.context_tc(imgs_norm[0]).permute(0, 2, 3, 1)
-        else:
-            c = self.context_net(imgs_norm)[0].permute(0, 2, 3, 1)
+        c = self.context_tc(imgs_norm[0]).permute(0, 2, 3, 1)
         return torch.tanh(c[..., :128]), torch.relu(c[..., 128:])
 
     @staticmethod
@@ -362,23 +352,13 @@ class RaftVisualFrontend:
         [E,ht,wd,2] (target None -> zero residual) -> net' [E,ht,wd,128], delta/weight [E,ht,wd,2] fp32
         (, eta [K,ht,wd], upmask NHWC [K,ht,wd,576]) — the reference's UpdateModule return convention
         (droid_net.py:118-150).  ii_host: numpy source indices of the edges (enables GraphAgg)."""
-        if self.update_tc is not None:
-            agg = None if ii_host is None else self._agg_tables(ii_host, self.device)
-            out = self.update_tc(net, inp, corr_nhwc, coords1.contiguous(), self.coords0, target=target, agg=agg)
-            delta = out[1] - coords1
-            if ii_host is None:
-                return out[0], delta, out[2]
-            eta = 0.01 * torch.nn.functional.softplus(out[3][..., 0].float())
-            return out[0], delta, out[2], eta, out[4]
-        tgt = coords1 if target is None else target
-        motion = torch.cat([coords1 - self.coords0, tgt - coords1], dim=-1).permute(0, 3, 1, 2).clamp(-64.0, 64.0)
-        nchw = lambda t: t.permute(0, 3, 1, 2)
-        ii = None if ii_host is None else _lib.h2d(np.asarray(ii_host), self.device)
-        out = self.update_net(nchw(net)[None], nchw(inp)[None], nchw(corr_nhwc[..., :196])[None], motion[None], ii, ii)
-        net2 = out[0][0].permute(0, 2, 3, 1).contiguous()
-        if ii is None:
-            return net2, out[1][0].float(), out[2][0].float()
-        return net2, out[1][0].float(), out[2][0].float(), out[3][0].float(), out[4][0].permute(0, 2, 3, 1).contiguous()
+        agg = None if ii_host is None else self._agg_tables(ii_host, self.device)
+        out = self.update_tc(net, inp, corr_nhwc, coords1.contiguous(), self.coords0, target=target, agg=agg)
+        delta = out[1] - coords1
+        if ii_host is None:
+            return out[0], delta, out[2]
+        eta = 0.01 * torch.nn.functional.softplus(out[3][..., 0].float())
+        return out[0], delta, out[2], eta, out[4]
 
     def _put_features(self, idx, feats):
         self.features_imgs[idx] = feats.permute(0, 2, 3, 1)
@@ -429,6 +409,7 @@ class RaftVisualFrontend:
         else:
             if not self._update():
                 self.rm_keyframe(self.kf_idx - 1)
+                self._prefetch_proximity()
                 return x0, factors, viz_out
 
         self.last_k, self.last_kf_idx = k, self.kf_idx
@@ -438,6 +419,7 @@ class RaftVisualFrontend:
             viz_out = self.get_viz_out(batch)
             return x0, factors, viz_out
         self.kf_idx += 1
+        self._prefetch_proximity()
         return x0, factors, viz_out
 
     __call__ = forward
@@ -527,7 +509,9 @@ class RaftVisualFrontend:
         ii, jj = np.meshgrid(ix, jx, indexing="ij")
         ii, jj = ii.reshape(-1), jj.reshape(-1)
         with self.timers.section("prox.distance + cpu (device wait)"):
-            d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
+            d = self._take_prefetched_distances(kf0, kf1, t, beta)
+            if d is None:
+                d = self.distance(ii, jj, beta=beta).cpu().numpy().copy()
         ii1 = np.concatenate([self.ii_h, self.ii_bad_h, self.ii_inactive_h])
         jj1 = np.concatenate([self.jj_h, self.jj_bad_h, self.jj_inactive_h])
         with self.timers.section("prox.selection (host)"):
@@ -536,6 +520,38 @@ class RaftVisualFrontend:
             return
         with self.timers.section("prox.add_factors"):
             self.add_factors(es[:, 0], es[:, 1], remove)
+
+    # The pairwise distances of the NEXT keyframe candidate's proximity search depend only on poses / inverse depths
+    # that are final once the current candidate has been processed (the new slot's initial guess is written at the end
+    # of __update / __initialize; a rejected candidate ends with rm_keyframe).  They are therefore computed and copied
+    # to pinned host memory asynchronously at the end of forward(), behind the updates still queued on the stream,
+    # and are simply there when the next candidate arrives: no device round trip in front of the edge selection.
+    # `_state_version` guards the cache: anything that changes poses or depths after the prefetch invalidates it.
+    def _touch_state(self):
+        self._state_version = getattr(self, "_state_version", 0) + 1
+
+    def _prefetch_proximity(self):
+        if not self.is_initialized or self.kf_idx >= self.buffer or not self.cam0_T_world.is_cuda:
+            self._prox_prefetch = None
+            return
+        k = self.kf_idx
+        kf0, kf1, t = k - 4, max(k + 1 - self.frontend_window, 0), k + 1
+        ii, jj = np.meshgrid(np.arange(kf0, t), np.arange(kf1, t), indexing="ij")
+        d = self.distance(ii.reshape(-1), jj.reshape(-1), beta=self.beta)
+        n = d.numel()
+        if getattr(self, "_prox_host", None) is None or self._prox_host.numel() < n:
+            self._prox_host = torch.empty(max(n, 1024), dtype=torch.float32).pin_memory()
+        self._prox_host[:n].copy_(d, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._prox_prefetch = (getattr(self, "_state_version", 0), (kf0, kf1, t, float(self.beta)), n, ev)
+
+    def _take_prefetched_distances(self, kf0, kf1, t, beta):
+        pf, self._prox_prefetch = getattr(self, "_prox_prefetch", None), None
+        if pf is None or pf[0] != getattr(self, "_state_version", 0) or pf[1] != (kf0, kf1, t, float(beta)):
+            return None
+        pf[3].synchronize()
+        return self._prox_host[:pf[2]].numpy().copy()
 
     def _filter_repeated_edges(self, ii, jj):
         """visual_frontend.py:896-907: drop candidates that are already active or stored as inactive (duplicates INSIDE
@@ -602,6 +618,7 @@ class RaftVisualFrontend:
 
     def rm_keyframe(self, kf):
         """visual_frontend.py:530-574"""
+        self._touch_state()
         for buf in (self.gt_poses, self.gt_depths, self.cam0_images, self.cam0_timestamps, self.cam0_T_world,
                     self.world_T_body, self.world_T_body_cov, self.cam0_idepths, self.cam0_idepths_cov,
                     self.cam0_depths_cov, self.cam0_idepths_sensed, self.cam0_intrinsics, self.features_imgs,
@@ -637,6 +654,7 @@ class RaftVisualFrontend:
         for _ in range(8):
             self.update(use_inactive=True)
         k = self.kf_idx
+        self._touch_state()
         self.cam0_T_world[k + 1] = self.cam0_T_world[k].clone()
         self.world_T_body[k + 1] = self.world_T_body[k].clone()
         self.world_T_body_cov[k + 1] = self.world_T_body_cov[k].clone()
@@ -658,6 +676,7 @@ class RaftVisualFrontend:
                                        rad=self.frontend_radius, nms=self.frontend_nms,
                                        thresh=self.frontend_thresh, beta=self.beta, remove=True)
         k = self.kf_idx
+        self._touch_state()
         self.cam0_idepths[k] = torch.where(self.cam0_idepths_sensed[k] > 0, self.cam0_idepths_sensed[k], self.cam0_idepths[k])
         with T("kf.updates iters1 (host issue)"):
             for _ in range(self.iters1):
@@ -671,6 +690,7 @@ class RaftVisualFrontend:
             for _ in range(self.iters2):
                 self.update(use_inactive=True)
         nk = k + 1
+        self._touch_state()
         if nk < self.buffer:
             self.cam0_T_world[nk] = self.cam0_T_world[k]
             self.world_T_body[nk] = self.world_T_body[k]
@@ -718,7 +738,7 @@ class RaftVisualFrontend:
         st.prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
                                self.cam0_idepths_sensed, st.target, st.weight, st.damp, ii, jj, kf0, kf1)
         st.has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
-        if self.update_tc is not None and self.use_op_step:
+        if self.use_op_step:
             # the whole update operator as one host call on fixed buffers (csrc/update_step.cu)
             E = int(self.ii.shape[0])
             c, st.op_ws = self.update_tc.make_step(E, st.K, ht, wd, dev)
@@ -753,18 +773,10 @@ class RaftVisualFrontend:
         else:
             coords1, _ = db.reproject(self.cam0_T_world, self.cam0_idepths, self.cam0_intrinsics, self.ii, self.jj, want_valid=False)
             corr = self.corr_pool.lookup(self.slots_d, coords1, nhwc=True)          # [E,ht,wd,CORR_PAD] fp16
-        if st.op_ctx is not None:
-            pass
-        elif self.update_tc is not None:
-            # flow/confidence land directly in the frontend state AND in the BA's planar input buffers
-            net, _, _, e16, upmask = self.update_tc(
-                self.gru_hidden_states, st.inp, corr, coords1, self.coords0, target=self.gru_estimated_flow, agg=st.agg,
-                post=(self.gru_estimated_flow, self.gru_estimated_flow_weight, st.target[st.n_in:], st.weight[st.n_in:]))
-            self.gru_hidden_states.copy_(net)
-            _lib.check(_lib.load().nslam_eta_damping(_lib.ptr(e16), _lib.ptr(st.ux), _lib.ptr(self.damping), st.K,
-                                                     _lib.ptr(st.kx_ba), _lib.ptr(st.damp), int(st.kx_ba.numel()),
-                                                     self.ht * self.wd, float(st.EP), _lib.stream_ptr()), "eta_damping")
-        else:
+        if st.op_ctx is None and self.update_tc is None:
+            # test harness only (tests/test_cpu_droid.py replays the reference's update() traces on the CPU with a stand-in
+            # operator in `_run_update_net`; the constructor never selects this): the bookkeeping of
+            # visual_frontend.py:390-452 spelled out in tensor ops — what the fused kernels below do in place
             net, delta, weight, damping, upmask = self._run_update_net(self.gru_hidden_states, st.inp, corr, coords1,
                                                                        self.gru_estimated_flow, self.ii_h)
             self.gru_hidden_states.copy_(net)
@@ -775,6 +787,16 @@ class RaftVisualFrontend:
             st.weight[st.n_in:].copy_(self.gru_estimated_flow_weight.permute(0, 3, 1, 2))
             torch.mul(self.damping[st.kx_ba], 0.2, out=st.damp)
             st.damp.add_(st.EP)
+        elif st.op_ctx is None:
+            # the same operator sequenced from Python (kept for the test that ties the fused C call to this sequencing):
+            # flow/confidence land directly in the frontend state AND in the BA's planar input buffers
+            net, _, _, e16, upmask = self.update_tc(
+                self.gru_hidden_states, st.inp, corr, coords1, self.coords0, target=self.gru_estimated_flow, agg=st.agg,
+                post=(self.gru_estimated_flow, self.gru_estimated_flow_weight, st.target[st.n_in:], st.weight[st.n_in:]))
+            self.gru_hidden_states.copy_(net)
+            _lib.check(_lib.load().nslam_eta_damping(_lib.ptr(e16), _lib.ptr(st.ux), _lib.ptr(self.damping), st.K,
+                                                     _lib.ptr(st.kx_ba), _lib.ptr(st.damp), int(st.kx_ba.numel()),
+                                                     self.ht * self.wd, float(st.EP), _lib.stream_ptr()), "eta_damping")
         # the whole BA step (2 Gauss-Newton iterations + covariance block) is one host call; results land in place
         # in the pose / depth / covariance arenas; a failed factorisation changes nothing and bumps _ba_status[1]
         st.prob.frontend_update(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body, self._ba_status,
@@ -818,6 +840,7 @@ class RaftVisualFrontend:
         else:
             self._update_body(st, itrs, cc)
         st.calls += 1
+        self._touch_state()
         self.viz_idx[st.kf0:self.kf_idx + 1] = True
         self.age_h += 1
         self.stats["updates"] += 1
@@ -833,6 +856,7 @@ class RaftVisualFrontend:
         prob = db.BAProblem(self.cam0_T_world, self.cam0_idepths, self.intr0, self.cam0_T_body,
                             self.cam0_idepths_sensed, target, weight, damping, ii, jj, kf0, kf1)
         has_prior = self.kf_idx_to_f_idx.get(kf0, -1) == 0
+        self._touch_state()
         prob.frontend_update(itrs, self.world_T_body, self.cam0_T_world, self.cam0_T_body, self._ba_status,
                              prior_idx=0 if has_prior else -1, prior_pose=self.prior_pose if has_prior else None,
                              prior_info=self.prior_info if has_prior else 0.0, clamp_min=1e-3,
@@ -844,6 +868,7 @@ class RaftVisualFrontend:
 
     # ------------------------------------------------------------------ global BA (backend)
     def normalize(self, last_kf=-1):
+        self._touch_state()
         s = self.cam0_idepths[:last_kf].mean()
         self.cam0_idepths[:last_kf] /= s
         self.cam0_T_world[:last_kf, :3] *= s
@@ -855,36 +880,48 @@ class RaftVisualFrontend:
 
     @torch.no_grad()
     def update_lowmem(self, itrs=2, EP=1e-7, steps=8):
-        """visual_frontend.py:474-526: alt-corr path, edges processed in chunks of 8 source frames"""
-        kfs, cams = self.buffer, self.cameras
-        fm = self.features_imgs.permute(0, 1, 4, 2, 3).reshape(1, kfs * cams, 128, self.ht, self.wd)
+        """visual_frontend.py:474-526: global-BA path — correlation features computed on the fly (alt-corr, no stored
+        volumes), edges processed in chunks of 8 source frames, then one BA over the whole window per step.
+        Chunk membership and all gather / scatter indices are built on the host (the edge list lives there): no boolean
+        device masks, no device synchronisation inside the loop.  Rows of the damping / upsampling maps of a chunk are
+        its unique SOURCE frames (DROID's semantics, networks/factor_graph.py:259-303; see DESIGN.md on the reference's
+        own variant, which raises)."""
+        from .conv import CORR_PAD
+        dev, cams = self.device, self.cameras
+        fm = self.features_imgs.permute(0, 1, 4, 2, 3).reshape(1, self.buffer * cams, 128, self.ht, self.wd)
         corr_op = AltCorrBlock(fm)
+        ii_h, jj_h = self.ii_h, self.jj_h
+        s = 8
+        chunks = []
+        for i in range(0, int(jj_h.max()) + 1, s):
+            sel = np.nonzero((ii_h >= i) & (ii_h < i + s))[0]
+            if sel.size:
+                iis, jjs = ii_h[sel], jj_h[sel]
+                chunks.append(types_ns(sel=_lib.h2d(sel, dev), iis_h=iis, iis=_lib.h2d(iis, dev),
+                                       fi=_lib.h2d(cams * iis, dev), fj=_lib.h2d(cams * jjs + (iis == jjs), dev),
+                                       kx=_lib.h2d(np.unique(iis), dev)))
+        ux_all = _lib.h2d(np.unique(ii_h), dev)
         for _ in range(steps):
             coords1, _ = self.reproject(self.ii, self.jj)
-            s = 8
-            for i in range(0, int(self.jj_h.max()) + 1, s):
-                v = (self.ii_h >= i) & (self.ii_h < i + s)
-                if not v.any():
-                    continue
-                vd = torch.as_tensor(v, device=self.device)
-                iis, jjs = self.ii[vd], self.jj[vd]
-                from .conv import CORR_PAD
-                corr = corr_op(coords1[vd][None], cams * iis, cams * jjs + (iis == jjs).long())[0]      # [e,196,ht,wd] fp32
+            for c in chunks:
+                c1 = coords1.index_select(0, c.sel)
+                corr = corr_op(c1[None], c.fi, c.fj)[0]                                  # [e,196,ht,wd] fp32
                 corr = torch.nn.functional.pad(corr.permute(0, 2, 3, 1), (0, CORR_PAD - 196)).half().contiguous()
                 net, delta, weight, damping, upmask = self._run_update_net(
-                    self.gru_hidden_states[vd], self.cst_contexts_imgs[iis, 0], corr, coords1[vd].contiguous(),
-                    self.gru_estimated_flow[vd].contiguous(), self.ii_h[v])
-                self.gru_hidden_states[vd] = net
-                self.gru_estimated_flow[vd] = coords1[vd] + delta
-                self.gru_estimated_flow_weight[vd] = weight
-                kx = torch.unique(iis)
-                self.damping[kx] = damping
-                self.cam0_idepths_up[kx] = db.cvx_upsample(self.cam0_idepths[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
-                self.cam0_depths_cov_up[kx] = db.cvx_upsample(self.cam0_depths_cov[kx].unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
-            dmp = .2 * self.damping[torch.as_tensor(np.unique(self.ii_h), device=self.device)].contiguous() + EP
+                    self.gru_hidden_states.index_select(0, c.sel), self.cst_contexts_imgs[:, 0].index_select(0, c.iis),
+                    corr, c1.contiguous(), self.gru_estimated_flow.index_select(0, c.sel), c.iis_h)
+                self.gru_hidden_states.index_copy_(0, c.sel, net)
+                self.gru_estimated_flow.index_copy_(0, c.sel, c1 + delta)
+                self.gru_estimated_flow_weight.index_copy_(0, c.sel, weight)
+                self.damping.index_copy_(0, c.kx, damping)
+                up = db.cvx_upsample(self.cam0_idepths.index_select(0, c.kx).unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
+                self.cam0_idepths_up.index_copy_(0, c.kx, up)
+                upc = db.cvx_upsample(self.cam0_depths_cov.index_select(0, c.kx).unsqueeze(-1), upmask, mask_nhwc=True).squeeze(-1)
+                self.cam0_depths_cov_up.index_copy_(0, c.kx, upc)
+            dmp = (.2 * self.damping.index_select(0, ux_all) + EP).contiguous()
             target = self.gru_estimated_flow.permute(0, 3, 1, 2).contiguous()
             wgt = self.gru_estimated_flow_weight.permute(0, 3, 1, 2).contiguous()
-            self.ba(target, wgt, dmp, self.ii_h, self.jj_h, kf0=0, kf1=None, itrs=itrs, compute_covariances=False)
+            self.ba(target, wgt, dmp, ii_h, jj_h, kf0=0, kf1=None, itrs=itrs, compute_covariances=False)
 
     def backend(self, steps=12):
         """visual_frontend.py:1255-1306"""
