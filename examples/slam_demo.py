@@ -10,8 +10,9 @@ reference's format with nerf_slam_b200.datasets.write_transforms_dataset to feed
 What differs from the reference (examples/slam_demo.py:57-191): one process per GPU instead of a process per module —
 data, SLAM and fusion run in this process on streams of one GPU (the sequential branch, :160-181, without its queues);
 with `--multi_gpu` launch it under torchrun with 2+ ranks (rank 0 = SLAM, other ranks = NeRF trainers, NCCL hand-off;
-see bench.py / nerf_slam_b200.dist).  Out of scope, rejected with a message: euroc / real datasets, tsdf / sigma
-fusion, the Open3D GUI."""
+see bench.py / nerf_slam_b200.dist).  Out of scope, rejected with a message: euroc / real datasets, the Open3D GUI.
+The reference's own examples/slam_demo.py also runs unchanged with `nerf_slam_b200/shim` first on PYTHONPATH
+(tests/test_cpu_shim.py, tests/test_gpu_demo.py)."""
 import argparse
 import os
 import sys
@@ -66,8 +67,8 @@ def make_data(args):
 def run(args):
     import numpy as np
     import torch
-    if args.fusion in ("tsdf", "sigma") or args.gui:
-        raise NotImplementedError("tsdf / sigma fusion and the Open3D GUI are outside the hot-path scope (DESIGN.md)")
+    if args.gui:
+        raise NotImplementedError("the Open3D GUI is outside the hot-path scope (DESIGN.md)")
     device = "cuda:0"
     data = make_data(args)
     if args.weights and not os.path.exists(args.weights):
@@ -82,6 +83,9 @@ def run(args):
     if args.fusion == "nerf":
         from nerf_slam_b200.nerf_fusion import NerfFusion
         fusion = NerfFusion("nerf", args, device)
+    elif args.fusion in ("tsdf", "sigma"):
+        from nerf_slam_b200.tsdf_fusion import TsdfFusion
+        fusion = TsdfFusion(args.fusion, args, device)
     t0 = time.perf_counter()
     frames = 0
     for packet in data.stream():
@@ -92,16 +96,18 @@ def run(args):
             out = [None, viz_out]
         if fusion is not None:
             fusion.fuse({"slam": out} if slam is not None else {"data": packet})
-            for _ in range(max(args.nerf_iters_per_frame - 1, 0)):
-                fusion.fit_volume_once()
+            if args.fusion == "nerf":
+                for _ in range(max(args.nerf_iters_per_frame - 1, 0)):
+                    fusion.fit_volume_once()
         if slam is not None and slam.stop_condition():
             break
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"{frames} frames in {dt:.2f} s ({frames / dt:.1f} frames/s)"
           + (f", {slam.kf_idx} keyframes, {slam.stats['updates']} update() calls" if slam is not None else "")
-          + (f", {fusion.total_iters} NeRF iterations" if fusion is not None else ""))
-    if fusion is not None:
+          + (f", {fusion.total_iters} NeRF iterations" if args.fusion == "nerf" else "")
+          + (f", {fusion.integrated_frames} keyframe integrations into the {args.fusion} volume" if args.fusion in ("tsdf", "sigma") else ""))
+    if args.fusion == "nerf":
         for _ in range(args.fit_iters_after):
             fusion.fit_volume_once()
         if args.eval:

@@ -95,6 +95,17 @@ int nslam_cvx_upsample2(const float* data, const float* data2, const void* mask,
                         float* out, float* out2, const long long* index, int K, int ht, int wd, float pw,
                         int mask_nhwc, void* stream);
 
+/* §8(f3) Sigma / TSDF fusion of the SLAM packet into a DENSE voxel grid — the per-voxel update of
+ * TsdfFusion.custom_volume_integrate (reference fusion/tsdf_fusion.py:185-302; Open3D VoxelBlockGrid there).
+ * tsdf, weight [nz,ny,nx] fp32, color [nz,ny,nx,3] fp32 (DEVICE, updated in place); origin3 = world position of voxel
+ * (0,0,0) (HOST); idepth_up / depth_cov_up [H,W] fp32, rgb u8 [3,H,W] (DEVICE; depth_cov_up NULL = uniform weights,
+ * the "tsdf" mode; given = weights 1/sqrt(variance), the "sigma" mode); intr4 = fx, fy, cx, cy at full resolution (HOST);
+ * cam_T_world_tq = the packet's pose [t, q_xyzw] (DEVICE, 7 floats: no host copy of the pose). */
+int nslam_tsdf_integrate(float* tsdf, float* weight, float* color, int nx, int ny, int nz, const float* origin3_host,
+                         float voxel_size, const float* idepth_up, const float* depth_cov_up, const unsigned char* rgb_chw,
+                         int H, int W, const float* intr4_host, const float* cam_T_world_tq, float max_depth,
+                         float sdf_trunc, float max_weight, float max_depth_sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "nslam_update_op_step": [ctypes.POINTER(UpdateCtx), _P],
     "nslam_inorm_stats": [_P, _P, c_int, c_int, c_int, c_int, _P],
     "nslam_inorm_apply": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P],
+    "nslam_tsdf_integrate": [_P, _P, _P, c_int, c_int, c_int, _P, c_float, _P, _P, _P, c_int, c_int, _P, _P, c_float, c_float,
+                             c_float, c_float, _P],
     "nslam_ba_reduced_camera_matrix": [ctypes.POINTER(BAGraph), ctypes.POINTER(BABuffers), _P],
     "nslam_ba_tile_pixels": [],
     "nslam_ba_solve": [_P, _P, c_int, c_int, _P, c_float, c_float, c_float, _P, _P, _P, _P, _P],

@@ -27,9 +27,11 @@ def main():
     lib = ctypes.CDLL(SO)
     lib.umma_row_shift_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     out = np.zeros((128, 4), np.float32)
-    for sbo in (1024, 2048):
-        for s in range(0, 8):
-            for bo in sorted({0, s}):
+    # SBO 1024: 128 consecutive rows; 2048: 8-px tile in a 16-px-wide box; 1280: 8-px-wide tile in a 10-px-wide halo box
+    # (16h x 8w tile, ONE box {64c,10w,18h} for all nine taps: start row = dy*10 + dx); 2304: 16-px tile rows in an 18-px box
+    for sbo in (1024, 1280, 2048, 2304):
+        for s in (0, 1, 2, 3, 5, 7, 8, 9, 10, 11, 12, 20, 21, 22):
+            for bo in sorted({0, s % 8}):
                 rc = lib.umma_row_shift_probe(s, bo, sbo, out.ctypes.data)
                 if rc != 0:
                     print(f"sbo {sbo} shift {s} base_offset {bo}: CUDA error {rc}")
