@@ -68,17 +68,31 @@ int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_imag
                                   void* stream);
 int nslam_ngp_density_sample_tc(const nslam_ngp_model* m, const void* packed, int n_per_cascade, unsigned seed,
                                 float decay, int num_sms, void* stream);
+/* packed (see nslam_ngp_pack_mlp) != NULL: network on tensor cores; NULL: fp32 CUDA-core forward */
 int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, const float* cam18_host,
                           int x0, int y0, int tw, int th, int max_per_ray, float bg_r, float bg_g,
-                          float bg_b, float* out_rgbd, void* stream);
+                          float bg_b, float* out_rgbd, const void* packed, int num_sms, void* stream);
 int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            int H, int W, void* rgba_slot, float* depth_slot, float* cov_slot, void* stream);
 /* process_slam + send_data (fusion/nerf_fusion.py:140-289) for a whole packet in one launch, device to device: images,
  * depths (1 / idepth), covariances into slots ids[k]; camera records from the packet's cam_T_world poses [n,7] (t, q_xyzw;
- * world_T_cam 3x4 = inverse, nerf scale 1 / offset 0) or untouched when cam_T_world is NULL.  ids: DEVICE int64 [n]. */
+ * world_T_cam 3x4 = inverse, nerf scale 1 / offset 0) or untouched when cam_T_world is NULL.  ids: DEVICE int64 [n].
+ * cams_base [N] / cam_state [3,N,6] (offsets | Adam m | v) / cam_steps [N], all or none: pose-refinement state, the slots
+ * written get the new base camera and a reset refinement (see nslam_ngp_cam_adam_apply). */
 int nslam_ngp_ingest_batch(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            const long long* ids, int n, int H, int W, void* rgba, float* depth, float* depth_cov,
-                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* stream);
+                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* cams_base,
+                           float* cam_state, int* cam_steps, int n_slots, void* stream);
+
+/* Camera-pose refinement (`nerf.training.optimize_extrinsics`, fusion/nerf_fusion.py:99; csrc/ngp_extrinsics.cu):
+ * gradient of the batch just back-propagated w.r.t. each camera's translation and rotation vector, accumulated into
+ * cam_grad [n_images,6]; then Adam on the offsets [n_images,6] and the effective cameras the sampler reads. */
+int nslam_ngp_cam_grad(const void* grid_half, const float* scale16, const int* res16, const unsigned* size16,
+                       const unsigned* offset16, const int* dense16, float aabb_scale, const float* rays, int max_rays,
+                       const float* coords, const float* tdist, const void* denc, float loss_scale, float* cam_grad,
+                       void* stream);
+int nslam_ngp_cam_adam_apply(const void* base_cams, void* eff_cams, float* offsets, float* cam_grad, float* m, float* v,
+                             int* steps, int n, float lr, float beta1, float beta2, float eps, float l2, void* stream);
 
 /* tensor-core (tcgen05) variants of the network forward / backward, fused with the hash encoding
  * (csrc/ngp_tc.cu).  `packed` = 61 440-byte buffer of fp16 UMMA-ready weight images (forward images

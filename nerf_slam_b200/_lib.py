@@ -99,9 +99,12 @@ _SIGNATURES = {
     "nslam_ngp_loss_backward": [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_int, _P],
     "nslam_ngp_update_density_grid": [_P, _P, c_int, ctypes.c_uint, c_float, c_float, _P, c_int, _P],
     "nslam_ngp_density_sample_tc": [_P, _P, c_int, ctypes.c_uint, c_float, c_int, _P],
-    "nslam_ngp_render_tile": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P],
+    "nslam_ngp_render_tile": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, c_int, _P],
     "nslam_ngp_ingest_image": [_P, _P, _P, c_int, c_int, _P, _P, _P, _P],
-    "nslam_ngp_ingest_batch": [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P],
+    "nslam_ngp_ingest_batch": [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P,
+                               _P, _P, c_int, _P],
+    "nslam_ngp_cam_grad": [_P, _P, _P, _P, _P, _P, c_float, _P, c_int, _P, _P, _P, c_float, _P, _P],
+    "nslam_ngp_cam_adam_apply": [_P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, _P],
     "nslam_ngp_pack_mlp": [_P, _P, _P],
     "nslam_ngp_forward_tc": [_P, _P, _P, _P, c_int, c_int, _P, _P, c_int, _P],
     "nslam_ngp_backward_tc": [_P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int, _P],

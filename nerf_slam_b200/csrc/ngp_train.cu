@@ -754,7 +754,9 @@ __global__ void ingest_batch_kernel(const uint8_t* __restrict__ rgb_chw, const f
                                     const float* __restrict__ dcov, const long long* __restrict__ ids, int H, int W,
                                     __half* __restrict__ rgba, float* __restrict__ depth, float* __restrict__ depth_cov,
                                     const float* __restrict__ cam_T_world, float fx, float fy, float cx, float cy,
-                                    Camera* __restrict__ cams) {
+                                    Camera* __restrict__ cams, Camera* __restrict__ cams_base,
+                                    float* __restrict__ cam_state /* [3][N][6] offsets | m | v */, int* __restrict__ cam_steps,
+                                    int n_slots) {
   const int k = blockIdx.y;
   const size_t hw = (size_t)H * W;
   const size_t slot = (size_t)ids[k];
@@ -774,6 +776,13 @@ __global__ void ingest_batch_kernel(const uint8_t* __restrict__ rgb_chw, const f
     }
     c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.w = W; c.h = H;
     cams[slot] = c;
+    if (cams_base) {
+      // a new base pose from SLAM: the pose refinement of this camera starts again from zero (offsets, Adam moments)
+      cams_base[slot] = c;
+      for (int part = 0; part < 3; part++)
+        for (int q = 0; q < 6; q++) cam_state[((size_t)part * n_slots + slot) * 6 + q] = 0.f;
+      cam_steps[slot] = 0;
+    }
   }
   if (i >= H * W) return;
   const uint8_t* src = rgb_chw + (size_t)k * 3 * hw;
@@ -969,10 +978,11 @@ int nslam_ngp_update_density_grid(const nslam_ngp_model* m, const nslam_ngp_imag
   return 0;
 }
 
-/* render a tile of a camera view: out_rgbd [th*tw,4] = (r,g,b,z-depth) */
+/* render a tile of a camera view: out_rgbd [th*tw,4] = (r,g,b,z-depth).  packed != NULL: the network runs on tensor
+ * cores (nslam_ngp_forward_tc, the kernel the trainer uses); NULL: the fp32 CUDA-core forward (the tests' cross-check). */
 int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, const float* cam16,
                           int x0, int y0, int tw, int th, int max_per_ray, float bg_r, float bg_g,
-                          float bg_b, float* out_rgbd, void* stream) {
+                          float bg_b, float* out_rgbd, const void* packed, int num_sms, void* stream) {
   using namespace ngp;
   int r = ensure_attrs();
   if (r) return r;
@@ -987,9 +997,14 @@ int nslam_ngp_render_tile(const nslam_ngp_model* m, const nslam_ngp_batch* b, co
   render_rays_kernel<<<(tw * th + 3) / 4, 128, 0, st>>>(cam, make_scene(m), m->bits, x0, y0, tw, th,
                                                            b->max_samples, max_per_ray, b->rays, b->coords, b->tdist, b->counters);
   NGP_CHECK_LAUNCH();
-  forward_kernel<<<(b->max_samples + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>(b->coords, b->counters, -1,
-                                                                            (const __half2*)m->grid_half, lv, m->mlp, b->rgbsigma);
-  NGP_CHECK_LAUNCH();
+  if (packed) {
+    r = nslam_ngp_forward_tc(m, packed, b->coords, b->counters, -1, b->max_samples, b->rgbsigma, nullptr, num_sms, stream);
+    if (r) return r;
+  } else {
+    forward_kernel<<<(b->max_samples + TILE - 1) / TILE, TILE, FWD_SMEM, st>>>(b->coords, b->counters, -1,
+                                                                              (const __half2*)m->grid_half, lv, m->mlp, b->rgbsigma);
+    NGP_CHECK_LAUNCH();
+  }
   loss_kernel<<<(tw * th + 3) / 4, 128, 0, st>>>(b->rays, tw * th, b->coords, b->tdist, b->rgbsigma, b->counters,
                                                       0.f, make_float3(bg_r, bg_g, bg_b), 1, nullptr, nullptr, out_rgbd);
   NGP_CHECK_LAUNCH();
@@ -1007,15 +1022,18 @@ int nslam_ngp_ingest_image(const unsigned char* rgb_chw, const float* idepth_up,
 
 /* B1/B2 in one launch: n keyframes of a SLAM packet (images u8 [n,3,H,W], idepth_up / depth_cov_up [n,H,W], slot ids
  * [n] int64, cam_T_world [n,7] or NULL) into the trainer's slot arrays (rgba [N,H,W,4] fp16, depth / depth_cov [N,H,W])
- * and camera records cams [N] (when cam_T_world is given).  All pointers DEVICE. */
+ * and camera records cams [N] (when cam_T_world is given).  cams_base / cam_state [3,N,6] / cam_steps [N] (or NULL): the
+ * pose-refinement state of the trainer (csrc/ngp_extrinsics.cu) — base camera rewritten, offsets and moments reset.
+ * All pointers DEVICE. */
 int nslam_ngp_ingest_batch(const unsigned char* rgb_chw, const float* idepth_up, const float* depth_cov_up,
                            const long long* ids, int n, int H, int W, void* rgba, float* depth, float* depth_cov,
-                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* stream) {
+                           const float* cam_T_world, float fx, float fy, float cx, float cy, void* cams, void* cams_base,
+                           float* cam_state, int* cam_steps, int n_slots, void* stream) {
   if (n <= 0) return 0;
   dim3 grid((H * W + 255) / 256, n);
   ngp::ingest_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       rgb_chw, idepth_up, depth_cov_up, ids, H, W, (__half*)rgba, depth, depth_cov, cam_T_world, fx, fy, cx, cy,
-      (ngp::Camera*)cams);
+      (ngp::Camera*)cams, (ngp::Camera*)cams_base, cam_state, cam_steps, n_slots);
   NGP_CHECK_LAUNCH();
   return 0;
 }

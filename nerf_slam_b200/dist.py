@@ -86,6 +86,11 @@ def allreduce_grads(tb, group, world):
     over its own rays)."""
     dist.all_reduce(tb.grid_grad, group=group)
     dist.all_reduce(tb.mlp_grad, group=group)
+    cg = getattr(tb, "cam_grad", None)
+    if cg is not None:
+        dist.all_reduce(cg, group=group)
     if world > 1:
         tb.grid_grad.mul_(1.0 / world)
         tb.mlp_grad.mul_(1.0 / world)
+        if cg is not None:
+            cg.mul_(1.0 / world)

@@ -63,7 +63,7 @@ class NerfFusion:
         self.ngp.nerf.training.n_images_for_training = 0
         self.ngp.reload_network_from_file(getattr(args, "network", None))
         self.ngp.shall_train = True
-        self.ngp.nerf.training.optimize_extrinsics = True      # accepted; pose refinement not implemented
+        self.ngp.nerf.training.optimize_extrinsics = True      # :99 — per-camera pose refinement (csrc/ngp_extrinsics.cu)
         self.ngp.nerf.training.depth_supervision_lambda = 1.0
         self.ngp.nerf.training.depth_loss_type = ngp.LossType.L2
         self.mask_type = getattr(args, "mask_type", "ours")

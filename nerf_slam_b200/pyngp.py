@@ -90,6 +90,9 @@ class _Training:
         self.depth_loss_type = LossType.L2
         self.near_distance = 0.05
         self.density_grid_decay = 0.95
+        # camera-pose refinement (instant-ngp's published defaults; active when optimize_extrinsics is set)
+        self.extrinsic_learning_rate = 1e-3
+        self.extrinsic_l2_reg = 1e-4
 
     def update_training_images(self, frame_ids, poses, images, depths, depths_cov, resolution,
                                principal_point, focal_length, depth_scale, depth_cov_scale):
@@ -131,7 +134,8 @@ class _Training:
                 _lib.ptr(images_u8_chw.contiguous()), _lib.ptr(idepths_up.contiguous()), _lib.ptr(depths_cov_up.contiguous()),
                 _lib.ptr(ids_d), n, H, W, _lib.ptr(tb.rgba), _lib.ptr(tb.depth), _lib.ptr(tb.depth_cov), _lib.ptr(pose),
                 float(fl[0]), float(fl[1]), float(pp[0]), float(pp[1]), _lib.ptr(tb.cams) if pose is not None else None,
-                _lib.stream_ptr()), "ngp_ingest_batch")
+                _lib.ptr(tb.cams_base) if pose is not None else None, _lib.ptr(tb.cam_state), _lib.ptr(tb.cam_steps),
+                tb.n_images, _lib.stream_ptr()), "ngp_ingest_batch")
             if pose is not None:
                 tb._cams_host_stale = True
             else:
@@ -223,7 +227,15 @@ class Testbed:
         self.model = m
         self._cams_h = np.zeros((self.n_images, 18), np.float32)
         self._cams_host_stale, self._cams_upload = False, []
-        self.cams = torch.zeros(self.n_images, 18, **f)
+        self.cams = torch.zeros(self.n_images, 18, **f)          # effective cameras (base pose (+) refinement offsets)
+        # pose refinement (nerf.training.optimize_extrinsics, csrc/ngp_extrinsics.cu): base cameras as SLAM sent them,
+        # per-camera offsets / Adam moments [3,N,6] = (translation, rotation vector), gradient accumulator, step counts
+        self.cams_base = torch.zeros(self.n_images, 18, **f)
+        self.cam_state = torch.zeros(3, self.n_images, 6, **f)
+        self.cam_grad = torch.zeros(self.n_images, 6, **f)
+        self.cam_steps = torch.zeros(self.n_images, dtype=torch.int32, device=dev)
+        self._lv = {k: np.ascontiguousarray(np.asarray([r[i] for r in rows], dt)) for i, (k, dt) in
+                    enumerate((("scale", np.float32), ("res", np.int32), ("size", np.uint32), ("offset", np.uint32), ("dense", np.int32)))}
         self.active = torch.zeros(self.n_images, dtype=torch.int32, device=dev)
         self.active_set = []
         b = NgpBatch()
@@ -278,7 +290,11 @@ class Testbed:
                 self.active_set.append(int(i))
         if self._cams_upload:                       # host-set camera rows only (device-written rows are not touched)
             rows = sorted(set(self._cams_upload))
-            self.cams.index_copy_(0, _lib.h2d(np.asarray(rows, np.int64), self.device), _lib.h2d(self._cams_h[rows], self.device))
+            rd, vals = _lib.h2d(np.asarray(rows, np.int64), self.device), _lib.h2d(self._cams_h[rows], self.device)
+            self.cams.index_copy_(0, rd, vals)
+            self.cams_base.index_copy_(0, rd, vals)          # new base pose: the refinement of these cameras restarts
+            self.cam_state[:, rd] = 0
+            self.cam_steps[rd] = 0
             self._cams_upload = []
         n = len(self.active_set)
         self.active[:n].copy_(torch.as_tensor(self.active_set, dtype=torch.int32).pin_memory(), non_blocking=True)
@@ -325,8 +341,23 @@ class Testbed:
             _lib.check(lib.nslam_ngp_train_step(ctypes.byref(self.model), ctypes.byref(im), ctypes.byref(self.batch),
                                                 self.rays_per_batch, seed, lam, bg[0], bg[1], bg[2], self.num_sms,
                                                 _lib.stream_ptr()), "ngp_train_step")
+        tr = self.nerf.training
+        refine = tr.optimize_extrinsics and self.mlp_backend == "tcgen05" and tr.extrinsic_learning_rate > 0
+        if refine:
+            lv = self._lv
+            _lib.check(lib.nslam_ngp_cam_grad(_lib.ptr(self.grid_half), lv["scale"].ctypes.data, lv["res"].ctypes.data,
+                                              lv["size"].ctypes.data, lv["offset"].ctypes.data, lv["dense"].ctypes.data,
+                                              float(self.aabb_scale), _lib.ptr(self._bufs["rays"]), int(self.rays_per_batch),
+                                              _lib.ptr(self._bufs["coords"]), _lib.ptr(self._bufs["tdist"]), _lib.ptr(self._bufs["denc"]),
+                                              float(self.loss_scale), _lib.ptr(self.cam_grad), _lib.stream_ptr()), "ngp_cam_grad")
         if self.grad_hook is not None:
             self.grad_hook(self)
+        if refine:
+            _lib.check(lib.nslam_ngp_cam_adam_apply(_lib.ptr(self.cams_base), _lib.ptr(self.cams), _lib.ptr(self.cam_state[0]),
+                                                    _lib.ptr(self.cam_grad), _lib.ptr(self.cam_state[1]), _lib.ptr(self.cam_state[2]),
+                                                    _lib.ptr(self.cam_steps), self.n_images, float(tr.extrinsic_learning_rate),
+                                                    0.9, 0.99, 1e-10, float(tr.extrinsic_l2_reg), _lib.stream_ptr()), "ngp_cam_adam")
+            self._cams_host_stale = True
         self.training_step += 1
         decay = 0.33 ** max(0, (self.training_step - 20000) // 10000 + (1 if self.training_step >= 20000 else 0))
         _lib.check(lib.nslam_ngp_adam(ctypes.byref(self.model), self.training_step, self.lr * decay, self.beta1,
@@ -399,7 +430,9 @@ class Testbed:
         for y0 in range(0, height, rows):
             th = min(rows, height - y0)
             _lib.check(lib.nslam_ngp_render_tile(ctypes.byref(self.model), ctypes.byref(self.batch), cam, 0, y0, width, th,
-                                                 per_ray, bg[0], bg[1], bg[2], _lib.ptr(out[y0]), _lib.stream_ptr()),
+                                                 per_ray, bg[0], bg[1], bg[2], _lib.ptr(out[y0]),
+                                                 _lib.ptr(self.packed) if self.mlp_backend == "tcgen05" else None, self.num_sms,
+                                                 _lib.stream_ptr()),
                        "ngp_render_tile")
         o = out.cpu().numpy()
         if self.render_mode == Depth:

@@ -228,6 +228,41 @@ def rnd01(a, b, c):
     return np.float32(np.float32(pcg(pcg(pcg(a) ^ (b & 0xFFFFFFFF)) ^ (c & 0xFFFFFFFF)) >> 8) * np.float32(1.0 / 16777216.0))
 
 
+def render_view(P, c2w34, intr, width, height, aabb_scale, cascades, bits, near, bg, max_per_ray=1024, cone=1.0 / 256,
+                min_T=1e-4):
+    """B4 — Testbed.render of a pinhole view (fusion/nerf_fusion.py:411-424): per pixel centre the ray of the camera
+    record, the occupancy-lattice march without jitter, the network, front-to-back compositing over `bg`.
+    -> rgb [H,W,3] float32, z-depth [H,W] (sum_k w_k t_k * inv_len, the depth convention of the training loss)."""
+    fx, fy, cx, cy = [np.float32(v) for v in intr]
+    c2w = np.asarray(c2w34, np.float32).reshape(3, 4)
+    lo, hi = np.float32(0.5 - 0.5 * aabb_scale), np.float32(0.5 + 0.5 * aabb_scale)
+    rgb_out = np.zeros((height, width, 3), np.float32); dep_out = np.zeros((height, width), np.float32)
+    for py in range(height):
+        for px in range(width):
+            dx, dy = (np.float32(px + 0.5) - cx) / fx, (np.float32(py + 0.5) - cy) / fy
+            inv_len = np.float32(1.0) / np.sqrt(dx * dx + dy * dy + np.float32(1.0))
+            dc = np.array([dx * inv_len, dy * inv_len, inv_len], np.float32)
+            d = (c2w[:, :3] @ dc).astype(np.float32); o = c2w[:, 3].copy()
+            samples = march_lattice(o, d, lo, hi, near, cone, cascades, bits, 0.0, max_per_ray)
+            c = np.array(bg, np.float32).copy()
+            if samples:
+                t = torch.tensor([float(s[0]) for s in samples]); dt = torch.tensor([float(s[1]) for s in samples])
+                x01 = (torch.from_numpy(o)[None] + t[:, None] * torch.from_numpy(d)[None] - float(lo)) / float(hi - lo)
+                with torch.no_grad():
+                    rgb, sigma = network(x01, torch.from_numpy(d)[None].repeat(len(samples), 1), P, aabb_scale)
+                T, c, dep = 1.0, np.zeros(3, np.float32), 0.0
+                for k in range(len(samples)):
+                    if T < min_T:
+                        break
+                    a = 1.0 - math.exp(-float(sigma[k]) * float(dt[k]))
+                    w = a * T
+                    c = c + w * rgb[k].numpy(); dep += w * float(t[k]); T *= 1.0 - a
+                c = c + T * np.array(bg, np.float32)
+                dep_out[py, px] = dep * float(inv_len)
+            rgb_out[py, px] = c
+    return rgb_out, dep_out
+
+
 # ------------------------------------------------------------------------------------------ B1 / B2
 def srgb_to_linear(x):
     """utils/utils.py:136-139 (fp32 torch)"""

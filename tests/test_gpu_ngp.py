@@ -140,6 +140,114 @@ def test_loss_and_gradients_match_autograd(backend, R, per, tol):
     assert cos > (0.999999 if backend == "simt" else 0.9995), cos
 
 
+def test_camera_pose_gradients_match_autograd():
+    """optimize_extrinsics (fusion/nerf_fusion.py:99): nslam_ngp_cam_grad — dL/d(translation) and dL/d(rotation vector)
+    per camera from the batch's encoding gradients — against autograd through the oracle network with the sample
+    positions p = (o + dt_c) + t (d + w_c x d) (direction held fixed inside the spherical harmonics, as the published
+    scheme does).  Then one Adam step moves the effective camera against the gradient and an ingest resets it."""
+    from nerf_slam_b200 import _lib
+    tb = _testbed(seed=8)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    R, per = 64, 12
+    n = R * per
+    img = (torch.arange(R) % 2).int()
+    cam_o = torch.tensor([[0.1, -0.2, 0.0], [-0.3, 0.1, 0.2]])
+    o = cam_o[img.long()]
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    tdist = (torch.arange(per).float()[None] * 0.06 + 0.25 + torch.rand(R, 1, generator=g) * 0.05).reshape(R, per)
+    dt = torch.full((n,), 0.06)
+    lo, ext = 0.5 - 0.5 * 4.0, 4.0
+    xw = o[:, None] + tdist[..., None] * d[:, None]
+    x01 = ((xw - lo) / ext).reshape(n, 3)
+    coords = torch.cat([x01, dt[:, None], d.repeat_interleave(per, 0)], -1).contiguous()
+    rays = torch.zeros(R, 16)
+    rays[:, 0:3], rays[:, 3:6], rays[:, 6] = o, d, 0.9
+    tgt_rgb = torch.rand(R, 3, generator=g); tgt_dep = torch.rand(R, generator=g) * 0.5 + 0.2; cov = torch.rand(R, generator=g) * 0.5 + 0.1
+    rays[:, 7], rays[:, 8], rays[:, 9:12] = tgt_dep, cov, tgt_rgb
+    ri = rays.view(torch.int32)
+    ri[:, 12] = torch.arange(R, dtype=torch.int32) * per
+    ri[:, 13] = per
+    ri[:, 14] = img
+    tb._bufs["rays"][:R].copy_(rays.to(DEV)); tb._bufs["coords"][:n].copy_(coords.to(DEV)); tb._bufs["tdist"][:n].copy_(tdist.reshape(-1).to(DEV))
+    tb.mlp_grad.zero_(); tb.grid_grad.zero_(); tb.cam_grad.zero_()
+    tb.pack_weights()
+    bg = (0.2, 0.4, 0.6)
+    _lib.check(lib.nslam_ngp_loss_backward_tc(ctypes.byref(tb.model), ctypes.byref(tb.batch), _lib.ptr(tb.packed), R, n,
+                                              1.0, *bg, 1024.0, tb.num_sms, _lib.stream_ptr()), "loss_bwd_tc")
+    lv = tb._lv
+    _lib.check(lib.nslam_ngp_cam_grad(_lib.ptr(tb.grid_half), lv["scale"].ctypes.data, lv["res"].ctypes.data, lv["size"].ctypes.data,
+                                      lv["offset"].ctypes.data, lv["dense"].ctypes.data, 4.0, _lib.ptr(tb._bufs["rays"]), R,
+                                      _lib.ptr(tb._bufs["coords"]), _lib.ptr(tb._bufs["tdist"]), _lib.ptr(tb._bufs["denc"]), 1024.0,
+                                      _lib.ptr(tb.cam_grad), _lib.stream_ptr()), "cam_grad")
+    torch.cuda.synchronize()
+    # oracle
+    P = _oracle_params(tb)
+    dtc = torch.zeros(2, 3, requires_grad=True); wc = torch.zeros(2, 3, requires_grad=True)
+    il = img.long()
+    o2 = o + dtc[il]
+    d2 = d + torch.cross(wc[il], d, dim=-1)
+    x2 = ((o2[:, None] + tdist[..., None] * d2[:, None] - lo) / ext).reshape(n, 3)
+    rgb, sigma = ongp.network(x2, d.repeat_interleave(per, 0), P, 4.0)
+    loss, _, _ = ongp.composite_loss(rgb, sigma, dt, tdist.reshape(-1) * 0.9, [i * per for i in range(R + 1)], tgt_rgb, tgt_dep, cov,
+                                     torch.tensor(bg).repeat(R, 1), 1.0)
+    loss.backward()
+    ref = torch.cat([dtc.grad, wc.grad], 1)                     # [2,6]
+    got = tb.cam_grad[:2].cpu()
+    assert float(tb.cam_grad[2:].abs().max()) == 0.0
+    rel = float((got - ref).norm() / ref.norm())
+    cos = float(torch.dot(got.reshape(-1), ref.reshape(-1)) / (got.norm() * ref.norm()))
+    assert rel < 5e-2 and cos > 0.999, (rel, cos, got, ref)
+    # Adam step + effective cameras; then an ingest of camera 0 resets its refinement
+    base = torch.zeros(8, 18); base[:, [0, 5, 10]] = 1.0; base[:2, [3, 7, 11]] = cam_o
+    tb.cams_base.copy_(base.to(DEV)); tb.cams.copy_(base.to(DEV))
+    _lib.check(lib.nslam_ngp_cam_adam_apply(_lib.ptr(tb.cams_base), _lib.ptr(tb.cams), _lib.ptr(tb.cam_state[0]), _lib.ptr(tb.cam_grad),
+                                            _lib.ptr(tb.cam_state[1]), _lib.ptr(tb.cam_state[2]), _lib.ptr(tb.cam_steps), 8, 1e-3, 0.9, 0.99,
+                                            1e-10, 0.0, _lib.stream_ptr()), "cam_adam")
+    torch.cuda.synchronize()
+    off = tb.cam_state[0].cpu()
+    assert torch.allclose(off[:2], -1e-3 * torch.sign(ref), atol=2e-5)           # first Adam step = -lr * sign(g)
+    assert float(off[2:].abs().max()) == 0.0 and float(tb.cam_grad.abs().max()) == 0.0 and tb.cam_steps[:3].tolist() == [1, 1, 0]
+    eff = tb.cams.cpu()
+    assert torch.allclose(eff[:2, [3, 7, 11]], cam_o + off[:2, :3], atol=1e-7)
+    w = off[0, 3:]
+    Rw = torch.linalg.matrix_exp(torch.tensor([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]))
+    assert torch.allclose(eff[0, :12].view(3, 4)[:, :3], Rw, atol=1e-6)
+    assert torch.equal(eff[2:], base[2:])
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "simt"])
+def test_render_matches_oracle(backend):
+    """B4: Testbed.render (Shade and Depth) of a camera view against oracle/ngp.py::render_view — same pixel-centre rays,
+    same jitter-free occupancy march, network, compositing over the background.  tcgen05 = the tensor-core forward the
+    product renders with (fp16 operands: 1e-2 abs on colours); simt = fp32 CUDA-core forward (2e-4)."""
+    from nerf_slam_b200 import pyngp
+    tb = _testbed(seed=12)
+    tb.mlp_backend = backend
+    g = torch.Generator().manual_seed(6)
+    tb.mlp.mul_(0.5)                                    # moderate densities: rays neither empty nor saturated at once
+    tb.pack_weights()
+    bits = (torch.rand(tb.bits.shape, generator=g) < 0.3).to(torch.uint8) * torch.randint(1, 256, tb.bits.shape, generator=g, dtype=torch.uint8)
+    tb.bits.copy_(bits.to(DEV))
+    W, H = 20, 12
+    c2w = np.eye(4)[:3].copy(); c2w[:, 3] = [0.45, 0.55, 0.1]
+    th = 0.2
+    c2w[:3, :3] = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    tb.camera_matrix = c2w.astype(np.float64)
+    tb._view_intr = np.array([18.0, 18.0, W / 2 - 0.5, H / 2 - 0.5], np.float32)
+    tb.background_color = [0.1, 0.3, 0.5, 1.0]
+    tb.render_mode = pyngp.Shade
+    rgb = tb.render(W, H, 1, True)[..., :3]
+    tb.render_mode = pyngp.Depth
+    dep = tb.render(W, H, 1, True)[..., 0]
+    ref_rgb, ref_dep = ongp.render_view(_oracle_params(tb), c2w, tb._view_intr, W, H, tb.aabb_scale, tb.cascades, bits.numpy(),
+                                        tb.nerf.training.near_distance, tb.background_color[:3])
+    tol = 1e-2 if backend == "tcgen05" else 2e-4
+    assert np.abs(rgb - ref_rgb).max() < tol, np.abs(rgb - ref_rgb).max()
+    assert np.abs(dep - ref_dep).max() < (3e-2 if backend == "tcgen05" else 1e-3) * max(1.0, ref_dep.max()), np.abs(dep - ref_dep).max()
+    assert ref_dep.max() > 0.2 and np.ptp(ref_rgb) > 0.05          # the view is not trivial
+
+
 def test_adam_step_matches_torch():
     from nerf_slam_b200 import _lib
     tb = _testbed(seed=6)
