@@ -129,17 +129,18 @@ class SlamNerfJob:
         self._res_ring = [torch.zeros(7).pin_memory() for _ in range(4)]
         self._res_events = [torch.cuda.Event() for _ in range(4)]
         self.handoff = None
-        self.nerf_group = None
+        self.trainer = None
         if world > 1:
             import torch.distributed as dist
             from nerf_slam_b200 import dist as nd
-            self.handoff = nd.Handoff(self.dev, 40, H_IMG, W_IMG)
-            self.nerf_group = dist.new_group(list(range(1, world)))
-            if self.is_nerf and world > 2:
-                nw = world - 1
-                self.nf.ngp.grad_hook = lambda tb: nd.allreduce_grads(tb, self.nerf_group, nw)
+            self.handoff = nd.Handoff(self.dev, 16, H_IMG, W_IMG)
+            nerf_group = dist.new_group(list(range(1, world)))
             if self.is_nerf:
+                nw = world - 1
+                if nw > 1:
+                    self.nf.ngp.grad_hook = lambda tb: nd.allreduce_grads(tb, nerf_group, nw)
                 self.nf.ngp.seed = 1337 + 7919 * rank     # disjoint ray batches per trainer
+                self.trainer = nd.TrainerLoop(self.handoff, self.nf, self._ingest, nerf_group, nw, device=self.dev)
 
     # frames -------------------------------------------------------------------------------
     def make_frames(self, n, on_device):
@@ -182,31 +183,24 @@ class SlamNerfJob:
                     self._res_events[slot].record()
                     result = slot
                     self.d2h += 7 * 4
-        elif self.world > 1:
-            self._recv()
-        if self.is_nerf:
+        if self.is_nerf and self.world == 1:
             with torch.cuda.stream(self.nerf_stream):
                 for _ in range(self.nerf_iters):
                     self.nf.fit_volume_once()
-            if e2e and self.world == 1:
+            if e2e:
                 self.d2h += 4
         return result
 
     def _send(self, viz):
-        torch = self.torch
+        """rank 0: asynchronous hand-off of the dirty keyframes of this tick (nothing is sent on other frames)"""
         if viz is None or "cam0_poses" not in viz:
-            z = torch.zeros(0, dtype=torch.long, device=self.dev)
-            self.handoff.send(z, None, torch.zeros(0, 3, H_IMG, W_IMG, dtype=torch.uint8, device=self.dev), None, None)
             return
         self.handoff.send(viz["viz_idx"], viz["cam0_poses"], viz["cam0_images"], viz["cam0_idepths_up"], viz["cam0_depths_cov_up"])
 
-    def _recv(self):
-        n, last, data = self.handoff.recv()
-        if n:
-            idx, tq, img, idep, cov = data
-            intr = self.room.calib.camera_model.numpy()
-            self.nf.ngp.nerf.training.update_training_images_device(idx.tolist(), None, img, idep, cov, intr[:2], intr[2:],
-                                                                    cam_T_world=tq)
+    def _ingest(self, idx, tq, img, idep, cov):
+        intr = self.room.calib.camera_model.numpy()
+        self.nf.ngp.nerf.training.update_training_images_device(idx.tolist(), None, img, idep, cov, intr[:2], intr[2:],
+                                                                cam_T_world=tq)
 
     def drain_results(self):
         """all asynchronous result read-backs of the e2e arm have landed on the host"""
@@ -232,7 +226,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=30))
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
     torch.set_grad_enabled(False)
     def barrier():
@@ -247,29 +242,40 @@ def run_ours(a):
     n_frames = a.steps + a.warmup + 40
     kf_buffer = 100 if n_frames <= 460 else int(24 + 0.2 * n_frames)
 
+    def phase_end():
+        """N > 1: rank 0 marks a phase boundary for the free-running trainers, then everybody meets at the barrier;
+        trainers train (and ingest what arrives) until they see the marker"""
+        if world > 1:
+            from nerf_slam_b200 import dist as nd
+            if job_ref[0].is_slam:
+                nd.send_sync(job_ref[0].handoff)
+            else:
+                job_ref[0].trainer.run_until_sync()
+        barrier()
+
+    job_ref = [None]
+
     def new_primed_job():
         """fresh SLAM+NeRF state, primed (untimed) until SLAM is initialised and in steady state"""
         job = SlamNerfJob(rank, world, a.nerf_iters, buffer=kf_buffer)
+        job_ref[0] = job
         primed = 0
-        while True:
+        while job.is_slam:
             for p in job.make_frames(8, on_device=True):
                 job.step(p, e2e=False)
                 primed += 1
-            flag = torch.tensor([1 if (not job.is_slam or (job.fe.is_initialized and job.fe.kf_idx >= 12)) else 0], device=job.dev)
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 1 or primed >= 400:
+            if (job.fe.is_initialized and job.fe.kf_idx >= 12) or primed >= 400:
                 break
-        barrier()
+        phase_end()
         return job, primed
 
     job, primed = new_primed_job()
 
     def timed(frames, e2e):
-        for p in frames[:a.warmup]:
-            job.step(p, e2e)
-        barrier()
+        if job.is_slam:
+            for p in frames[:a.warmup]:
+                job.step(p, e2e)
+        phase_end()
         kf0 = job.fe.kf_idx if job.is_slam else 0
         up0 = job.fe.stats["updates"] if job.is_slam else 0
         it0 = job.nf.total_iters if job.is_nerf else 0
@@ -279,14 +285,23 @@ def run_ours(a):
             torch.cuda.profiler.start()          # ncu --profile-from-start off captures only the timed region
         t0 = time.perf_counter()
         e0.record()
-        for p in frames[a.warmup:]:
-            job.step(p, e2e)
-        if e2e and job.is_slam:
-            job.drain_results()
-        if world == 1:
-            torch.cuda.current_stream().wait_stream(job.nerf_stream)
-            torch.cuda.current_stream().wait_stream(job.slam_stream)
-        e1.record()
+        if job.is_slam:
+            for p in frames[a.warmup:]:
+                job.step(p, e2e)
+            if e2e:
+                job.drain_results()
+            if world == 1:
+                torch.cuda.current_stream().wait_stream(job.nerf_stream)
+                torch.cuda.current_stream().wait_stream(job.slam_stream)
+            e1.record()
+        # rank 0's device time ends here (e1); the trainers' ends when they have seen the phase marker — recorded after
+        # the marker so that max-over-ranks covers hand-off completion on the receiving side too
+        if world > 1 and job.is_slam:
+            from nerf_slam_b200 import dist as nd
+            nd.send_sync(job.handoff)
+        elif world > 1:
+            job.trainer.run_until_sync()
+            e1.record()
         barrier()
         if prof:
             torch.cuda.profiler.stop()
@@ -294,28 +309,38 @@ def run_ours(a):
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=job.dev)
         n_it = torch.tensor([(job.nf.total_iters - it0) if job.is_nerf else 0], device=job.dev, dtype=torch.float32)
+        n_it_max = n_it.clone()
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(n_it, op=dist.ReduceOp.SUM)          # NeRF iterations of all trainer ranks
+            dist.all_reduce(n_it_max, op=dist.ReduceOp.MAX)      # optimiser steps of the (data-parallel) model
         stats = dict(kf=(job.fe.kf_idx - kf0) if job.is_slam else 0, updates=(job.fe.stats["updates"] - up0) if job.is_slam else 0,
-                     nerf_iters=int(n_it.item()), wall_s=wall)
+                     nerf_iters=int(n_it.item()), nerf_steps=int(n_it_max.item()), wall_s=wall)
         return float(t.item()), stats
 
     clocks = ClockSampler(local)
-    dev_frames = job.make_frames(a.warmup + a.steps, on_device=True)
+    dev_frames = job.make_frames(a.warmup + a.steps, on_device=True) if job.is_slam else []
     if rank == 0:
         clocks.start()
     ms_dev, st_dev = timed(dev_frames, e2e=False)
     clk = clocks.stop() if rank == 0 else None
     # the e2e arm starts from a fresh, re-primed state so that both arms see the same keyframe budget (buffer=100)
+    job_ref[0] = None
     del dev_frames, job
     torch.cuda.empty_cache()
     job, _ = new_primed_job()
-    host_frames = job.make_frames(a.warmup + a.steps, on_device=False)
+    host_frames = job.make_frames(a.warmup + a.steps, on_device=False) if job.is_slam else []
     job.h2d = job.d2h = 0
     ms_e2e, st_e2e = timed(host_frames, e2e=True)
 
+    if world > 1:
+        # everything below is rank 0's single-GPU post-processing: leave the process group cleanly first
+        import torch.distributed as dist
+        if job.is_slam:
+            job.handoff.flush()
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pk = peaks()
@@ -330,7 +355,11 @@ def run_ours(a):
                    "weights": "droid.pth" if job.args.weights else "random-init (seeded)", "nerf_iters_per_frame": a.nerf_iters,
                    "nerf_samples_per_iter": 1 << 18, "primed_frames": primed, "keyframes_in_timed_region": st_dev["kf"],
                    "update_calls_in_timed_region": st_dev["updates"], "nerf_iters_in_timed_region": st_dev["nerf_iters"],
-                   "parallelism": "1 GPU: SLAM + NeRF on two streams" if world == 1 else f"rank0 SLAM, {world - 1} NeRF trainer rank(s), NCCL keyframe broadcast",
+                   "nerf_optimizer_steps_in_timed_region": st_dev["nerf_steps"],
+                   "nerf_iters_per_s": round(st_dev["nerf_iters"] / (ms_dev / 1e3), 1),
+                   "nerf_schedule": f"{a.nerf_iters} iterations per input frame on the SLAM GPU's second stream" if world == 1 else
+                                    "free-running trainers (fit whenever no keyframe message is pending, fusion_module.py:30-33)",
+                   "parallelism": "1 GPU: SLAM + NeRF on two streams" if world == 1 else f"rank0 SLAM, {world - 1} NeRF trainer rank(s) data-parallel over rays, asynchronous NCCL keyframe broadcast",
                    "l2": "inputs change every step and the working set exceeds L2; no explicit flush"},
         "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(job.h2d / max(a.steps + a.warmup, 1)),
                 "d2h_bytes_per_step": int(job.d2h / max(a.steps + a.warmup, 1)), "keyframes": st_e2e["kf"]},
