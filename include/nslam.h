@@ -50,6 +50,11 @@ int nslam_corr_volume_build_simt(const void* fmaps, int NF, int H, int W, int C,
  * 32-byte pieces (csrc/corr_volume_rows.cu).  C = 128, H even, W in {64, 80}; cudaErrorNotSupported otherwise. */
 int nslam_corr_volume_build_rows(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj,
                                  int E, void* out0, void* out1, void* out2, void* out3, void* stream);
+/* the same kernel writing edge e into slot slots[e] of pyramid ARENAS out0..3 = [n_slots,H,W,H>>l,W>>l]: all new edges of
+ * a keyframe in one launch (CorrPool.build); cudaErrorNotSupported for shapes the row-pair kernel does not cover. */
+int nslam_corr_volume_build_slots(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj,
+                                  const int* slots, int E, int n_slots, void* out0, void* out1, void* out2, void* out3,
+                                  void* stream);
 
 /* droid_backends.altcorr_forward (src/droid.cpp:303-313; kernel src/altcorr_kernel.cu:27-149)
  * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,N,H1,W1,2] fp32, corr [B,N,(2r+1)^2,H1,W1]. */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "nslam_corr_lookup_pyramid": [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "nslam_corr_volume_build": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_corr_volume_build_rows": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "nslam_corr_volume_build_slots": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P],
     "nslam_corr_volume_build_simt": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P],
     "nslam_altcorr_forward": [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "nslam_reproject": [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P],
@@ -118,6 +119,7 @@ _SIGNATURES = {
 }
 
 _lib = None
+_cuda_ok = False
 
 
 def exported_symbols():
@@ -137,11 +139,13 @@ def load(require_cuda=True):
             fn.argtypes = args
             fn.restype = c_int
         _lib = lib
-    if require_cuda:
+    global _cuda_ok
+    if require_cuda and not _cuda_ok:
         import torch
         if not torch.cuda.is_available():
             raise NslamUnavailable("nerf_slam_b200 operators need a CUDA device (sm_100a); "
                                    "there is no CPU fallback")
+        _cuda_ok = True          # checked once: the query costs ~4 us and every operator comes through here
     return _lib
 
 

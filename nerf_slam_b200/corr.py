@@ -84,6 +84,14 @@ class CorrPool:
         dev = self.device
         ii = _lib.h2d(np.asarray(fi, np.int32), dev)
         jj = _lib.h2d(np.asarray(fj, np.int32), dev)
+        NF, H, W, C = fmaps_nhwc.shape
+        if C == 128 and H % 2 == 0 and W in (64, 80):
+            # one launch for all new edges, each into the slot it was given
+            sl = _lib.h2d(np.asarray(slots, np.int32), dev)
+            _lib.check(_lib.load().nslam_corr_volume_build_slots(
+                _lib.ptr(fmaps_nhwc), NF, H, W, C, _lib.ptr(ii), _lib.ptr(jj), _lib.ptr(sl), n, self.capacity,
+                *[_lib.ptr(lv) for lv in self.levels], _lib.stream_ptr()), "corr_volume_build_slots")
+            return
         s = sorted(slots)
         contiguous = s == list(range(s[0], s[0] + n)) and list(slots) == s
         if contiguous:

@@ -1,4 +1,4 @@
-// A2 (EXPERIMENTAL, off by default: NSLAM_CORRVOL_ROWS=1) — correlation volume + pyramid with ROW-PAIR tiles.
+// A2 — correlation volume + pyramid with ROW-PAIR tiles (default for W in {64, 80}; bit-identical to corr_volume.cu).
 //
 // Same function as csrc/corr_volume.cu (reference networks/modules/corr.py:23-38,63-72).  That kernel walks the
 // target image in 8x16-pixel tiles, so every source row writes its volume row in 32-byte pieces (1024 segments
@@ -14,8 +14,7 @@
 // producer (A strip once per item, B = 2W2 x 128 channels per row pair, 3-stage ring), warp 1 = MMA issuer
 // (8 x tcgen05.mma M128 x N(2W2) x K16 into one of two TMEM stages), warps 2..9 = epilogue: the two warps of a
 // TMEM lane quarter split the columns in halves (w < W2/2 | w >= W2/2), thread = source pixel.
-// Requirements: C = 128, W2 % 16 == 0, 2*W2 <= 192, H2 even.  Validation pending (round-1 GPU budget was spent);
-// tests/test_gpu_parity.py::test_corr_volume_rows is enabled with the same environment variable.
+// Requirements: C = 128, W2 % 16 == 0, 2*W2 <= 192, H2 even.  tests/test_gpu_parity.py::test_corr_volume_rows_*.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -28,6 +27,7 @@ struct CrParams {
   __half* out[4];
   const int* ii;
   const int* jj;
+  const int* slots;    // output slot of edge e in the pyramid arena (NULL: e itself)
   int HW, H2, RP;      // RP = H2 / 2 row pairs
   int MT, nwork, split, rp_chunk;
 };
@@ -159,6 +159,7 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       item(w, e, m0, rp_lo, rp_hi);
       const int m = m0 + row;
       const bool mok = m < p.HW;
+      const int eo = p.slots ? p.slots[e] : e;      // where this edge's volumes live (CorrPool slot)
       __half l1p[WH / 2], l2p[WH / 4];           // carries: level 1 of the previous (even) row pair, level 2 of the previous (even) quad
       for (int rp = rp_lo; rp < rp_hi; rp++, t++) {
         const int as = t & 1, aph = (t >> 1) & 1;
@@ -198,14 +199,14 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           for (int y = 0; y < WH / 4; y++) l2[y] = cr_pool(l1p[2 * y], l1p[2 * y + 1], l1[2 * y], l1[2 * y + 1]);
           const int q2 = rp >> 1;
           if (mok && q2 < H2l) {
-            __half* dst = p.out[2] + ((size_t)e * p.HW + m) * ((size_t)H2l * (W2 / 4)) + (size_t)q2 * (W2 / 4) + c0 / 4;
+            __half* dst = p.out[2] + ((size_t)eo * p.HW + m) * ((size_t)H2l * (W2 / 4)) + (size_t)q2 * (W2 / 4) + c0 / 4;
 #pragma unroll
             for (int y = 0; y < WH / 4; y += 2) *reinterpret_cast<__half2*>(dst + y) = *reinterpret_cast<const __half2*>(l2 + y);
           }
           if ((rp & 3) == 3) {
             const int q3 = rp >> 2;
             if (mok && q3 < H3l) {
-              __half* dst3 = p.out[3] + ((size_t)e * p.HW + m) * ((size_t)H3l * (W2 / 8)) + (size_t)q3 * (W2 / 8) + c0 / 8;
+              __half* dst3 = p.out[3] + ((size_t)eo * p.HW + m) * ((size_t)H3l * (W2 / 8)) + (size_t)q3 * (W2 / 8) + c0 / 8;
 #pragma unroll
               for (int z = 0; z < WH / 8; z++) dst3[z] = cr_pool(l2p[2 * z], l2p[2 * z + 1], l2[2 * z], l2[2 * z + 1]);
             }
@@ -221,8 +222,8 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tc::fence_proxy_async();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
-          cr_tma_store_3d(&tmO0, sm + SM::ST0, 2 * rp * W2, m0, e);
-          cr_tma_store_3d(&tmO1, sm + SM::ST1, rp * (W2 / 2), m0, e);
+          cr_tma_store_3d(&tmO0, sm + SM::ST0, 2 * rp * W2, m0, eo);
+          cr_tma_store_3d(&tmO1, sm + SM::ST1, rp * (W2 / 2), m0, eo);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -236,7 +237,7 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
 template <int W2>
 static int launch_rows(const void* fmaps, int NF, int H, const int* ii, const int* jj, int E, void* const* outs,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int* slots = nullptr, int n_slots = 0) {
   using SM = CrSmem<W2>;
   const int W = W2, HW = H * W, C = 128;
   CUtensorMap tmA, tmB, tmO0, tmO1;
@@ -251,8 +252,9 @@ static int launch_rows(const void* fmaps, int NF, int H, const int* ii, const in
   }
   {
     const uint64_t n0 = (uint64_t)H * W, n1 = (uint64_t)(H / 2) * (W / 2);
-    uint64_t d0[3] = {n0, (uint64_t)HW, (uint64_t)E}, s0[2] = {n0 * 2, (uint64_t)HW * n0 * 2};
-    uint64_t d1[3] = {n1, (uint64_t)HW, (uint64_t)E}, s1[2] = {n1 * 2, (uint64_t)HW * n1 * 2};
+    const uint64_t NE = slots ? (uint64_t)n_slots : (uint64_t)E;      // edges (or arena slots) along the outer dimension
+    uint64_t d0[3] = {n0, (uint64_t)HW, NE}, s0[2] = {n0 * 2, (uint64_t)HW * n0 * 2};
+    uint64_t d1[3] = {n1, (uint64_t)HW, NE}, s1[2] = {n1 * 2, (uint64_t)HW * n1 * 2};
     uint32_t b0[3] = {(uint32_t)(2 * W), 128, 1}, b1[3] = {(uint32_t)(W / 2), 128, 1};
     int r = tc::make_tmap_f16(&tmO0, outs[0], 3, d0, s0, b0, false, nullptr, false);
     if (r) return r;
@@ -261,7 +263,7 @@ static int launch_rows(const void* fmaps, int NF, int H, const int* ii, const in
   }
   CrParams p;
   for (int l = 0; l < 4; l++) p.out[l] = (__half*)outs[l];
-  p.ii = ii; p.jj = jj; p.HW = HW; p.H2 = H; p.RP = H / 2;
+  p.ii = ii; p.jj = jj; p.slots = slots; p.HW = HW; p.H2 = H; p.RP = H / 2;
   p.MT = (HW + 127) / 128;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -291,7 +293,7 @@ static int launch_rows(const void* fmaps, int NF, int H, const int* ii, const in
 
 extern "C" {
 
-/* EXPERIMENTAL row-pair variant of nslam_corr_volume_build (same arguments and outputs).  Supported shapes:
+/* row-pair variant of nslam_corr_volume_build (same arguments and outputs).  Supported shapes:
  * C = 128, H even, W in {64, 80}; returns cudaErrorNotSupported otherwise (callers then use the tiled kernel). */
 int nslam_corr_volume_build_rows(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj, int E,
                                  void* out0, void* out1, void* out2, void* out3, void* stream) {
@@ -302,6 +304,22 @@ int nslam_corr_volume_build_rows(const void* fmaps, int NF, int H, int W, int C,
   switch (W) {
     case 80: return launch_rows<80>(fmaps, NF, H, ii, jj, E, outs, (cudaStream_t)stream);
     case 64: return launch_rows<64>(fmaps, NF, H, ii, jj, E, outs, (cudaStream_t)stream);
+    default: return (int)cudaErrorNotSupported;
+  }
+}
+
+/* As nslam_corr_volume_build_rows, but edge e is written into slot slots[e] of pyramid ARENAS out0..3 =
+ * [n_slots,H,W,H>>l,W>>l] (CorrPool): all new edges of a keyframe in ONE launch, whatever slots they were given. */
+int nslam_corr_volume_build_slots(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj,
+                                  const int* slots, int E, int n_slots, void* out0, void* out1, void* out2, void* out3,
+                                  void* stream) {
+  using namespace nslam;
+  if (E == 0) return 0;
+  if (C != 128 || (H & 1) || slots == nullptr || n_slots <= 0) return (int)cudaErrorNotSupported;
+  void* outs[4] = {out0, out1, out2, out3};
+  switch (W) {
+    case 80: return launch_rows<80>(fmaps, NF, H, ii, jj, E, outs, (cudaStream_t)stream, slots, n_slots);
+    case 64: return launch_rows<64>(fmaps, NF, H, ii, jj, E, outs, (cudaStream_t)stream, slots, n_slots);
     default: return (int)cudaErrorNotSupported;
   }
 }

@@ -139,6 +139,7 @@ class RefCudaFrontend(RaftVisualFrontend):
 
     # ---- per-frame front (motion filter, visual_frontend.py:976-1007), eager
     def _frame_front(self, imgs_k):
+        self._img_static = imgs_k                                               # the base class' context encoder reads it
         feats = self._feature_encoder(self._normalize_imgs(imgs_k))             # [cams,128,ht,wd]
         k = self.last_kf_idx
         pool = RefCorrPool(self.ht, self.wd, self.device, self.refcorr)

@@ -26,6 +26,8 @@ def _frontend(case, monkeypatch):
     from nerf_slam_b200 import _lib, corr, frontend as fr
     monkeypatch.setattr(_lib, "h2d", lambda a, device, dtype=None: (torch.from_numpy(np.ascontiguousarray(a)) if dtype is None
                                                                     else torch.from_numpy(np.ascontiguousarray(a)).to(dtype)))
+    import contextlib
+    monkeypatch.setattr(_lib, "fixed_stream", contextlib.nullcontext)
     motion, accept = sc.plan(case["seed"], case["n_frames"], case["last_has_motion"])
     log = []
 
@@ -45,12 +47,14 @@ def _frontend(case, monkeypatch):
             self.timers = fr._Timers()
             self.stats = {"updates": 0}
             self._img_static = None
+            self.use_cuda_graphs = False
 
         def _normalize_imgs(self, images):
             return images[:, :, :3].float()
 
         def _frame_front(self, imgs_k):
             k = int(imgs_k[0, 0, 0, 0, 0])
+            self._img_static = imgs_k                   # what the real per-frame front leaves for the context encoder
             self.last_motion = torch.tensor(10.0 if motion[k] else 0.0)
             return torch.full((1, 128, self.ht, self.wd), float(k), dtype=torch.half)
 
