@@ -21,7 +21,7 @@
 namespace nslam {
 
 constexpr int CR_THREADS = 320;
-constexpr int CR_STAGES = 3;
+constexpr int CR_STAGES = 2;      // the epilogue / store path bounds the kernel (MMAs: 640 of ~2500 cycles per tile)
 
 struct CrParams {
   __half* out[4];
@@ -49,10 +49,14 @@ struct CrSmem {
   static constexpr int A = 0;                                  // 2 x 16384
   static constexpr int B = 32768;                              // STAGES x 2 x NB*128
   static constexpr int BSTAGE = 2 * NB * 128;
-  static constexpr int ST0 = B + CR_STAGES * BSTAGE;           // [128][NB] halfs
-  static constexpr int ST1 = ST0 + 128 * NB * 2;               // [128][W2/2] halfs
-  static constexpr int BAR = ST1 + 128 * W2;
+  // staging of levels 0 / 1, DOUBLE buffered: the TMA store of tile t reads buffer t&1 while tile t+1 is written
+  static constexpr int ST0 = B + CR_STAGES * BSTAGE;           // 2 x [128][NB] halfs
+  static constexpr int ST0_BYTES = 128 * NB * 2;
+  static constexpr int ST1 = ST0 + 2 * ST0_BYTES;              // 2 x [128][W2/2] halfs
+  static constexpr int ST1_BYTES = 128 * W2;
+  static constexpr int BAR = ST1 + 2 * ST1_BYTES;
   static constexpr int TOTAL = BAR + 128;
+  static_assert(TOTAL + 1024 <= 227 * 1024, "shared memory plan");
 };
 
 template <int W2>
@@ -150,8 +154,6 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const int c0 = hsel * WH;
-    unsigned char* st0 = sm + SM::ST0 + row * (NB * 2);
-    unsigned char* st1 = sm + SM::ST1 + row * W2;
     const int H2l = p.H2 >> 2, H3l = p.H2 >> 3;
     uint32_t t = 0;
     for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
@@ -163,28 +165,39 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       __half l1p[WH / 2], l2p[WH / 4];           // carries: level 1 of the previous (even) row pair, level 2 of the previous (even) quad
       for (int rp = rp_lo; rp < rp_hi; rp++, t++) {
         const int as = t & 1, aph = (t >> 1) & 1;
+        unsigned char* st0 = sm + SM::ST0 + (t & 1) * SM::ST0_BYTES + row * (NB * 2);
+        unsigned char* st1 = sm + SM::ST1 + (t & 1) * SM::ST1_BYTES + row * W2;
         tc::mbar_wait(&tm_full[as], aph);
         tc::tc_fence_after();
-        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+        // staging buffer t&1 is free once the store of tile t-2 has read it (at most ONE newer store group may be pending)
+        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+        // both target rows of the tile: all TMEM loads in flight, ONE wait (was: a wait per 8 columns)
+        uint32_t ra[2][WH];
+#pragma unroll
+        for (int tr = 0; tr < 2; tr++) {
+          tc::tmem_ld_32x32(taddr + tr * W2 + c0, ra[tr]);
+#pragma unroll
+          for (int k = 32; k < WH; k += 8) tc::tmem_ld_32x8(taddr + tr * W2 + c0 + k, ra[tr] + k);
+        }
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[as]);        // the accumulator stage is free for the next MMAs already
         __half h0[WH], h1[WH];
 #pragma unroll
         for (int tr = 0; tr < 2; tr++) {
+          __half* h = tr ? h1 : h0;
 #pragma unroll
-          for (int k = 0; k < WH / 8; k++) {
-            uint32_t r8[8];
-            tc::tmem_ld_32x8(taddr + tr * W2 + c0 + 8 * k, r8);
-            tc::tmem_ld_wait();
-            __half* h = tr ? h1 : h0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) h[8 * k + i] = __float2half_rn(__uint_as_float(r8[i]) * 0.0625f);
-            *reinterpret_cast<uint4*>(st0 + (tr * W2 + c0 + 8 * k) * 2) = *reinterpret_cast<const uint4*>(h + 8 * k);
+          for (int i = 0; i < WH; i += 2) {
+            const __half2 v = __floats2half2_rn(__uint_as_float(ra[tr][i]) * 0.0625f, __uint_as_float(ra[tr][i + 1]) * 0.0625f);
+            h[i] = __low2half(v); h[i + 1] = __high2half(v);
           }
+#pragma unroll
+          for (int k = 0; k < WH / 8; k++)
+            *reinterpret_cast<uint4*>(st0 + (tr * W2 + c0 + 8 * k) * 2) = *reinterpret_cast<const uint4*>(h + 8 * k);
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tm_empty[as]);
         // level 1: 2x2 means of the two rows of this tile
         __half l1[WH / 2];
 #pragma unroll
@@ -222,8 +235,8 @@ corr_volume_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tc::fence_proxy_async();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
-          cr_tma_store_3d(&tmO0, sm + SM::ST0, 2 * rp * W2, m0, eo);
-          cr_tma_store_3d(&tmO1, sm + SM::ST1, rp * (W2 / 2), m0, eo);
+          cr_tma_store_3d(&tmO0, sm + SM::ST0 + (t & 1) * SM::ST0_BYTES, 2 * rp * W2, m0, eo);
+          cr_tma_store_3d(&tmO1, sm + SM::ST1 + (t & 1) * SM::ST1_BYTES, rp * (W2 / 2), m0, eo);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }

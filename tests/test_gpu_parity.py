@@ -399,13 +399,17 @@ def test_pose_prior_error(db):
     assert np.allclose(t, p[0, :3], atol=1e-5)
 
 
-def test_corr_lookup_nhwc_equals_reference_layout(db):
-    """channels-last / slot-indirected variant == reference-layout kernel (bit for bit)"""
+@pytest.mark.parametrize("H,W,spread", [(30, 41, 6), (60, 80, 12), (16, 64, 40), (21, 48, 9)])
+def test_corr_lookup_nhwc_equals_reference_layout(db, H, W, spread):
+    """channels-last / slot-indirected variant == reference-layout kernel (bit for bit).  (30,41): odd width, partial
+    32-pixel groups, scalar gathers; (60,80), (16,64), (22,48): level widths multiples of 8 -> the 128-bit kernel
+    (aligned chunk pairs + select network on levels 0/1, staged slices on levels 2/3; (21,48) has a partial last CTA
+    and odd pooled sizes); spread 40 px sends many windows partly or wholly out of the volume."""
     rng = np.random.default_rng(14)
-    E, C, H, W = 3, 16, 30, 41          # odd width: partial 32-pixel groups
+    E, C = 3, 16
     f = rng.normal(0, 1, (2 * E, C, H, W)).astype(np.float16)
     pyr = [T(p) for p in ocorr.corr_volume_pyramid(f[:E], f[E:])]
-    coords = (np.stack(np.meshgrid(np.arange(W), np.arange(H)), 0)[None] + rng.uniform(-6, 6, (E, 2, H, W))).astype(np.float32)
+    coords = (np.stack(np.meshgrid(np.arange(W), np.arange(H)), 0)[None] + rng.uniform(-spread, spread, (E, 2, H, W))).astype(np.float32)
     ref = db.corr_lookup_pyramid(pyr, T(coords), 3)                                     # [E,196,H,W]
     slots = T(np.array([2, 0, 1], np.int32))
     perm = [pyr_l[[1, 2, 0]] for pyr_l in pyr]                                         # slot s holds edge perm^-1
@@ -413,6 +417,27 @@ def test_corr_lookup_nhwc_equals_reference_layout(db):
                                  slots=slots, nhwc_stride=200, coords_nhwc=True)        # [E,H,W,200]
     assert torch.equal(got[..., :196].permute(0, 3, 1, 2).float(), ref.float())
     assert float(got[..., 196:].abs().max()) == 0.0
+
+
+def test_corr_pool_builds_scattered_slots_in_one_launch():
+    """CorrPool.build: all new edges of a keyframe in ONE launch, each volume into the arena slot it was given
+    (nslam_corr_volume_build_slots) == one build per edge; other slots untouched"""
+    from nerf_slam_b200 import droid_backends as db
+    from nerf_slam_b200.corr import CorrPool
+    g = torch.Generator().manual_seed(78)
+    H, W, NF = 16, 64, 5
+    fm = torch.randn(NF, H, W, 128, generator=g).half().to("cuda:0")
+    pool = CorrPool(9, H, W, "cuda:0")
+    for lv in pool.levels:
+        lv.fill_(-3.0)
+    fi, fj, slots = [0, 3, 1, 4], [1, 3, 2, 0], [7, 2, 5, 0]
+    pool.build(fm, fi, fj, slots)
+    torch.cuda.synchronize()
+    ref = db.corr_volume_build(fm, torch.tensor(fi, dtype=torch.int32, device="cuda:0"), torch.tensor(fj, dtype=torch.int32, device="cuda:0"))
+    for l in range(4):
+        assert torch.equal(pool.levels[l][slots], ref[l])
+        rest = [s for s in range(9) if s not in slots]
+        assert bool((pool.levels[l][rest] == -3.0).all())
 
 
 @pytest.mark.parametrize("H,W,E", [(60, 80, 3), (16, 64, 2), (30, 80, 1)])
