@@ -81,7 +81,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // whole warp in the loop, elected lane issues (uniform control flow, see tc::umma_f16_lead)
+    {
+      const uint32_t lead = tc::elect_one() ? 1u : 0u;
       if (HALO) {
         // unit = (channel block, dx): one shifted halo tile + the three weight blocks of its taps (dy = 0..2).
         // The tile of the NEXT unit is requested before this unit's weight blocks so that two units are in flight.
@@ -89,8 +91,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
         auto load_a = [&](int s, int cb, int dx, int w0, int h0, int n) {
           const int sa = ia % AS, pa = (ia / AS) & 1;
           tc::mbar_wait(&empty_a[sa], pa ^ 1);
-          tc::mbar_arrive_expect_tx(&full_a[sa], SM::A_STAGE);
-          tc::tma_load_4d(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + dx - 1, h0 - 1, n);
+          tc::mbar_arrive_expect_tx_lead(&full_a[sa], SM::A_STAGE, lead);
+          tc::tma_load_4d_lead(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + dx - 1, h0 - 1, n, lead);
           ia++;
         };
         const int units = p.cb_total * 3;
@@ -112,9 +114,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
             for (int dy = 0; dy < 3; dy++, ib++) {
               const int sb = ib % BS, pb = (ib / BS) & 1;
               tc::mbar_wait(&empty_b[sb], pb ^ 1);
-              tc::mbar_arrive_expect_tx(&full_b[sb], N * 128);
-              bulk_copy_g2s(sm + SM::B + sb * (N * 128), p.wpacked + (size_t)((dy * 3 + dx) * p.cb_total + cbg) * N * 64,
-                            N * 128, &full_b[sb]);
+              tc::mbar_arrive_expect_tx_lead(&full_b[sb], N * 128, lead);
+              tc::bulk_copy_g2s_lead(sm + SM::B + sb * (N * 128), p.wpacked + (size_t)((dy * 3 + dx) * p.cb_total + cbg) * N * 64,
+                                     N * 128, &full_b[sb], lead);
             }
           }
         }
@@ -130,10 +132,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
               for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
                 const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
                 tc::mbar_wait(&empty_b[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&full_b[st], 16384 + N * 128);
-                tc::tma_load_4d(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n);
-                bulk_copy_g2s(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
-                              N * 128, &full_b[st]);
+                tc::mbar_arrive_expect_tx_lead(&full_b[st], 16384 + N * 128, lead);
+                tc::tma_load_4d_lead(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n, lead);
+                tc::bulk_copy_g2s_lead(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
+                                       N * 128, &full_b[st], lead);
               }
             }
           }
@@ -142,7 +144,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The WHOLE warp runs the loop (uniform control flow: loop counters, barrier addresses and descriptors live in
+    // uniform registers); only the elected lane issues tcgen05.mma / tcgen05.commit (tc::umma_f16_lead).
+    {
+      const uint32_t lead = tc::elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, 0);
       uint32_t it = 0, ia = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
@@ -154,36 +159,36 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
           for (int u = 0; u < units; u++, ia++) {
             const int sa = ia % AS, pa = (ia / AS) & 1;
             tc::mbar_wait(&full_a[sa], pa);
-            const uint32_t a_base = tc::smem_u32(sm + SM::A + sa * SM::A_STAGE);
+            // descriptor of the tile's first row; +dy * 16 rows (2048 B) and +k * 32 B are added in descriptor units (16 B)
+            const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::A + sa * SM::A_STAGE));
+#pragma unroll
             for (int dy = 0; dy < 3; dy++, it++) {
               const int sb = it % BS, pb = (it / BS) & 1;
               tc::mbar_wait(&full_b[sb], pb);
               tc::tc_fence_after();
-              const uint32_t a_addr = a_base + dy * (CG_TW * 128);          // 16 pixel rows further down: +2048 B
-              const uint32_t b_addr = tc::smem_u32(sm + SM::B + sb * (N * 128));
+              const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::B + sb * (N * 128)));
 #pragma unroll
               for (int k = 0; k < 4; k++)
-                tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
-                             (u | dy | k) ? 1u : 0u);
-              tc::umma_commit(&empty_b[sb]);
+                tc::umma_f16_lead(d_tmem, a_desc + (uint64_t)(dy * (CG_TW * 128 / 16) + k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                  (u | dy | k) ? 1u : 0u, lead);
+              tc::umma_commit_lead(&empty_b[sb], lead);
             }
-            tc::umma_commit(&empty_a[sa]);
+            tc::umma_commit_lead(&empty_a[sa], lead);
           }
         } else {
           for (int kb = 0; kb < nkb; kb++, it++) {
             const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
             tc::mbar_wait(&full_b[st], ph);
             tc::tc_fence_after();
-            const uint32_t a_addr = tc::smem_u32(sm + SM::A + st * 16384);
-            const uint32_t b_addr = tc::smem_u32(sm + SM::B + st * (N * 128));
+            const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::A + st * 16384));
+            const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::B + st * (N * 128)));
 #pragma unroll
             for (int k = 0; k < 4; k++)
-              tc::umma_f16(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
-                           (kb | k) ? 1u : 0u);
-            tc::umma_commit(&empty_b[st]);
+              tc::umma_f16_lead(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u, lead);
+            tc::umma_commit_lead(&empty_b[st], lead);
           }
         }
-        tc::umma_commit(&tm_full[as]);
+        tc::umma_commit_lead(&tm_full[as], lead);
       }
     }
   } else {

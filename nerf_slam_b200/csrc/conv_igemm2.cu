@@ -127,7 +127,9 @@ conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // whole warp in the loop (uniform control flow), one elected lane issues: see tc::umma_f16_lead
+    if (leader) {
+      const uint32_t lead = tc::elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = tc::umma_idesc_f16(256, N, 0);
       uint32_t it = 0, ia = 0, tcount = 0;
       for (int pair = cid; pair < npairs; pair += nclusters, tcount++) {
@@ -138,22 +140,22 @@ conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
         for (int u = 0; u < units; u++, ia++) {
           const int sa = ia % AS, pa = (ia / AS) & 1;
           tc::mbar_wait(&full_a[sa], pa);
-          const uint32_t a_base = tc::smem_u32(sm + SM::A + sa * SM::A_STAGE);
+          const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::A + sa * SM::A_STAGE));
+#pragma unroll
           for (int dy = 0; dy < 3; dy++, it++) {
             const int sb = it % BS, pb = (it / BS) & 1;
             tc::mbar_wait(&full_b[sb], pb);
             tc::tc_fence_after();
-            const uint32_t a_addr = a_base + dy * (CG_TW * 128);
-            const uint32_t b_addr = tc::smem_u32(sm + SM::B + sb * SM::B_STAGE);
+            const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(sm + SM::B + sb * SM::B_STAGE));
 #pragma unroll
             for (int k = 0; k < 4; k++)
-              tc::umma_f16_pair(d_tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc,
-                                (u | dy | k) ? 1u : 0u);
-            tc::umma_commit_pair(&empty_b[sb]);
+              tc::umma_f16_pair_lead(d_tmem, a_desc + (uint64_t)(dy * (CG_TW * 128 / 16) + k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                     (u | dy | k) ? 1u : 0u, lead);
+            tc::umma_commit_pair_lead(&empty_b[sb], lead);
           }
-          tc::umma_commit_pair(&empty_a[sa]);
+          tc::umma_commit_pair_lead(&empty_a[sa], lead);
         }
-        tc::umma_commit_pair(&tm_full[as]);
+        tc::umma_commit_pair_lead(&tm_full[as], lead);
       }
     }
   } else {

@@ -58,12 +58,15 @@ __device__ __forceinline__ void store_row_chunk(unsigned char* arow, int row, in
 
 // one layer: A tile (already written + fenced + synced) x packed weights -> TMEM cols [0,N)
 template <int N>
-__device__ __forceinline__ void issue_layer(uint32_t a_addr, uint32_t b_addr, uint32_t tmem, int ksteps, uint64_t* bar) {
+// called by the WHOLE warp 0 (uniform control flow), issued by its elected lane (`lead`): see tc::umma_f16_lead
+__device__ __forceinline__ void issue_layer(uint32_t a_addr, uint32_t b_addr, uint32_t tmem, int ksteps, uint64_t* bar,
+                                            uint32_t lead) {
   constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, 0);
   tc::tc_fence_after();
+  const uint64_t ad = tc::umma_desc_sw128(a_addr), bd = tc::umma_desc_sw128(b_addr);
   for (int k = 0; k < ksteps; k++)
-    tc::umma_f16(tmem, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc, k ? 1u : 0u);
-  tc::umma_commit(bar);
+    tc::umma_f16_lead(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k ? 1u : 0u, lead);
+  tc::umma_commit_lead(bar, lead);
 }
 
 __global__ void __launch_bounds__(128)
@@ -81,6 +84,7 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
   for (int i = tid; i < PW_TOTAL / 16; i += 128)
     reinterpret_cast<uint4*>(sm + FwdSmem::W)[i] = reinterpret_cast<const uint4*>(packed)[i];
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  const uint32_t lead = (tid < 32) ? (tc::elect_one() ? 1u : 0u) : 0u;      // MMA-issuing lane of warp 0
   if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
   tc::fence_proxy_async();
   tc::tc_fence_before();
@@ -121,7 +125,7 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
     tc::tc_fence_before();
     __syncthreads();
     // ---- layer 1: 32 -> 64, ReLU
-    if (tid == 0) issue_layer<64>(a_addr, w_addr + PW1, tmem, 2, bar);
+    if (tid < 32) issue_layer<64>(a_addr, w_addr + PW1, tmem, 2, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -143,7 +147,7 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
     tc::tc_fence_before();
     __syncthreads();
     // ---- layer 2: 64 -> 16 (density head)
-    if (tid == 0) issue_layer<16>(a_addr, w_addr + PW2, tmem, 4, bar);
+    if (tid < 32) issue_layer<16>(a_addr, w_addr + PW2, tmem, 4, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     float sigma;
@@ -168,7 +172,7 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
     // ---- layers 3, 4: -> 64, ReLU
 #pragma unroll 1
     for (int l = 0; l < 2; l++) {
-      if (tid == 0) issue_layer<64>(a_addr, w_addr + (l == 0 ? PW3 : PW4), tmem, l == 0 ? 2 : 4, bar);
+      if (tid < 32) issue_layer<64>(a_addr, w_addr + (l == 0 ? PW3 : PW4), tmem, l == 0 ? 2 : 4, bar, lead);
       tc::mbar_wait(bar, phase & 1); phase++;
       tc::tc_fence_after();
       uint32_t r[32];
@@ -189,7 +193,7 @@ forward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ coun
       __syncthreads();
     }
     // ---- layer 5: 64 -> 3 (16), sigmoid
-    if (tid == 0) issue_layer<16>(a_addr, w_addr + PW5, tmem, 4, bar);
+    if (tid < 32) issue_layer<16>(a_addr, w_addr + PW5, tmem, 4, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -293,7 +297,7 @@ __device__ __forceinline__ void store_delta(unsigned char* dtile, unsigned char*
 // ACC = D x WB (N_out columns, `ks` K-steps).  Issued by one thread; one commit covers both.
 template <int N, int NOUT>
 __device__ __forceinline__ void issue_bwd_layer(uint32_t at_addr, uint32_t dt_addr, uint32_t d_addr, uint32_t wb_addr,
-                                                uint32_t tmem, int tm_dw, int ks, bool first_tile, uint64_t* bar) {
+                                                uint32_t tmem, int tm_dw, int ks, bool first_tile, uint64_t* bar, uint32_t lead) {
   constexpr uint32_t idw = tc::umma_idesc_f16(128, N, 0);
   constexpr uint32_t idp = tc::umma_idesc_f16(128, NOUT, 0);
   tc::tc_fence_after();
@@ -301,11 +305,11 @@ __device__ __forceinline__ void issue_bwd_layer(uint32_t at_addr, uint32_t dt_ad
   for (int h = 0; h < 2; h++)
 #pragma unroll
     for (int k = 0; k < 4; k++)
-      tc::umma_f16(tmem + tm_dw, tc::umma_desc_sw128(at_addr + h * 16384 + k * 32),
-                   tc::umma_desc_sw128(dt_addr + h * 8192 + k * 32), idw, (first_tile && h == 0 && k == 0) ? 0u : 1u);
+      tc::umma_f16_lead(tmem + tm_dw, tc::umma_desc_sw128(at_addr + h * 16384 + k * 32),
+                        tc::umma_desc_sw128(dt_addr + h * 8192 + k * 32), idw, (first_tile && h == 0 && k == 0) ? 0u : 1u, lead);
   for (int k = 0; k < ks; k++)
-    tc::umma_f16(tmem + TM_ACC, tc::umma_desc_sw128(d_addr + k * 32), tc::umma_desc_sw128(wb_addr + k * 32), idp, k ? 1u : 0u);
-  tc::umma_commit(bar);
+    tc::umma_f16_lead(tmem + TM_ACC, tc::umma_desc_sw128(d_addr + k * 32), tc::umma_desc_sw128(wb_addr + k * 32), idp, k ? 1u : 0u, lead);
+  tc::umma_commit_lead(bar, lead);
 }
 
 __device__ __forceinline__ void ld_relu_store(uint32_t taddr, unsigned char* arow, int row, uint32_t* mask) {
@@ -354,6 +358,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
   for (int i = tid; i < PB_TOTAL / 16; i += 128) reinterpret_cast<uint4*>(sm + BwdSmem::WB)[i] = reinterpret_cast<const uint4*>(packed_bwd)[i];
   for (int i = tid; i < (32768 + 16384 + 16384) / 16; i += 128) reinterpret_cast<uint4*>(sm + BwdSmem::AT)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  const uint32_t lead = (tid < 32) ? (tc::elect_one() ? 1u : 0u) : 0u;      // MMA-issuing lane of warp 0
   if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
   NGP_TC_SYNC();
   tc::tc_fence_after();
@@ -404,12 +409,12 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
       for (int c = 4; c < 8; c++) store_row_chunk(a0, tid, c, z8);
     }
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<64>(act_addr + 0 * 16384, w_addr + PW1, tmem + TM_ACC, 2, bar);
+    if (tid < 32) issue_layer<64>(act_addr + 0 * 16384, w_addr + PW1, tmem + TM_ACC, 2, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     ld_relu_store(taddr + TM_ACC, act + 1 * 16384 + tid * 128, tid, m1);
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<16>(act_addr + 1 * 16384, w_addr + PW2, tmem + TM_ACC, 4, bar);
+    if (tid < 32) issue_layer<16>(act_addr + 1 * 16384, w_addr + PW2, tmem + TM_ACC, 4, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -428,12 +433,12 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
       for (int c = 4; c < 8; c++) store_row_chunk(a2, tid, c, z8);
     }
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<64>(act_addr + 2 * 16384, w_addr + PW3, tmem + TM_ACC, 2, bar);
+    if (tid < 32) issue_layer<64>(act_addr + 2 * 16384, w_addr + PW3, tmem + TM_ACC, 2, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     ld_relu_store(taddr + TM_ACC, act + 3 * 16384 + tid * 128, tid, m3);
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<64>(act_addr + 3 * 16384, w_addr + PW4, tmem + TM_ACC, 4, bar);
+    if (tid < 32) issue_layer<64>(act_addr + 3 * 16384, w_addr + PW4, tmem + TM_ACC, 4, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     ld_relu_store(taddr + TM_ACC, act + 4 * 16384 + tid * 128, tid, m4);
@@ -446,7 +451,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     __syncthreads();                                   // ACT4 rows complete before anyone transposes... (own row only) 
     transpose_row(act + 4 * 16384, AT, tid, 64);
     NGP_TC_SYNC();
-    if (tid == 0) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB5, tmem, TM_DW5, 1, first, bar);
+    if (tid < 32) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB5, tmem, TM_DW5, 1, first, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -465,7 +470,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     store_delta<64>(Dt, DT, tid, d64);
     transpose_row(act + 3 * 16384, AT, tid, 64);
     NGP_TC_SYNC();
-    if (tid == 0) issue_bwd_layer<64, 64>(at_addr, dt_addr, d_addr, wb_addr + PB4, tmem, TM_DW4, 4, first, bar);
+    if (tid < 32) issue_bwd_layer<64, 64>(at_addr, dt_addr, d_addr, wb_addr + PB4, tmem, TM_DW4, 4, first, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -484,7 +489,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     store_delta<64>(Dt, DT, tid, d64);
     transpose_row(act + 2 * 16384, AT, tid, 32);
     NGP_TC_SYNC();
-    if (tid == 0) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB3, tmem, TM_DW3, 4, first, bar);
+    if (tid < 32) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB3, tmem, TM_DW3, 4, first, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     float d16[16];
@@ -502,7 +507,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     store_delta<16>(Dt, DT, tid, d16);
     transpose_row(act + 1 * 16384, AT, tid, 64);
     NGP_TC_SYNC();
-    if (tid == 0) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB2, tmem, TM_DW2, 1, first, bar);
+    if (tid < 32) issue_bwd_layer<16, 64>(at_addr, dt_addr, d_addr, wb_addr + PB2, tmem, TM_DW2, 1, first, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -521,7 +526,7 @@ backward_tc_kernel(const float* __restrict__ coords, const int* __restrict__ cou
     store_delta<64>(Dt, DT, tid, d64);
     transpose_row(act + 0 * 16384, AT, tid, 32);
     NGP_TC_SYNC();
-    if (tid == 0) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB1, tmem, TM_DW1, 4, first, bar);
+    if (tid < 32) issue_bwd_layer<64, 32>(at_addr, dt_addr, d_addr, wb_addr + PB1, tmem, TM_DW1, 4, first, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -659,6 +664,7 @@ density_tc_kernel(const __half2* __restrict__ grid, LevelInfo lv, const unsigned
   for (int i = tid; i < PW3 / 16; i += 128)          // W1 and W2 images only
     reinterpret_cast<uint4*>(sm + FwdSmem::W)[i] = reinterpret_cast<const uint4*>(packed)[i];
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  const uint32_t lead = (tid < 32) ? (tc::elect_one() ? 1u : 0u) : 0u;      // MMA-issuing lane of warp 0
   if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
   NGP_TC_SYNC();
   tc::tc_fence_after();
@@ -701,7 +707,7 @@ density_tc_kernel(const __half2* __restrict__ grid, LevelInfo lv, const unsigned
       for (int c = 4; c < 8; c++) store_row_chunk(arow, tid, c, z8);
     }
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<64>(a_addr, w_addr + PW1, tmem, 2, bar);
+    if (tid < 32) issue_layer<64>(a_addr, w_addr + PW1, tmem, 2, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {
@@ -720,7 +726,7 @@ density_tc_kernel(const __half2* __restrict__ grid, LevelInfo lv, const unsigned
       }
     }
     NGP_TC_SYNC();
-    if (tid == 0) issue_layer<16>(a_addr, w_addr + PW2, tmem, 4, bar);
+    if (tid < 32) issue_layer<16>(a_addr, w_addr + PW2, tmem, 4, bar, lead);
     tc::mbar_wait(bar, phase & 1); phase++;
     tc::tc_fence_after();
     {

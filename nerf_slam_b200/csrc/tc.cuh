@@ -82,6 +82,32 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// warp-uniform producer variants: the whole warp runs the loop, the elected lane (`lead` != 0) issues
+__device__ __forceinline__ void mbar_arrive_expect_tx_lead(uint64_t* bar, uint32_t bytes, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_lead(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_lead(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"(lead)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
@@ -117,6 +143,30 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           smem_u32(bar))
+      : "memory");
+}
+// WARP-UNIFORM issue (all 32 lanes execute the surrounding loop, the instruction itself is predicated on `lead`, e.g.
+// lead = elect_one()).  A tcgen05.mma issued from inside `if (lane == 0)` makes the compiler treat descriptors, loop
+// counters and barrier addresses as divergent values: every MMA is then preceded by an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop that moves them into uniform registers — ~25 dependent instructions, ~90 cycles per MMA, more than the
+// 64 cycles an M128 x N128 x K16 MMA takes (profiles/r02_conv_issue_bound.md).  In uniform control flow the operands stay
+// in uniform registers and an MMA costs a handful of instructions.
+__device__ __forceinline__ void umma_f16_lead(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_lead(uint64_t* bar, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(lead)
       : "memory");
 }
 // 32 lanes x 32 columns of 32-bit: thread i of the warp gets lane (base_lane+i), columns c..c+31
@@ -232,6 +282,27 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
       "h"((uint16_t)3)
+      : "memory");
+}
+
+// warp-uniform variants (see umma_f16_lead)
+__device__ __forceinline__ void umma_f16_pair_lead(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_lead(uint64_t* bar, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3), "r"(lead)
       : "memory");
 }
 

@@ -52,7 +52,8 @@ def test_reference_pipeline_wiring_on_hardware(tmp_path, monkeypatch, fusion):
     assert steps >= 50 and fe.is_initialized and fe.kf_idx >= 9 and fe.ba_failures(wait=True) == 0
     if fusion == "nerf":
         nf = fus.fusion
-        assert nf.total_iters >= steps and nf.ngp.nerf.training.n_images_for_training >= 8
+        # one fit per spin without a new packet (fusion/nerf_fusion.py:237-258: a packet with keyframes is ingested, not fitted)
+        assert nf.total_iters >= steps // 2 and nf.ngp.nerf.training.n_images_for_training >= 8
         assert np.isfinite(nf.ngp.sync_stats())
     else:
         vol = fus.fusion

@@ -240,8 +240,9 @@ def test_render_matches_oracle(backend):
     rgb = tb.render(W, H, 1, True)[..., :3]
     tb.render_mode = pyngp.Depth
     dep = tb.render(W, H, 1, True)[..., 0]
+    per_ray = max(8, min(1024, tb.max_samples // (min(32, tb.max_rays // W) * W)))      # Testbed.render's sample budget per ray
     ref_rgb, ref_dep = ongp.render_view(_oracle_params(tb), c2w, tb._view_intr, W, H, tb.aabb_scale, tb.cascades, bits.numpy(),
-                                        tb.nerf.training.near_distance, tb.background_color[:3])
+                                        tb.nerf.training.near_distance, tb.background_color[:3], max_per_ray=per_ray)
     tol = 1e-2 if backend == "tcgen05" else 2e-4
     assert np.abs(rgb - ref_rgb).max() < tol, np.abs(rgb - ref_rgb).max()
     assert np.abs(dep - ref_dep).max() < (3e-2 if backend == "tcgen05" else 1e-3) * max(1.0, ref_dep.max()), np.abs(dep - ref_dep).max()

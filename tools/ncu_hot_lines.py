@@ -3,7 +3,7 @@ usage: python tools/ncu_hot_lines.py REP KERNEL_REGEX [TOP] [LAUNCH_INDEX]"""
 import csv, subprocess, sys, io
 rep, rx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name-base", "demangled", "--kernel-name", "regex:" + rx,
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + rx,
        "--print-source", "sass,cuda"]
 if len(sys.argv) > 4:
     cmd += ["--launch-skip", sys.argv[4], "--launch-count", "1"]   # noqa
