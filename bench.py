@@ -38,6 +38,19 @@ if ROOT not in sys.path:
 
 W_IMG, H_IMG = 640, 480
 STREAM_STEP = 0.035           # camera pace: ~every 3rd-4th frame becomes a keyframe
+# --workload: cfg2 = BASELINE.json configs[1] (the metric's configuration, default); cfg5 = configs[4]'s shapes
+# (1280x720, buffer 200); cfg4 = configs[3] (640x480, buffer 400, plus the global-BA / alt-corr pass over the filled
+# window, timed separately as `global_ba`).  The driver runs the default; the others are recorded under profiles/.
+WORKLOADS = {"cfg2": dict(w=640, h=480, buffer=100, corr_slots=112, name="configs[1]: Replica-office0-shaped synthetic 640x480"),
+             "cfg4": dict(w=640, h=480, buffer=400, corr_slots=112, name="configs[3]: long synthetic 640x480 trajectory, buffer=400, global BA on the alt-corr path"),
+             "cfg5": dict(w=1280, h=720, buffer=200, corr_slots=64, name="configs[4]: synthetic 1280x720, buffer=200")}
+WL = WORKLOADS["cfg2"]
+
+
+def set_workload(name):
+    global WL, W_IMG, H_IMG
+    WL = WORKLOADS[name]
+    W_IMG, H_IMG = WL["w"], WL["h"]
 
 
 def peaks():
@@ -90,7 +103,7 @@ class ClockSampler:
 def make_args(buffer):
     w = os.path.join(ROOT, "oracle", "_ref", "droid.pth")
     return types.SimpleNamespace(buffer=buffer, stereo=False, multi_gpu=False, eval=False, mask_type="ours",
-                                 weights=w if os.path.exists(w) else None, corr_slots=112)
+                                 weights=w if os.path.exists(w) else None, corr_slots=WL["corr_slots"])
 
 
 class SlamNerfJob:
@@ -240,7 +253,7 @@ def run_ours(a):
     # keyframe buffer: the reference's default (100) holds ~500 frames of this stream (0.16 keyframes per frame);
     # longer runs get a proportionally larger buffer so that the timed region never reaches the buffer-full stop
     n_frames = a.steps + a.warmup + 40
-    kf_buffer = 100 if n_frames <= 460 else int(24 + 0.2 * n_frames)
+    kf_buffer = WL["buffer"] if n_frames <= 4.6 * WL["buffer"] else int(24 + 0.2 * n_frames)
 
     def phase_end():
         """N > 1: rank 0 marks a phase boundary for the free-running trainers, then everybody meets at the barrier;
@@ -351,7 +364,7 @@ def run_ours(a):
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_dev / a.steps, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands + f32 accumulate (encoders, update operator, correlation, NeRF MLP) / f32 (BA, losses, Adam) / f64 (BA solve)",
         "data": "synthetic (procedural box room, seeded)",
-        "config": {"workload": f"configs[1]: Replica-office0-shaped synthetic 640x480, buffer={kf_buffer}, --slam --fusion=nerf",
+        "config": {"workload": f"{WL['name']}, buffer={kf_buffer}, --slam --fusion=nerf",
                    "weights": "droid.pth" if job.args.weights else "random-init (seeded)", "nerf_iters_per_frame": a.nerf_iters,
                    "nerf_samples_per_iter": 1 << 18, "primed_frames": primed, "keyframes_in_timed_region": st_dev["kf"],
                    "update_calls_in_timed_region": st_dev["updates"], "nerf_iters_in_timed_region": st_dev["nerf_iters"],
@@ -374,7 +387,18 @@ def run_ours(a):
     line["kernel_shares"] = shares
     line["gpu_launches"] = counts["total"]
     line["gpu_launches_detail"] = counts
-    line["cpu_baseline"] = cpu_baseline_sample()
+    if a.workload == "cfg4":
+        # configs[3]: the global-BA pass (backend(): proximity graph over the whole window, update_lowmem on the alt-corr
+        # path, window-wide BA) over the keyframes this run accumulated — timed on its own, not part of frames/s
+        fe = job.fe
+        with torch.cuda.stream(job.slam_stream):
+            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            n_kf = fe.kf_idx
+            g0.record(); fe.backend(steps=7); g1.record()
+        torch.cuda.synchronize()
+        line["global_ba"] = {"keyframes": int(n_kf), "max_factors": int(fe.max_factors), "steps": 7, "ms": round(g0.elapsed_time(g1), 2),
+                             "ba_failures": fe.ba_failures(wait=True)}
+    line["cpu_baseline"] = cpu_baseline_sample() if a.workload == "cfg2" else None
     sys.stdout.flush()
     os.dup2(_saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -457,6 +481,7 @@ def roofline_entries(job, pk):
     fe, dev = job.fe, job.dev
     E, hw = int(fe.ii.shape[0]), fe.ht * fe.wd
     tf_peak, hbm_peak = pk["bf16_tflops"], pk["hbm_gbs"]
+    NCU = NCU_TRAFFIC if WL is WORKLOADS["cfg2"] else {}          # the committed captures are of the 640x480 workload
     src = pk["_src"] + " (burst figures: each kernel is timed alone, device idle around it)"
     out = {}
 
@@ -464,7 +489,7 @@ def roofline_entries(job, pk):
         e = {"kernel": name, "bound": "tensor", "achieved": round(flops / ms / 1e9, 1), "peak": tf_peak, "unit": "TFLOP/s",
              "frac": round(flops / ms / 1e9 / tf_peak, 3), "launch_ms": round(ms, 4), "edges": E,
              "algorithmic_flops_per_launch": flops, "peak_source": src,
-             "traffic": NCU_TRAFFIC.get(key, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(key, (None, None))[1]}
+             "traffic": NCU.get(key, (None, None))[0], "traffic_source": NCU.get(key, (None, None))[1]}
         e.update(extra or {})
         out[key] = e
 
@@ -472,7 +497,7 @@ def roofline_entries(job, pk):
         e = {"kernel": name, "bound": "hbm", "achieved": round(nbytes / ms / 1e6, 1), "peak": hbm_peak, "unit": "GB/s",
              "frac": round(nbytes / ms / 1e6 / hbm_peak, 3), "launch_ms": round(ms, 4), "edges": edges,
              "algorithmic_bytes_per_launch": nbytes, "peak_source": src,
-             "traffic": NCU_TRAFFIC.get(key, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(key, (None, None))[1]}
+             "traffic": NCU.get(key, (None, None))[0], "traffic_source": NCU.get(key, (None, None))[1]}
         e.update(extra or {})
         out[key] = e
     op = fe.update_tc
@@ -679,7 +704,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--nerf-iters", type=int, default=2)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     a = ap.parse_args()
+    set_workload(a.workload)
     if a.impl == "reference":
         run_reference(a)
     elif a.impl == "reference-cuda":

@@ -1,6 +1,7 @@
 // Shared pieces of the implicit-GEMM convolution kernels (conv_igemm.cu: one CTA per tile;
 // conv_igemm2.cu: CTA pairs, cta_group::2): launch parameters, shared-memory plan, epilogue math.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -146,6 +147,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32
     }
   }
 }
+
+// second generation for 3x3 / pad 1 (conv_halo.cu): 16x16 super-tiles, one halo box per channel block
+bool conv_halo_supported(int N, int mode, int KH, int KW, int pad);
+int launch_conv_halo(int N, const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t st);
 
 // CTA-pair variant (conv_igemm2.cu), opt-in: NSLAM_CONV_CTA2=1
 bool conv_pairs_enabled();

@@ -33,9 +33,11 @@
 //           and (b) optional stride-2 output: the conv is evaluated at stride 1 and only even rows/columns
 //           are stored and counted (a 3x3/s2 conv reads every input pixel anyway).
 // Roofline: tensor pipe; FLOPs = 2 * pixels * taps * Cin * Cout.
+#include <cstdlib>
 #include "conv_common.cuh"
 
 namespace nslam {
+constexpr uint32_t CH2_BOX = 18;        // halo box edge of conv_halo.cu (16 + 2)
 
 template <int N, int MODE, bool HALO>
 __global__ void __launch_bounds__(CG_THREADS, 1)
@@ -420,7 +422,11 @@ int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_
   p.wpacked = (const __half*)wpacked; p.bias = bias; p.gctx = gctx; p.net = (const __half*)net;
   p.zbuf = (const __half*)zbuf; p.gsum = gsum; p.stats = stats; p.sub = (mode == 4 && sub == 2) ? 2 : 1;
   if (mode == 4 && sub != 1 && sub != 2) return (int)cudaErrorInvalidValue;
-  // 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap
+  // 3x3 / pad 1, epilogue modes 0-2: second-generation kernel (conv_halo.cu: 16x16 super-tiles, one halo box per channel
+  // block).  NSLAM_CONV_GEN1=1 keeps the first generation (A/B measurements, tests of both).
+  static const bool gen1 = [] { const char* e = std::getenv("NSLAM_CONV_GEN1"); return e && e[0] == '1'; }();
+  const bool halo2 = !gen1 && !conv_pairs_enabled() && conv_halo_supported(N, mode, KH, KW, pad);
+  // first generation, 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap
   const bool halo = (KH == 3 && KW == 3 && pad == 1 && mode != 3);
   int cbt = 0;
   for (int s = 0; s < n_src; s++) {
@@ -431,6 +437,7 @@ int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
     uint32_t box[4] = {64, CG_TW, (uint32_t)(halo ? CG_TH + 2 : CG_TH), 1};
+    if (halo2) { box[1] = CH2_BOX; box[2] = CH2_BOX; }
     int r = tc::make_tmap_f16(&maps.src[s], srcs[s], 4, dims, strides, box);
     if (r) return r;
   }
@@ -444,9 +451,14 @@ int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
       uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)Wo * C * 2, (uint64_t)Ho * Wo * C * 2};
       uint32_t box[4] = {(uint32_t)(C < 64 ? C : 64), (uint32_t)(CG_TW / p.sub), (uint32_t)(CG_TH / p.sub), 1};
+      if (halo2) { box[1] = 8; box[2] = 16; }                    // sub-tile of the second-generation kernel
       int r = tc::make_tmap_f16(&maps.out[o], outs[o], 4, dims, strides, box, false, nullptr, /*swizzle128=*/N >= 64);
       if (r) return r;
     }
+  }
+  if (halo2) {
+    p.tiles_h = (H + 15) / 16; p.tiles_w = (W + 15) / 16;        // super-tiles
+    return launch_conv_halo(N, maps, p, num_sms, (cudaStream_t)stream);
   }
   if (conv_pairs_enabled() && conv_pairs_supported(N, mode, halo)) return launch_conv_pairs(N, maps, p, num_sms, (cudaStream_t)stream);
   return launch_conv(N, maps, p, halo, num_sms, (cudaStream_t)stream);

@@ -255,28 +255,32 @@ corr_lookup_nhwc_vec_kernel(LookupLevels lv, const float* __restrict__ coords, _
   const int sl2 = lv.h2[2] * lv.w2[2], sl3 = lv.h2[3] * lv.w2[3];         // halves per source pixel
   __half* st2 = tile + 32 * nhwc_stride;                                   // [32][sl2]
   __half* st3 = st2 + 32 * sl2;                                            // [32][sl3]
-  // ---- stage the level-2 / level-3 slices of the CTA's pixels (contiguous in memory), zero the padding channels
-  {
+  // ---- warps 2, 3 (the level-2 / level-3 threads) stage the slices of the CTA's pixels — contiguous in memory — with
+  // coalesced 16-byte loads and synchronise among themselves only (named barrier, 64 threads); warps 0, 1 go straight to
+  // their own gathers: every global load of the CTA is in flight at once (one memory latency, not two)
+  if (l >= 2) {
+    const int t64 = threadIdx.x - 64;
     const size_t base2 = ((size_t)vn * hw + p0) * (size_t)sl2, base3 = ((size_t)vn * hw + p0) * (size_t)sl3;
     const __half* g2 = reinterpret_cast<const __half*>(lv.vol[2]) + base2;
     const __half* g3 = reinterpret_cast<const __half*>(lv.vol[3]) + base3;
     const int n2 = npx * sl2, n3 = npx * sl3;
     // 16-byte path when base and length allow it (always for full CTAs: 32 * sl * 2 B is a multiple of 64)
     if ((((uintptr_t)g2 | (uintptr_t)st2) & 15) == 0 && (n2 & 7) == 0) {
-      for (int i = threadIdx.x; i < n2 / 8; i += 128) reinterpret_cast<uint4*>(st2)[i] = __ldg(reinterpret_cast<const uint4*>(g2) + i);
+      for (int i = t64; i < n2 / 8; i += 64) reinterpret_cast<uint4*>(st2)[i] = __ldg(reinterpret_cast<const uint4*>(g2) + i);
     } else {
-      for (int i = threadIdx.x; i < n2; i += 128) st2[i] = __ldg(g2 + i);
+      for (int i = t64; i < n2; i += 64) st2[i] = __ldg(g2 + i);
     }
     if ((((uintptr_t)g3 | (uintptr_t)st3) & 15) == 0 && (n3 & 7) == 0) {
-      for (int i = threadIdx.x; i < n3 / 8; i += 128) reinterpret_cast<uint4*>(st3)[i] = __ldg(reinterpret_cast<const uint4*>(g3) + i);
+      for (int i = t64; i < n3 / 8; i += 64) reinterpret_cast<uint4*>(st3)[i] = __ldg(reinterpret_cast<const uint4*>(g3) + i);
     } else {
-      for (int i = threadIdx.x; i < n3; i += 128) st3[i] = __ldg(g3 + i);
+      for (int i = t64; i < n3; i += 64) st3[i] = __ldg(g3 + i);
     }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+  } else {
     const int used = 4 * RD * RD;
-    for (int id = threadIdx.x; id < 32 * (nhwc_stride - used); id += 128)
+    for (int id = threadIdx.x; id < 32 * (nhwc_stride - used); id += 64)
       tile[(id / (nhwc_stride - used)) * nhwc_stride + used + id % (nhwc_stride - used)] = A::zero();
   }
-  __syncthreads();
   if (p < hw) {
     const int h2 = lv.h2[l], w2 = lv.w2[l];
     float x0, y0;

@@ -208,6 +208,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// the same with an explicit stride between 8-row groups (SBO, bytes, multiple of 16): e.g. the rows of a pixel tile that
+// sits inside a wider halo box.  The start address may be any 128-byte row of a 1024-byte-aligned swizzled buffer.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 // Instruction descriptor for kind::f16: D=f32, A/B = f16 (0) or bf16 (1), both K-major.
 //   [4,6) c_format=1 (F32) | [7,10) a_format | [10,13) b_format | [15] a_major=0 | [16] b_major=0

@@ -50,8 +50,10 @@ def test_tsdf_integrate_matches_oracle(mode):
     gw, gt, gc = weight.cpu().numpy(), tsdf.cpu().numpy(), color.cpu().numpy()
     # the same voxels are updated, except where a test of the rule sits exactly on its boundary (pixel rounding at .5,
     # sdf == -trunc): the fp64 projection is contracted to FMAs on the device, numpy rounds every product
-    ok = ((gw > 0) == (rw > 0)) & np.isclose(gw, rw, rtol=1e-6, atol=0) & np.isclose(gt, rt, rtol=2e-6, atol=2e-6) \
-        & np.isclose(gc, rc, rtol=2e-6, atol=1e-3).all(-1)                        # fp32 running averages (fma contraction)
+    # fp32 running averages: the device contracts w*t + wr*s to an FMA, numpy rounds both products (matters once the
+    # weights are not integers, i.e. in sigma mode) -> 1e-5
+    ok = ((gw > 0) == (rw > 0)) & np.isclose(gw, rw, rtol=1e-6, atol=0) & np.isclose(gt, rt, rtol=1e-5, atol=1e-5) \
+        & np.isclose(gc, rc, rtol=1e-5, atol=5e-3).all(-1)
     assert ok.mean() > 0.999, ok.mean()                                           # boundary voxels: < 0.1 %
     assert rw.max() == 20.0 and gw.max() == 20.0
 
