@@ -17,6 +17,7 @@
 // combines them in registers and writes each output channel exactly once (coalesced along x).
 // Algorithmic traffic per edge at 640x480: 4.38 MB.
 #include <atomic>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace nslam {
@@ -363,7 +364,8 @@ static int launch_lookup(const LookupLevels& lv, const float* coords, void* out,
   if (n == 0) return 0;
   if (nhwc_stride > 0 && radius == 3 && scale_coords && (nhwc_stride * sizeof(T)) % 16 == 0 && num_levels <= 4) {
     dim3 g2((h1 * w1 + 31) / 32, 1, n);
-    if (sizeof(T) == 2 && num_levels == 4 && (lv.w2[0] % 8) == 0 && (lv.w2[1] % 8) == 0 && (nhwc_stride % 8) == 0) {
+    static const bool force_scalar = [] { const char* e = std::getenv("NSLAM_LOOKUP_SCALAR"); return e && e[0] == '1'; }();   // A/B timing only
+    if (!force_scalar && sizeof(T) == 2 && num_levels == 4 && (lv.w2[0] % 8) == 0 && (lv.w2[1] % 8) == 0 && (nhwc_stride % 8) == 0) {
       // 128-bit path: volume base pointers are 16-byte aligned (torch allocations, arena slots: h2*w2 multiples of 8 on
       // levels 0 / 1 because w2 is)
       bool aligned = true;
