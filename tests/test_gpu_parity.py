@@ -251,8 +251,8 @@ def test_ba_full_iteration(db):
     # retract
     from nerf_slam_b200 import _lib
     lib = _lib.load()
-    wTb = T(wTb0.copy()); cTw = T(p["poses"].copy())
-    _lib.check(lib.nslam_ba_retract(_lib.ptr(wTb), _lib.ptr(cTw), _lib.ptr(T(p["ext"])), _lib.ptr(dx),
+    wTb = T(wTb0.copy()); cTw = T(p["poses"].copy()); ext = T(p["ext"])
+    _lib.check(lib.nslam_ba_retract(_lib.ptr(wTb), _lib.ptr(cTw), _lib.ptr(ext), _lib.ptr(dx),
                                     p["kf0"], prob.gh.P, _lib.stream_ptr()), "retract")
     rw, rc = oba.gtsam_retract(wTb0, p["ext"], dx.cpu().numpy(), p["kf0"])
 

@@ -40,9 +40,11 @@ def test_tsdf_integrate_matches_oracle(mode):
         idepth, cov, rgb, tq, intr = _frame(rng, with_cov=(mode == "sigma"))
         if k == 2:
             rw[rw > 0] = 19.9; weight.copy_(T(rw))      # next reading saturates the weight
+        d_tq = T(tq)
+        d_idepth, d_cov, d_rgb = T(idepth), (T(cov) if cov is not None else None), T(rgb)   # named: they must outlive the launch
         _lib.check(lib.nslam_tsdf_integrate(_lib.ptr(tsdf), _lib.ptr(weight), _lib.ptr(color), n, n, n, origin.ctypes.data, vs,
-                                            _lib.ptr(T(idepth)), _lib.ptr(T(cov)) if cov is not None else None, _lib.ptr(T(rgb)),
-                                            idepth.shape[0], idepth.shape[1], intr.ctypes.data, _lib.ptr(T(tq)), 6.0, 0.10, 20.0,
+                                            _lib.ptr(d_idepth), _lib.ptr(d_cov) if d_cov is not None else None, _lib.ptr(d_rgb),
+                                            idepth.shape[0], idepth.shape[1], intr.ctypes.data, _lib.ptr(d_tq), 6.0, 0.10, 20.0,
                                             10000.0, _lib.stream_ptr()), "tsdf")
         touched += otsdf.integrate(rt, rw, rc, origin, vs, idepth, cov, rgb, intr, tq)
     torch.cuda.synchronize()
