@@ -422,10 +422,10 @@ int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_
   p.wpacked = (const __half*)wpacked; p.bias = bias; p.gctx = gctx; p.net = (const __half*)net;
   p.zbuf = (const __half*)zbuf; p.gsum = gsum; p.stats = stats; p.sub = (mode == 4 && sub == 2) ? 2 : 1;
   if (mode == 4 && sub != 1 && sub != 2) return (int)cudaErrorInvalidValue;
-  // 3x3 / pad 1, epilogue modes 0-2: second-generation kernel (conv_halo.cu: 16x16 super-tiles, one halo box per channel
-  // block).  NSLAM_CONV_GEN1=1 keeps the first generation (A/B measurements, tests of both).
-  static const bool gen1 = [] { const char* e = std::getenv("NSLAM_CONV_GEN1"); return e && e[0] == '1'; }();
-  const bool halo2 = !gen1 && !conv_pairs_enabled() && conv_halo_supported(N, mode, KH, KW, pad);
+  // NSLAM_CONV_HALO=1: the 16x16 super-tile kernel with one halo box per channel block (conv_halo.cu) for 3x3 / pad 1,
+  // epilogue modes 0-2 — parity-green but not faster on a B200 (profiles/r02_conv_issue_bound.md); measurement switch.
+  static const bool want_halo2 = [] { const char* e = std::getenv("NSLAM_CONV_HALO"); return e && e[0] == '1'; }();
+  const bool halo2 = want_halo2 && !conv_pairs_enabled() && conv_halo_supported(N, mode, KH, KW, pad);
   // first generation, 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap
   const bool halo = (KH == 3 && KW == 3 && pad == 1 && mode != 3);
   int cbt = 0;

@@ -205,157 +205,10 @@ corr_lookup_nhwc_kernel(LookupLevels lv, const float* __restrict__ coords, T* __
     *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(src + b);
 }
 
-// fp16, radius 3, 4 levels, level widths w2[0], w2[1] multiples of 8 (rows start on 16-byte boundaries): the same
-// function with 128-bit loads.  The scalar kernel above issues 64 two-byte gathers per (pixel, level): 8192 load
-// instructions per 32-pixel CTA, each a warp-wide scatter over 32 lines — it is bound by the load/store unit, not by
-// DRAM (41 % of the DRAM peak, profiles/r02_*).  Here
-//   * levels 0 and 1: an 8-tap window row [x, x+8) lies in two ALIGNED 16-byte chunks of its volume row: two LDG.128
-//     per row (16 per window instead of 64 LDG.U16), the eight taps are cut out of the 32 bytes with a 3-step select /
-//     funnel-shift network on the dynamic offset; chunks outside the row are replaced by zeros (= the reference's
-//     skipped out-of-range taps);
-//   * levels 2 and 3: the volume slices of the CTA's 32 consecutive source pixels are CONTIGUOUS in memory
-//     (32 x h2*w2 halves: 19.2 KB + 4.5 KB at 60x80) — they are staged into shared memory with fully coalesced
-//     16-byte loads (1480 instead of 4096 scattered two-byte loads) and the windows are read from there.
-// Arithmetic, tap order and rounding are those of the scalar kernel: bit-identical output (tests).
-// dynamic smem: 32 * nhwc_stride * 2 (output tile) + 32 * (h2[2]*w2[2] + h2[3]*w2[3]) * 2 (staged slices)
-__device__ __forceinline__ void cut8(const uint4 a, const uint4 b, int s, __half (&t)[8]) {
-  // halves s .. s+7 of the 16 halves (a, b); s in [0, 8)
-  uint32_t w[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0u};
-  if (s & 4) {
-#pragma unroll
-    for (int k = 0; k < 7; k++) w[k] = w[k + 2];
-  }
-  if (s & 2) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) w[k] = w[k + 1];
-  }
-  uint32_t o[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) o[k] = (s & 1) ? __funnelshift_r(w[k], w[k + 1], 16) : w[k];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&o[k]);
-    t[2 * k] = __low2half(h); t[2 * k + 1] = __high2half(h);
-  }
-}
-
-__global__ void __launch_bounds__(128)
-corr_lookup_nhwc_vec_kernel(LookupLevels lv, const float* __restrict__ coords, __half* __restrict__ out,
-                            int h1, int w1, const int* __restrict__ slots, int nhwc_stride, int coords_nhwc) {
-  constexpr int R = 3, RD = 7, NT = 8;
-  using A = Arith<__half>;
-  extern __shared__ unsigned char lk_smem[];
-  __half* tile = reinterpret_cast<__half*>(lk_smem);                       // [32][nhwc_stride]
-  const int hw = h1 * w1;
-  const int pp = threadIdx.x & 31, l = threadIdx.x >> 5;
-  const int p0 = blockIdx.x * 32;
-  const int p = p0 + pp;
-  const int n = blockIdx.z;
-  const int vn = slots ? slots[n] : n;
-  const int npx = min(32, hw - p0);
-  const int sl2 = lv.h2[2] * lv.w2[2], sl3 = lv.h2[3] * lv.w2[3];         // halves per source pixel
-  __half* st2 = tile + 32 * nhwc_stride;                                   // [32][sl2]
-  __half* st3 = st2 + 32 * sl2;                                            // [32][sl3]
-  // ---- warps 2, 3 (the level-2 / level-3 threads) stage the slices of the CTA's pixels — contiguous in memory — with
-  // coalesced 16-byte loads and synchronise among themselves only (named barrier, 64 threads); warps 0, 1 go straight to
-  // their own gathers: every global load of the CTA is in flight at once (one memory latency, not two)
-  if (l >= 2) {
-    const int t64 = threadIdx.x - 64;
-    const size_t base2 = ((size_t)vn * hw + p0) * (size_t)sl2, base3 = ((size_t)vn * hw + p0) * (size_t)sl3;
-    const __half* g2 = reinterpret_cast<const __half*>(lv.vol[2]) + base2;
-    const __half* g3 = reinterpret_cast<const __half*>(lv.vol[3]) + base3;
-    const int n2 = npx * sl2, n3 = npx * sl3;
-    // 16-byte path when base and length allow it (always for full CTAs: 32 * sl * 2 B is a multiple of 64)
-    if ((((uintptr_t)g2 | (uintptr_t)st2) & 15) == 0 && (n2 & 7) == 0) {
-      for (int i = t64; i < n2 / 8; i += 64) reinterpret_cast<uint4*>(st2)[i] = __ldg(reinterpret_cast<const uint4*>(g2) + i);
-    } else {
-      for (int i = t64; i < n2; i += 64) st2[i] = __ldg(g2 + i);
-    }
-    if ((((uintptr_t)g3 | (uintptr_t)st3) & 15) == 0 && (n3 & 7) == 0) {
-      for (int i = t64; i < n3 / 8; i += 64) reinterpret_cast<uint4*>(st3)[i] = __ldg(reinterpret_cast<const uint4*>(g3) + i);
-    } else {
-      for (int i = t64; i < n3; i += 64) st3[i] = __ldg(g3 + i);
-    }
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-  } else {
-    const int used = 4 * RD * RD;
-    for (int id = threadIdx.x; id < 32 * (nhwc_stride - used); id += 64)
-      tile[(id / (nhwc_stride - used)) * nhwc_stride + used + id % (nhwc_stride - used)] = A::zero();
-  }
-  if (p < hw) {
-    const int h2 = lv.h2[l], w2 = lv.w2[l];
-    float x0, y0;
-    if (coords_nhwc) {
-      const float2 c = reinterpret_cast<const float2*>(coords)[(size_t)n * hw + p];
-      x0 = c.x; y0 = c.y;
-    } else {
-      x0 = coords[((size_t)n * 2 + 0) * hw + p];
-      y0 = coords[((size_t)n * 2 + 1) * hw + p];
-    }
-    const float sc = 1.0f / (float)(1 << l);
-    x0 *= sc; y0 *= sc;
-    const float fx0 = floorf(x0), fy0 = floorf(y0);
-    const float dx = x0 - fx0, dy = y0 - fy0;
-    const int xb = (int)fx0 - R, yb = (int)fy0 - R;
-    __half tap[NT][NT];                                   // [x index i][y index j]
-    if (l < 2) {
-      const __half* __restrict__ vol = reinterpret_cast<const __half*>(lv.vol[l]) + ((size_t)vn * hw + p) * (size_t)(h2 * w2);
-      // aligned chunk pair covering halves [xb, xb+8): chunk c0 = floor(xb / 8) (arithmetic shift: xb may be negative)
-      const int c0 = xb >> 3, s = xb & 7, nchunk = w2 >> 3;
-      const bool in0 = (c0 >= 0) && (c0 < nchunk), in1 = (c0 + 1 >= 0) && (c0 + 1 < nchunk);
-      uint4 ca[NT], cb[NT];
-#pragma unroll
-      for (int j = 0; j < NT; j++) {
-        const int y1 = yb + j;
-        const bool yin = (y1 >= 0) && (y1 < h2);
-        const uint4* row = reinterpret_cast<const uint4*>(vol + (size_t)(yin ? y1 : 0) * w2);
-        ca[j] = (yin && in0) ? __ldg(row + c0) : make_uint4(0u, 0u, 0u, 0u);
-        cb[j] = (yin && in1) ? __ldg(row + c0 + 1) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int j = 0; j < NT; j++) {
-        __half t8[8];
-        cut8(ca[j], cb[j], s, t8);
-#pragma unroll
-        for (int i = 0; i < NT; i++) tap[i][j] = t8[i];
-      }
-    } else {
-      const __half* sl = (l == 2) ? st2 + pp * sl2 : st3 + pp * sl3;
-#pragma unroll
-      for (int j = 0; j < NT; j++) {
-        const int y1 = yb + j;
-        const bool yin = (y1 >= 0) && (y1 < h2);
-        const __half* row = sl + (yin ? y1 : 0) * w2;
-#pragma unroll
-        for (int i = 0; i < NT; i++) {
-          const int x1 = xb + i;
-          tap[i][j] = (yin && x1 >= 0 && x1 < w2) ? row[x1] : A::zero();
-        }
-      }
-    }
-    const __half w11 = A::cvt(dx * dy), w10 = A::cvt(dx * (1.0f - dy));
-    const __half w01 = A::cvt((1.0f - dx) * dy), w00 = A::cvt((1.0f - dx) * (1.0f - dy));
-    __half* o = tile + pp * nhwc_stride + l * (RD * RD);
-#pragma unroll
-    for (int i = 0; i < RD; i++) {
-#pragma unroll
-      for (int j = 0; j < RD; j++) {
-        __half acc = A::zero();
-        acc = A::mac(acc, tap[i][j], w00);
-        acc = A::mac(acc, tap[i][j + 1], w01);
-        acc = A::mac(acc, tap[i + 1][j], w10);
-        acc = A::mac(acc, tap[i + 1][j + 1], w11);
-        o[i * RD + j] = acc;
-      }
-    }
-  }
-  __syncthreads();
-  const size_t bytes = (size_t)npx * nhwc_stride * sizeof(__half);
-  unsigned char* dst = reinterpret_cast<unsigned char*>(out + ((size_t)n * hw + p0) * nhwc_stride);
-  const unsigned char* src = reinterpret_cast<const unsigned char*>(tile);
-  for (size_t b = (size_t)threadIdx.x * 16; b < bytes; b += (size_t)blockDim.x * 16)
-    *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(src + b);
-}
+// (Round 2 tried a 128-bit variant of the kernel above — aligned 16-byte chunk pairs + a select network on levels 0/1,
+// the CTA's contiguous level-2/3 slices staged in shared memory.  Bit-identical output, but 74 us instead of 56 us per
+// update() at 18 edges on a B200 (profiles/r02_kernel_table_call5_*): the two-byte gathers already coalesce into the
+// same 32-byte sectors, and the select network costs more issue slots than the gathers it replaces.  Removed.)
 
 template <typename T>
 static int launch_lookup(const LookupLevels& lv, const float* coords, void* out, int n, int h1,
@@ -364,28 +217,6 @@ static int launch_lookup(const LookupLevels& lv, const float* coords, void* out,
   if (n == 0) return 0;
   if (nhwc_stride > 0 && radius == 3 && scale_coords && (nhwc_stride * sizeof(T)) % 16 == 0 && num_levels <= 4) {
     dim3 g2((h1 * w1 + 31) / 32, 1, n);
-    static const bool force_scalar = [] { const char* e = std::getenv("NSLAM_LOOKUP_SCALAR"); return e && e[0] == '1'; }();   // A/B timing only
-    if (!force_scalar && sizeof(T) == 2 && num_levels == 4 && (lv.w2[0] % 8) == 0 && (lv.w2[1] % 8) == 0 && (nhwc_stride % 8) == 0) {
-      // 128-bit path: volume base pointers are 16-byte aligned (torch allocations, arena slots: h2*w2 multiples of 8 on
-      // levels 0 / 1 because w2 is)
-      bool aligned = true;
-      for (int l = 0; l < 2; l++) aligned &= ((uintptr_t)lv.vol[l] % 16) == 0 && ((lv.h2[l] * lv.w2[l]) % 8) == 0;
-      const size_t smem = (size_t)32 * nhwc_stride * 2 + (size_t)32 * (lv.h2[2] * lv.w2[2] + lv.h2[3] * lv.w2[3]) * 2;
-      if (aligned && smem <= 200 * 1024) {
-        static std::atomic<size_t> configured[NSLAM_MAX_DEVICES];
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev = (dev >= 0 && dev < NSLAM_MAX_DEVICES) ? dev : 0;
-        if (smem > 48 * 1024 && smem > configured[dev].load()) {
-          cudaError_t e = cudaFuncSetAttribute(corr_lookup_nhwc_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (e != cudaSuccess) return (int)e;
-          configured[dev].store(smem);
-        }
-        corr_lookup_nhwc_vec_kernel<<<g2, 128, smem, st>>>(lv, coords, (__half*)out, h1, w1, slots, nhwc_stride, coords_nhwc);
-        NSLAM_CHECK_LAUNCH();
-        return 0;
-      }
-    }
     corr_lookup_nhwc_kernel<T, 3><<<g2, 32 * num_levels, 32 * nhwc_stride * sizeof(T), st>>>(
         lv, coords, (T*)out, h1, w1, num_levels, slots, nhwc_stride, coords_nhwc);
     NSLAM_CHECK_LAUNCH();

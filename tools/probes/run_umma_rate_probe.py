@@ -1,0 +1,49 @@
+"""Runs tools/probes/umma_rate_probe.cu on the GPU box:  python tools/probes/run_umma_rate_probe.py > gpurun_out/umma_rate.log
+
+Prints cycles per tcgen05.mma (M128 x N x K16, SS operands) for aligned and row-shifted A descriptors, on one SM and on
+all 148 at once, and the L2 -> shared-memory bulk-copy rate per SM with all SMs streaming."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SRC = os.path.join(ROOT, "tools", "probes", "umma_rate_probe.cu")
+SO = "/tmp/umma_rate_probe.so"
+
+
+def main():
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "nerf_slam_b200", "csrc"),
+           "-shared", "-Xcompiler", "-fPIC", SRC, "-o", SO, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        print(r.stdout + r.stderr)
+        sys.exit(1)
+    lib = ctypes.CDLL(SO)
+    lib.umma_rate_probe.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    lib.l2_fill_probe.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    reps = 4096
+    for ctas in (1, 148):
+        out = np.zeros(ctas, np.int64)
+        for N in (16, 64, 128, 256):
+            for shift, sbo in ((0, 1024), (1, 1024), (0, 2304), (19, 2304), (38, 2304)):
+                rc = lib.umma_rate_probe(N, ctas, reps, shift, sbo, out.ctypes.data)
+                if rc:
+                    print(f"N {N} ctas {ctas} shift {shift} sbo {sbo}: CUDA error {rc}")
+                    continue
+                print(f"mma N {N:3d} ctas {ctas:3d} start row {shift:2d} SBO {sbo}: {out.max() / reps:7.1f} cycles/MMA (ideal {N / 2:.0f})")
+    out = np.zeros(148, np.int64)
+    for shared, span in ((1, 1 << 20), (1, 1 << 18), (0, 1 << 18), (0, 1 << 20)):
+        for ctas in (1, 148):
+            rc = lib.l2_fill_probe(ctas, 2048, span, shared, out.ctypes.data)
+            if rc:
+                print(f"fill shared {shared} span {span} ctas {ctas}: CUDA error {rc}")
+                continue
+            cyc = out[:ctas].max()
+            print(f"fill {'same' if shared else 'own '} {span >> 10:5d} KB per CTA, ctas {ctas:3d}: {2048 * 16384 / cyc:6.1f} B/cycle/SM")
+
+
+if __name__ == "__main__":
+    main()
