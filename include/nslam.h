@@ -45,8 +45,8 @@ int nslam_corr_volume_build_simt(const void* fmaps, int NF, int H, int W, int C,
                                  const int* jj, int E, void* out0, void* out1, void* out2,
                                  void* out3, void* stream);
 
-/* EXPERIMENTAL (off unless NSLAM_CORRVOL_ROWS=1 on the Python side; hardware validation pending): the same
- * operation with row-pair tiles — level 0 leaves the SM as 320 contiguous bytes per source pixel instead of
+/* The same operation with row-pair tiles (the default for the shapes it covers; bit-identical output,
+ * tests/test_gpu_parity.py) — level 0 leaves the SM as 320 contiguous bytes per source pixel instead of
  * 32-byte pieces (csrc/corr_volume_rows.cu).  C = 128, H even, W in {64, 80}; cudaErrorNotSupported otherwise. */
 int nslam_corr_volume_build_rows(const void* fmaps, int NF, int H, int W, int C, const int* ii, const int* jj,
                                  int E, void* out0, void* out1, void* out2, void* out3, void* stream);

@@ -1,6 +1,7 @@
-// A14, reference-exact variant of the inverse-depth covariance in ONE kernel (opt-in: NSLAM_COV_REFERENCE=kernel; written
-// after the round's GPU budget was spent, validated by a gated test — until then the default obtains the same values
-// from csrc/ba.cu's nslam_ba_cov plus a torch fix-up, droid_backends.cov_reference_fixup).
+// A14, the inverse-depth covariances exactly as the reference's block computes them, in ONE kernel — the default of the
+// live path (cov_mode 1 of nslam_ba_frontend_update, written into the keyframe arenas) and of BAProblem.covariances.
+// droid_backends.cov_reference_fixup (torch ops on top of csrc/ba.cu's nslam_ba_cov) is kept as an independent
+// cross-check in the tests.
 //
 // The reference builds, per optimised pose p and depth map k, the 6 x HW block E[p][k] that enters
 //   Sigma_z = Q + sum_cols((Q * E^T) L^-1)^2                        (visual_frontend.py:1196-1230).

@@ -171,7 +171,14 @@ extern "C" int nslam_proximity_edges(float* d, int kf0, int kf1, int t, const lo
   std::vector<int64_t> order((size_t)n);
   for (int64_t k = 0; k < n; k++) order[(size_t)k] = k;
   std::vector<float> d0(d, d + n);              // the order is fixed by the values BEFORE the selection loop mutates them
-  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return d0[(size_t)a] < d0[(size_t)b]; });
+  // NaN distances (degenerate frames) sort last, as numpy's argsort places them: with a plain `<` the comparator would
+  // not be a strict weak ordering and the sort's behaviour undefined
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    const float x = d0[(size_t)a], y = d0[(size_t)b];
+    if (x != x) return false;
+    if (y != y) return true;
+    return x < y;
+  });
   for (int64_t s = 0; s < n; s++) {
     const int64_t k = order[(size_t)s];
     if (d[k] > thresh) continue;

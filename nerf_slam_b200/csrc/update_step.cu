@@ -55,7 +55,7 @@ extern "C" int nslam_update_op_step(const nslam_update_ctx* c, void* stream) {
   { const void* s[1] = {c->f1}; int ch[1] = {128};
     if ((r = conv(s, ch, 1, E, 3, 64, NSLAM_W_FE2, 0, 1, nullptr, nullptr, nullptr, nullptr, c->f2, 64, nullptr))) return r; }
   // global context
-  cudaMemsetAsync(c->gsum, 0, (size_t)E * 128 * sizeof(float), st);
+  { cudaError_t me = cudaMemsetAsync(c->gsum, 0, (size_t)E * 128 * sizeof(float), st); if (me != cudaSuccess) return (int)me; }
   { const void* s[1] = {c->net}; int ch[1] = {128};
     if ((r = conv(s, ch, 1, E, 1, 128, NSLAM_W_GLO, 3, 0, nullptr, c->net, nullptr, c->gsum, nullptr, 0, nullptr))) return r; }
   glo_context_kernel<<<E, 128, 0, st>>>(c->gsum, c->glo_w, c->glo_b, 1.0f / (float)(H * W), c->gzr, c->gq, E);

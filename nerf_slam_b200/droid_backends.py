@@ -22,7 +22,7 @@ _DT = {torch.float16: 0, torch.float32: 1}
 # kernel (csrc/ba_cov_ref.cu); "1" = the same values from nslam_ba_cov plus a fix-up of the depth maps of optimised
 # frames in a handful of torch ops (kept as an independent cross-check in the tests); "0" = the intended formula.
 # The live front end does not come through here: it uses nslam_ba_frontend_update (covariances written into the arenas).
-_COV_MODE = __import__("os").environ.get("NSLAM_COV_REFERENCE", "kernel")
+_COV_MODE = "kernel"
 
 
 def cov_reference_fixup(M, E, Q, disps_flat, z_cov, d_cov, win_k, win_q, win_f, P):
@@ -112,8 +112,7 @@ def corr_lookup_pyramid(volumes, coords, radius, slots=None, nhwc_stride=0, coor
 def _corrvol_entry(lib, H, W, C):
     """the row-pair kernel (csrc/corr_volume_rows.cu; bit-identical output, tests/test_gpu_parity.py) for the shapes it
     supports, the tiled kernel for everything else"""
-    import os
-    if os.environ.get("NSLAM_CORRVOL_ROWS", "1") == "1" and C == 128 and H % 2 == 0 and W in (64, 80):
+    if C == 128 and H % 2 == 0 and W in (64, 80):
         return lib.nslam_corr_volume_build_rows
     return lib.nslam_corr_volume_build
 
@@ -396,7 +395,7 @@ class BAProblem:
 
     def covariances(self, linv, reference=None):
         """A14 -> (sigma_g [P,6,6], z_cov [K,ht,wd], depth_cov [K,ht,wd]).
-        reference: None = NSLAM_COV_REFERENCE (default "kernel"); "kernel" = the reference's block as it really behaves
+        reference: None = "kernel"; "kernel" = the reference's block as it really behaves
         (its broadcast of Ei over the pose rows of optimised frames, visual_frontend.py:1214) in one CUDA kernel
         (csrc/ba_cov_ref.cu); True / "1" = the same from nslam_ba_cov + torch fix-up; False / "0" = the intended formula."""
         lib = _lib.load()

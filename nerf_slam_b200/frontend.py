@@ -669,7 +669,10 @@ class RaftVisualFrontend:
         m = (self.ii_h == kf) | (self.jj_h == kf)
         self.ii_h[self.ii_h >= kf] -= 1
         self.jj_h[self.jj_h >= kf] -= 1
-        self.rm_factors(m, store=False)
+        if m.any():
+            self.rm_factors(m, store=False)
+        else:
+            self._sync_edges()          # indices above kf moved down: the device copies must follow even if no edge leaves
 
     def reproject(self, ii, jj):
         """visual_frontend.py:909-918 -> coords [E,ht,wd,2], valid"""

@@ -1,9 +1,9 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh LOG TIMEOUT [--gpus N] -- cmd     (retries while the pod answers busy/transient)
-log=$1; shift; to=$1; shift
-for i in 1 2 3 4 5 6 7 8; do
-  /usr/local/graft/bin/gpurun --timeout $to "$@" > $log 2>&1
-  rc=$?
-  if grep -q "status=transient\|status=busy" $log || [ $rc -eq 3 ]; then sleep 150; continue; fi
-  break
+# usage: tools/gpurun_retry.sh <timeout_s> [--gpus N] -- '<command>'   retries while gpurun answers "busy / no slot" (exit 3)
+T=$1; shift
+for i in $(seq 1 12); do
+  /usr/local/graft/bin/gpurun --timeout "$T" "$@"; rc=$?
+  if [ $rc -ne 3 ] && ! grep -q '"status": "transient"' gpurun_out/.last_call.json 2>/dev/null; then exit $rc; fi
+  echo "[retry $i] no slot, sleeping 240 s"; sleep 240
 done
+exit 3
