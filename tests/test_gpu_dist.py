@@ -50,7 +50,7 @@ def _gradient(tb, seed):
     return tb.grid_grad.clone(), tb.mlp_grad.clone()
 
 
-def _worker(rank, world, port, q):
+def _worker_body(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -97,6 +97,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:                      # report instead of leaving the parent waiting for the queue
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_rank_nccl_gradients_equal_single_process_and_handoff_is_exact():
     import torch.multiprocessing as mp
@@ -106,7 +114,12 @@ def test_two_rank_nccl_gradients_equal_single_process_and_handoff_is_exact():
     ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    res = [q.get(timeout=300) for _ in ps]
-    for p in ps:
-        p.join(timeout=60)
-    assert all(ok for _, ok in res), res
+    try:
+        res = [q.get(timeout=300) for _ in ps]
+        for p in ps:
+            p.join(timeout=60)
+    finally:
+        for p in ps:                       # a rank that died or hangs must not outlive the test
+            if p.is_alive():
+                p.terminate()
+    assert all(ok is True for _, ok in res), res
