@@ -127,10 +127,15 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, ConvParams p, HaloWork h
       if (sub_mask(st, mask) == 0) continue;
       const int n = st / tiles_per_img, tt = st % tiles_per_img;
       const int h0 = (tt / p.tiles_w) * 16, w0 = (tt % p.tiles_w) * 16;
+      // The next channel block's box goes out AFTER the first weight blocks of the current one: its ring slot is only
+      // free once the MMAs of block g-1 have retired, and a producer that waits for that before it streams block g's
+      // weights leaves the weight ring empty at every channel-block boundary.  At tap A_AT the producer is at most WS
+      // taps ahead of the MMA warp, so the ring stays full while it waits.
+      constexpr int A_AT = WS >= 6 ? 3 : (WS >= 4 ? 2 : 1);
       load_a(0, w0, h0, n);
       for (int g = 0; g < p.cb_total; g++) {
-        if (g + 1 < p.cb_total) load_a(g + 1, w0, h0, n);               // the next channel block's box is in flight
         for (int tap = 0; tap < 9; tap++, iw++) {
+          if (tap == A_AT && g + 1 < p.cb_total) load_a(g + 1, w0, h0, n);
           const int sw = iw % WS, pw = (iw / WS) & 1;
           tc::mbar_wait(&empty_w[sw], pw ^ 1);
           tc::mbar_arrive_expect_tx_lead(&full_w[sw], SM::W_BLOCK, lead);

@@ -24,6 +24,10 @@ def main():
     lib = ctypes.CDLL(SO)
     lib.umma_rate_probe.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
     lib.l2_fill_probe.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    lib.l2_fill_box_probe.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    if "--boxes-only" in sys.argv:
+        boxes(lib)
+        return
     reps = 4096
     for ctas in (1, 148):
         out = np.zeros(ctas, np.int64)
@@ -43,6 +47,22 @@ def main():
                 continue
             cyc = out[:ctas].max()
             print(f"fill {'same' if shared else 'own '} {span >> 10:5d} KB per CTA, ctas {ctas:3d}: {2048 * 16384 / cyc:6.1f} B/cycle/SM")
+    boxes(lib)
+
+
+def boxes(lib):
+    """TMA tensor loads of the convolutions' activation boxes (128-byte rows, one global segment each)"""
+    out = np.zeros(148, np.int64)
+    for C in (128, 448):
+        for bw, bh, stages in ((16, 10, 4), (18, 18, 2), (16, 8, 4)):
+            for ctas in (1, 148):
+                reps = 1024
+                rc = lib.l2_fill_box_probe(ctas, reps, C if C % 64 == 0 else 128, bw, bh, stages, out.ctypes.data)
+                if rc:
+                    print(f"box C {C} {bw}x{bh} ctas {ctas}: CUDA error {rc}")
+                    continue
+                print(f"box fill C {C:3d} box 64c x {bw:2d}w x {bh:2d}h ({128 * bw * bh / 1024:.1f} KB, {stages} stages) ctas {ctas:3d}: "
+                      f"{reps * 128 * bw * bh / out[:ctas].max():6.1f} B/cycle/SM")
 
 
 if __name__ == "__main__":

@@ -90,7 +90,55 @@ __global__ void __launch_bounds__(32, 1) fill_kernel(const unsigned char* src, i
   if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
 }
 
+// The same for TMA TENSOR loads of the convolutions' activation boxes: box {64 channels, bw pixels, bh rows} of an NHWC fp16
+// tensor [B,H,W,C] (every 128-byte box row is its own segment of global memory), SWIZZLE_128B, 2-4 stages.
+__global__ void __launch_bounds__(32, 1) fill_box_kernel(const __grid_constant__ CUtensorMap map, int reps, int bw, int bh, int H, int W,
+                                                         int cblocks, int stages, long long* out) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[4];
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) tc::mbar_init(&bar[i], 1); tc::fence_barrier_init(); }
+  __syncwarp();
+  const uint32_t lead = tc::elect_one() ? 1u : 0u;
+  const uint32_t bytes = 128u * bw * bh, stage_bytes = (bytes + 1023) & ~1023u;
+  const int tw = W / 16, th = H / 16;
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; r++) {
+    const int st = r % stages, q = r / stages;
+    if (q >= 1) tc::mbar_wait(&bar[st], (q - 1) & 1);
+    const int tile = (blockIdx.x * 7 + r / cblocks) % (tw * th);
+    tc::mbar_arrive_expect_tx_lead(&bar[st], bytes, lead);
+    tc::tma_load_4d_lead(sm + st * stage_bytes, &map, &bar[st], (r % cblocks) * 64, (tile % tw) * 16 - 1, (tile / tw) * 16 - 1,
+                         blockIdx.x % 18, lead);
+  }
+  for (int r = reps - stages; r < reps; r++) tc::mbar_wait(&bar[r % stages], (r / stages) & 1);
+  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
 }  // namespace
+
+// bytes/cycle/SM of TMA tensor loads (box {64, bw, bh, 1}) from an L2-resident NHWC tensor [18, 64, 80, C]
+extern "C" int l2_fill_box_probe(int ctas, int reps, int C, int bw, int bh, int stages, long long* cycles_host) {
+  const int B = 18, H = 64, W = 80;
+  __half* src = nullptr; long long* d = nullptr;
+  const size_t total = (size_t)B * H * W * C * 2;
+  if (cudaMalloc(&src, total) != cudaSuccess || cudaMalloc(&d, ctas * sizeof(long long)) != cudaSuccess) return 2;
+  cudaMemset(src, 0, total);
+  CUtensorMap map;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  int rc = tc::make_tmap_f16(&map, src, 4, dims, strides, box);
+  const int smem = stages * ((128 * bw * bh + 1023) & ~1023) + 1024;
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(fill_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int pass = 0; pass < 2 && rc == 0; pass++) {
+    fill_box_kernel<<<ctas, 32, smem>>>(map, reps, bw, bh, H, W, C / 64, stages, d);
+    rc = (int)cudaDeviceSynchronize();
+  }
+  if (rc == 0) rc = (int)cudaMemcpy(cycles_host, d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(src); cudaFree(d);
+  return rc;
+}
 
 // bytes/cycle/SM of L2 -> smem bulk copies (after one untimed pass that brings `span` into L2)
 extern "C" int l2_fill_probe(int ctas, int reps, int span, int shared_src, long long* cycles_host) {
