@@ -25,6 +25,10 @@ def main():
     lib.umma_rate_probe.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
     lib.l2_fill_probe.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p]
     lib.l2_fill_box_probe.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    lib.tma_multi_warp_probe.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    if "--multi-only" in sys.argv:
+        multi(lib)
+        return
     if "--boxes-only" in sys.argv:
         boxes(lib)
         return
@@ -48,6 +52,26 @@ def main():
             cyc = out[:ctas].max()
             print(f"fill {'same' if shared else 'own '} {span >> 10:5d} KB per CTA, ctas {ctas:3d}: {2048 * 16384 / cyc:6.1f} B/cycle/SM")
     boxes(lib)
+
+
+def multi(lib):
+    """do TMA operations issued by different warps of one SM overlap?"""
+    reps = 1024
+    for ctas in (1, 148):
+        out = np.zeros(ctas * 8, np.int64)
+        for nbytes in (4096, 16384, 20480):
+            for warps in (1, 2):
+                rc = lib.tma_multi_warp_probe(ctas, warps, reps, nbytes, 0, out.ctypes.data)
+                if rc:
+                    print(f"multi bytes {nbytes} warps {warps} ctas {ctas}: error {rc}"); continue
+                cyc = out.reshape(ctas, 8)[:, :warps].max()
+                print(f"bulk copies of {nbytes:5d} B, {warps} issuing warp(s), ctas {ctas:3d}: {cyc / reps:6.0f} cycles per copy per warp, "
+                      f"{warps * reps * nbytes / cyc:6.1f} B/cycle/SM")
+        rc = lib.tma_multi_warp_probe(ctas, 2, reps, 16384, 1, out.ctypes.data)
+        if rc == 0:
+            c = out.reshape(ctas, 8).max(0)
+            print(f"mixed, ctas {ctas:3d}: warp 0 boxes 64c x 16w x 10h: {c[0] / reps:6.0f} cycles per box; warp 1 bulk 16 KB: {c[1] / reps:6.0f} cycles per copy; "
+                  f"together {(reps * 20480 + reps * 16384) / max(c[0], c[1]):6.1f} B/cycle/SM")
 
 
 def boxes(lib):

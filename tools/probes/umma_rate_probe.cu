@@ -115,7 +115,63 @@ __global__ void __launch_bounds__(32, 1) fill_box_kernel(const __grid_constant__
   if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
 }
 
+// Do TMA operations of DIFFERENT warps of one SM overlap?  `warps` warps, each with its own 4-stage ring: warp 0 loads
+// activation boxes {64c,16w,10h} when `mixed`, all others (and warp 0 otherwise) stream bulk copies of `bytes`.
+// out[cta * 8 + w] = cycles of warp w for `reps` operations.
+__global__ void __launch_bounds__(256, 1) fill_multi_kernel(const __grid_constant__ CUtensorMap map, const unsigned char* src, int reps,
+                                                            int bytes, int mixed, int H, int W, long long* out) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[8][4];
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) for (int w = 0; w < 8; w++) tc::mbar_init(&bar[w][i], 1); tc::fence_barrier_init(); }
+  __syncthreads();
+  const uint32_t lead = tc::elect_one() ? 1u : 0u;
+  const bool boxes = mixed && warp == 0;
+  const uint32_t nb = boxes ? 20480u : (uint32_t)bytes;
+  unsigned char* mine = sm + warp * 4 * 20480;              // the host caps the launch at 2 warps (160 KB of rings)
+  const int tw = W / 16, th = H / 8;
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; r++) {
+    const int st = r & 3;
+    if (r >= 4) tc::mbar_wait(&bar[warp][st], ((r >> 2) - 1) & 1);
+    tc::mbar_arrive_expect_tx_lead(&bar[warp][st], nb, lead);
+    if (boxes) {
+      const int tile = (blockIdx.x * 5 + r / 2) % (tw * th);
+      tc::tma_load_4d_lead(mine + st * 20480, &map, &bar[warp][st], (r & 1) * 64, (tile % tw) * 16 - 1, (tile / tw) * 8 - 1, blockIdx.x % 18, lead);
+    } else {
+      tc::bulk_copy_g2s_lead(mine + st * 20480, src + ((size_t)(r * 4 + warp) * bytes) % (1 << 20), nb, &bar[warp][st], lead);
+    }
+  }
+  for (int r = reps - 4; r < reps; r++) tc::mbar_wait(&bar[warp][r & 3], (r >> 2) & 1);
+  if (lead) out[blockIdx.x * 8 + warp] = clock64() - t0;
+}
+
 }  // namespace
+
+// cycles_host[ctas*8]; warps in {1,2}; bytes <= 20480 per bulk copy
+extern "C" int tma_multi_warp_probe(int ctas, int warps, int reps, int bytes, int mixed, long long* cycles_host) {
+  const int B = 18, H = 64, W = 80, C = 128;
+  unsigned char* src = nullptr; __half* act = nullptr; long long* d = nullptr;
+  if (warps < 1 || warps > 2 || bytes > 20480 || bytes % 16) return 1;
+  if (cudaMalloc(&src, 2 << 20) != cudaSuccess || cudaMalloc(&act, (size_t)B * H * W * C * 2) != cudaSuccess ||
+      cudaMalloc(&d, ctas * 8 * sizeof(long long)) != cudaSuccess) return 2;
+  cudaMemset(src, 0, 2 << 20); cudaMemset(act, 0, (size_t)B * H * W * C * 2); cudaMemset(d, 0, ctas * 8 * sizeof(long long));
+  CUtensorMap map;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, 16, 10, 1};
+  int rc = tc::make_tmap_f16(&map, act, 4, dims, strides, box);
+  const int smem = warps * 4 * 20480 + 1024;
+  if (rc == 0) rc = (int)cudaFuncSetAttribute(fill_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int pass = 0; pass < 2 && rc == 0; pass++) {
+    fill_multi_kernel<<<ctas, 32 * warps, smem>>>(map, src, reps, bytes, mixed, H, W, d);
+    rc = (int)cudaDeviceSynchronize();
+  }
+  if (rc == 0) rc = (int)cudaMemcpy(cycles_host, d, ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(src); cudaFree(act); cudaFree(d);
+  return rc;
+}
 
 // bytes/cycle/SM of TMA tensor loads (box {64, bw, bh, 1}) from an L2-resident NHWC tensor [18, 64, 80, C]
 extern "C" int l2_fill_box_probe(int ctas, int reps, int C, int bw, int bh, int stages, long long* cycles_host) {
