@@ -8,7 +8,13 @@
 namespace nslam {
 
 constexpr int CG_EPI_WARPS = 8;
-constexpr int CG_THREADS = 64 + 32 * CG_EPI_WARPS;     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int CG_THREADS_BASE = 64 + 32 * CG_EPI_WARPS;     // TMA warp, MMA warp, 8 epilogue warps (conv_halo.cu, conv_igemm2.cu)
+// conv_igemm.cu adds three more TMA-issuing warps behind the epilogue warps.  One warp issues a cp.async.bulk every ~280
+// cycles and a tensor-map load every ~500-630, whatever their size — but different warps of an SM overlap
+// (tools/probes/umma_rate_probe.cu, profiles/r02_tma_multi_warp_probe_call9.log): with a single producer warp a 64-channel
+// block of a 3x3 convolution (3 boxes + 9 weight blocks) cost ~5200 cycles of issue against 2304 cycles of MMAs at N = 128.
+constexpr int CG_A_WARPS = 2, CG_W_WARPS = 2;              // activation-box issuers: warps 0 and 10; weight issuers: 11, 12
+constexpr int CG_THREADS = CG_THREADS_BASE + 32 * (CG_A_WARPS - 1 + CG_W_WARPS);
 template <int N> struct CgStages { static constexpr int value = (N >= 256) ? 3 : 4; };
 constexpr int CG_TH = 8, CG_TW = 16;
 

@@ -62,7 +62,7 @@ __device__ __forceinline__ void halo_item(const HaloWork& hw, int w, int& st, in
 }
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(CG_THREADS, 1)
+__global__ void __launch_bounds__(CG_THREADS_BASE, 1)
 conv_halo_kernel(const __grid_constant__ ConvMaps maps, ConvParams p, HaloWork hw) {
   using SM = ChSmem<N>;
   constexpr int WS = SM::W_STAGES, AS = CH_A_STAGES;
@@ -95,7 +95,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, ConvParams p, HaloWork h
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<TCOLS>(tmem_slot);
-  for (int i = threadIdx.x; i < N; i += CG_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < N; i += CG_THREADS_BASE) sbias[i] = p.bias ? p.bias[i] : 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -316,7 +316,7 @@ static int launch_halo_nm(const ConvMaps& maps, const ConvParams& p, int num_sms
   hw.grid = grid;
   hw.n_items = hw.full * grid + (hw.split ? 2 * hw.rem : hw.rem);
   const int launch = hw.n_items < grid ? hw.n_items : grid;
-  conv_halo_kernel<N, MODE><<<launch, CG_THREADS, smem, st>>>(maps, p, hw);
+  conv_halo_kernel<N, MODE><<<launch, CG_THREADS_BASE, smem, st>>>(maps, p, hw);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }

@@ -69,7 +69,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; s++) tc::tma_prefetch_desc(&maps.src[s]);
-    for (int s = 0; s < BS; s++) { tc::mbar_init(&full_b[s], 1); tc::mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < BS; s++) { tc::mbar_init(&full_b[s], HALO ? 1 : 2); tc::mbar_init(&empty_b[s], 1); }
     for (int s = 0; s < AS; s++) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < 2; s++) { tc::mbar_init(&tm_full[s], 1); tc::mbar_init(&tm_empty[s], CG_EPI_WARPS); }
     tc::fence_barrier_init();
@@ -81,39 +81,38 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    // whole warp in the loop, elected lane issues (uniform control flow, see tc::umma_f16_lead)
-    {
-      const uint32_t lead = tc::elect_one() ? 1u : 0u;
-      if (HALO) {
-        // unit = (channel block, dx): one shifted halo tile + the three weight blocks of its taps (dy = 0..2).
-        // The tile of the NEXT unit is requested before this unit's weight blocks so that two units are in flight.
-        uint32_t ia = 0, ib = 0;
-        auto load_a = [&](int s, int cb, int dx, int w0, int h0, int n) {
-          const int sa = ia % AS, pa = (ia / AS) & 1;
-          tc::mbar_wait(&empty_a[sa], pa ^ 1);
-          tc::mbar_arrive_expect_tx_lead(&full_a[sa], SM::A_STAGE, lead);
-          tc::tma_load_4d_lead(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + dx - 1, h0 - 1, n, lead);
-          ia++;
-        };
-        const int units = p.cb_total * 3;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
-          const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
-          // (source, block) of global channel block g
-          auto src_of = [&](int g, int& sidx, int& cb) { sidx = 0; cb = g; while (cb >= p.src_cb[sidx]) { cb -= p.src_cb[sidx]; sidx++; } };
-          int s0, c0;
-          src_of(0, s0, c0);
-          load_a(s0, c0, 0, w0, h0, n);
+  // warp roles: 0 and 10 = activation (A) producers, 11 and 12 = weight (B) producers, 1 = MMA issuer, 2..9 = epilogue
+  const int a_part = (warp == 0) ? 0 : (warp == 2 + CG_EPI_WARPS) ? 1 : -1;
+  const int w_part = (warp >= 3 + CG_EPI_WARPS) ? warp - (3 + CG_EPI_WARPS) : -1;
+  if (a_part >= 0 || w_part >= 0) {
+    // ===================== TMA producers =====================
+    // Every producer warp walks the same sequence of load units and issues those of its own parity: an A warp the
+    // activation loads with (counter % CG_A_WARPS) == a_part, a W warp the weight blocks with (counter % CG_W_WARPS) ==
+    // w_part.  Whole warp in the loop, elected lane issues (uniform control flow, see tc::umma_f16_lead).
+    const uint32_t lead = tc::elect_one() ? 1u : 0u;
+    auto src_of = [&](int g, int& sidx, int& cb) { sidx = 0; cb = g; while (cb >= p.src_cb[sidx]) { cb -= p.src_cb[sidx]; sidx++; } };
+    if (HALO) {
+      // unit = (channel block, dx): one shifted halo tile (A ring) + the three weight blocks of its taps dy = 0..2 (B ring)
+      const int units = p.cb_total * 3;
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+        if (a_part >= 0) {
+          for (int u = 0; u < units; u++, ia++) {
+            if ((int)(ia % CG_A_WARPS) != a_part) continue;
+            int s, cb;
+            src_of(u / 3, s, cb);
+            const int sa = ia % AS, pa = (ia / AS) & 1;
+            tc::mbar_wait(&empty_a[sa], pa ^ 1);
+            tc::mbar_arrive_expect_tx_lead(&full_a[sa], SM::A_STAGE, lead);
+            tc::tma_load_4d_lead(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + (u % 3) - 1, h0 - 1, n, lead);
+          }
+        } else {
           for (int u = 0; u < units; u++) {
             const int cbg = u / 3, dx = u % 3;
-            if (u + 1 < units) {
-              int s1, c1;
-              src_of((u + 1) / 3, s1, c1);
-              load_a(s1, c1, (u + 1) % 3, w0, h0, n);
-            }
             for (int dy = 0; dy < 3; dy++, ib++) {
+              if ((int)(ib % CG_W_WARPS) != w_part) continue;
               const int sb = ib % BS, pb = (ib / BS) & 1;
               tc::mbar_wait(&empty_b[sb], pb ^ 1);
               tc::mbar_arrive_expect_tx_lead(&full_b[sb], N * 128, lead);
@@ -122,20 +121,28 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, ConvParams p) {
             }
           }
         }
-      } else {
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
-          const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
-          for (int tap = 0; tap < taps; tap++) {
-            const int dy = tap / p.KW - p.pad, dx = tap % p.KW - p.pad;
-            int cbg = 0;
-            for (int s = 0; s < p.n_src; s++) {
-              for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
-                const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
-                tc::mbar_wait(&empty_b[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx_lead(&full_b[st], 16384 + N * 128, lead);
+      }
+    } else {
+      // unit = (tap, channel block): one activation tile and one weight block complete on the SAME barrier (init count 2:
+      // one arrive.expect_tx from the A warp, one from the W warp)
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+        const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+        for (int tap = 0; tap < taps; tap++) {
+          const int dy = tap / p.KW - p.pad, dx = tap % p.KW - p.pad;
+          int cbg = 0;
+          for (int s = 0; s < p.n_src; s++) {
+            for (int cb = 0; cb < p.src_cb[s]; cb++, cbg++, it++) {
+              const bool mine = (a_part >= 0) ? ((int)(it % CG_A_WARPS) == a_part) : ((int)(it % CG_W_WARPS) == w_part);
+              if (!mine) continue;
+              const int st = it % CG_STAGES, ph = (it / CG_STAGES) & 1;
+              tc::mbar_wait(&empty_b[st], ph ^ 1);
+              if (a_part >= 0) {
+                tc::mbar_arrive_expect_tx_lead(&full_b[st], 16384, lead);
                 tc::tma_load_4d_lead(sm + SM::A + st * 16384, &maps.src[s], &full_b[st], cb * 64, w0 + dx, h0 + dy, n, lead);
+              } else {
+                tc::mbar_arrive_expect_tx_lead(&full_b[st], N * 128, lead);
                 tc::bulk_copy_g2s_lead(sm + SM::B + st * (N * 128), p.wpacked + (size_t)(tap * p.cb_total + cbg) * N * 64,
                                        N * 128, &full_b[st], lead);
               }

@@ -44,7 +44,7 @@ struct Cg2Smem {
 };
 
 template <int N, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS_BASE, 1)
 conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap wmap, ConvParams p) {
   static_assert(N == 128 || N == 256, "CTA-pair kernel: N = 128 or 256");
   static_assert(MODE == 0 || MODE == 1 || MODE == 2, "CTA-pair kernel: epilogue modes 0, 1, 2");
@@ -83,7 +83,7 @@ conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc_pair<TCOLS>(tmem_slot);
-  for (int i = threadIdx.x; i < N; i += CG_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < N; i += CG_THREADS_BASE) sbias[i] = p.bias ? p.bias[i] : 0.f;
   tc::tc_fence_before();
   tc::cluster_sync_all();                        // barriers of BOTH CTAs initialised before any remote signal
   tc::tc_fence_after();
@@ -266,7 +266,7 @@ static int launch_conv2_nm(const ConvMaps& maps, const CUtensorMap& wmap, const 
   int clusters = num_sms / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > npairs) clusters = npairs;
-  conv_igemm2_kernel<N, MODE><<<2 * clusters, CG_THREADS, smem, st>>>(maps, wmap, p);
+  conv_igemm2_kernel<N, MODE><<<2 * clusters, CG_THREADS_BASE, smem, st>>>(maps, wmap, p);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }
