@@ -43,8 +43,11 @@ struct Cg2Smem {
   static constexpr int TOTAL = BAR + 512;
 };
 
+constexpr int CG2_W_WARPS = 3;
+constexpr int CG2_THREADS = CG_THREADS_BASE + 32 * CG2_W_WARPS;
+
 template <int N, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS_BASE, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG2_THREADS, 1)
 conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap wmap, ConvParams p) {
   static_assert(N == 128 || N == 256, "CTA-pair kernel: N = 128 or 256");
   static_assert(MODE == 0 || MODE == 1 || MODE == 2, "CTA-pair kernel: epilogue modes 0, 1, 2");
@@ -83,44 +86,47 @@ conv_igemm2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc_pair<TCOLS>(tmem_slot);
-  for (int i = threadIdx.x; i < N; i += CG_THREADS_BASE) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < N; i += CG2_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
   tc::tc_fence_before();
   tc::cluster_sync_all();                        // barriers of BOTH CTAs initialised before any remote signal
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      uint32_t ia = 0, ib = 0;
-      auto load_a = [&](int s, int cb, int dx, int w0, int h0, int n) {
-        const int sa = ia % AS, pa = (ia / AS) & 1;
-        tc::mbar_wait(&empty_a[sa], pa ^ 1);
-        if (leader) tc::mbar_arrive_expect_tx(&full_a[sa], 2 * SM::A_STAGE);
-        tc::tma_load_4d_pair(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + dx - 1, h0 - 1, n);
-        ia++;
-      };
-      auto src_of = [&](int g, int& sidx, int& cb) { sidx = 0; cb = g; while (cb >= p.src_cb[sidx]) { cb -= p.src_cb[sidx]; sidx++; } };
-      for (int pair = cid; pair < npairs; pair += nclusters) {
-        const int tile = 2 * pair + rank;        // == ntiles for the missing half of the last pair: image index B, zero-filled
-        const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
-        const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
-        int s0, c0;
-        src_of(0, s0, c0);
-        load_a(s0, c0, 0, w0, h0, n);
+  // warp roles: 0 = activation (A) producer, 10..12 = weight (B) producers, 1 = MMA issuer (leader), 2..9 = epilogue.
+  // All loads of this kernel are tensor-map loads (~500-630 cycles of issue each per warp, whatever their size;
+  // profiles/r02_tma_multi_warp_probe_call9.log): 3 + 9 of them per channel block from ONE warp cost 6600 cycles against
+  // 2304 (N = 128) / 4608 (N = 256) cycles of MMAs — the reason the first version of this kernel was no faster than the
+  // one-CTA kernel.  Four issuing warps: 3 loads per channel block each.
+  const int w_part = (warp >= 2 + CG_EPI_WARPS) ? warp - (2 + CG_EPI_WARPS) : -1;
+  if (warp == 0 || w_part >= 0) {
+    // ===================== TMA producers (both CTAs; whole warp in the loop, elected lane issues) =====================
+    const uint32_t lead = tc::elect_one() ? 1u : 0u;
+    const uint32_t lead_leader = (lead && leader) ? 1u : 0u;
+    auto src_of = [&](int g, int& sidx, int& cb) { sidx = 0; cb = g; while (cb >= p.src_cb[sidx]) { cb -= p.src_cb[sidx]; sidx++; } };
+    uint32_t ia = 0, ib = 0;
+    for (int pair = cid; pair < npairs; pair += nclusters) {
+      const int tile = 2 * pair + rank;        // == ntiles for the missing half of the last pair: image index B, zero-filled
+      const int n = tile / tiles_per_img, tt = tile % tiles_per_img;
+      const int h0 = (tt / p.tiles_w) * CG_TH, w0 = (tt % p.tiles_w) * CG_TW;
+      if (warp == 0) {
+        for (int u = 0; u < units; u++, ia++) {
+          int s, cb;
+          src_of(u / 3, s, cb);
+          const int sa = ia % AS, pa = (ia / AS) & 1;
+          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+          tc::mbar_arrive_expect_tx_lead(&full_a[sa], 2 * SM::A_STAGE, lead_leader);
+          tc::tma_load_4d_pair_lead(sm + SM::A + sa * SM::A_STAGE, &maps.src[s], &full_a[sa], cb * 64, w0 + (u % 3) - 1, h0 - 1, n, lead);
+        }
+      } else {
         for (int u = 0; u < units; u++) {
           const int cbg = u / 3, dx = u % 3;
-          if (u + 1 < units) {
-            int s1, c1;
-            src_of((u + 1) / 3, s1, c1);
-            load_a(s1, c1, (u + 1) % 3, w0, h0, n);
-          }
           for (int dy = 0; dy < 3; dy++, ib++) {
+            if ((int)(ib % CG2_W_WARPS) != w_part) continue;
             const int sb = ib % BS, pb = (ib / BS) & 1;
             tc::mbar_wait(&empty_b[sb], pb ^ 1);
-            if (leader) tc::mbar_arrive_expect_tx(&full_b[sb], N * 128);
+            tc::mbar_arrive_expect_tx_lead(&full_b[sb], N * 128, lead_leader);
             const int blk = (dy * 3 + dx) * p.cb_total + cbg;
-            tc::tma_load_2d_pair(sm + SM::B + sb * SM::B_STAGE, &wmap, &full_b[sb], 0, blk * N + rank * (N / 2));
+            tc::tma_load_2d_pair_lead(sm + SM::B + sb * SM::B_STAGE, &wmap, &full_b[sb], 0, blk * N + rank * (N / 2), lead);
           }
         }
       }
@@ -266,7 +272,7 @@ static int launch_conv2_nm(const ConvMaps& maps, const CUtensorMap& wmap, const 
   int clusters = num_sms / 2;
   if (clusters < 1) clusters = 1;
   if (clusters > npairs) clusters = npairs;
-  conv_igemm2_kernel<N, MODE><<<2 * clusters, CG_THREADS_BASE, smem, st>>>(maps, wmap, p);
+  conv_igemm2_kernel<N, MODE><<<2 * clusters, CG2_THREADS, smem, st>>>(maps, wmap, p);
   NSLAM_CHECK_LAUNCH();
   return 0;
 }

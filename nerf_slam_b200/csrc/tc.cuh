@@ -266,6 +266,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// warp-uniform variants (whole warp in the loop, `lead` lane issues)
+__device__ __forceinline__ void tma_load_4d_pair_lead(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                      int c3, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_lead(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(lead)
+      : "memory");
+}
 // TMEM: the same warp of BOTH CTAs allocates / frees (one collective operation of the pair)
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
