@@ -421,9 +421,10 @@ def _time_kernel(torch, fn, dev, iters=8, skip=3):
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures,
 # keyed by kernel; None where no capture at the live size exists.  See profiles/README.md.
 NCU_TRAFFIC = {
-    "conv_zr": (92820000, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
-    "conv_q": (132800512, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
-    "corr_lookup": (174600000, "profiles/r01_ncu_raw_run22.csv (18 edges)"),
+    "conv_zr": (93056256, "profiles/r02_ncu_raw_call12.csv (18 edges)"),
+    "conv_q": (129829120, "profiles/r02_ncu_raw_call12.csv (18 edges)"),
+    "corr_lookup": (174011648, "profiles/r02_ncu_raw_call12.csv (18 edges)"),
+    "ngp_backward": (28515840, "profiles/r02_ncu_raw_call12.csv (2^18 samples)"),
 }
 
 
@@ -544,6 +545,14 @@ def roofline_entries(job, pk):
             c = torch.nn.functional.avg_pool2d(c, 2, stride=2)
     ms = _time_kernel(torch, ref_volume, dev)
     out["corr_volume_E16"]["library_composite_ms"] = round(ms, 4)
+    # the volume kernel only WRITES (features are L2-resident): the write-only ceiling of this GPU, measured with a plain
+    # fill of the same size, next to the copy figure `peak` is quoted against
+    nb = out["corr_volume_E16"]["algorithmic_bytes_per_launch"]
+    fillbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+    ms_fill = _time_kernel(torch, lambda: fillbuf.zero_(), dev)
+    out["corr_volume_E16"]["write_only_fill_gbs"] = round(nb / ms_fill / 1e6, 1)
+    out["corr_volume_E16"]["frac_of_write_only_fill"] = round(out["corr_volume_E16"]["achieved"] / (nb / ms_fill / 1e6), 3)
+    del fillbuf
     out["corr_volume_E16"]["library_composite"] = "torch.matmul fp16 + 3x avg_pool2d at the same 16 edges (what CorrBlock.__init__ runs)"
     del f1, f2_
     # NeRF (B3): the tensor-core MLP backward = largest single kernel of the trainer

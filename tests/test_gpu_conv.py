@@ -53,15 +53,39 @@ def test_conv_matches_torch(cfg, act):
     assert float((err - 1e-2 * ref.abs()).max()) < 1e-2, float(err.max())
 
 
-@pytest.mark.skipif(os.environ.get("NSLAM_CONV_CTA2") != "1", reason="CTA-pair kernel is opt-in (NSLAM_CONV_CTA2=1)")
-@pytest.mark.parametrize("cfg", [
-    dict(chs=[128, 64], k=3, N=128, B=1, H=20, W=40),          # 9 tiles: the last pair has one tile only
+CONV_CFGS_3X3 = [
+    dict(chs=[128], k=3, N=128, B=3, H=30, W=40),
+    dict(chs=[128, 128, 128, 64], k=3, N=128, B=2, H=60, W=80),
+    dict(chs=[128], k=3, N=64, B=2, H=20, W=24),
+    dict(chs=[256], k=3, N=16, B=2, H=30, W=40),
+    dict(chs=[128], k=3, N=256, B=2, H=30, W=40),
+    dict(chs=[128, 64], k=3, N=128, B=1, H=20, W=40),          # 9 tiles: the last CTA pair has one tile only
     dict(chs=[128], k=3, N=256, B=1, H=8, W=16),               # a single tile: one pair, second half empty
     dict(chs=[128, 128, 128, 64], k=3, N=128, B=5, H=60, W=80),    # 200 tiles on 74 pairs: several pairs per cluster
-])
-def test_conv_pairs_odd_and_multi_wave(cfg):
-    """csrc/conv_igemm2.cu (cta_group::2): tile counts that leave half a pair empty, and more pairs than clusters"""
-    test_conv_matches_torch(cfg, 1)
+]
+
+
+def run_variant_checks():
+    """body of test_conv_kernel_variants (runs in a child process whose environment selects the kernel variant)"""
+    for cfg in CONV_CFGS_3X3:
+        for act in (0, 1):
+            test_conv_matches_torch(cfg, act)
+    test_gru_fused_epilogues()
+    test_update_operator_tc_vs_library_path(True)
+    print("variant checks ok")
+
+
+@pytest.mark.parametrize("switch", ["NSLAM_CONV_CTA2", "NSLAM_CONV_HALO"])
+def test_conv_kernel_variants(switch):
+    """the two alternative 3x3 kernels kept for measurements — CTA pairs (csrc/conv_igemm2.cu, tcgen05 cta_group::2) and
+    16x16 super-tiles with one halo box per channel block (csrc/conv_halo.cu) — stay parity-green: same cases as the default
+    kernel plus tile counts that leave half a pair empty / need several waves, the fused GRU epilogues and the whole update
+    operator.  The switch is read once per process, hence the child process."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", "import tests.test_gpu_conv as t; t.run_variant_checks()"], cwd=ROOT,
+                       env=dict(os.environ, **{switch: "1"}), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "variant checks ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 
 
 def test_gru_fused_epilogues():
