@@ -430,7 +430,7 @@ int nslam_conv_igemm_ex(const void* const* srcs, const int* src_channels, int n_
   p.zbuf = (const __half*)zbuf; p.gsum = gsum; p.stats = stats; p.sub = (mode == 4 && sub == 2) ? 2 : 1;
   if (mode == 4 && sub != 1 && sub != 2) return (int)cudaErrorInvalidValue;
   // NSLAM_CONV_HALO=1: the 16x16 super-tile kernel with one halo box per channel block (conv_halo.cu) for 3x3 / pad 1,
-  // epilogue modes 0-2 — parity-green but not faster on a B200 (profiles/r02_conv_issue_bound.md); measurement switch.
+  // epilogue modes 0-2 — parity-green but not faster on a B200 (profiles/r02_conv_analysis.md); measurement switch.
   static const bool want_halo2 = [] { const char* e = std::getenv("NSLAM_CONV_HALO"); return e && e[0] == '1'; }();
   const bool halo2 = want_halo2 && !conv_pairs_enabled() && conv_halo_supported(N, mode, KH, KW, pad);
   // first generation, 3x3 / pad 1: column-shifted halo tiles (see CgSmem); everything else: one tile per tap

@@ -149,7 +149,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // lead = elect_one()).  A tcgen05.mma issued from inside `if (lane == 0)` makes the compiler treat descriptors, loop
 // counters and barrier addresses as divergent values: every MMA is then preceded by an ELECT / R2UR.BROADCAST /
 // BRA.U.ANY loop that moves them into uniform registers — ~25 dependent instructions, ~90 cycles per MMA, more than the
-// 64 cycles an M128 x N128 x K16 MMA takes (profiles/r02_conv_issue_bound.md).  In uniform control flow the operands stay
+// 64 cycles an M128 x N128 x K16 MMA takes (profiles/r02_conv_analysis.md).  In uniform control flow the operands stay
 // in uniform registers and an MMA costs a handful of instructions.
 __device__ __forceinline__ void umma_f16_lead(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate, uint32_t lead) {
