@@ -44,9 +44,13 @@ def _gradient(tb, seed):
     lib = _lib.load()
     tb.grid_grad.zero_(); tb.mlp_grad.zero_()
     im = tb._images()
-    _lib.check(lib.nslam_ngp_train_step_tc(ctypes.byref(tb.model), ctypes.byref(im), ctypes.byref(tb.batch), _lib.ptr(tb.packed), 512,
+    _lib.check(lib.nslam_ngp_train_step_tc(ctypes.byref(tb.model), ctypes.byref(im), ctypes.byref(tb.batch), _lib.ptr(tb.packed), 96,
                                            seed, 1.0, 0.0, 0.0, 0.0, float(tb.loss_scale), tb.num_sms, _lib.stream_ptr()), "train_step_tc")
     torch.cuda.synchronize()
+    # the batch must fit the sample buffer: rays that find it full are dropped in arrival order, which would make the
+    # gradient depend on the scheduling of the march (the trainer itself sizes its batches to ~fill the buffer)
+    used, kept = [int(v) for v in tb._bufs["counters"][:2].tolist()]
+    assert kept == 96 and used < tb.max_samples, (used, kept)
     return tb.grid_grad.clone(), tb.mlp_grad.clone()
 
 
