@@ -46,19 +46,22 @@ __global__ void __launch_bounds__(256)
 tsdf_integrate_kernel(TsdfGrid g, TsdfFrame f) {
   __shared__ double sR[9], st[3];
   if (threadIdx.x == 0) {
+    // SE3(poses).matrix() is a float32 matrix that build_volume promotes to float64 (:186, :209): round the rotation to fp32
     const double qx = f.pose[3], qy = f.pose[4], qz = f.pose[5], qw = f.pose[6];
-    sR[0] = 1 - 2 * (qy * qy + qz * qz); sR[1] = 2 * (qx * qy - qz * qw); sR[2] = 2 * (qx * qz + qy * qw);
-    sR[3] = 2 * (qx * qy + qz * qw); sR[4] = 1 - 2 * (qx * qx + qz * qz); sR[5] = 2 * (qy * qz - qx * qw);
-    sR[6] = 2 * (qx * qz - qy * qw); sR[7] = 2 * (qy * qz + qx * qw); sR[8] = 1 - 2 * (qx * qx + qy * qy);
+    const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                         2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                         2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
+    for (int i = 0; i < 9; i++) sR[i] = (double)(float)R[i];
     st[0] = f.pose[0]; st[1] = f.pose[1]; st[2] = f.pose[2];
   }
   __syncthreads();
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   const int iy = blockIdx.y, iz = blockIdx.z;
   if (ix >= g.nx) return;
-  // fp64 like the reference's projection (:243-252): voxel coordinates, extrinsic and intrinsic are cast to float64
-  const double wx = (double)g.ox + (double)g.voxel * ix, wy = (double)g.oy + (double)g.voxel * iy,
-               wz = (double)g.oz + (double)g.voxel * iz;
+  // the reference's voxel coordinates are float32 tensors (metric: voxel_size * index, lattice through `origin`), promoted to
+  // float64 together with extrinsic and intrinsic for the projection (:243-252): float32 product, float32 sum, no contraction
+  const double wx = (double)__fadd_rn(__fmul_rn(g.voxel, (float)ix), g.ox), wy = (double)__fadd_rn(__fmul_rn(g.voxel, (float)iy), g.oy),
+               wz = (double)__fadd_rn(__fmul_rn(g.voxel, (float)iz), g.oz);
   const double x = sR[0] * wx + sR[1] * wy + sR[2] * wz + st[0];
   const double y = sR[3] * wx + sR[4] * wy + sR[5] * wz + st[1];
   const double d = sR[6] * wx + sR[7] * wy + sR[8] * wz + st[2];
@@ -80,12 +83,13 @@ tsdf_integrate_kernel(TsdfGrid g, TsdfFrame f) {
   const size_t vi = ((size_t)iz * g.ny + iy) * g.nx + ix;
   const float w = g.weight[vi];
   const float wp = w + wr;
-  g.tsdf[vi] = (w * g.tsdf[vi] + wr * sdf) / wp;
+  // products and sum rounded separately, like the tensor expression (:280-281) — no FMA contraction
+  g.tsdf[vi] = __fdiv_rn(__fadd_rn(__fmul_rn(w, g.tsdf[vi]), __fmul_rn(wr, sdf)), wp);
   const size_t hw = (size_t)f.H * f.W;
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     const float col = (float)f.rgb[(size_t)c * hw + pix];
-    g.color[vi * 3 + c] = (w * g.color[vi * 3 + c] + wr * col) / wp;
+    g.color[vi * 3 + c] = __fdiv_rn(__fadd_rn(__fmul_rn(w, g.color[vi * 3 + c]), __fmul_rn(wr, col)), wp);
   }
   g.weight[vi] = fminf(wp, f.max_weight);
 }

@@ -1,9 +1,12 @@
 """ORACLE (test infrastructure only — never imported by the product path).
 
 CPU restatement (numpy) of the per-voxel update of TsdfFusion.custom_volume_integrate, reference
-fusion/tsdf_fusion.py:231-296, applied to EVERY voxel of a dense grid (Open3D's block activation, :216-228, is absent
-from /root/reference — parity of the active set is unpinned; the update rule itself is the reference's own Python and
-is followed operation for operation: fp64 projection, Tensor.round(), fp32 sdf / weights / running averages)."""
+fusion/tsdf_fusion.py:231-296 (and of the pixel masking / weighting of build_volume, :185-203), applied to EVERY voxel of a
+dense grid.  Open3D's block activation is absent from /root/reference — parity of the ACTIVE SET is unpinned; the update rule
+itself is pinned: tests/golden/ref_tsdf_integrate.npz holds the output of the reference's own `build_volume` +
+`custom_volume_integrate` executed verbatim on torch stand-ins for Open3D's tensors (tests/golden/make_golden_tsdf.py), and
+this restatement follows it operation for operation: float32 voxel coordinates and pose matrix promoted to fp64 for the
+projection, Tensor.round(), fp32 sdf / weights / running averages (tests/test_cpu_golden.py)."""
 import numpy as np
 
 F32 = np.float32
@@ -17,7 +20,7 @@ def pose_tq_to_matrix(tq):
     T = np.eye(4)
     T[:3, :3] = R
     T[:3, 3] = np.asarray(tq[:3], np.float64)
-    return T
+    return T.astype(np.float32).astype(np.float64)      # SE3(poses).matrix() is fp32; build_volume promotes it (:209)
 
 
 def integrate(tsdf, weight, color, origin, voxel_size, idepth_up, depth_cov_up, rgb_chw, intr, cam_T_world_tq,
@@ -36,9 +39,13 @@ def integrate(tsdf, weight, color, origin, voxel_size, idepth_up, depth_cov_up, 
     T = pose_tq_to_matrix(np.asarray(cam_T_world_tq, np.float32))
     fx, fy, cx, cy = [float(F32(v)) for v in intr]
     iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-    org = np.asarray(origin, np.float32).astype(np.float64)
-    vs = float(F32(voxel_size))
-    wx, wy, wz = org[0] + vs * ix, org[1] + vs * iy, org[2] + vs * iz
+    # voxel coordinates are float32 tensors in the reference (Open3D hands out float32 metric coordinates), promoted to
+    # float64 for the projection (:246): float32 product, float32 sum
+    org = np.asarray(origin, np.float32)
+    vs = F32(voxel_size)
+    wx = (vs * ix.astype(F32) + org[0]).astype(F32).astype(np.float64)
+    wy = (vs * iy.astype(F32) + org[1]).astype(F32).astype(np.float64)
+    wz = (vs * iz.astype(F32) + org[2]).astype(F32).astype(np.float64)
     x = T[0, 0] * wx + T[0, 1] * wy + T[0, 2] * wz + T[0, 3]
     y = T[1, 0] * wx + T[1, 1] * wy + T[1, 2] * wz + T[1, 3]
     d = T[2, 0] * wx + T[2, 1] * wy + T[2, 2] * wz + T[2, 3]

@@ -200,3 +200,34 @@ def test_product_corr_wrappers_match_reference_wrappers(monkeypatch):
     assert tuple(out.shape) == g["volume_lookup"].shape
     ref = g["volume_lookup"]
     assert np.abs(out.numpy() - ref).max() < 2e-2 * max(1.0, np.abs(ref).max())      # features pass through fp16 in the product wrapper
+
+
+def _tsdf_golden():
+    g = np.load(os.path.join(G, "ref_tsdf_integrate.npz"))
+    intr = g["intr"]
+    return g, np.array([intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2]], np.float32)
+
+
+def test_tsdf_oracle_matches_the_reference_methods_executed_verbatim():
+    """oracle/tsdf.py against the output of the reference's own build_volume + custom_volume_integrate
+    (fusion/tsdf_fusion.py:185-302, run on torch stand-ins for Open3D's tensors by tests/golden/make_golden_tsdf.py): three
+    keyframes, snapshots after each, both flavours, with and without weight saturation.  "tsdf" (uniform weights) is
+    bit-exact; in "sigma" the weights 1/sqrt(cov) differ in the last bit wherever torch's vectorised CPU sqrt is not
+    correctly rounded (0.7 % of arguments; numpy's — and CUDA's sqrtf — is)."""
+    from oracle import tsdf as otsdf
+    g, intr4 = _tsdf_golden()
+    n, vs, org = int(g["n"]), float(g["voxel_size"]), g["origin"]
+    for tag in ("sigma", "tsdf"):
+        for mw in (20.0, 2.5):
+            t = np.zeros((n, n, n), np.float32); w = np.zeros((n, n, n), np.float32); c = np.zeros((n, n, n, 3), np.float32)
+            for k in range(3):
+                otsdf.integrate(t, w, c, org, vs, g["idepths"][k], g["covs"][k] if tag == "sigma" else None, g["imgs"][k], intr4,
+                                g["poses"][k], max_weight=mw)
+                rt, rw, rc = g[f"{tag}_w{mw}_tsdf_{k}"], g[f"{tag}_w{mw}_weight_{k}"], g[f"{tag}_w{mw}_color_{k}"]
+                assert np.array_equal(w > 0, rw > 0), (tag, mw, k)                       # the same voxels are updated
+                if tag == "tsdf":
+                    assert np.array_equal(t, rt) and np.array_equal(w, rw) and np.array_equal(c, rc), (tag, mw, k)
+                else:
+                    assert np.allclose(w, rw, rtol=3e-7, atol=0) and np.allclose(t, rt, rtol=0, atol=3e-7) \
+                        and np.allclose(c, rc, rtol=0, atol=1e-4), (tag, mw, k)
+            assert (rw > 0).sum() > 5000 and float(rw.max()) == (mw if (tag == "sigma" or mw < 3) else 3.0)

@@ -60,6 +60,43 @@ def test_tsdf_integrate_matches_oracle(mode):
     assert rw.max() == 20.0 and gw.max() == 20.0
 
 
+@pytest.mark.parametrize("tag,mw", [("sigma", 20.0), ("sigma", 2.5), ("tsdf", 20.0), ("tsdf", 2.5)])
+def test_tsdf_kernel_matches_the_reference_methods_executed_verbatim(tag, mw):
+    """nslam_tsdf_integrate against tests/golden/ref_tsdf_integrate.npz = the reference's own build_volume +
+    custom_volume_integrate executed verbatim on stand-ins for Open3D's tensors (tests/golden/make_golden_tsdf.py): three
+    keyframes, checked after each.  The kernel performs the reference's operations in the reference's order (float32 voxel
+    coordinates and pose matrix promoted to fp64, round-half-even, separately rounded products): bit-exact against the numpy
+    oracle in both flavours and against the golden in "tsdf"; in "sigma" the golden's weights carry the last-bit error of
+    torch's vectorised CPU sqrt (see tests/test_cpu_golden.py), hence 3e-7."""
+    import os
+    from nerf_slam_b200 import _lib
+    from oracle import tsdf as otsdf
+    lib = _lib.load()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tsdf_integrate.npz"))
+    n, vs, org, intr = int(g["n"]), float(g["voxel_size"]), g["origin"], g["intr"]
+    intr4 = np.array([intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2]], np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    tsdf = torch.zeros(n, n, n, device=DEV); weight = torch.zeros(n, n, n, device=DEV); color = torch.zeros(n, n, n, 3, device=DEV)
+    ot, ow, oc = np.zeros((n, n, n), np.float32), np.zeros((n, n, n), np.float32), np.zeros((n, n, n, 3), np.float32)
+    for k in range(3):
+        cov = g["covs"][k] if tag == "sigma" else None
+        d_idepth, d_cov, d_rgb, d_tq = T(g["idepths"][k]), (T(cov) if cov is not None else None), T(g["imgs"][k]), T(g["poses"][k])
+        H, W = g["idepths"][k].shape
+        _lib.check(lib.nslam_tsdf_integrate(_lib.ptr(tsdf), _lib.ptr(weight), _lib.ptr(color), n, n, n, org.ctypes.data, vs,
+                                            _lib.ptr(d_idepth), _lib.ptr(d_cov) if d_cov is not None else None, _lib.ptr(d_rgb),
+                                            H, W, intr4.ctypes.data, _lib.ptr(d_tq), 6.0, 0.10, mw, 10000.0, _lib.stream_ptr()), "tsdf")
+        torch.cuda.synchronize()
+        otsdf.integrate(ot, ow, oc, org, vs, g["idepths"][k], cov, g["imgs"][k], intr4, g["poses"][k], max_weight=mw)
+        gt, gw, gc = tsdf.cpu().numpy(), weight.cpu().numpy(), color.cpu().numpy()
+        assert np.array_equal(gw, ow) and np.array_equal(gt, ot) and np.array_equal(gc, oc), (k, float(np.abs(gt - ot).max()))
+        rt, rw, rc = g[f"{tag}_w{mw}_tsdf_{k}"], g[f"{tag}_w{mw}_weight_{k}"], g[f"{tag}_w{mw}_color_{k}"]
+        assert np.array_equal(gw > 0, rw > 0), k
+        if tag == "tsdf":
+            assert np.array_equal(gt, rt) and np.array_equal(gw, rw) and np.array_equal(gc, rc), k
+        else:
+            assert np.allclose(gw, rw, rtol=3e-7, atol=0) and np.allclose(gt, rt, rtol=0, atol=3e-7) and np.allclose(gc, rc, rtol=0, atol=1e-4), k
+
+
 def test_tsdf_fusion_of_ground_truth_packets_recovers_the_room():
     """TsdfFusion('sigma') fed SLAM-shaped packets built from the synthetic room's ground-truth poses and depths: the
     zero crossings of the fused TSDF lie on the room's walls (within two voxels), history / rebuild work"""
