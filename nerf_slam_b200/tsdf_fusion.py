@@ -46,7 +46,11 @@ class TsdfFusion:
         self.tsdf = torch.zeros(n, n, n, dtype=torch.float32, device=dev)
         self.weight = torch.zeros(n, n, n, dtype=torch.float32, device=dev)
         self.color = torch.zeros(n, n, n, 3, dtype=torch.float32, device=dev)
-        self.origin = (self.grid_center - 0.5 * self.voxel_size * (n - 1)).astype(np.float32)
+        # voxel (i, j, k) sits at origin + voxel_size * (i, j, k) with the lattice passing through the world origin, like the
+        # metric voxel coordinates Open3D's VoxelBlockGrid hands out (integer index x voxel_size): same sample points as the
+        # reference wherever both volumes have a voxel
+        vs = np.float32(self.voxel_size)
+        self.origin = ((np.round(self.grid_center / vs) - n // 2) * vs).astype(np.float32)
 
     def reset_volume(self):
         """:304-316 — NB the reference re-creates its volume with HALF the voxel size here; kept"""
