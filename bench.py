@@ -38,6 +38,7 @@ if ROOT not in sys.path:
 
 W_IMG, H_IMG = 640, 480
 STREAM_STEP = 0.035           # camera pace: ~every 3rd-4th frame becomes a keyframe
+NERF_SM_BUDGET_SHARED = 72    # SMs of the persistent NeRF kernels when SLAM and NeRF share one GPU (N = 1)
 # --workload: cfg2 = BASELINE.json configs[1] (the metric's configuration, default); cfg5 = configs[4]'s shapes
 # (1280x720, buffer 200); cfg4 = configs[3] (640x480, buffer 400, plus the global-BA / alt-corr pass over the filled
 # window, timed separately as `global_ba`).  The driver runs the default; the others are recorded under profiles/.
@@ -133,9 +134,11 @@ class SlamNerfJob:
             self.nf = NerfFusion("nerf", args, self.dev)
             self.nerf_stream = torch.cuda.Stream(priority=0) if world == 1 else torch.cuda.current_stream()
             if world == 1 and "NSLAM_NERF_SMS" not in os.environ:
-                # sharing the GPU with SLAM: the persistent NeRF kernels stay on 40 of the 148 SMs so that the
-                # latency-critical SLAM kernels never wait for a NeRF CTA to retire (profiles/r01_sm_split_run20.log)
-                self.nf.ngp.num_sms = min(self.nf.ngp.num_sms, 40)
+                # sharing the GPU with SLAM: the persistent NeRF kernels stay on 72 of the 148 SMs.  Unbounded, the
+                # latency-critical SLAM kernels wait for NeRF CTAs to retire (persistent CTAs are not pre-empted); too
+                # small a share stretches every NeRF kernel and with it the time both streams fight for the rest of the GPU.
+                # Measured at 28 / 40 / 56 / 72 SMs: 182 / 186-192 / 197 / 202 frames/s (profiles/r02_bench_call2[12]_nerf_sms*.json)
+                self.nf.ngp.num_sms = min(self.nf.ngp.num_sms, NERF_SM_BUDGET_SHARED)
         # SLAM is the latency-critical chain (host decisions wait on it): its kernels run on a HIGH-priority
         # stream so that NeRF training on the same GPU only fills the gaps
         self.slam_stream = torch.cuda.Stream(priority=-1) if (self.is_slam and world == 1) else torch.cuda.current_stream()
