@@ -69,3 +69,20 @@ def test_reference_slam_demo_runs_unchanged_on_the_shim(tmp_path, monkeypatch):
     assert log["ctor"] == ((4, 4), (4, 4), "cuda:0", 50)
     assert log["fused"] == 6 and log["fit_only"] >= 3      # every SLAM output reached the fusion module; then it kept fitting
     assert "slam.slam_module" in sys.modules and sys.modules["slam.slam_module"].__file__.startswith(SHIM)
+
+
+def test_pipeline_modules_replay_the_reference_modules():
+    """DataModule / SlamModule / FusionModule (+ the MIMO base) of nerf_slam_b200/pipeline.py against traces of the
+    reference's OWN classes under the same scripted scenarios (tests/golden/ref_pipeline_traces.json, recorded by
+    make_golden_pipeline.py from /root/reference with only `colored_glog` / `icecream` stubbed): sequential spin loops incl. a
+    falsy and a None SLAM output and the stop condition, parallel loops until self-shutdown, shutdown / restart, a raising
+    consumer, unknown module names, empty inputs"""
+    import json
+    from nerf_slam_b200 import pipeline
+    from tests.golden import pipeline_scenario as sc
+    with open(os.path.join(ROOT, "tests", "golden", "ref_pipeline_traces.json")) as f:
+        ref = json.load(f)
+    got = json.loads(json.dumps(sc.run((pipeline.DataModule, pipeline.SlamModule, pipeline.FusionModule))))
+    assert set(got) == set(ref)
+    for name in ref:
+        assert got[name] == ref[name], name
