@@ -104,3 +104,23 @@ def test_product_process_data_matches_reference():
     assert np.allclose([dscale, cscale], GOLD["data.scales"], rtol=1e-12)
     s, o = get_scale_and_offset([[-2.0, -1.0, -2.0], [2.0, 3.0, 2.0]])
     assert s == 0.25 and np.allclose(o, [0.5, 0.25, 0.5])
+
+
+def test_tsdf_fusion_history_matches_the_reference_methods():
+    """TsdfFusion.update_history / get_history_packet against the reference's own methods executed verbatim
+    (tests/golden/ref_tsdf_history.json, make_golden_tsdf_history.py): overlapping dirty windows overwrite their entries,
+    insertion order and frame-id keys, the last-frame packet is refused, stacked packet shapes and contents"""
+    import json
+    import types
+    from nerf_slam_b200.tsdf_fusion import TsdfFusion
+    from tests.golden import make_golden_tsdf_history as mk
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tsdf_history.json")) as f:
+        ref = json.load(f)
+    fus = TsdfFusion("sigma", types.SimpleNamespace(eval=False, tsdf_resolution=8), device="cpu")
+    returns = [bool(fus.update_history(p)) for p in mk.packets()]
+    got = json.loads(json.dumps(mk.summarize(fus, returns)))
+    gt_ref, gt_got = ref["packet"].pop("gt_depths_sum"), got["packet"].pop("gt_depths_sum")
+    assert got == ref
+    # same values x depth_scale; the reference additionally applies `.permute(2,0,1)` to the [1,H,W] maps (:528, its own TODO
+    # questions that line) — consumed only by its Open3D evaluation rendering, which is out of scope
+    assert abs(gt_ref - gt_got) < 1e-3
