@@ -124,3 +124,18 @@ def test_tsdf_fusion_history_matches_the_reference_methods():
     # same values x depth_scale; the reference additionally applies `.permute(2,0,1)` to the [1,H,W] maps (:528, its own TODO
     # questions that line) — consumed only by its Open3D evaluation rendering, which is out of scope
     assert abs(gt_ref - gt_got) < 1e-3
+
+
+def test_nerf_fusion_control_loop_matches_the_reference_methods():
+    """NerfFusion.fuse / fit_volume / fit_volume_once / stop_condition against the reference's own methods executed verbatim
+    around a recording `ngp` (tests/golden/ref_nerf_fusion_loop.json, make_golden_nerf_fusion_loop.py): which packets trigger
+    fitting, iterations per call, annealing and evaluation cadence, the stop rule, the error for unknown packet names"""
+    import json
+    from nerf_slam_b200.nerf_fusion import NerfFusion
+    from tests.golden import make_golden_nerf_fusion_loop as mk
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_nerf_fusion_loop.json")) as f:
+        ref = json.load(f)
+    for e in (False, True):
+        for a in (False, True):
+            got = json.loads(json.dumps(mk.drive(NerfFusion.__new__(NerfFusion), e, a)))
+            assert got == ref[f"eval{int(e)}_anneal{int(a)}"], (e, a)
